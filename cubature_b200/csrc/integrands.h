@@ -1,0 +1,324 @@
+// integrands.h -- built-in integrand families (the "device-side plugin" of BASELINE.json).
+//
+// Each family is a small functor template<int DIM>: the constructor derives per-thread constants
+// from the parameter vector, eval() computes all fdim components at one point x[DIM].
+// The header compiles unchanged with g++ (CPU oracle), nvcc and NVRTC; all transcendental math
+// goes through detmath.h so host and device produce identical bits (compile without contraction).
+// Every loop runs over the dimension in ascending order: that order is part of the definition.
+//
+// Families
+//   1..6   Genz test family on [0,1]^d; params = a[0..d) then u[0..d)
+//   10     isotropic Gaussian exp(-sigma * sum x_i^2); params = {sigma}
+//          (the reference's only golden vector: TestCubature.java:435-465 / README.md:224)
+//   20     the reference's test integrands 0..8 (TestCubature.java:46-177); params = which[fdim]
+//   30     oscillatory vector f_k(x) = cos((k+1) * sum x_i), k < fdim   (BASELINE config C2)
+//   31     complex exponentials g_m(x) = exp(-(1 + i w_m) sum x_i), interleaved (re, im)
+//          (BASELINE config C4; params = w[fdim/2])
+#ifndef CUBATURE_INTEGRANDS_H
+#define CUBATURE_INTEGRANDS_H
+
+#include "detmath.h"
+
+#define CUB_FAM_GENZ_OSCILLATORY 1
+#define CUB_FAM_GENZ_PRODUCT_PEAK 2
+#define CUB_FAM_GENZ_CORNER_PEAK 3
+#define CUB_FAM_GENZ_GAUSSIAN 4
+#define CUB_FAM_GENZ_C0 5
+#define CUB_FAM_GENZ_DISCONTINUOUS 6
+#define CUB_FAM_GAUSS_ISO 10
+#define CUB_FAM_REFTEST 20
+#define CUB_FAM_OSC_VEC 30
+#define CUB_FAM_CEXP 31
+#define CUB_FAM_USER 1000
+
+#define CUB_TWO_PI 6.283185307179586
+
+// ---- Genz family --------------------------------------------------------------------------------
+
+template <int DIM>
+struct GenzOscillatory {  // cos(2 pi u_0 + sum a_i x_i)
+    static const bool kSeparable = false;
+    double a[DIM], phase;
+    DM_HD GenzOscillatory(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) a[i] = p[i];
+        phase = CUB_TWO_PI * p[DIM];
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = phase;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
+        f[0] = dm_cos(s);
+    }
+};
+
+template <int DIM>
+struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 / prod(...)
+    static const bool kSeparable = false;
+    double c[DIM], u[DIM];
+    DM_HD GenzProductPeak(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) {
+            c[i] = 1.0 / (p[i] * p[i]);
+            u[i] = p[DIM + i];
+        }
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double den = 1.0;
+        for (int i = 0; i < DIM; ++i) {
+            double t = x[i] - u[i];
+            den = den * dm_fma(t, t, c[i]);
+        }
+        f[0] = 1.0 / den;
+    }
+};
+
+template <int DIM>
+struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
+    static const bool kSeparable = false;
+    double a[DIM];
+    DM_HD GenzCornerPeak(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) a[i] = p[i];
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 1.0;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
+        double r = s;
+        for (int i = 0; i < DIM; ++i) r = r * s;  // s^(d+1), left to right
+        f[0] = 1.0 / r;
+    }
+};
+
+template <int DIM>
+struct GenzGaussian {  // exp(-sum a_i^2 (x_i - u_i)^2)
+    static const bool kSeparable = false;
+    double a[DIM], u[DIM];
+    DM_HD GenzGaussian(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) {
+            a[i] = p[i];
+            u[i] = p[DIM + i];
+        }
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) {
+            double t = a[i] * (x[i] - u[i]);
+            s = dm_fma(t, t, s);
+        }
+        f[0] = dm_exp(-s);
+    }
+};
+
+template <int DIM>
+struct GenzC0 {  // exp(-sum a_i |x_i - u_i|)
+    static const bool kSeparable = false;
+    double a[DIM], u[DIM];
+    DM_HD GenzC0(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) {
+            a[i] = p[i];
+            u[i] = p[DIM + i];
+        }
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], dm_abs(x[i] - u[i]), s);
+        f[0] = dm_exp(-s);
+    }
+};
+
+template <int DIM>
+struct GenzDiscontinuous {  // 0 if x_0 > u_0 or x_1 > u_1, else exp(sum a_i x_i)
+    static const bool kSeparable = false;
+    double a[DIM], u0, u1;
+    DM_HD GenzDiscontinuous(const double* p, int) {
+        for (int i = 0; i < DIM; ++i) a[i] = p[i];
+        u0 = p[DIM];
+        u1 = DIM > 1 ? p[DIM + (DIM > 1 ? 1 : 0)] : 0.0;
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
+        bool outside = x[0] > u0;
+        if (DIM > 1) outside = outside || (x[DIM > 1 ? 1 : 0] > u1);
+        f[0] = outside ? 0.0 : dm_exp(s);
+    }
+};
+
+// ---- the reference's golden-vector integrand -----------------------------------------------------
+// TestCubature.java:442-455: sum += x*x left to right (Java never fuses), exp(-sigma*sum).
+template <int DIM>
+struct GaussIso {
+    static const bool kSeparable = false;
+    double sigma;
+    DM_HD GaussIso(const double* p, int) { sigma = p[0]; }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = s + x[i] * x[i];
+        f[0] = dm_exp(-sigma * s);
+    }
+};
+
+// ---- the reference's test integrands, TestCubature.java:46-177 ------------------------------------
+// Same operation order as the Java source; Math.exp/cos/sin/pow replaced by the detmath versions
+// (Math.pow with an integer exponent -> dm_powi; pow(x, 2.0) -> x*x which is what an exact pow gives).
+#define CUB_REFTEST_MAX_FDIM 16
+template <int DIM>
+struct RefTest {
+    static const bool kSeparable = false;
+    int fdim;
+    int which[CUB_REFTEST_MAX_FDIM];
+    DM_HD RefTest(const double* p, int fdim_) {
+        fdim = fdim_ < CUB_REFTEST_MAX_FDIM ? fdim_ : CUB_REFTEST_MAX_FDIM;
+        for (int j = 0; j < CUB_REFTEST_MAX_FDIM; ++j) which[j] = j < fdim ? (int)p[j] : 0;
+    }
+    DM_HD static double one(const double* x, int w) {
+        const double K_2_SQRTPI = 1.12837916709551257390;
+        const double radius = 0.50124145262344534123412;
+        double val = 0.0;
+        switch (w) {
+            case 0: {  // prod cos(x_i)                                   TestCubature.java:118-123
+                val = 1.0;
+                for (int i = 0; i < DIM; ++i) val = val * dm_cos(x[i]);
+            } break;
+            case 1: {  // exp(-z^2) remapped from (0, inf)                 TestCubature.java:124-139
+                double scale = 1.0;
+                bool zero = false;
+                for (int i = 0; i < DIM; ++i) {
+                    if (zero) continue;
+                    if (x[i] > 0) {
+                        double z = (1 - x[i]) / x[i];
+                        val = val + z * z;
+                        scale = scale * (K_2_SQRTPI / (x[i] * x[i]));
+                    } else {
+                        scale = 0;
+                        zero = true;
+                    }
+                }
+                val = dm_exp(-val) * scale;
+            } break;
+            case 2: {  // hypersphere indicator                              TestCubature.java:140-147
+                for (int i = 0; i < DIM; ++i) val = val + x[i] * x[i];
+                val = val < radius * radius ? 1.0 : 0.0;
+            } break;
+            case 3: {  // prod 2 x_i                                         TestCubature.java:46-53
+                val = 1.0;
+                for (int i = 0; i < DIM; ++i) val = val * (2.0 * x[i]);
+            } break;
+            case 4: {  // Gaussian a = 0.1 centred at 1/2                    TestCubature.java:58-66
+                const double a = 0.1;
+                double sum = 0.0;
+                for (int i = 0; i < DIM; ++i) {
+                    double dx = x[i] - 0.5;
+                    sum = sum + dx * dx;
+                }
+                val = dm_powi(K_2_SQRTPI / (2.0 * a), DIM) * dm_exp(-sum / (a * a));
+            } break;
+            case 5: {  // double Gaussian                                    TestCubature.java:69-81
+                const double a = 0.1;
+                double sum1 = 0.0, sum2 = 0.0;
+                for (int i = 0; i < DIM; ++i) {
+                    double dx1 = x[i] - 1.0 / 3.0;
+                    double dx2 = x[i] - 2.0 / 3.0;
+                    sum1 = sum1 + dx1 * dx1;
+                    sum2 = sum2 + dx2 * dx2;
+                }
+                val = 0.5 * dm_powi(K_2_SQRTPI / (2.0 * a), DIM) *
+                      (dm_exp(-sum1 / (a * a)) + dm_exp(-sum2 / (a * a)));
+            } break;
+            case 6: {  // Tsuda, c = (1 + sqrt(10)) / 9                      TestCubature.java:84-91
+                const double c = (1.0 + dm_sqrt(10.0)) / 9.0;
+                val = 1.0;
+                for (int i = 0; i < DIM; ++i) {
+                    double q = (c + 1) / (c + x[i]);
+                    val = val * (c / (c + 1) * (q * q));
+                }
+            } break;
+            case 7: {  // Morokoff-Caflisch                                  TestCubature.java:98-106
+                double pw = 1.0 / DIM;
+                val = dm_powi(1 + pw, DIM);
+                for (int i = 0; i < DIM; ++i) val = val * dm_pow(x[i], pw);
+            } break;
+            case 8: {  // HCubature.jl#4 (dim 3 only)                        TestCubature.java:164-171
+                if (DIM == 3) {
+                    val = x[0] * 0.2 * (x[DIM > 2 ? 2 : 0] - 0.5) * 0.4 *
+                          dm_sin(x[DIM > 1 ? 1 : 0] * 6.283185307179586);
+                    val = 1 + val * val;
+                }
+            } break;
+            default:
+                val = 0.0;
+        }
+        return val;
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        for (int j = 0; j < fdim; ++j) f[j] = one(x, which[j]);
+    }
+};
+
+// ---- vector families ------------------------------------------------------------------------------
+
+template <int DIM>
+struct OscVec {  // f_k = cos((k+1) * sum x_i): every component independent -> separable
+    static const bool kSeparable = true;
+    int fdim;
+    DM_HD OscVec(const double*, int fdim_) { fdim = fdim_; }
+    DM_HD static double sumx(const double* x) {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = s + x[i];
+        return s;
+    }
+    DM_HD double eval1(const double* x, int j) const { return dm_cos((double)(j + 1) * sumx(x)); }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = sumx(x);
+        for (int j = 0; j < fdim; ++j) f[j] = dm_cos((double)(j + 1) * s);
+    }
+};
+
+template <int DIM>
+struct CExp {  // g_m = exp(-(1 + i w_m) s), s = sum x_i ; f[2m] = Re, f[2m+1] = Im
+    static const bool kSeparable = false;
+    int fdim;
+    const double* w;
+    DM_HD CExp(const double* p, int fdim_) {
+        fdim = fdim_;
+        w = p;
+    }
+    DM_HD void eval(const double* x, double* f) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = s + x[i];
+        double e = dm_exp(-s);
+        for (int m = 0; 2 * m + 1 < fdim; ++m) {
+            double ph = w[m] * s;
+            f[2 * m] = e * dm_cos(ph);
+            f[2 * m + 1] = -(e * dm_sin(ph));
+        }
+        if (fdim & 1) f[fdim - 1] = e;
+    }
+};
+
+// ---- infinite-interval variable transforms (README.md:237-272, fused into point generation) -------
+// code 0: x = t
+// code 1: [a, inf)    x = a + t/(1-t),   t in [0,1),  dx = dt / (1-t)^2
+// code 2: (-inf, b]   x = b - t/(1-t),   t in [0,1),  dx = dt / (1-t)^2
+// code 3: (-inf, inf) x = t/(1-t^2),     t in (-1,1), dx = (1+t^2)/(1-t^2)^2 dt
+// One division per transformed coordinate; returns the Jacobian factor of that coordinate.
+#define CUB_TR_NONE 0
+#define CUB_TR_SEMI_INF_UP 1
+#define CUB_TR_SEMI_INF_DOWN 2
+#define CUB_TR_INF 3
+
+DM_HD double cub_transform_coord(int code, double shift, double t, double* x) {
+    if (code == CUB_TR_SEMI_INF_UP || code == CUB_TR_SEMI_INF_DOWN) {
+        double inv = 1.0 / (1.0 - t);
+        double q = t * inv;
+        *x = code == CUB_TR_SEMI_INF_UP ? shift + q : shift - q;
+        return inv * inv;
+    }
+    if (code == CUB_TR_INF) {
+        double t2 = t * t;
+        double inv = 1.0 / (1.0 - t2);
+        *x = t * inv;
+        return ((1.0 + t2) * inv) * inv;
+    }
+    *x = t;
+    return 1.0;
+}
+
+#endif  // CUBATURE_INTEGRANDS_H
