@@ -1,0 +1,1177 @@
+// cubature_cuda.cpp -- host side of libcubature_cuda.so: the C ABI (include/cubature_cuda.h) and the
+// two drivers of the h-adaptive loop.
+//
+//   DEVICE mode (default): the region pool lives in HBM as a structure of arrays and never leaves it.
+//     Per refinement iteration the GPU computes the pool totals (K5), decides the batch of regions to
+//     bisect (K3: select-all shortcut, else stable radix sort by errmax + prefix sums + the reference's
+//     residual test evaluated for every k in parallel), and runs the fused bisect + rule kernel (K4+K1/K2).
+//     The host only reads back a few scalars per iteration to size the next launches.
+//   HEAP_EXACT mode: the host replays Rule.cubature literally (Rule.java:51-160) with a
+//     java.util.PriorityQueue-compatible heap of (errmax, slot) and the reference's incremental
+//     running sums (RegionHeap.java:21-36), so batch sizes, tie order and the final summation order
+//     are the reference's bit for bit; the GPU evaluates the rule and bisects.
+//
+// Nothing in this file (or anywhere in cubature_b200/) touches oracle/: there is no CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "converge.h"
+#include "cub_internal.h"
+#include "integrands.h"
+#include "pool_kernels.h"
+
+int64_t cub_points_per_region(int dim) {
+    if (dim == 1) return 15;
+    if (dim < 1 || dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
+    return 1 + 4 * (int64_t)dim + 2 * (int64_t)dim * (dim - 1) + ((int64_t)1 << dim);
+}
+
+namespace {
+
+struct VecAcc {  // accessor over dense val[f], err[f] for cub_converged
+    const double* v;
+    const double* e;
+    CUB_HD double val(int j) const { return v[j]; }
+    CUB_HD double err(int j) const { return e[j]; }
+};
+
+struct DevBuf {  // RAII device allocation
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+struct Pool {
+    DevBuf center, halfw, val, err, errmax, splitdim;
+    long long cap = 0;
+    int dim = 0, fdim = 0;
+    PoolView view() const {
+        PoolView v;
+        v.center = center.as<double>();
+        v.halfw = halfw.as<double>();
+        v.val = val.as<double>();
+        v.err = err.as<double>();
+        v.errmax = errmax.as<double>();
+        v.splitdim = splitdim.as<int>();
+        v.cap = cap;
+        return v;
+    }
+    static size_t bytes_per_region(int dim, int fdim) { return (size_t)8 * (2 * dim + 2 * fdim + 1) + 4; }
+    cudaError_t alloc(int dim_, int fdim_, long long cap_) {
+        dim = dim_;
+        fdim = fdim_;
+        cap = cap_;
+        cudaError_t e;
+        if ((e = center.ensure((size_t)8 * dim * cap)) != cudaSuccess) return e;
+        if ((e = halfw.ensure((size_t)8 * dim * cap)) != cudaSuccess) return e;
+        if ((e = val.ensure((size_t)8 * fdim * cap)) != cudaSuccess) return e;
+        if ((e = err.ensure((size_t)8 * fdim * cap)) != cudaSuccess) return e;
+        if ((e = errmax.ensure((size_t)8 * cap)) != cudaSuccess) return e;
+        if ((e = splitdim.ensure((size_t)4 * cap)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    // re-stride every row into a pool of larger capacity (n live regions)
+    cudaError_t grow(long long new_cap, long long n, cudaStream_t s) {
+        Pool np;
+        cudaError_t e = np.alloc(dim, fdim, new_cap);
+        if (e != cudaSuccess) return e;
+        auto rows = [&](DevBuf& dst, DevBuf& src, int nrows, size_t elt) {
+            return cudaMemcpy2DAsync(dst.p, (size_t)new_cap * elt, src.p, (size_t)cap * elt, (size_t)n * elt, nrows,
+                                     cudaMemcpyDeviceToDevice, s);
+        };
+        if ((e = rows(np.center, center, dim, 8)) != cudaSuccess) return e;
+        if ((e = rows(np.halfw, halfw, dim, 8)) != cudaSuccess) return e;
+        if ((e = rows(np.val, val, fdim, 8)) != cudaSuccess) return e;
+        if ((e = rows(np.err, err, fdim, 8)) != cudaSuccess) return e;
+        if ((e = rows(np.errmax, errmax, 1, 8)) != cudaSuccess) return e;
+        if ((e = rows(np.splitdim, splitdim, 1, 4)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        std::swap(center, np.center);
+        std::swap(halfw, np.halfw);
+        std::swap(val, np.val);
+        std::swap(err, np.err);
+        std::swap(errmax, np.errmax);
+        std::swap(splitdim, np.splitdim);
+        cap = new_cap;
+        return cudaSuccess;
+    }
+};
+
+// java.util.PriorityQueue semantics over slot ids keyed by errmax[slot];
+// comparator = Region.compareTo (Region.java:41-55): equal keys compare 0, larger errmax first.
+struct SlotHeap {
+    std::vector<int> q;
+    const std::vector<double>* key = nullptr;
+    int cmp(int a, int b) const {
+        const double ka = (*key)[a], kb = (*key)[b];
+        if (ka == kb) return 0;
+        return ka < kb ? 1 : -1;
+    }
+    void add(int x) {
+        size_t k = q.size();
+        q.push_back(x);
+        while (k > 0) {
+            const size_t parent = (k - 1) >> 1;
+            if (cmp(x, q[parent]) >= 0) break;
+            q[k] = q[parent];
+            k = parent;
+        }
+        q[k] = x;
+    }
+    int poll() {
+        const int top = q[0];
+        const int x = q.back();
+        q.pop_back();
+        const size_t n = q.size();
+        if (n > 0) {
+            size_t k = 0;
+            const size_t half = n >> 1;
+            while (k < half) {
+                size_t child = 2 * k + 1;
+                if (child + 1 < n && cmp(q[child], q[child + 1]) > 0) ++child;
+                if (cmp(x, q[child]) <= 0) break;
+                q[k] = q[child];
+                k = child;
+            }
+            q[k] = x;
+        }
+        return top;
+    }
+};
+
+struct TransformSpec {
+    bool any = false;
+    int code[CUB_MAX_DIM];
+    double shift[CUB_MAX_DIM];
+    double tmin[CUB_MAX_DIM], tmax[CUB_MAX_DIM];
+};
+
+int make_transform(int dim, const double* xmin, const double* xmax, const int* transform, TransformSpec* t) {
+    t->any = false;
+    for (int d = 0; d < dim; ++d) {
+        int code;
+        if (transform) {
+            code = transform[d];
+            if (code < 0 || code > 3) return CUB_ERR_BAD_ARGS;
+        } else {
+            const bool lo_inf = std::isinf(xmin[d]) && xmin[d] < 0, hi_inf = std::isinf(xmax[d]) && xmax[d] > 0;
+            code = lo_inf && hi_inf ? CUB_TRANSFORM_INF : hi_inf ? CUB_TRANSFORM_SEMI_INF_UP : lo_inf ? CUB_TRANSFORM_SEMI_INF_DOWN : 0;
+        }
+        t->code[d] = code;
+        t->shift[d] = 0.0;
+        t->tmin[d] = xmin[d];
+        t->tmax[d] = xmax[d];
+        if (code == CUB_TRANSFORM_SEMI_INF_UP) {
+            t->shift[d] = xmin[d];
+            t->tmin[d] = 0.0;
+            t->tmax[d] = 1.0;
+        } else if (code == CUB_TRANSFORM_SEMI_INF_DOWN) {
+            t->shift[d] = xmax[d];
+            t->tmin[d] = 0.0;
+            t->tmax[d] = 1.0;
+        } else if (code == CUB_TRANSFORM_INF) {
+            t->tmin[d] = -1.0;
+            t->tmax[d] = 1.0;
+        }
+        if (code) t->any = true;
+    }
+    return CUB_OK;
+}
+
+// One integrate / eval call: device, stream, kernels, launch helpers.
+struct Session {
+    cub_integrand* integ = nullptr;
+    int dim = 0, fdim = 0, device = 0;
+    int64_t P = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+    RuleKernels* kern = nullptr;
+    TransformSpec tr;
+    std::vector<unsigned char> tr_arg;   // device-side CubTransform bytes
+    std::vector<double> prm_arg;         // device-side CubParams
+    int64_t launches = 0;
+    double rule_ms = 0.0;
+    char* msg = nullptr;
+    char msgbuf[256];
+    bool rule_pending = false;
+
+    ~Session() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evr0) cudaEventDestroy(evr0);
+        if (evr1) cudaEventDestroy(evr1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int open(cub_integrand* in, int dim_, int device_, const TransformSpec& t, cub_stats_t* stats) {
+        integ = in;
+        dim = dim_;
+        fdim = in->fdim;
+        tr = t;
+        msgbuf[0] = 0;
+        msg = stats ? stats->message : msgbuf;
+        P = cub_points_per_region(dim);
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            cub_set_message(msg, "no CUDA device available (libcubature_cuda has no CPU fallback)");
+            return CUB_ERR_NO_DEVICE;
+        }
+        if (device_ < 0) {
+            CUB_CUDA_CHECK(cudaGetDevice(&device), msg);
+        } else {
+            device = device_;
+            CUB_CUDA_CHECK(cudaSetDevice(device), msg);
+        }
+        CUB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), msg);
+        CUB_CUDA_CHECK(cudaEventCreate(&ev0), msg);
+        CUB_CUDA_CHECK(cudaEventCreate(&ev1), msg);
+        CUB_CUDA_CHECK(cudaEventCreate(&evr0), msg);
+        CUB_CUDA_CHECK(cudaEventCreate(&evr1), msg);
+        std::string log;
+        int rc = cub_jit_get_kernels(integ, tr.any ? 1 : 0, device, &kern, &log);
+        if (rc != CUB_OK) {
+            cub_set_message(msg, "%s", log.c_str());
+            return rc;
+        }
+        // CubTransform { int code[DIM]; double shift[DIM]; }
+        const size_t off = ((size_t)4 * dim + 7) & ~(size_t)7;
+        tr_arg.assign(off + (size_t)8 * dim, 0);
+        memcpy(tr_arg.data(), tr.code, (size_t)4 * dim);
+        memcpy(tr_arg.data() + off, tr.shift, (size_t)8 * dim);
+        prm_arg = integ->params;
+        if (prm_arg.empty()) prm_arg.push_back(0.0);
+        return CUB_OK;
+    }
+
+    // Launches the rule kernel for `work`; for fdim > 1 a BISECT request is split into the stand-alone
+    // bisect kernel + CHILDREN mode.  Rule-kernel time is accumulated with a pair of events.
+    int launch_rule(const PoolView& pool, HostWork work) {
+        if (work.n_items <= 0) return CUB_OK;
+        flush_rule_timer();
+        const bool one_thread_per_region = (dim >= 2 && fdim == 1) || (dim == 1 && fdim == 1);
+        if (work.mode == MODE_BISECT && !one_thread_per_region) {
+            pk_bisect(pool, dim, work.list, work.n_items / 2, work.base, stream);
+            ++launches;
+            work.mode = MODE_CHILDREN;
+        }
+        PoolView pv = pool;
+        void* args[5] = {&pv, &work, prm_arg.data(), tr_arg.data(), nullptr};
+        cudaEventRecord(evr0, stream);
+        cudaError_t e;
+        if (dim >= 2 && fdim == 1) {
+            const unsigned grid = (unsigned)((work.n_items + 127) / 128);
+            e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(128), args, 0, stream);
+            ++launches;
+        } else if (dim == 1 && (fdim == 1 || integ->separable)) {
+            const long long threads = work.n_items * fdim;
+            const unsigned grid = (unsigned)((threads + 127) / 128);
+            e = cudaLaunchKernel((const void*)kern->gk_separable, dim3(grid), dim3(128), args, 0, stream);
+            ++launches;
+            if (e == cudaSuccess && fdim > 1) {
+                pk_errmax_rows(pool, fdim, work.list, work.n_items, work.base, work.mode, stream);
+                ++launches;
+            }
+        } else {
+            const int FS = fdim | 1;
+            const size_t per_region = ((size_t)P * FS + 3 * (size_t)dim + (size_t)fdim) * 8 + 8;
+            const size_t max_smem = (size_t)kern->staged_max_smem;
+            if (per_region > max_smem) {
+                cub_set_message(msg, "fdim=%d at dim=%d needs %zu bytes of shared memory per region (max %zu)", fdim, dim,
+                                per_region, max_smem);
+                return CUB_ERR_UNSUPPORTED;
+            }
+            size_t budget = 100 * 1024;  // two CTAs per SM
+            if (per_region > budget) budget = max_smem;
+            int rpb = (int)std::min<size_t>(budget / per_region, 16);
+            if (rpb < 1) rpb = 1;
+            const long long groups = (work.n_items + rpb - 1) / rpb;
+            const unsigned grid = (unsigned)std::min<long long>(groups, 148 * 8);
+            args[4] = &rpb;
+            e = cudaLaunchKernel((const void*)kern->staged, dim3(grid), dim3(256), args, per_region * rpb, stream);
+            ++launches;
+        }
+        cudaEventRecord(evr1, stream);
+        rule_pending = true;
+        if (e != cudaSuccess) {
+            cub_set_message(msg, "rule kernel launch failed: %s", cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        return CUB_OK;
+    }
+    void flush_rule_timer() {
+        if (!rule_pending) return;
+        if (cudaEventSynchronize(evr1) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, evr0, evr1) == cudaSuccess) rule_ms += ms;
+        }
+        rule_pending = false;
+    }
+};
+
+int set_root(Session& S, Pool& pool) {
+    // Hypercube.initFromRanges, Hypercube.java:19-30 (in t-space)
+    std::vector<double> c(S.dim), h(S.dim);
+    for (int d = 0; d < S.dim; ++d) {
+        c[d] = (S.tr.tmax[d] + S.tr.tmin[d]) / 2.0;
+        h[d] = (S.tr.tmax[d] - S.tr.tmin[d]) / 2.0;
+    }
+    CUB_CUDA_CHECK(cudaMemcpy2DAsync(pool.center.p, (size_t)pool.cap * 8, c.data(), 8, 8, S.dim, cudaMemcpyHostToDevice, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaMemcpy2DAsync(pool.halfw.p, (size_t)pool.cap * 8, h.data(), 8, 8, S.dim, cudaMemcpyHostToDevice, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    return CUB_OK;
+}
+
+long long auto_capacity(int dim, int fdim, int64_t P, int64_t maxEval, long long requested, size_t extra_per_region) {
+    if (requested > 0) return requested;
+    long long cap = 1 << 16;
+    if (maxEval > 0) {
+        const long long need = maxEval / (2 * P) + 8;
+        cap = std::max<long long>(need, 1024);
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t per = Pool::bytes_per_region(dim, fdim) + extra_per_region;
+        const long long fit = (long long)((free_b * 0.85) / per);
+        cap = std::min(cap, std::max<long long>(fit, 1024));
+    }
+    return cap;
+}
+
+void fill_trace_regions(Session& S, Pool& pool, const std::vector<int>* order, long long n, cub_trace_t* tr) {
+    if (!tr) return;
+    tr->n_regions = n;
+    const long long m = std::min<long long>(n, tr->region_cap);
+    if (m <= 0) return;
+    // pull the SoA rows [0, pool_n) to the host and re-pack as [n][dim] / [n][fdim]
+    long long span = 0;
+    if (order) {
+        for (long long i = 0; i < m; ++i) span = std::max<long long>(span, (*order)[i] + 1);
+    } else {
+        span = m;
+    }
+    std::vector<double> row((size_t)span);
+    std::vector<int> irow((size_t)span);
+    auto slot = [&](long long i) { return order ? (long long)(*order)[i] : i; };
+    for (int d = 0; d < S.dim; ++d) {
+        if (tr->centers) {
+            cudaMemcpy(row.data(), pool.center.as<double>() + (size_t)d * pool.cap, (size_t)span * 8, cudaMemcpyDeviceToHost);
+            for (long long i = 0; i < m; ++i) tr->centers[i * S.dim + d] = row[(size_t)slot(i)];
+        }
+        if (tr->halfwidths) {
+            cudaMemcpy(row.data(), pool.halfw.as<double>() + (size_t)d * pool.cap, (size_t)span * 8, cudaMemcpyDeviceToHost);
+            for (long long i = 0; i < m; ++i) tr->halfwidths[i * S.dim + d] = row[(size_t)slot(i)];
+        }
+    }
+    for (int j = 0; j < S.fdim; ++j) {
+        if (tr->val) {
+            cudaMemcpy(row.data(), pool.val.as<double>() + (size_t)j * pool.cap, (size_t)span * 8, cudaMemcpyDeviceToHost);
+            for (long long i = 0; i < m; ++i) tr->val[i * S.fdim + j] = row[(size_t)slot(i)];
+        }
+        if (tr->err) {
+            cudaMemcpy(row.data(), pool.err.as<double>() + (size_t)j * pool.cap, (size_t)span * 8, cudaMemcpyDeviceToHost);
+            for (long long i = 0; i < m; ++i) tr->err[i * S.fdim + j] = row[(size_t)slot(i)];
+        }
+    }
+    if (tr->split_dim) {
+        cudaMemcpy(irow.data(), pool.splitdim.as<int>(), (size_t)span * 4, cudaMemcpyDeviceToHost);
+        for (long long i = 0; i < m; ++i) tr->split_dim[i] = irow[(size_t)slot(i)];
+    }
+}
+
+// Iteration guard: with maxEval == 0 and an unreachable tolerance (e.g. err == 0 == val, strict `<`)
+// the reference loops forever.  Every iteration at least doubles nothing, so the
+// guard is generous; hitting it returns the best estimate with converged = 0.
+const int64_t kMaxIterations = 100000;
+
+struct LoopResult {
+    int converged = 0;
+    int64_t num_eval = 0, num_regions = 0, iterations = 0, ambiguous = 0;
+};
+
+void push_batch(cub_trace_t* tr, int64_t nR) {
+    if (!tr) return;
+    if (tr->batches && tr->n_batches < tr->batch_cap) tr->batches[tr->n_batches] = nR;
+    tr->n_batches += 1;
+}
+
+// ---- HEAP_EXACT: Rule.cubature replayed on the host, rule evaluation + bisection on the GPU --------
+int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt,
+                         double* out, LoopResult* res) {
+    const int f = S.fdim;
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    Pool pool;
+    long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, (size_t)16 * f + 4);
+    if (!(opt && opt->pool_capacity > 0)) cap = std::min<long long>(cap, 1 << 18);  // grows on demand
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
+    int rc = set_root(S, pool);
+    if (rc != CUB_OK) return rc;
+
+    DevBuf d_list, d_stage_val, d_stage_err;
+    PinnedBuf h_list, h_stage;
+    long long stage_stride = 0;
+    auto ensure_stage = [&](long long n_items) -> int {
+        if (n_items <= stage_stride) return CUB_OK;
+        long long ns = std::max<long long>(n_items * 2, 1024);
+        CUB_CUDA_CHECK(d_stage_val.ensure((size_t)8 * f * ns), S.msg);
+        CUB_CUDA_CHECK(d_stage_err.ensure((size_t)8 * f * ns), S.msg);
+        CUB_CUDA_CHECK(h_stage.ensure((size_t)16 * f * ns), S.msg);
+        CUB_CUDA_CHECK(d_list.ensure((size_t)4 * ns), S.msg);
+        CUB_CUDA_CHECK(h_list.ensure((size_t)4 * ns), S.msg);
+        stage_stride = ns;
+        return CUB_OK;
+    };
+
+    std::vector<double> hval, herr, herrmax;  // per slot, host mirror ([slot][f])
+    auto reserve_slots = [&](long long n) {
+        if ((long long)herrmax.size() < n) {
+            const size_t m = (size_t)std::max<long long>(n, (long long)herrmax.size() * 2);
+            hval.resize(m * f);
+            herr.resize(m * f);
+            herrmax.resize(m);
+        }
+    };
+    SlotHeap heap;
+    heap.key = &herrmax;
+    std::vector<double> sum_val(f, 0.0), sum_err(f, 0.0);  // RegionHeap.ee (running, incremental)
+    auto heap_add = [&](int slot) {  // RegionHeap.java:30-36
+        for (int j = 0; j < f; ++j) {
+            sum_val[j] += hval[(size_t)slot * f + j];
+            sum_err[j] += herr[(size_t)slot * f + j];
+        }
+        heap.add(slot);
+    };
+    // evaluates n_items work items and returns their val/err in h_stage: [val f rows][err f rows], row stride = n_items
+    auto run_rule = [&](HostWork w) -> int {
+        int r = ensure_stage(w.n_items);
+        if (r != CUB_OK) return r;
+        w.stage_val = d_stage_val.as<double>();
+        w.stage_err = d_stage_err.as<double>();
+        w.stage_stride = stage_stride;
+        r = S.launch_rule(pool.view(), w);
+        if (r != CUB_OK) return r;
+        const size_t width = (size_t)w.n_items * 8;
+        CUB_CUDA_CHECK(cudaMemcpy2DAsync(h_stage.p, width, d_stage_val.p, (size_t)stage_stride * 8, width, f,
+                                         cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaMemcpy2DAsync(h_stage.as<double>() + (size_t)f * w.n_items, width, d_stage_err.p,
+                                         (size_t)stage_stride * 8, width, f, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        return CUB_OK;
+    };
+    auto store_item = [&](long long item, long long n_items, int slot) {
+        const double* sv = h_stage.as<double>();
+        const double* se = sv + (size_t)f * n_items;
+        double emax = 0.0;  // Rule.errMax, Rule.java:281-289
+        for (int j = 0; j < f; ++j) {
+            const double v = sv[(size_t)j * n_items + item], e = se[(size_t)j * n_items + item];
+            hval[(size_t)slot * f + j] = v;
+            herr[(size_t)slot * f + j] = e;
+            if (e > emax) emax = e;
+        }
+        herrmax[(size_t)slot] = emax;
+    };
+
+    // Rule.java:62-69: the whole box
+    reserve_slots(1);
+    {
+        HostWork w{};
+        w.n_items = 1;
+        w.base = 0;
+        w.mode = MODE_PLAIN;
+        rc = run_rule(w);
+        if (rc != CUB_OK) return rc;
+        store_item(0, 1, 0);
+        heap_add(0);
+    }
+    long long N = 1;
+    int64_t numEval = P;
+    bool conv = false;
+    std::vector<double> res_err(f), res_val(f);
+    std::vector<int> list;
+    while (numEval < maxEval || maxEval == 0) {  // Rule.java:72
+        if (cub_converged(f, VecAcc{sum_val.data(), sum_err.data()}, absTol, relTol, norm)) {
+            conv = true;
+            break;
+        }
+        for (int j = 0; j < f; ++j) {  // Rule.java:102-107: a copy of BOTH sums; only err is updated below
+            res_err[j] = sum_err[j];
+            res_val[j] = sum_val[j];
+        }
+        list.clear();
+        do {  // Rule.java:109-133
+            const int s = heap.poll();
+            for (int j = 0; j < f; ++j) {  // RegionHeap.java:21-28
+                sum_val[j] -= hval[(size_t)s * f + j];
+                sum_err[j] -= herr[(size_t)s * f + j];
+            }
+            for (int j = 0; j < f; ++j) res_err[j] -= herr[(size_t)s * f + j];
+            list.push_back(s);
+            numEval += 2 * P;
+            if (cub_converged(f, VecAcc{res_val.data(), res_err.data()}, absTol, relTol, norm)) break;
+        } while (!heap.q.empty() && (numEval < maxEval || maxEval == 0));
+        const long long K = (long long)list.size();
+        if (N + K > pool.cap) {
+            long long nc = std::max<long long>(pool.cap * 2, N + K);
+            cudaError_t e = pool.grow(nc, N, S.stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+        }
+        if (N + K > (long long)std::numeric_limits<int>::max()) {
+            cub_set_message(S.msg, "region pool exceeds 2^31 slots");
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+        rc = ensure_stage(2 * K);
+        if (rc != CUB_OK) return rc;
+        memcpy(h_list.p, list.data(), (size_t)4 * K);
+        CUB_CUDA_CHECK(cudaMemcpyAsync(d_list.p, h_list.p, (size_t)4 * K, cudaMemcpyHostToDevice, S.stream), S.msg);
+        HostWork w{};
+        w.list = d_list.as<int>();
+        w.n_items = 2 * K;
+        w.base = N;
+        w.mode = MODE_BISECT;
+        rc = run_rule(w);
+        if (rc != CUB_OK) return rc;
+        reserve_slots(N + K);
+        for (long long i = 0; i < 2 * K; ++i) {  // Rule.java:137-140: left0, right0, left1, right1, ...
+            const int slot = (i & 1) ? (int)(N + (i >> 1)) : list[(size_t)(i >> 1)];
+            store_item(i, 2 * K, slot);
+            heap_add(slot);
+        }
+        N += K;
+        res->iterations += 1;
+        push_batch(trace, 2 * K);
+        if (res->iterations >= kMaxIterations) {  // the reference would spin forever (App. C); we stop and say so
+            cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)res->iterations);
+            break;
+        }
+    }
+    // Rule.java:148-159: re-sum in heap ARRAY order
+    for (int j = 0; j < f; ++j) out[j] = out[f + j] = 0;
+    for (size_t i = 0; i < heap.q.size(); ++i) {
+        const int s = heap.q[i];
+        for (int j = 0; j < f; ++j) {
+            out[j] += hval[(size_t)s * f + j];
+            out[f + j] += herr[(size_t)s * f + j];
+        }
+    }
+    S.flush_rule_timer();
+    res->converged = conv ? 1 : 0;
+    res->num_eval = numEval;
+    res->num_regions = (int64_t)heap.q.size();
+    fill_trace_regions(S, pool, &heap.q, (long long)heap.q.size(), trace);
+    return CUB_OK;
+}
+
+// ---- DEVICE mode ------------------------------------------------------------------------------------
+struct SelectBuffers {
+    DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
+    long long cap = 0;
+    int fdim = 0;
+    cudaError_t ensure(long long n, int f) {
+        if (n <= cap && f == fdim) return cudaSuccess;
+        const long long c = std::max<long long>(n, 1024);
+        cudaError_t e;
+        if ((e = keysA.ensure((size_t)8 * c)) != cudaSuccess) return e;
+        if ((e = keysB.ensure((size_t)8 * c)) != cudaSuccess) return e;
+        if ((e = idxA.ensure((size_t)4 * c)) != cudaSuccess) return e;
+        if ((e = idxB.ensure((size_t)4 * c)) != cudaSuccess) return e;
+        if ((e = hist.ensure((size_t)4 * 256 * pk_sort_chunks(c))) != cudaSuccess) return e;
+        if ((e = bin_totals.ensure(8 * 256)) != cudaSuccess) return e;
+        if ((e = binbase.ensure(8 * 256)) != cudaSuccess) return e;
+        if ((e = prefix.ensure((size_t)8 * f * c)) != cudaSuccess) return e;
+        if ((e = tile_tot.ensure((size_t)8 * f * pk_scan_tiles(c))) != cudaSuccess) return e;
+        cap = c;
+        fdim = f;
+        return cudaSuccess;
+    }
+};
+
+int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                     LoopResult* res) {
+    const int f = S.fdim;
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    Pool pool;
+    const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
+    long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
+    int rc = set_root(S, pool);
+    if (rc != CUB_OK) return rc;
+
+    SelectBuffers sel;
+    DevBuf d_partial, d_small;  // d_small: totals[2f] | minvec[2f] | u64 scratch[8]
+    PinnedBuf h_small;
+    const size_t small_doubles = (size_t)4 * f;
+    CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * 1184), S.msg);
+    CUB_CUDA_CHECK(d_small.ensure(small_doubles * 8 + 64), S.msg);
+    CUB_CUDA_CHECK(h_small.ensure(small_doubles * 8 + 64), S.msg);
+    double* d_totals = d_small.as<double>();
+    double* d_minvec = d_totals + 2 * f;
+    unsigned long long* d_u64 = (unsigned long long*)(d_minvec + 2 * f);
+    double* h_totals = h_small.as<double>();
+    double* h_minvec = h_totals + 2 * f;
+    unsigned long long* h_u64 = (unsigned long long*)(h_minvec + 2 * f);
+
+    {
+        HostWork w{};
+        w.n_items = 1;
+        w.base = 0;
+        w.mode = MODE_PLAIN;
+        rc = S.launch_rule(pool.view(), w);
+        if (rc != CUB_OK) return rc;
+    }
+    long long N = 1;
+    int64_t numEval = P;
+    bool conv = false;
+    double ops = 1.0;  // additions the reference's running sums have seen so far (rounding band)
+    std::vector<double> tmp_err(f);
+    const double eps = 2.220446049250313e-16;
+
+    while (numEval < maxEval || maxEval == 0) {
+        const PoolView pv = pool.view();
+        pk_totals(pv, f, N, d_partial.as<double>(), d_totals, S.stream);
+        pk_min_region(pv, f, N, d_u64, d_minvec, S.stream);
+        S.launches += 5;
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, small_doubles * 8 + 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        const double band = 4.0 * eps * std::sqrt(ops);
+        const double* tv = h_totals;
+        const double* te = h_totals + f;
+        {
+            const bool c0 = cub_converged(f, VecAcc{tv, te}, absTol, relTol, norm);
+            for (int j = 0; j < f; ++j) tmp_err[j] = te[j] * (1.0 + band);
+            const bool c1 = cub_converged(f, VecAcc{tv, tmp_err.data()}, absTol, relTol, norm);
+            for (int j = 0; j < f; ++j) tmp_err[j] = te[j] * (1.0 - band);
+            const bool c2 = cub_converged(f, VecAcc{tv, tmp_err.data()}, absTol, relTol, norm);
+            if (c0 != c1 || c0 != c2) res->ambiguous += 1;
+            if (c0) {
+                conv = true;
+                break;
+            }
+        }
+        long long Kcap = N;
+        if (maxEval > 0) {
+            const int64_t room = maxEval - numEval;  // > 0 here
+            Kcap = std::min<long long>(N, std::max<int64_t>(1, (room + 2 * P - 1) / (2 * P)));
+        }
+        // select-all shortcut: the residual after popping all but the smallest-errmax region is that
+        // region's own error vector; if that is not converged, no smaller k is (monotone predicate).
+        const double* last_err = h_minvec + f;
+        bool all = !cub_converged(f, VecAcc{tv, last_err}, absTol, relTol, norm);
+        {
+            for (int j = 0; j < f; ++j) tmp_err[j] = last_err[j] + band * te[j];
+            const bool a1 = !cub_converged(f, VecAcc{tv, tmp_err.data()}, absTol, relTol, norm);
+            for (int j = 0; j < f; ++j) tmp_err[j] = last_err[j] - band * te[j];
+            const bool a2 = !cub_converged(f, VecAcc{tv, tmp_err.data()}, absTol, relTol, norm);
+            if (a1 != all || a2 != all) res->ambiguous += 1;
+        }
+        if (N == 1) all = true;
+        long long K = N;
+        const int* list = nullptr;
+        if (!(all && Kcap == N)) {
+            // sort by errmax (descending, ties by ascending slot), then prefix sums and the residual test
+            CUB_CUDA_CHECK(sel.ensure(pool.cap, f), S.msg);
+            pk_sort_prepare(pv.errmax, N, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64 + 4, S.stream);
+            S.launches += 1;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            const unsigned long long vary = h_u64[4] ^ h_u64[5];  // bits that differ between keys
+            unsigned long long* ka = sel.keysA.as<unsigned long long>();
+            unsigned long long* kb = sel.keysB.as<unsigned long long>();
+            int* ia = sel.idxA.as<int>();
+            int* ib = sel.idxB.as<int>();
+            for (int shift = 0; shift < 64; shift += 8) {
+                if (((vary >> shift) & 0xffULL) == 0) continue;  // every key has the same digit here
+                pk_sort_pass(ka, ia, kb, ib, N, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
+                             sel.binbase.as<unsigned long long>(), S.stream);
+                S.launches += 4;
+                std::swap(ka, kb);
+                std::swap(ia, ib);
+            }
+            list = ia;
+            if (all) {
+                K = Kcap;  // maxEval truncation: the Kcap largest
+            } else {
+                pk_prefix(pv, f, ia, N, sel.prefix.as<double>(), sel.tile_tot.as<double>(), S.stream);
+                pk_find_k(d_totals, sel.prefix.as<double>(), sel.tile_tot.as<double>(), N, f, absTol, relTol, norm, band, d_u64 + 4,
+                          S.stream);
+                S.launches += 3;
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                long long k0 = (long long)h_u64[4], k1 = (long long)h_u64[5], k2 = (long long)h_u64[6];
+                if (k0 > N) k0 = N;  // never converged: pop until the heap is empty (Rule.java:133)
+                if (k1 > N) k1 = N;
+                if (k2 > N) k2 = N;
+                if (std::min(k1, Kcap) != std::min(k0, Kcap) || std::min(k2, Kcap) != std::min(k0, Kcap)) res->ambiguous += 1;
+                K = std::min(k0, Kcap);
+            }
+        }
+        if (N + K > pool.cap) {
+            long long nc = std::max<long long>(pool.cap * 2, N + K);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            cudaError_t e = pool.grow(nc, N, S.stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+            if (list) {
+                cub_set_message(S.msg, "internal: pool grew while a selection list was live");
+            }
+        }
+        if (N + K > (long long)std::numeric_limits<int>::max()) {
+            cub_set_message(S.msg, "region pool exceeds 2^31 slots");
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+        HostWork w{};
+        w.list = list;
+        w.n_items = 2 * K;
+        w.base = N;
+        w.mode = MODE_BISECT;
+        rc = S.launch_rule(pool.view(), w);
+        if (rc != CUB_OK) return rc;
+        N += K;
+        numEval += 2 * P * K;
+        ops += 3.0 * (double)K;
+        res->iterations += 1;
+        push_batch(trace, 2 * K);
+        if (res->iterations >= kMaxIterations) {
+            cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)res->iterations);
+            break;
+        }
+    }
+    pk_totals(pool.view(), f, N, d_partial.as<double>(), d_totals, S.stream);
+    S.launches += 2;
+    CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, (size_t)16 * f, cudaMemcpyDeviceToHost, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
+    S.flush_rule_timer();
+    res->converged = conv ? 1 : 0;
+    res->num_eval = numEval;
+    res->num_regions = N;
+    fill_trace_regions(S, pool, nullptr, N, trace);
+    return CUB_OK;
+}
+
+void init_stats(cub_stats_t* st) {
+    if (!st) return;
+    const int32_t sz = st->struct_size;
+    memset(st, 0, sizeof *st);
+    st->struct_size = sz ? sz : (int32_t)sizeof(cub_stats_t);
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------------
+extern "C" {
+
+int cubature_cuda_version(void) { return 1000 * CUBATURE_CUDA_ABI_VERSION + 0; }
+
+const char* cubature_cuda_strerror(int status) {
+    switch (status) {
+        case CUB_OK: return "ok";
+        case CUB_ERR_BAD_ARGS: return "bad arguments (xmin/xmax/out null or empty, sizes inconsistent)";
+        case CUB_ERR_BAD_TOL: return "either relTol or absTol or both have to be not NaN";
+        case CUB_ERR_BAD_DIM: return "unsupported dimension";
+        case CUB_ERR_BAD_NORM: return "unknown error norm";
+        case CUB_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case CUB_ERR_CUDA: return "CUDA runtime error";
+        case CUB_ERR_NVRTC: return "NVRTC compilation of the integrand failed";
+        case CUB_ERR_POOL_EXHAUSTED: return "region pool exhausted";
+        case CUB_ERR_NCCL: return "NCCL error";
+        case CUB_ERR_UNSUPPORTED: return "unsupported configuration";
+        case CUB_ERR_BAD_FAMILY: return "unknown integrand family or wrong parameter count";
+    }
+    return "unknown status";
+}
+
+int64_t cubature_cuda_points_per_region(int dim) { return cub_points_per_region(dim); }
+
+int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams, cub_integrand_t** out) {
+    if (!out) return CUB_ERR_BAD_ARGS;
+    *out = nullptr;
+    if (dim < 1 || dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
+    if (fdim < 1) return CUB_ERR_BAD_ARGS;
+    if (nparams > 0 && !params) return CUB_ERR_BAD_ARGS;
+    size_t need = 0;
+    bool separable = false;
+    int need_fdim = 0;
+    switch (family_id) {
+        case CUB_FAMILY_GENZ_OSCILLATORY:
+        case CUB_FAMILY_GENZ_PRODUCT_PEAK:
+        case CUB_FAMILY_GENZ_CORNER_PEAK:
+        case CUB_FAMILY_GENZ_GAUSSIAN:
+        case CUB_FAMILY_GENZ_C0:
+        case CUB_FAMILY_GENZ_DISCONTINUOUS:
+            need = 2 * (size_t)dim;
+            need_fdim = 1;
+            break;
+        case CUB_FAMILY_GAUSS_ISO:
+            need = 1;
+            need_fdim = 1;
+            break;
+        case CUB_FAMILY_REFTEST:
+            need = (size_t)fdim;
+            if (fdim > CUB_REFTEST_MAX_FDIM) return CUB_ERR_UNSUPPORTED;
+            break;
+        case CUB_FAMILY_OSC_VEC:
+            need = 0;
+            separable = true;
+            break;
+        case CUB_FAMILY_CEXP:
+            need = (size_t)(fdim / 2);
+            break;
+        default:
+            return CUB_ERR_BAD_FAMILY;
+    }
+    if (nparams != need) return CUB_ERR_BAD_FAMILY;
+    if (need_fdim && fdim != need_fdim) return CUB_ERR_BAD_FAMILY;
+    if (nparams > CUB_MAX_PARAMS_BY_VALUE) return CUB_ERR_UNSUPPORTED;
+    cub_integrand* in = new cub_integrand();
+    in->family = family_id;
+    in->dim = dim;
+    in->fdim = fdim;
+    in->separable = separable;
+    if (nparams) in->params.assign(params, params + nparams);
+    *out = in;
+    return CUB_OK;
+}
+
+int cubature_cuda_integrand_nvrtc(const char* cuda_src, const char* entry, int dim, int fdim, const double* params, size_t nparams,
+                                  cub_integrand_t** out, char* log, size_t log_cap) {
+    if (log && log_cap) log[0] = 0;
+    if (!out || !cuda_src || !entry || !*entry) return CUB_ERR_BAD_ARGS;
+    *out = nullptr;
+    if (dim < 1 || dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
+    if (fdim < 1) return CUB_ERR_BAD_ARGS;
+    if (nparams > 0 && !params) return CUB_ERR_BAD_ARGS;
+    if (nparams > CUB_MAX_PARAMS_BY_VALUE) return CUB_ERR_UNSUPPORTED;
+    std::unique_ptr<cub_integrand> in(new cub_integrand());
+    in->family = CUB_FAM_USER;
+    in->dim = dim;
+    in->fdim = fdim;
+    in->user_src = cuda_src;
+    in->entry = entry;
+    if (nparams) in->params.assign(params, params + nparams);
+    std::string l;
+    int rc = cub_jit_compile(in.get(), 0, &l);  // compile now so that source errors surface here
+    if (log && log_cap) {
+        strncpy(log, l.c_str(), log_cap - 1);
+        log[log_cap - 1] = 0;
+    }
+    if (rc != CUB_OK) return rc;
+    *out = in.release();
+    return CUB_OK;
+}
+
+void cubature_cuda_integrand_free(cub_integrand_t* integrand) {
+    if (!integrand) return;
+    for (int v = 0; v < 2; ++v)
+        for (auto& kv : integrand->loaded[v])
+            if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+    cudaGetLastError();
+    delete integrand;
+}
+
+int64_t cubature_cuda_integrand_cubin(cub_integrand_t* integrand, int has_transform, void* buf, size_t buf_cap) {
+    if (!integrand) return CUB_ERR_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(integrand->mu);
+    std::string log;
+    int rc = cub_jit_compile(integrand, has_transform, &log);
+    if (rc != CUB_OK) {
+        fprintf(stderr, "cubature_cuda: %s\n", log.c_str());
+        return rc;
+    }
+    const std::vector<char>& c = integrand->cubin[has_transform ? 1 : 0];
+    if (buf && buf_cap >= c.size()) memcpy(buf, c.data(), c.size());
+    return (int64_t)c.size();
+}
+
+int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax, const int* transform,
+                            double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* options, double* out,
+                            cub_stats_t* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    init_stats(stats);
+    // argument checks mirror the reference's exceptions (Cubature.java:119-128, Rule.java:164-167)
+    if (!integrand || !xmin || !xmax || !out) return CUB_ERR_BAD_ARGS;
+    if (dim < 1 || dim != integrand->dim) return dim < 1 ? CUB_ERR_BAD_ARGS : CUB_ERR_BAD_DIM;
+    if (dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
+    if (std::isnan(relTol) && std::isnan(absTol)) return CUB_ERR_BAD_TOL;
+    if (norm < 0 || norm > 4) return CUB_ERR_BAD_NORM;
+    if (maxEval < 0) return CUB_ERR_BAD_ARGS;
+    TransformSpec tr;
+    int rc = make_transform(dim, xmin, xmax, transform, &tr);
+    if (rc != CUB_OK) return rc;
+    const int select = options ? options->select : CUB_SELECT_DEVICE;
+    if (select != CUB_SELECT_DEVICE && select != CUB_SELECT_HEAP_EXACT) return CUB_ERR_BAD_ARGS;
+    if (options && options->trace) {
+        options->trace->n_batches = 0;
+        options->trace->n_regions = 0;
+    }
+    Session S;
+    rc = S.open(integrand, dim, options ? options->device : -1, tr, stats);
+    if (rc != CUB_OK) return rc;
+    LoopResult res;
+    cudaEventRecord(S.ev0, S.stream);
+    if (select == CUB_SELECT_HEAP_EXACT)
+        rc = integrate_heap_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
+    else
+        rc = integrate_device(S, relTol, absTol, norm, maxEval, options, out, &res);
+    cudaEventRecord(S.ev1, S.stream);
+    cudaEventSynchronize(S.ev1);
+    if (stats) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) stats->device_ms = ms;
+        stats->converged = res.converged;
+        stats->num_eval = res.num_eval;
+        stats->num_regions = res.num_regions;
+        stats->iterations = res.iterations;
+        stats->regions_evaluated = S.P > 0 ? res.num_eval / S.P : 0;
+        stats->ambiguous_decisions = res.ambiguous;
+        stats->gpu_launches = S.launches;
+        stats->rule_ms = S.rule_ms;
+        stats->jit_ms = integrand->jit_ms_pending;
+        integrand->jit_ms_pending = 0.0;
+        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    cudaGetLastError();
+    return rc;
+}
+
+int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* transform, const double* shift, int64_t nR,
+                               const double* centers, const double* halfwidths, double* val, double* err, int32_t* split_dim,
+                               cub_stats_t* stats) {
+    init_stats(stats);
+    if (!integrand || !centers || !halfwidths || !val || !err || !split_dim || nR < 0) return CUB_ERR_BAD_ARGS;
+    if (dim != integrand->dim) return CUB_ERR_BAD_DIM;
+    if (nR == 0) return CUB_OK;
+    TransformSpec tr;
+    tr.any = false;
+    for (int d = 0; d < dim; ++d) {
+        tr.code[d] = transform ? transform[d] : 0;
+        tr.shift[d] = shift ? shift[d] : 0.0;
+        tr.tmin[d] = tr.tmax[d] = 0.0;
+        if (tr.code[d]) tr.any = true;
+    }
+    Session S;
+    int rc = S.open(integrand, dim, -1, tr, stats);
+    if (rc != CUB_OK) return rc;
+    const int f = S.fdim;
+    Pool pool;
+    CUB_CUDA_CHECK(pool.alloc(dim, f, nR), S.msg);
+    // [nR][dim] -> [dim][nR]
+    std::vector<double> tmp((size_t)nR * std::max(dim, f));
+    for (int pass = 0; pass < 2; ++pass) {
+        const double* src = pass ? halfwidths : centers;
+        for (int64_t i = 0; i < nR; ++i)
+            for (int d = 0; d < dim; ++d) tmp[(size_t)d * nR + i] = src[i * dim + d];
+        CUB_CUDA_CHECK(cudaMemcpy(pass ? pool.halfw.p : pool.center.p, tmp.data(), (size_t)8 * dim * nR, cudaMemcpyHostToDevice), S.msg);
+    }
+    HostWork w{};
+    w.n_items = nR;
+    w.base = 0;
+    w.mode = MODE_PLAIN;
+    cudaEventRecord(S.ev0, S.stream);
+    rc = S.launch_rule(pool.view(), w);
+    cudaEventRecord(S.ev1, S.stream);
+    if (rc != CUB_OK) return rc;
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    for (int pass = 0; pass < 2; ++pass) {
+        CUB_CUDA_CHECK(cudaMemcpy(tmp.data(), pass ? pool.err.p : pool.val.p, (size_t)8 * f * nR, cudaMemcpyDeviceToHost), S.msg);
+        double* dst = pass ? err : val;
+        for (int64_t i = 0; i < nR; ++i)
+            for (int j = 0; j < f; ++j) dst[i * f + j] = tmp[(size_t)j * nR + i];
+    }
+    CUB_CUDA_CHECK(cudaMemcpy(split_dim, pool.splitdim.p, (size_t)4 * nR, cudaMemcpyDeviceToHost), S.msg);
+    S.flush_rule_timer();
+    if (stats) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) stats->device_ms = ms;
+        stats->rule_ms = S.rule_ms;
+        stats->gpu_launches = S.launches;
+        stats->regions_evaluated = nR;
+        stats->num_eval = nR * S.P;
+        stats->jit_ms = integrand->jit_ms_pending;
+        integrand->jit_ms_pending = 0.0;
+    }
+    return CUB_OK;
+}
+
+int cubature_cuda_eval_points(cub_integrand_t* integrand, int dim, int64_t n, const double* x, double* fout) {
+    if (!integrand || !x || !fout || n < 0) return CUB_ERR_BAD_ARGS;
+    if (dim != integrand->dim) return CUB_ERR_BAD_DIM;
+    if (n == 0) return CUB_OK;
+    TransformSpec tr;
+    tr.any = false;
+    for (int d = 0; d < dim; ++d) {
+        tr.code[d] = 0;
+        tr.shift[d] = tr.tmin[d] = tr.tmax[d] = 0.0;
+    }
+    Session S;
+    int rc = S.open(integrand, dim, -1, tr, nullptr);
+    if (rc != CUB_OK) {
+        fprintf(stderr, "cubature_cuda_eval_points: %s\n", S.msgbuf);
+        return rc;
+    }
+    DevBuf dx, df;
+    CUB_CUDA_CHECK(dx.ensure((size_t)8 * dim * n), S.msg);
+    CUB_CUDA_CHECK(df.ensure((size_t)8 * S.fdim * n), S.msg);
+    CUB_CUDA_CHECK(cudaMemcpy(dx.p, x, (size_t)8 * dim * n, cudaMemcpyHostToDevice), S.msg);
+    const double* xp = dx.as<double>();
+    double* fp = df.as<double>();
+    long long nn = n;
+    void* args[5] = {&xp, &fp, &nn, S.prm_arg.data(), S.tr_arg.data()};
+    CUB_CUDA_CHECK(cudaLaunchKernel((const void*)S.kern->eval_points, dim3((unsigned)((n + 127) / 128)), dim3(128), args, 0, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaMemcpy(fout, df.p, (size_t)8 * S.fdim * n, cudaMemcpyDeviceToHost), S.msg);
+    return CUB_OK;
+}
+
+int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax, int64_t n_regions,
+                             int repeats, double* ms_per_launch, double* checksum) {
+    if (!integrand || !xmin || !xmax || n_regions < 1 || repeats < 1 || !ms_per_launch) return CUB_ERR_BAD_ARGS;
+    if (dim != integrand->dim) return CUB_ERR_BAD_DIM;
+    TransformSpec tr;
+    int rc = make_transform(dim, xmin, xmax, nullptr, &tr);
+    if (rc != CUB_OK) return rc;
+    Session S;
+    rc = S.open(integrand, dim, -1, tr, nullptr);
+    if (rc != CUB_OK) {
+        fprintf(stderr, "cubature_cuda_bench_rule: %s\n", S.msgbuf);
+        return rc;
+    }
+    const int f = S.fdim;
+    Pool pool;
+    CUB_CUDA_CHECK(pool.alloc(dim, f, n_regions), S.msg);
+    // uniform slabs along dimension 0: region i covers [xmin0 + i*w, xmin0 + (i+1)*w] x the full box elsewhere
+    {
+        std::vector<double> row((size_t)n_regions);
+        for (int d = 0; d < dim; ++d) {
+            const double lo = tr.tmin[d], hi = tr.tmax[d];
+            for (int64_t i = 0; i < n_regions; ++i) {
+                if (d == 0) {
+                    const double w = (hi - lo) / (double)n_regions;
+                    row[(size_t)i] = lo + (i + 0.5) * w;
+                } else {
+                    row[(size_t)i] = 0.5 * (lo + hi);
+                }
+            }
+            CUB_CUDA_CHECK(cudaMemcpy(pool.center.as<double>() + (size_t)d * n_regions, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
+            for (int64_t i = 0; i < n_regions; ++i) row[(size_t)i] = d == 0 ? 0.5 * (hi - lo) / (double)n_regions : 0.5 * (hi - lo);
+            CUB_CUDA_CHECK(cudaMemcpy(pool.halfw.as<double>() + (size_t)d * n_regions, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
+        }
+    }
+    HostWork w{};
+    w.n_items = n_regions;
+    w.mode = MODE_PLAIN;
+    rc = S.launch_rule(pool.view(), w);  // warm-up
+    if (rc != CUB_OK) return rc;
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    S.flush_rule_timer();
+    S.rule_ms = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+        rc = S.launch_rule(pool.view(), w);
+        if (rc != CUB_OK) return rc;
+    }
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    S.flush_rule_timer();
+    *ms_per_launch = S.rule_ms / repeats;
+    if (checksum) {
+        DevBuf part, tot;
+        CUB_CUDA_CHECK(part.ensure((size_t)8 * 2 * f * 1184), S.msg);
+        CUB_CUDA_CHECK(tot.ensure((size_t)16 * f), S.msg);
+        pk_totals(pool.view(), f, n_regions, part.as<double>(), tot.as<double>(), S.stream);
+        std::vector<double> h((size_t)2 * f);
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h.data(), tot.p, (size_t)16 * f, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        *checksum = h[0];
+    }
+    return CUB_OK;
+}
+
+int cubature_cuda_fp64_peak(int device, double* tflops, double* ms_out) {
+    if (!tflops) return CUB_ERR_BAD_ARGS;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return CUB_ERR_NO_DEVICE;
+    }
+    char msg[256];
+    if (device >= 0) CUB_CUDA_CHECK(cudaSetDevice(device), msg);
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t s;
+    CUB_CUDA_CHECK(cudaStreamCreate(&s), msg);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    DevBuf out;
+    CUB_CUDA_CHECK(out.ensure(64), msg);
+    const int blocks = sms * 8, iters = 1 << 16;
+    pk_dfma_peak(out.as<double>(), blocks, 1024, s);  // warm-up
+    cudaStreamSynchronize(s);
+    double best = 1e30;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(a, s);
+        pk_dfma_peak(out.as<double>(), blocks, iters, s);
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaStreamDestroy(s);
+    return cudaGetLastError() == cudaSuccess ? CUB_OK : CUB_ERR_CUDA;
+}
+
+}  // extern "C"

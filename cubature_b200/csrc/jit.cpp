@@ -1,0 +1,260 @@
+// jit.cpp -- run-time specialisation of the rule kernels with NVRTC (sm_100a).
+//
+// The integrand is a device-side plugin (BASELINE.json north_star): a built-in family from
+// integrands.h or CUDA C source passed as a string.  Either way the rule kernels of
+// rule_kernels.cuh are compiled once per (integrand, dim, fdim, transform on/off) with the
+// dimension, the component count and the integrand type as compile-time constants, so every
+// per-dimension loop is unrolled and point coordinates stay in registers.
+//
+// NVRTC is loaded with dlopen so that libcubature_cuda.so itself has no link-time dependency beyond
+// libstdc++ (it loads on a box without a GPU; tests check the exported symbols there), and cubins are
+// cached on disk ($CUBATURE_CUDA_CACHE_DIR, default ~/.cache/cubature_cuda; "off" disables).
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "cub_internal.h"
+#include "integrands.h"
+#include "embedded_sources.inc"
+
+namespace {
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+    void* handle = nullptr;
+    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    int (*Version)(int*, int*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+
+Nvrtc* nvrtc() {
+    static Nvrtc api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* env = getenv("CUBATURE_NVRTC_PATH");
+        const char* names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "libnvrtc.so.13"};
+        for (const char* n : names) {
+            if (!n) continue;
+            api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = "cannot dlopen libnvrtc.so.12 (set CUBATURE_NVRTC_PATH)";
+            return;
+        }
+#define LOAD(field, sym)                                                  \
+    *(void**)(&api.field) = dlsym(api.handle, sym);                      \
+    if (!api.field) {                                                     \
+        api.error = std::string("libnvrtc lacks symbol ") + sym;         \
+        return;                                                           \
+    }
+        LOAD(CreateProgram, "nvrtcCreateProgram")
+        LOAD(CompileProgram, "nvrtcCompileProgram")
+        LOAD(DestroyProgram, "nvrtcDestroyProgram")
+        LOAD(GetCUBINSize, "nvrtcGetCUBINSize")
+        LOAD(GetCUBIN, "nvrtcGetCUBIN")
+        LOAD(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        LOAD(GetProgramLog, "nvrtcGetProgramLog")
+        LOAD(Version, "nvrtcVersion")
+        LOAD(GetErrorString, "nvrtcGetErrorString")
+#undef LOAD
+    });
+    return &api;
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ULL;
+    }
+    return h;
+}
+
+std::string cache_dir() {
+    const char* env = getenv("CUBATURE_CUDA_CACHE_DIR");
+    if (env) return std::string(env) == "off" ? std::string() : std::string(env);
+    const char* home = getenv("HOME");
+    if (!home) return std::string();
+    return std::string(home) + "/.cache/cubature_cuda";
+}
+
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i < path.size(); ++i) {
+        cur.push_back(path[i]);
+        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0755);
+    }
+}
+
+const char* family_type(int family) {
+    switch (family) {
+        case CUB_FAM_GENZ_OSCILLATORY: return "GenzOscillatory<CUB_DIM>";
+        case CUB_FAM_GENZ_PRODUCT_PEAK: return "GenzProductPeak<CUB_DIM>";
+        case CUB_FAM_GENZ_CORNER_PEAK: return "GenzCornerPeak<CUB_DIM>";
+        case CUB_FAM_GENZ_GAUSSIAN: return "GenzGaussian<CUB_DIM>";
+        case CUB_FAM_GENZ_C0: return "GenzC0<CUB_DIM>";
+        case CUB_FAM_GENZ_DISCONTINUOUS: return "GenzDiscontinuous<CUB_DIM>";
+        case CUB_FAM_GAUSS_ISO: return "GaussIso<CUB_DIM>";
+        case CUB_FAM_REFTEST: return "RefTest<CUB_DIM>";
+        case CUB_FAM_OSC_VEC: return "OscVec<CUB_DIM>";
+        case CUB_FAM_CEXP: return "CExp<CUB_DIM>";
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+void cub_set_message(char* msg, const char* fmt, ...) {
+    if (!msg) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, 256, fmt, ap);
+    va_end(ap);
+}
+
+std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transform) {
+    std::ostringstream tu;
+    tu << "#define CUB_DIM " << integ->dim << "\n";
+    tu << "#define CUB_FDIM " << integ->fdim << "\n";
+    tu << "#define CUB_NPARAMS " << integ->params.size() << "\n";
+    tu << "#define CUB_HAS_TRANSFORM " << (has_transform ? 1 : 0) << "\n";
+    tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
+    if (integ->family == CUB_FAM_USER) {
+        tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";
+        tu << "struct CubUserIntegrand {\n"
+              "    static const bool kSeparable = false;\n"
+              "    const double* p;\n"
+              "    __device__ CubUserIntegrand(const double* p_, int) : p(p_) {}\n"
+              "    __device__ void eval(const double* x, double* f) const { "
+           << integ->entry
+           << "(x, f, p); }\n"
+              "};\n#define CUB_INTEGRAND CubUserIntegrand\n";
+    } else {
+        tu << "#define CUB_INTEGRAND " << family_type(integ->family) << "\n";
+    }
+    tu << "#include \"rule_kernels.cuh\"\n";
+    return tu.str();
+}
+
+int cub_jit_compile(cub_integrand* integ, int has_transform, std::string* log) {
+    has_transform = has_transform ? 1 : 0;
+    if (!integ->cubin[has_transform].empty()) return CUB_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    const std::string tu = cub_jit_translation_unit(integ, has_transform);
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
+                                     "-default-device"};
+    // cache key: translation unit + embedded headers + options
+    uint64_t h = fnv1a(tu);
+    for (int i = 0; i < kNumEmbedded; ++i) h = fnv1a(kEmbeddedSources[i], h);
+    for (const std::string& o : opts) h = fnv1a(o, h);
+    char key[64];
+    snprintf(key, sizeof key, "%016llx.sm_100a.cubin", (unsigned long long)h);
+    const std::string dir = cache_dir();
+    if (!dir.empty()) {
+        std::ifstream in(dir + "/" + key, std::ios::binary);
+        if (in) {
+            std::vector<char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+            if (buf.size() > 64) {
+                integ->cubin[has_transform].swap(buf);
+                return CUB_OK;
+            }
+        }
+    }
+    Nvrtc* rt = nvrtc();
+    if (!rt->error.empty()) {
+        if (log) *log = rt->error;
+        return CUB_ERR_NVRTC;
+    }
+    nvrtcProgram prog = nullptr;
+    int rc = rt->CreateProgram(&prog, tu.c_str(), "cubature_rule_kernels.cu", kNumEmbedded, kEmbeddedSources, kEmbeddedNames);
+    if (rc != 0) {
+        if (log) *log = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc);
+        return CUB_ERR_NVRTC;
+    }
+    std::vector<const char*> copts;
+    for (const std::string& o : opts) copts.push_back(o.c_str());
+    rc = rt->CompileProgram(prog, (int)copts.size(), copts.data());
+    size_t log_size = 0;
+    rt->GetProgramLogSize(prog, &log_size);
+    if (log && log_size > 1) {
+        log->resize(log_size);
+        rt->GetProgramLog(prog, &(*log)[0]);
+    }
+    if (rc != 0) {
+        if (log && log->empty()) *log = std::string("nvrtcCompileProgram: ") + rt->GetErrorString(rc);
+        rt->DestroyProgram(&prog);
+        return CUB_ERR_NVRTC;
+    }
+    size_t size = 0;
+    rt->GetCUBINSize(prog, &size);
+    integ->cubin[has_transform].resize(size);
+    rt->GetCUBIN(prog, integ->cubin[has_transform].data());
+    rt->DestroyProgram(&prog);
+    if (!dir.empty()) {
+        mkdirs(dir);
+        char tmpl[64];
+        snprintf(tmpl, sizeof tmpl, ".tmp.%d.%016llx", (int)getpid(), (unsigned long long)h);
+        const std::string tmp = dir + "/" + tmpl;
+        std::ofstream o(tmp, std::ios::binary);
+        if (o) {
+            o.write(integ->cubin[has_transform].data(), (std::streamsize)size);
+            o.close();
+            rename(tmp.c_str(), (dir + "/" + key).c_str());
+        }
+    }
+    integ->jit_ms_pending += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return CUB_OK;
+}
+
+int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, RuleKernels** out, std::string* log) {
+    has_transform = has_transform ? 1 : 0;
+    std::lock_guard<std::mutex> lock(integ->mu);
+    auto it = integ->loaded[has_transform].find(device);
+    if (it != integ->loaded[has_transform].end()) {
+        *out = &it->second;
+        return CUB_OK;
+    }
+    int rc = cub_jit_compile(integ, has_transform, log);
+    if (rc != CUB_OK) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    RuleKernels k;
+    cudaError_t e = cudaLibraryLoadData(&k.lib, integ->cubin[has_transform].data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
+        if (log) *log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e);
+        return CUB_ERR_CUDA;
+    }
+    if (integ->dim >= 2 && integ->fdim == 1) cudaLibraryGetKernel(&k.gm_scalar, k.lib, "cub_gm_scalar");
+    if (integ->dim == 1 && (integ->fdim == 1 || integ->separable)) cudaLibraryGetKernel(&k.gk_separable, k.lib, "cub_gk_separable");
+    cudaLibraryGetKernel(&k.staged, k.lib, "cub_rule_staged");
+    cudaLibraryGetKernel(&k.eval_points, k.lib, "cub_eval_points");
+    cudaGetLastError();
+    if (!k.staged || !k.eval_points) {
+        if (log) *log = "rule kernels missing from the JIT-compiled module";
+        return CUB_ERR_CUDA;
+    }
+    // allow the staged kernel the full 227 KB of shared memory
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    k.staged_max_smem = max_optin;
+    if (max_optin > 48 * 1024) cudaFuncSetAttribute((const void*)k.staged, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    cudaGetLastError();
+    integ->jit_ms_pending += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    auto ins = integ->loaded[has_transform].emplace(device, k);
+    *out = &ins.first->second;
+    return CUB_OK;
+}

@@ -1,0 +1,440 @@
+// pool_kernels.cu -- region-pool kernels that do not depend on the integrand (compiled by nvcc for
+// sm_100a, -fmad=false): stand-alone bisection (K4), errmax rows, pool totals (K5), and the
+// device-side batch selection (K3): stable radix sort of the regions by errmax, per-component prefix
+// sums in that order, and the parallel evaluation of the reference's residual test for every k.
+//
+// All of these are HBM-bound passes over the structure-of-arrays pool; they use coalesced 8-byte
+// accesses, fixed-shape reductions (bit-reproducible run to run) and integer atomics only where the
+// result is order-independent.
+//
+// Reference semantics reproduced (paths under src/main/java/de/labathome/cubature/):
+//   Region.cut                  Region.java:31-38           -> k_bisect
+//   Rule.errMax                 Rule.java:281-289           -> k_errmax_rows
+//   RegionHeap running sums     RegionHeap.java:21-36       -> k_totals_* (recomputed, not incremental)
+//   Gladwell batch pop          Rule.java:101-133           -> k_sort_*, k_scan_*, k_find_k
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "converge.h"
+#include "pool_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+
+// ---- K4: stand-alone bisection (used when several threads share a region, fdim > 1) ---------------
+__global__ void k_bisect(PoolView pool, int dim, const int* list, long long K, long long base) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const long long parent = list ? (long long)list[i] : i;
+    const long long right = base + i;
+    const int s = pool.splitdim[parent];
+    for (int d = 0; d < dim; ++d) {
+        double c = pool.center[(long long)d * pool.cap + parent];
+        double h = pool.halfw[(long long)d * pool.cap + parent];
+        if (d == s) {
+            h = h * 0.5;
+            pool.halfw[(long long)d * pool.cap + parent] = h;
+            pool.center[(long long)d * pool.cap + parent] = c - h;
+            pool.center[(long long)d * pool.cap + right] = c + h;
+        } else {
+            pool.center[(long long)d * pool.cap + right] = c;
+        }
+        pool.halfw[(long long)d * pool.cap + right] = h;
+    }
+}
+
+// ---- errmax over the components of each evaluated item (fdim > 1 separable GK path) ---------------
+__global__ void k_errmax_rows(PoolView pool, int fdim, const int* list, long long n_items, long long base, int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    long long slot;
+    if (mode == 0) {
+        slot = list ? (long long)list[i] : base + i;
+    } else {
+        const long long pi = i >> 1;
+        slot = (i & 1) ? base + pi : (list ? (long long)list[pi] : pi);
+    }
+    double emax = 0.0;
+    for (int j = 0; j < fdim; ++j) {
+        const double e = pool.err[(long long)j * pool.cap + slot];
+        if (e > emax) emax = e;
+    }
+    pool.errmax[slot] = emax;
+    pool.splitdim[slot] = 0;
+}
+
+// ---- K5: totals over the active regions [0, n) ----------------------------------------------------
+// grid = (TOT_BLOCKS, 2*fdim): blockIdx.y < fdim sums val row j, else err row j - fdim.
+// Fixed shape (TOT_BLOCKS x 256 threads, strided then tree) => bit-reproducible for a given n.
+constexpr int TOT_THREADS = 256;
+
+__global__ void k_totals_partial(PoolView pool, int fdim, long long n, double* partial /*[2f][gridDim.x]*/) {
+    const int row = blockIdx.y;
+    const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x;
+    long long hi = lo + per;
+    if (hi > n) hi = n;
+    double s = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += TOT_THREADS) s += src[i];
+    __shared__ double sh[TOT_THREADS];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(long long)row * gridDim.x + blockIdx.x] = sh[0];
+}
+
+__global__ void k_totals_final(const double* partial, int nblk, double* totals /*[2f]*/) {
+    const int row = blockIdx.x;
+    __shared__ double sh[TOT_THREADS];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += TOT_THREADS) s += partial[(long long)row * nblk + i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[row] = sh[0];
+}
+
+// min / max errmax key over [0, n) and, among the regions holding the minimum, the highest slot
+// (the region popped last under the "lower slot first" tie rule).  Integer atomics: order-independent.
+__global__ void k_minmax_key(const double* errmax, long long n, unsigned long long* out /*[0]=min,[1]=max*/) {
+    unsigned long long mn = ~0ULL, mx = 0ULL;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = dbits(errmax[i]);
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], mn);
+        atomicMax(&out[1], mx);
+    }
+}
+__global__ void k_argmin_slot(const double* errmax, long long n, const unsigned long long* minmax, unsigned long long* out_slot) {
+    const unsigned long long mn = minmax[0];
+    unsigned long long best = 0;
+    bool any = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (dbits(errmax[i]) == mn) {
+            best = (unsigned long long)i;  // ascending i: the last one seen is the largest
+            any = true;
+        }
+    }
+    if (any) atomicMax(out_slot, best);
+}
+
+// gathers one column (slot) of val / err into a dense [2f] vector
+__global__ void k_gather_slot(PoolView pool, int fdim, const unsigned long long* slot_ptr, double* out /*[2f]*/) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= fdim) return;
+    const long long s = (long long)*slot_ptr;
+    out[j] = pool.val[(long long)j * pool.cap + s];
+    out[fdim + j] = pool.err[(long long)j * pool.cap + s];
+}
+
+// ---- K3a: stable LSD radix sort of (key = ~bits(errmax), slot), 8 bits per pass --------------------
+// Ascending order of ~bits == descending errmax; stability keeps equal keys in ascending slot order.
+// One warp owns a contiguous chunk of SORT_CHUNK elements; per-(bin, chunk) counts are scanned per
+// bin (256 blocks) and across bins (one tiny block), then each warp scatters its chunk in order.
+constexpr int SORT_WARPS = 8;
+constexpr int SORT_CHUNK = 4096;
+
+__global__ void k_sort_prepare(const double* errmax, long long n, unsigned long long* keys, int* idx,
+                               unsigned long long* or_and /*[0]=OR,[1]=AND*/) {
+    unsigned long long o = 0ULL, a = ~0ULL;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = ~dbits(errmax[i]);
+        keys[i] = k;
+        idx[i] = (int)i;
+        o |= k;
+        a &= k;
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        o |= __shfl_xor_sync(0xffffffffu, o, s);
+        a &= __shfl_xor_sync(0xffffffffu, a, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&or_and[0], o);
+        atomicAnd(&or_and[1], a);
+    }
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+k_sort_hist(const unsigned long long* keys, long long n, int shift, long long nchunks, unsigned* hist /*[256][nchunks]*/) {
+    __shared__ unsigned sh[SORT_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = lane; b < 256; b += 32) sh[w][b] = 0;
+    __syncwarp();
+    const long long chunk = (long long)blockIdx.x * SORT_WARPS + w;
+    if (chunk < nchunks) {
+        const long long lo = chunk * SORT_CHUNK;
+        long long hi = lo + SORT_CHUNK;
+        if (hi > n) hi = n;
+        for (long long i = lo + lane; i < hi; i += 32) atomicAdd(&sh[w][(unsigned)(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int b = lane; b < 256; b += 32) hist[(long long)b * nchunks + chunk] = sh[w][b];
+    }
+}
+
+// exclusive scan of each bin's row (one block per bin); totals[bin] = row sum
+__global__ void k_sort_scan_rows(unsigned* hist, long long nchunks, unsigned long long* totals) {
+    const int bin = blockIdx.x;
+    unsigned* row = hist + (long long)bin * nchunks;
+    __shared__ unsigned long long sh[256];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < nchunks; base += 256) {
+        const long long i = base + threadIdx.x;
+        const unsigned v = i < nchunks ? row[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {  // Hillis-Steele inclusive scan
+            unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0ULL;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nchunks) row[i] = (unsigned)(carry + sh[threadIdx.x] - v);
+        __syncthreads();
+        if (threadIdx.x == 255) carry += sh[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[bin] = carry;
+}
+__global__ void k_sort_scan_bins(const unsigned long long* totals, unsigned long long* binbase) {
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int b = 0; b < 256; ++b) {
+            binbase[b] = s;
+            s += totals[b];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+k_sort_scatter(const unsigned long long* keys, const int* idx, long long n, int shift, long long nchunks,
+               const unsigned* hist, const unsigned long long* binbase, unsigned long long* out_keys, int* out_idx) {
+    __shared__ unsigned long long off[SORT_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chunk = (long long)blockIdx.x * SORT_WARPS + w;
+    if (chunk >= nchunks) return;
+    for (int b = lane; b < 256; b += 32) off[w][b] = binbase[b] + hist[(long long)b * nchunks + chunk];
+    __syncwarp();
+    const long long lo = chunk * SORT_CHUNK;
+    long long hi = lo + SORT_CHUNK;
+    if (hi > n) hi = n;
+    const unsigned lt = (1u << lane) - 1u;
+    for (long long base = lo; base < hi; base += 32) {
+        const long long i = base + lane;
+        const bool active = i < hi;
+        unsigned long long k = 0;
+        int v = 0;
+        unsigned d = 256u + (unsigned)lane;  // inactive lanes never match anybody
+        if (active) {
+            k = keys[i];
+            v = idx[i];
+            d = (unsigned)(k >> shift) & 255u;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned long long pos = 0;
+        if (active) pos = off[w][d] + (unsigned long long)__popc(peers & lt);
+        __syncwarp();
+        if (active && (peers & lt) == 0u) off[w][d] += (unsigned long long)__popc(peers);  // lowest peer lane updates
+        __syncwarp();
+        if (active) {
+            out_keys[pos] = k;
+            out_idx[pos] = v;
+        }
+    }
+}
+
+// ---- K3b: per-component inclusive prefix sums of err in sorted order ------------------------------
+// tile = SCAN_THREADS * SCAN_ITEMS consecutive sorted positions; local inclusive prefix + tile totals,
+// tile offsets by a second single-block pass per component.  Fixed shape => reproducible.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(PoolView pool, const int* perm, long long n, double* prefix /*[f][n]*/, long long ntiles, double* tile_tot /*[f][ntiles]*/) {
+    const int j = blockIdx.y;
+    const long long tile = blockIdx.x;
+    const double* src = pool.err + (long long)j * pool.cap;
+    const long long lo = tile * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    double v[SCAN_ITEMS];
+    double run = 0.0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        const long long k = lo + t;
+        const double e = k < n ? src[perm[k]] : 0.0;
+        run += e;
+        v[t] = run;
+    }
+    __shared__ double sh[SCAN_THREADS];
+    sh[threadIdx.x] = run;
+    __syncthreads();
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        const double t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0.0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    const double before = threadIdx.x > 0 ? sh[threadIdx.x - 1] : 0.0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        const long long k = lo + t;
+        if (k < n) prefix[(long long)j * n + k] = before + v[t];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) tile_tot[(long long)j * ntiles + tile] = sh[SCAN_THREADS - 1];
+}
+
+__global__ void k_scan_tile_offsets(double* tile_tot, long long ntiles) {  // exclusive, in place, one block per component
+    double* row = tile_tot + (long long)blockIdx.x * ntiles;
+    __shared__ double sh[256];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    for (long long base = 0; base < ntiles; base += 256) {
+        const long long i = base + threadIdx.x;
+        const double v = i < ntiles ? row[i] : 0.0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const double t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0.0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < ntiles) row[i] = carry + (sh[threadIdx.x] - v);
+        __syncthreads();
+        if (threadIdx.x == 255) carry += sh[255];
+        __syncthreads();
+    }
+}
+
+// ---- K3c: smallest k such that the residual after popping the k largest regions is converged ------
+// Rule.java:121-133: ee.err -= popped.err ; converged(ee) ? break.  Thread k evaluates the predicate
+// on  err_total - prefix[k]  (val_total unchanged, Rule.java:122-124 touches only err); three variants
+// (exact, residual +band, residual -band) give the decision and its sensitivity to the rounding of the
+// reference's running sums.  out[0..2] = min k+1 over converged threads (initialised to n+1 by the host).
+struct ResidualAcc {
+    const double* tot;  // [2f]: val then err
+    const double* prefix;
+    const double* tile_off;
+    long long n, ntiles, k;
+    int fdim;
+    double band;  // relative band applied to the residual: r +- band * err_total
+    __device__ double val(int j) const { return tot[j]; }
+    __device__ double err(int j) const {
+        const double p = tile_off[(long long)j * ntiles + k / SCAN_TILE] + prefix[(long long)j * n + k];
+        return (tot[fdim + j] - p) + band * tot[fdim + j];
+    }
+};
+
+__global__ void k_find_k(const double* totals, const double* prefix, const double* tile_off, long long n, long long ntiles,
+                         int fdim, double absTol, double relTol, int norm, double band, unsigned long long* out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ResidualAcc acc{totals, prefix, tile_off, n, ntiles, k, fdim, 0.0};
+    if (cub_converged(fdim, acc, absTol, relTol, norm)) atomicMin(&out[0], (unsigned long long)(k + 1));
+    acc.band = band;
+    if (cub_converged(fdim, acc, absTol, relTol, norm)) atomicMin(&out[1], (unsigned long long)(k + 1));
+    acc.band = -band;
+    if (cub_converged(fdim, acc, absTol, relTol, norm)) atomicMin(&out[2], (unsigned long long)(k + 1));
+}
+
+// ---- FP64 peak microbenchmark: independent DFMA chains, no memory traffic --------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;  // keeps the chains alive without a store in the common case
+}
+
+}  // namespace
+
+// ---- host launchers --------------------------------------------------------------------------------
+static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void pk_bisect(const PoolView& pool, int dim, const int* list, long long K, long long base, cudaStream_t s) {
+    if (K <= 0) return;
+    k_bisect<<<nblocks(K, 128), 128, 0, s>>>(pool, dim, list, K, base);
+}
+void pk_errmax_rows(const PoolView& pool, int fdim, const int* list, long long n_items, long long base, int mode, cudaStream_t s) {
+    if (n_items <= 0) return;
+    k_errmax_rows<<<nblocks(n_items, 128), 128, 0, s>>>(pool, fdim, list, n_items, base, mode);
+}
+int pk_totals_blocks(long long n) {
+    long long b = (n + 2047) / 2048;
+    if (b < 1) b = 1;
+    if (b > 1184) b = 1184;  // 8 x 148 SMs
+    return (int)b;
+}
+void pk_totals(const PoolView& pool, int fdim, long long n, double* partial, double* totals, cudaStream_t s) {
+    const int nb = pk_totals_blocks(n);
+    dim3 grid(nb, 2 * fdim);
+    k_totals_partial<<<grid, TOT_THREADS, 0, s>>>(pool, fdim, n, partial);
+    k_totals_final<<<2 * fdim, TOT_THREADS, 0, s>>>(partial, nb, totals);
+}
+void pk_min_region(const PoolView& pool, int fdim, long long n, unsigned long long* scratch /*[3]*/, double* out_vec /*[2f]*/,
+                   cudaStream_t s) {
+    const unsigned long long init[3] = {~0ULL, 0ULL, 0ULL};
+    cudaMemcpyAsync(scratch, init, sizeof init, cudaMemcpyHostToDevice, s);
+    long long b = (n + 255) / 256;
+    if (b > 1184) b = 1184;
+    k_minmax_key<<<(unsigned)b, 256, 0, s>>>(pool.errmax, n, scratch);
+    k_argmin_slot<<<(unsigned)b, 256, 0, s>>>(pool.errmax, n, scratch, scratch + 2);
+    k_gather_slot<<<nblocks(fdim, 128), 128, 0, s>>>(pool, fdim, scratch + 2, out_vec);
+}
+
+long long pk_sort_chunks(long long n) { return (n + SORT_CHUNK - 1) / SORT_CHUNK; }
+long long pk_scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+void pk_sort_prepare(const double* errmax, long long n, unsigned long long* keys, int* idx, unsigned long long* or_and,
+                     cudaStream_t s) {
+    const unsigned long long init[2] = {0ULL, ~0ULL};
+    cudaMemcpyAsync(or_and, init, sizeof init, cudaMemcpyHostToDevice, s);
+    long long b = (n + 255) / 256;
+    if (b > 2368) b = 2368;
+    k_sort_prepare<<<(unsigned)b, 256, 0, s>>>(errmax, n, keys, idx, or_and);
+}
+void pk_sort_pass(const unsigned long long* keys_in, const int* idx_in, unsigned long long* keys_out, int* idx_out, long long n,
+                  int shift, unsigned* hist, unsigned long long* bin_totals, unsigned long long* binbase, cudaStream_t s) {
+    const long long nchunks = pk_sort_chunks(n);
+    const unsigned blocks = (unsigned)((nchunks + SORT_WARPS - 1) / SORT_WARPS);
+    k_sort_hist<<<blocks, SORT_WARPS * 32, 0, s>>>(keys_in, n, shift, nchunks, hist);
+    k_sort_scan_rows<<<256, 256, 0, s>>>(hist, nchunks, bin_totals);
+    k_sort_scan_bins<<<1, 32, 0, s>>>(bin_totals, binbase);
+    k_sort_scatter<<<blocks, SORT_WARPS * 32, 0, s>>>(keys_in, idx_in, n, shift, nchunks, hist, binbase, keys_out, idx_out);
+}
+void pk_prefix(const PoolView& pool, int fdim, const int* perm, long long n, double* prefix, double* tile_tot, cudaStream_t s) {
+    const long long ntiles = pk_scan_tiles(n);
+    dim3 grid((unsigned)ntiles, fdim);
+    k_scan_tiles<<<grid, SCAN_THREADS, 0, s>>>(pool, perm, n, prefix, ntiles, tile_tot);
+    k_scan_tile_offsets<<<fdim, 256, 0, s>>>(tile_tot, ntiles);
+}
+void pk_find_k(const double* totals, const double* prefix, const double* tile_off, long long n, int fdim, double absTol,
+               double relTol, int norm, double band, unsigned long long* out /*[3]*/, cudaStream_t s) {
+    const unsigned long long init[3] = {(unsigned long long)(n + 1), (unsigned long long)(n + 1), (unsigned long long)(n + 1)};
+    cudaMemcpyAsync(out, init, sizeof init, cudaMemcpyHostToDevice, s);
+    k_find_k<<<nblocks(n, 128), 128, 0, s>>>(totals, prefix, tile_off, n, pk_scan_tiles(n), fdim, absTol, relTol, norm, band, out);
+}
+void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s) {
+    k_dfma_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-6);
+}

@@ -1,0 +1,36 @@
+// pool_kernels.h -- host launchers of the integrand-independent pool kernels (pool_kernels.cu).
+#ifndef CUB_POOL_KERNELS_H
+#define CUB_POOL_KERNELS_H
+
+#include <cuda_runtime.h>
+
+// Structure-of-arrays region pool in HBM; same bytes as CubPoolView in rule_kernels.cuh.
+struct PoolView {
+    double* center;  // [dim][cap]
+    double* halfw;   // [dim][cap]
+    double* val;     // [fdim][cap]
+    double* err;     // [fdim][cap]
+    double* errmax;  // [cap]
+    int* splitdim;   // [cap]
+    long long cap;
+};
+
+void pk_bisect(const PoolView& pool, int dim, const int* list, long long K, long long base, cudaStream_t s);
+void pk_errmax_rows(const PoolView& pool, int fdim, const int* list, long long n_items, long long base, int mode, cudaStream_t s);
+
+int pk_totals_blocks(long long n);
+void pk_totals(const PoolView& pool, int fdim, long long n, double* partial, double* totals, cudaStream_t s);
+void pk_min_region(const PoolView& pool, int fdim, long long n, unsigned long long* scratch, double* out_vec, cudaStream_t s);
+
+long long pk_sort_chunks(long long n);
+long long pk_scan_tiles(long long n);
+void pk_sort_prepare(const double* errmax, long long n, unsigned long long* keys, int* idx, unsigned long long* or_and,
+                     cudaStream_t s);
+void pk_sort_pass(const unsigned long long* keys_in, const int* idx_in, unsigned long long* keys_out, int* idx_out, long long n,
+                  int shift, unsigned* hist, unsigned long long* bin_totals, unsigned long long* binbase, cudaStream_t s);
+void pk_prefix(const PoolView& pool, int fdim, const int* perm, long long n, double* prefix, double* tile_tot, cudaStream_t s);
+void pk_find_k(const double* totals, const double* prefix, const double* tile_off, long long n, int fdim, double absTol,
+               double relTol, int norm, double band, unsigned long long* out, cudaStream_t s);
+void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s);
+
+#endif

@@ -1,0 +1,192 @@
+/* cubature_cuda.h -- C ABI of libcubature_cuda.so, the B200 (sm_100a) drop-in for the h-adaptive
+ * integration loop of jonathanschilling/Cubature.
+ *
+ * This is the boundary a host-language binding targets (Java Panama FFM / JNI, Python ctypes, C):
+ * plain pointers, sizes and scalars only, caller-owned buffers, no exceptions or callbacks across
+ * the ABI, negative return value = error (cubature_cuda_strerror).  INTEGRATION.md shows the
+ * reference-side binding a maintainer would add.
+ *
+ * Reference interfaces replaced (paths under src/main/java/de/labathome/cubature/ of the reference):
+ *   cubature_cuda_integrate        <- Cubature.integrate(...)              Cubature.java:108-170
+ *                                     (+ Rule.cubature, Rule.java:51-160; evalError of
+ *                                     Rule75GenzMalik.java:61-184 and RuleGaussKronrod_1d.java:56-164;
+ *                                     RegionHeap.java:5-37; Region.cut, Region.java:31-38)
+ *   cubature_cuda_integrand_*      <- the UnaryOperator<double[][]> integrand plugin, Cubature.java:98-99
+ *                                     (the integrand moves onto the device: built-in family or CUDA C
+ *                                     source compiled for sm_100a with NVRTC; fdim is declared instead
+ *                                     of probed at the box centre, Cubature.java:132-145)
+ *   norm argument                  <- CubatureError ordinals, CubatureError.java:9-29
+ *   cubature_cuda_eval_regions     <- Rule.evalError(integrand, Region[], nR), Rule.java:36
+ * Return layout of `out`: [2][fdim] row-major, values then error estimates (Cubature.java:169).
+ */
+#ifndef CUBATURE_CUDA_H
+#define CUBATURE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUBATURE_CUDA_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+#define CUB_OK 0
+#define CUB_ERR_BAD_ARGS (-1)       /* null/empty xmin, xmax, out ...          Cubature.java:119-128 */
+#define CUB_ERR_BAD_TOL (-2)        /* relTol and absTol both NaN              Rule.java:164-167     */
+#define CUB_ERR_BAD_DIM (-3)        /* dim < 1, dim >= 32 (Rule75GenzMalik.java:30-42) or > kernel limit */
+#define CUB_ERR_BAD_NORM (-4)       /* norm outside 0..4                       Rule.java:273-276     */
+#define CUB_ERR_NO_DEVICE (-5)      /* no usable CUDA device / driver                                 */
+#define CUB_ERR_CUDA (-6)           /* a CUDA runtime call failed (message in cub_stats_t)            */
+#define CUB_ERR_NVRTC (-7)          /* integrand source failed to compile (log returned)              */
+#define CUB_ERR_POOL_EXHAUSTED (-8) /* region pool capacity reached before convergence / maxEval      */
+#define CUB_ERR_NCCL (-9)           /* NCCL unavailable or a collective failed                        */
+#define CUB_ERR_UNSUPPORTED (-10)   /* valid request this build cannot serve (e.g. fdim too large)    */
+#define CUB_ERR_BAD_FAMILY (-11)    /* unknown built-in integrand family / wrong parameter count      */
+
+/* ---- error norms: ordinals of the reference's enum (CubatureError.java:9-29) ------------------- */
+#define CUB_NORM_INDIVIDUAL 0
+#define CUB_NORM_PAIRED 1
+#define CUB_NORM_L2 2
+#define CUB_NORM_L1 3
+#define CUB_NORM_LINF 4
+
+/* ---- built-in integrand families (cubature_b200/csrc/integrands.h) ---------------------------- */
+#define CUB_FAMILY_GENZ_OSCILLATORY 1   /* params: a[dim], u[dim]               */
+#define CUB_FAMILY_GENZ_PRODUCT_PEAK 2
+#define CUB_FAMILY_GENZ_CORNER_PEAK 3
+#define CUB_FAMILY_GENZ_GAUSSIAN 4
+#define CUB_FAMILY_GENZ_C0 5
+#define CUB_FAMILY_GENZ_DISCONTINUOUS 6
+#define CUB_FAMILY_GAUSS_ISO 10         /* params: sigma            (TestCubature.java:435-465)   */
+#define CUB_FAMILY_REFTEST 20           /* params: which[fdim] in 0..8 (TestCubature.java:109-177) */
+#define CUB_FAMILY_OSC_VEC 30           /* f_k = cos((k+1) sum x), no params                      */
+#define CUB_FAMILY_CEXP 31              /* params: w[fdim/2]; exp(-(1+i w_m) sum x), (re,im) pairs */
+
+/* ---- per-coordinate variable transforms (README.md:237-272), fused into point generation ------ */
+#define CUB_TRANSFORM_NONE 0
+#define CUB_TRANSFORM_SEMI_INF_UP 1     /* [xmin, +inf):  x = xmin + t/(1-t), t in [0,1)          */
+#define CUB_TRANSFORM_SEMI_INF_DOWN 2   /* (-inf, xmax]:  x = xmax - t/(1-t), t in [0,1)          */
+#define CUB_TRANSFORM_INF 3             /* (-inf, +inf):  x = t/(1-t^2),      t in (-1,1)         */
+
+/* ---- region-selection policy ------------------------------------------------------------------ */
+#define CUB_SELECT_DEVICE 0      /* everything on the GPU: convergence, top-K selection, bisection.
+                                    Ties in errmax are broken by lower slot index first.            */
+#define CUB_SELECT_HEAP_EXACT 1  /* the host keeps a java.util.PriorityQueue-compatible heap of
+                                    (errmax, slot) and the reference's running sums, so batch sizes,
+                                    tie order and the final summation order are the reference's,
+                                    bit for bit; the GPU does rule evaluation and bisection.        */
+
+typedef struct cub_integrand cub_integrand_t; /* opaque: compiled device plugin + parameters        */
+typedef struct cub_comm cub_comm_t;           /* opaque: one rank of a multi-GPU communicator       */
+
+/* Optional trace: caller-owned buffers, filled up to their capacities; n_* report the true counts. */
+typedef struct cub_trace {
+    int64_t batch_cap;   /* capacity of batches[]                                                   */
+    int64_t* batches;    /* nR (= 2K) of every refinement iteration (Rule.java:135)                 */
+    int64_t n_batches;   /* out                                                                     */
+    int64_t region_cap;  /* capacity (in regions) of the five arrays below                          */
+    double* centers;     /* [n][dim]  final regions (this rank's shard), heap-array order in         */
+    double* halfwidths;  /* [n][dim]  HEAP_EXACT mode, slot order in DEVICE mode                     */
+    int32_t* split_dim;  /* [n]                                                                     */
+    double* val;         /* [n][fdim]                                                               */
+    double* err;         /* [n][fdim]                                                               */
+    int64_t n_regions;   /* out                                                                     */
+} cub_trace_t;
+
+typedef struct cub_options {
+    int32_t struct_size;    /* = sizeof(cub_options_t)                                              */
+    int32_t select;         /* CUB_SELECT_*                                                         */
+    int32_t device;         /* CUDA device ordinal; -1 = current device                             */
+    int32_t reserved0;
+    int64_t pool_capacity;  /* regions; 0 = derive from maxEval and free memory                     */
+    cub_trace_t* trace;     /* NULL = no trace                                                      */
+    cub_comm_t* comm;       /* NULL = single GPU; else shard the pool over comm's ranks (DEVICE mode)*/
+    int64_t shard_min_regions; /* replicate the loop on every rank until the pool holds this many
+                                  regions, then shard (0 = default 4096 * nranks)                   */
+} cub_options_t;
+
+typedef struct cub_stats {
+    int32_t struct_size;     /* = sizeof(cub_stats_t)                                               */
+    int32_t converged;       /* 1 = tolerance met; 0 = stopped by maxEval (not an error: the reference
+                                prints a message and returns the best estimate, Rule.java:144-159)   */
+    int64_t num_eval;        /* the reference's numEval accounting (Rule.java:69,127), all ranks     */
+    int64_t num_regions;     /* regions in the final partition, all ranks                            */
+    int64_t iterations;      /* refinement iterations (evalError calls after the first)              */
+    int64_t regions_evaluated; /* = num_eval / points-per-region                                     */
+    int64_t ambiguous_decisions; /* DEVICE mode: iterations whose batch size was decided within the
+                                    rounding band of the reference's running sums    */
+    int64_t gpu_launches;    /* kernels launched by this call                                        */
+    double device_ms;        /* CUDA-event time of the whole loop on the library's stream            */
+    double rule_ms;          /* CUDA-event time summed over the rule-kernel launches only            */
+    double wall_ms;          /* host wall clock of the call                                          */
+    double jit_ms;           /* NVRTC compile + module load done inside this call (0 when cached)    */
+    char message[256];       /* human-readable detail for errors                                     */
+} cub_stats_t;
+
+/* Library / ABI version: major*1000 + minor. */
+int cubature_cuda_version(void);
+const char* cubature_cuda_strerror(int status);
+
+/* Number of rule points per region: 15 for dim == 1, else 2^dim + 2 dim^2 + 2 dim + 1
+ * (Cubature.java:153-165).  Returns a negative status for an unsupported dim. */
+int64_t cubature_cuda_points_per_region(int dim);
+
+/* Built-in integrand family -> device plugin. */
+int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams,
+                                    cub_integrand_t** out);
+
+/* CUDA C source -> device plugin, compiled with NVRTC for sm_100a (no FMA contraction).
+ * The source must define
+ *     __device__ void <entry>(const double* x, double* f, const double* p);
+ * reading x[CUB_DIM] and writing f[CUB_FDIM]; CUB_DIM / CUB_FDIM are predefined macros and the
+ * deterministic math of detmath.h (dm_exp, dm_sin, dm_cos, dm_log, dm_pow, dm_powi, dm_fma, dm_sqrt,
+ * dm_abs) is pre-included.  On failure the NVRTC log is copied to `log` (NUL-terminated). */
+int cubature_cuda_integrand_nvrtc(const char* cuda_src, const char* entry, int dim, int fdim, const double* params,
+                                  size_t nparams, cub_integrand_t** out, char* log, size_t log_cap);
+
+void cubature_cuda_integrand_free(cub_integrand_t* integrand);
+
+/* Copies the sm_100a cubin of the integrand's rule kernels (compiling it if necessary; needs no GPU)
+ * into buf; returns its size in bytes or a negative status.  For cuobjdump / ncu source views. */
+int64_t cubature_cuda_integrand_cubin(cub_integrand_t* integrand, int has_transform, void* buf, size_t buf_cap);
+
+/* The h-adaptive integration, Cubature.integrate(integrand, xmin, xmax, relTol, absTol, norm, maxEval).
+ *   transform: NULL (infinite bounds are then mapped automatically) or dim codes CUB_TRANSFORM_*
+ *   maxEval:   0 = unlimited (Rule.java:72); int64 because BASELINE config 5 needs 1e11
+ *   out:       [2][fdim] values then errors
+ *   options, stats: may be NULL */
+int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax,
+                            const int* transform, double relTol, double absTol, int norm, int64_t maxEval,
+                            const cub_options_t* options, double* out, cub_stats_t* stats);
+
+/* Rule evaluation alone (Rule.evalError) on nR caller-supplied boxes, host buffers:
+ *   centers, halfwidths [nR][dim] (in t-space when a transform is given; shift[dim] = finite bound)
+ *   val, err [nR][fdim]; split_dim [nR].  stats may be NULL. */
+int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* transform, const double* shift,
+                               int64_t nR, const double* centers, const double* halfwidths, double* val, double* err,
+                               int32_t* split_dim, cub_stats_t* stats);
+
+/* Integrand values alone at n points x[dim][n] -> f[fdim][n] (host buffers; bit-parity tests). */
+int cubature_cuda_eval_points(cub_integrand_t* integrand, int dim, int64_t n, const double* x, double* f);
+
+/* Throughput benchmark of the rule kernel alone: evaluates n_regions boxes resident in HBM
+ * (a uniform grid partition of [xmin,xmax]) `repeats` times; returns the CUDA-event time per launch. */
+int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax,
+                             int64_t n_regions, int repeats, double* ms_per_launch, double* checksum);
+
+/* Measured FP64 FMA peak of the current device (dependent-chain DFMA microbenchmark), TFLOP/s. */
+int cubature_cuda_fp64_peak(int device, double* tflops, double* ms);
+
+/* Multi-GPU: one rank per process (or per thread).  Rank 0 creates the id and ships the 128 bytes to
+ * the other ranks by any means (torch.distributed, MPI, a file); every rank then calls comm_init. */
+#define CUB_COMM_ID_BYTES 128
+int cubature_cuda_comm_unique_id(void* id_out);
+int cubature_cuda_comm_init(const void* id, int nranks, int rank, int device, cub_comm_t** out);
+void cubature_cuda_comm_free(cub_comm_t* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBATURE_CUDA_H */
