@@ -1,0 +1,269 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline metric of BASELINE.json on the hot path: Genz-Malik regions/s (and
+f-evals/s) of the h-adaptive loop on the 6-D corner-peak Genz integrand (config C5).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--max-eval E]
+
+A "step" is one complete adaptive integration (`cubature_cuda_integrate` through the C ABI) of
+    f(x) = (1 + sum a_i x_i)^-7  over [0,1]^6,  relTol 1e-13 (unreachable), maxEval E
+so maxEval is the stop, exactly as BASELINE config C5 describes; E = 1e11 (the config's own value) is
+the TOTAL over all GPUs at every N (strong scaling; the pool is sharded over the ranks).
+  value   = regions evaluated by all ranks / device time (CUDA events on the library's stream, max over
+            ranks); regions evaluated = numEval / 149.
+  e2e     = the same through the public host API with host buffers (xmin/xmax/params in, [2][fdim] out),
+            host<->device copies inside the timed region, host wall clock.
+  roofline= FP64 pipe: algorithmic flops of the rule kernel (3 643 per 6-D corner-peak
+            region) / its CUDA-event time, against the FP64 FMA peak measured live by a DFMA-chain
+            microbenchmark (MEASURED_PEAKS.json has no FP64 entry); the HBM view is reported beside it.
+  cpu_baseline = the CPU restatement of the reference (oracle/, kind "port": the Java reference cannot
+            run here, there is no JVM) on a bounded sample of the same workload, one thread like the reference.
+`--impl reference` times that CPU restatement alone (rank 0 only).
+Each step integrates a fresh pool far larger than the 126 MB L2 (3.4e8 regions x 124 B = 42 GB at E = 1e11),
+so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DIM = 6
+P = 149
+F_REGION = 3643.0      # algorithmic flops per evaluated 6-D corner-peak region
+BYTES_REGION = 124.0   # algorithmic HBM bytes per evaluated region
+NAN = float("nan")
+
+
+def workload_params():
+    import cases
+    return cases.genz_params("corner_peak", DIM)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port(max_eval):
+    """The oracle (CPU restatement of the reference) on the same integrand with a bounded maxEval."""
+    from oracle import oracle as O
+    p = workload_params()
+    t0 = time.perf_counter()
+    r = O.integrate(3, DIM, 1, p, [0.0] * DIM, [1.0] * DIM, 1e-13, NAN, 0, int(max_eval), want_regions=False)
+    dt = time.perf_counter() - t0
+    return r.num_eval / P / dt, r.num_eval, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = int(args.cpu_sample)
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, ne, dt = cpu_port(sample)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "genz_malik_regions_per_s", "value": value, "unit": "regions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "genz_corner_peak_d6 [0,1]^6 relTol=1e-13 maxEval=%d (bounded sample of the maxEval=1e11 job)" % sample},
+        "fevals_per_s": value * P,
+        "cpu_baseline": {"value": value, "unit": "regions/s", "cores": 1, "kind": "port",
+                         "sample": "same integrand and loop, maxEval=%d per step; C++ restatement of the Java reference "
+                                   "(no JVM in the image), single thread like the reference" % sample},
+        "e2e": {"value": value, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--max-eval", type=float, default=1e11, help="TOTAL maxEval of one step (all GPUs)")
+    ap.add_argument("--cpu-sample", type=float, default=1.5e8, help="maxEval of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import cubature_b200 as cb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libcubature_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # ship the NCCL unique id of the library's own communicator from rank 0
+        id_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            id_t = torch.frombuffer(bytearray(cb.Comm.unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(id_t, 0)
+        comm = cb.Comm.init(bytes(id_t.cpu().numpy().tobytes()), world, rank, local_rank)
+
+    params = workload_params()
+    ig = cb.Integrand.builtin(cb.Family.GENZ_CORNER_PEAK, DIM, 1, params)
+    max_eval = int(args.max_eval)
+    xmin, xmax = [0.0] * DIM, [1.0] * DIM
+
+    def step():
+        t0 = time.perf_counter()
+        r, st, _ = cb.Cubature.integrate_ex(ig, xmin, xmax, 1e-13, NAN, cb.CubatureError.INDIVIDUAL, max_eval, device=local_rank, comm=comm)
+        return r, st, time.perf_counter() - t0
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = cb.fp64_peak_tflops(local_rank)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms, wall_s, rule_ms, launches, regions, h2d, d2h = [], [], [], 0, 0, 0, 0
+    result = None
+    for _ in range(args.steps):
+        barrier()
+        r, st, wall = step()
+        barrier()
+        result = r
+        dev_ms.append(st.device_ms)
+        wall_s.append(wall)
+        rule_ms.append(st.rule_ms)
+        launches += st.gpu_launches
+        regions = st.num_eval // P          # all ranks (global numEval)
+        local_regions = st.regions_evaluated
+        h2d += st.h2d_bytes
+        d2h += st.d2h_bytes
+    clocks = sampler.stop() if rank == 0 else None
+
+    t_dev = torch.tensor([sum(dev_ms), sum(wall_s) * 1e3, sum(rule_ms)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+    tot_dev_ms, tot_wall_ms, tot_rule_ms = [float(v) for v in t_dev.cpu()]
+    if rank != 0:
+        if comm is not None:
+            comm.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    steps = args.steps
+    value = regions * steps / (tot_dev_ms * 1e-3)
+    e2e = regions * steps / (tot_wall_ms * 1e-3)
+    # rule kernel (cub_gm_scalar): regions per launch-set = this rank's share; time = summed launch durations
+    rule_regions_per_s = (regions / world) * steps / (tot_rule_ms * 1e-3)
+    achieved_tflops = rule_regions_per_s * F_REGION / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "genz_malik_regions_per_s", "value": value, "unit": "regions/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": tot_dev_ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "genz_corner_peak_d6 [0,1]^6 relTol=1e-13 maxEval=%d total (BASELINE config C5), select=device" % max_eval,
+                   "regions_per_step": regions, "points_per_region": P, "l2": "pool per step >> 126 MB L2, no flush needed",
+                   "parallelism": "pool sharded over %d GPU(s), NCCL allreduce per iteration" % world if world > 1 else "1 GPU"},
+        "fevals_per_s": value * P,
+        "result": {"val": float(result[0][0]), "err": float(result[1][0])},
+        "e2e": {"value": e2e, "unit": "regions/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
+                "ms_per_step": tot_wall_ms / steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "kernel": "cub_gm_scalar", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / fp64_peak, "traffic": None,
+                     "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     "flops_per_region": F_REGION, "rule_kernel_ms_per_step": tot_rule_ms / steps,
+                     "rule_regions_per_s_per_gpu": rule_regions_per_s,
+                     "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
+                             "frac": rule_regions_per_s * BYTES_REGION / 1e9 / hbm_peak}},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        v, ne, dt = cpu_port(args.cpu_sample)
+        line["cpu_baseline"] = {"value": v, "unit": "regions/s", "cores": 1, "kind": "port",
+                                "sample": "same integrand and loop with maxEval=%d (%.1f s); C++ restatement of the Java reference "
+                                          "(no JVM in the image), single thread like the reference" % (int(args.cpu_sample), dt)}
+    print(json.dumps(line))
+    if comm is not None:
+        comm.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,8 @@ class CubStats(C.Structure):
         ("regions_evaluated", C.c_int64),
         ("ambiguous_decisions", C.c_int64),
         ("gpu_launches", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
         ("device_ms", C.c_double),
         ("rule_ms", C.c_double),
         ("wall_ms", C.c_double),
@@ -66,6 +68,7 @@ SIGNATURES = {
     "cubature_cuda_version": (C.c_int, []),
     "cubature_cuda_strerror": (C.c_char_p, [C.c_int]),
     "cubature_cuda_points_per_region": (C.c_int64, [C.c_int]),
+    "cubature_cuda_converged": (C.c_int, [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int]),
     "cubature_cuda_integrand_builtin": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "cubature_cuda_integrand_nvrtc": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_size_t,
                                                 C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
@@ -77,6 +80,7 @@ SIGNATURES = {
                                              c_double_p, c_double_p, c_int32_p, C.POINTER(CubStats)]),
     "cubature_cuda_eval_points": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p]),
     "cubature_cuda_bench_rule": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p]),
+    "cubature_cuda_release_workspace": (None, []),
     "cubature_cuda_fp64_peak": (C.c_int, [C.c_int, c_double_p, c_double_p]),
     "cubature_cuda_comm_unique_id": (C.c_int, [C.c_void_p]),
     "cubature_cuda_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -64,9 +64,6 @@ int cub_jit_compile(cub_integrand* integ, int has_transform, std::string* log);
 int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, RuleKernels** out, std::string* log);
 std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transform);
 
-// convergence norms (host): Rule.java:162-279.  returns 1/0, or -1 when both tolerances are NaN
-int cub_converged_host(int fdim, const double* val, const double* err, double absTol, double relTol, int norm);
-
 // nccl_dyn.cpp
 struct cub_comm {
     void* nccl_comm = nullptr;

@@ -217,6 +217,72 @@ int make_transform(int dim, const double* xmin, const double* xmax, const int* t
     return CUB_OK;
 }
 
+struct SelectBuffers {
+    DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
+    long long cap = 0;
+    int fdim = 0;
+    cudaError_t ensure(long long n, int f) {
+        if (n <= cap && f == fdim) return cudaSuccess;
+        const long long c = std::max<long long>(n, 1024);
+        cudaError_t e;
+        if ((e = keysA.ensure((size_t)8 * c)) != cudaSuccess) return e;
+        if ((e = keysB.ensure((size_t)8 * c)) != cudaSuccess) return e;
+        if ((e = idxA.ensure((size_t)4 * c)) != cudaSuccess) return e;
+        if ((e = idxB.ensure((size_t)4 * c)) != cudaSuccess) return e;
+        if ((e = hist.ensure((size_t)4 * 256 * pk_sort_chunks(c))) != cudaSuccess) return e;
+        if ((e = bin_totals.ensure(8 * 256)) != cudaSuccess) return e;
+        if ((e = binbase.ensure(8 * 256)) != cudaSuccess) return e;
+        if ((e = prefix.ensure((size_t)8 * f * c)) != cudaSuccess) return e;
+        if ((e = tile_tot.ensure((size_t)8 * f * pk_scan_tiles(c))) != cudaSuccess) return e;
+        cap = c;
+        fdim = f;
+        return cudaSuccess;
+    }
+};
+
+// Device / pinned buffers of one integrate call, cached per device between calls so that repeated
+// integrations (the normal use: many integrals, one process) do not pay cudaMalloc / cudaFree each time.
+// cubature_cuda_release_workspace() returns the memory.
+struct Workspace {
+    int device = -1;
+    bool busy = false;
+    Pool pool;
+    SelectBuffers sel;
+    DevBuf d_list, d_stage_val, d_stage_err, d_partial, d_small;
+    PinnedBuf h_list, h_stage, h_small;
+    long long stage_stride = 0;
+};
+std::mutex g_ws_mu;
+std::vector<std::unique_ptr<Workspace>> g_ws;
+
+Workspace* acquire_workspace(int device) {
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    for (auto& w : g_ws)
+        if (!w->busy && w->device == device) {
+            w->busy = true;
+            return w.get();
+        }
+    g_ws.emplace_back(new Workspace());
+    g_ws.back()->device = device;
+    g_ws.back()->busy = true;
+    return g_ws.back().get();
+}
+void release_workspace(Workspace* w) {
+    if (!w) return;
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    w->busy = false;
+    // keep at most two idle workspaces per device
+    int idle = 0;
+    for (size_t i = 0; i < g_ws.size();) {
+        if (!g_ws[i]->busy && g_ws[i]->device == w->device && ++idle > 2) {
+            cudaSetDevice(g_ws[i]->device);
+            g_ws.erase(g_ws.begin() + (long)i);
+        } else {
+            ++i;
+        }
+    }
+}
+
 // One integrate / eval call: device, stream, kernels, launch helpers.
 struct Session {
     cub_integrand* integ = nullptr;
@@ -233,8 +299,11 @@ struct Session {
     char* msg = nullptr;
     char msgbuf[256];
     bool rule_pending = false;
+    Workspace* ws = nullptr;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
 
     ~Session() {
+        release_workspace(ws);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evr0) cudaEventDestroy(evr0);
@@ -262,6 +331,7 @@ struct Session {
             device = device_;
             CUB_CUDA_CHECK(cudaSetDevice(device), msg);
         }
+        ws = acquire_workspace(device);
         CUB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev0), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev1), msg);
@@ -358,6 +428,7 @@ int set_root(Session& S, Pool& pool) {
     CUB_CUDA_CHECK(cudaMemcpy2DAsync(pool.center.p, (size_t)pool.cap * 8, c.data(), 8, 8, S.dim, cudaMemcpyHostToDevice, S.stream), S.msg);
     CUB_CUDA_CHECK(cudaMemcpy2DAsync(pool.halfw.p, (size_t)pool.cap * 8, h.data(), 8, 8, S.dim, cudaMemcpyHostToDevice, S.stream), S.msg);
     CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    S.h2d_bytes += 16 * S.dim;
     return CUB_OK;
 }
 
@@ -440,16 +511,17 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
     const int f = S.fdim;
     const int64_t P = S.P;
     cub_trace_t* trace = opt ? opt->trace : nullptr;
-    Pool pool;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, (size_t)16 * f + 4);
     if (!(opt && opt->pool_capacity > 0)) cap = std::min<long long>(cap, 1 << 18);  // grows on demand
     CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
 
-    DevBuf d_list, d_stage_val, d_stage_err;
-    PinnedBuf h_list, h_stage;
-    long long stage_stride = 0;
+    DevBuf &d_list = W.d_list, &d_stage_val = W.d_stage_val, &d_stage_err = W.d_stage_err;
+    PinnedBuf &h_list = W.h_list, &h_stage = W.h_stage;
+    long long& stage_stride = W.stage_stride;
     auto ensure_stage = [&](long long n_items) -> int {
         if (n_items <= stage_stride) return CUB_OK;
         long long ns = std::max<long long>(n_items * 2, 1024);
@@ -496,6 +568,7 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
         CUB_CUDA_CHECK(cudaMemcpy2DAsync(h_stage.as<double>() + (size_t)f * w.n_items, width, d_stage_err.p,
                                          (size_t)stage_stride * 8, width, f, cudaMemcpyDeviceToHost, S.stream), S.msg);
         CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        S.d2h_bytes += (int64_t)2 * width * f;
         return CUB_OK;
     };
     auto store_item = [&](long long item, long long n_items, int slot) {
@@ -567,6 +640,7 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
         if (rc != CUB_OK) return rc;
         memcpy(h_list.p, list.data(), (size_t)4 * K);
         CUB_CUDA_CHECK(cudaMemcpyAsync(d_list.p, h_list.p, (size_t)4 * K, cudaMemcpyHostToDevice, S.stream), S.msg);
+        S.h2d_bytes += 4 * K;
         HostWork w{};
         w.list = d_list.as<int>();
         w.n_items = 2 * K;
@@ -606,44 +680,22 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
 }
 
 // ---- DEVICE mode ------------------------------------------------------------------------------------
-struct SelectBuffers {
-    DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
-    long long cap = 0;
-    int fdim = 0;
-    cudaError_t ensure(long long n, int f) {
-        if (n <= cap && f == fdim) return cudaSuccess;
-        const long long c = std::max<long long>(n, 1024);
-        cudaError_t e;
-        if ((e = keysA.ensure((size_t)8 * c)) != cudaSuccess) return e;
-        if ((e = keysB.ensure((size_t)8 * c)) != cudaSuccess) return e;
-        if ((e = idxA.ensure((size_t)4 * c)) != cudaSuccess) return e;
-        if ((e = idxB.ensure((size_t)4 * c)) != cudaSuccess) return e;
-        if ((e = hist.ensure((size_t)4 * 256 * pk_sort_chunks(c))) != cudaSuccess) return e;
-        if ((e = bin_totals.ensure(8 * 256)) != cudaSuccess) return e;
-        if ((e = binbase.ensure(8 * 256)) != cudaSuccess) return e;
-        if ((e = prefix.ensure((size_t)8 * f * c)) != cudaSuccess) return e;
-        if ((e = tile_tot.ensure((size_t)8 * f * pk_scan_tiles(c))) != cudaSuccess) return e;
-        cap = c;
-        fdim = f;
-        return cudaSuccess;
-    }
-};
-
 int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                      LoopResult* res) {
     const int f = S.fdim;
     const int64_t P = S.P;
     cub_trace_t* trace = opt ? opt->trace : nullptr;
-    Pool pool;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
     CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
 
-    SelectBuffers sel;
-    DevBuf d_partial, d_small;  // d_small: totals[2f] | minvec[2f] | u64 scratch[8]
-    PinnedBuf h_small;
+    SelectBuffers& sel = W.sel;
+    DevBuf &d_partial = W.d_partial, &d_small = W.d_small;  // d_small: totals[2f] | minvec[2f] | u64 scratch[8]
+    PinnedBuf& h_small = W.h_small;
     const size_t small_doubles = (size_t)4 * f;
     CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * 1184), S.msg);
     CUB_CUDA_CHECK(d_small.ensure(small_doubles * 8 + 64), S.msg);
@@ -676,6 +728,8 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         pk_min_region(pv, f, N, d_u64, d_minvec, S.stream);
         S.launches += 5;
         CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, small_doubles * 8 + 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += (int64_t)small_doubles * 8 + 24;
+        S.h2d_bytes += 24;
         CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
         const double band = 4.0 * eps * std::sqrt(ops);
         const double* tv = h_totals;
@@ -717,6 +771,8 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             pk_sort_prepare(pv.errmax, N, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64 + 4, S.stream);
             S.launches += 1;
             CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += 16;
+            S.h2d_bytes += 16;
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
             const unsigned long long vary = h_u64[4] ^ h_u64[5];  // bits that differ between keys
             unsigned long long* ka = sel.keysA.as<unsigned long long>();
@@ -740,6 +796,8 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                           S.stream);
                 S.launches += 3;
                 CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                S.d2h_bytes += 24;
+                S.h2d_bytes += 24;
                 CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
                 long long k0 = (long long)h_u64[4], k1 = (long long)h_u64[5], k2 = (long long)h_u64[6];
                 if (k0 > N) k0 = N;  // never converged: pop until the heap is empty (Rule.java:133)
@@ -787,6 +845,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     pk_totals(pool.view(), f, N, d_partial.as<double>(), d_totals, S.stream);
     S.launches += 2;
     CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, (size_t)16 * f, cudaMemcpyDeviceToHost, S.stream), S.msg);
+    S.d2h_bytes += 16 * f;
     CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
     for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
     S.flush_rule_timer();
@@ -830,6 +889,13 @@ const char* cubature_cuda_strerror(int status) {
 }
 
 int64_t cubature_cuda_points_per_region(int dim) { return cub_points_per_region(dim); }
+
+int cubature_cuda_converged(int fdim, const double* val, const double* err, double absTol, double relTol, int norm) {
+    if (fdim < 1 || !val || !err) return CUB_ERR_BAD_ARGS;
+    if (std::isnan(relTol) && std::isnan(absTol)) return CUB_ERR_BAD_TOL;
+    if (norm < 0 || norm > 4) return CUB_ERR_BAD_NORM;
+    return cub_converged(fdim, VecAcc{val, err}, absTol, relTol, norm) ? 1 : 0;
+}
 
 int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams, cub_integrand_t** out) {
     if (!out) return CUB_ERR_BAD_ARGS;
@@ -973,6 +1039,8 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
         stats->regions_evaluated = S.P > 0 ? res.num_eval / S.P : 0;
         stats->ambiguous_decisions = res.ambiguous;
         stats->gpu_launches = S.launches;
+        stats->h2d_bytes = S.h2d_bytes;
+        stats->d2h_bytes = S.d2h_bytes;
         stats->rule_ms = S.rule_ms;
         stats->jit_ms = integrand->jit_ms_pending;
         integrand->jit_ms_pending = 0.0;
@@ -1001,7 +1069,7 @@ int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* t
     int rc = S.open(integrand, dim, -1, tr, stats);
     if (rc != CUB_OK) return rc;
     const int f = S.fdim;
-    Pool pool;
+    Pool& pool = S.ws->pool;
     CUB_CUDA_CHECK(pool.alloc(dim, f, nR), S.msg);
     // [nR][dim] -> [dim][nR]
     std::vector<double> tmp((size_t)nR * std::max(dim, f));
@@ -1085,7 +1153,7 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
         return rc;
     }
     const int f = S.fdim;
-    Pool pool;
+    Pool& pool = S.ws->pool;
     CUB_CUDA_CHECK(pool.alloc(dim, f, n_regions), S.msg);
     // uniform slabs along dimension 0: region i covers [xmin0 + i*w, xmin0 + (i+1)*w] x the full box elsewhere
     {
@@ -1131,6 +1199,19 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
         *checksum = h[0];
     }
     return CUB_OK;
+}
+
+void cubature_cuda_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    for (size_t i = 0; i < g_ws.size();) {
+        if (!g_ws[i]->busy) {
+            cudaSetDevice(g_ws[i]->device);
+            g_ws.erase(g_ws.begin() + (long)i);
+        } else {
+            ++i;
+        }
+    }
+    cudaGetLastError();
 }
 
 int cubature_cuda_fp64_peak(int device, double* tflops, double* ms_out) {

@@ -118,6 +118,8 @@ typedef struct cub_stats {
     int64_t ambiguous_decisions; /* DEVICE mode: iterations whose batch size was decided within the
                                     rounding band of the reference's running sums    */
     int64_t gpu_launches;    /* kernels launched by this call                                        */
+    int64_t h2d_bytes;       /* bytes copied host->device by this call (geometry, lists, scalars)    */
+    int64_t d2h_bytes;       /* bytes copied device->host by this call (control scalars, results)    */
     double device_ms;        /* CUDA-event time of the whole loop on the library's stream            */
     double rule_ms;          /* CUDA-event time summed over the rule-kernel launches only            */
     double wall_ms;          /* host wall clock of the call                                          */
@@ -132,6 +134,10 @@ const char* cubature_cuda_strerror(int status);
 /* Number of rule points per region: 15 for dim == 1, else 2^dim + 2 dim^2 + 2 dim + 1
  * (Cubature.java:153-165).  Returns a negative status for an unsupported dim. */
 int64_t cubature_cuda_points_per_region(int dim);
+
+/* The convergence predicate alone, Rule.converged (Rule.java:162-279), on host vectors val[fdim],
+ * err[fdim]: returns 1 (converged), 0, or CUB_ERR_BAD_TOL / CUB_ERR_BAD_NORM.  Host-only utility. */
+int cubature_cuda_converged(int fdim, const double* val, const double* err, double absTol, double relTol, int norm);
 
 /* Built-in integrand family -> device plugin. */
 int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams,
@@ -175,6 +181,9 @@ int cubature_cuda_eval_points(cub_integrand_t* integrand, int dim, int64_t n, co
  * (a uniform grid partition of [xmin,xmax]) `repeats` times; returns the CUDA-event time per launch. */
 int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax,
                              int64_t n_regions, int repeats, double* ms_per_launch, double* checksum);
+
+/* Device and pinned buffers are cached per device between calls; this frees the idle ones. */
+void cubature_cuda_release_workspace(void);
 
 /* Measured FP64 FMA peak of the current device (dependent-chain DFMA microbenchmark), TFLOP/s. */
 int cubature_cuda_fp64_peak(int device, double* tflops, double* ms);

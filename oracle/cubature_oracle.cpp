@@ -870,6 +870,16 @@ int orc_eval_regions(int family, int dim, int fdim, const double* params, int np
     return 0;
 }
 
+// Rule.converged alone (Rule.java:162-279) on dense vectors: 1 / 0, or -1 when both tolerances are NaN
+int orc_converged_vec(int fdim, const double* val, const double* err, double absTol, double relTol, int norm) {
+    std::vector<orc::ErrorEstimate> ee((size_t)fdim);
+    for (int j = 0; j < fdim; ++j) {
+        ee[(size_t)j].val = val[j];
+        ee[(size_t)j].err = err[j];
+    }
+    return orc::converged(fdim, ee, absTol, relTol, norm);
+}
+
 // detmath entry points so tests can compare host bits with device bits and with mpmath
 double orc_dm_exp(double x) { return dm_exp(x); }
 double orc_dm_sin(double x) { return dm_sin(x); }

@@ -56,6 +56,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_double]
         L.orc_dm_pow.restype = C.c_double
         L.orc_dm_pow.argtypes = [C.c_double, C.c_double]
+        L.orc_converged_vec.restype = C.c_int
+        L.orc_converged_vec.argtypes = [C.c_int, dp, dp, C.c_double, C.c_double, C.c_int]
         L.orc_eval_family_points.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_longlong, dp, dp]
         _LIB = L
     return _LIB
@@ -155,3 +157,9 @@ def eval_points(family, dim, fdim, params, x):
     out = np.zeros((fdim, n))
     L.orc_eval_family_points(family, dim, fdim, _dp(params), len(params), n, _dp(x), _dp(out))
     return out
+
+
+def converged(val, err, abs_tol, rel_tol, norm):
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    err = np.ascontiguousarray(err, dtype=np.float64)
+    return lib().orc_converged_vec(len(val), _dp(val), _dp(err), abs_tol, rel_tol, norm)

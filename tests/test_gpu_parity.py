@@ -1,0 +1,256 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI of
+libcubature_cuda.so (via the ctypes mirror) and is compared with the CPU oracle on the same inputs:
+
+  * integrand values, rule values / errors / split dimensions: bit-exact;
+  * HEAP_EXACT mode: value, error, numEval, region count, every batch size, every final region
+    (centre, half-width, split dimension) bit-exact with the restated reference;
+  * DEVICE mode: numEval, region count and every batch size identical; value / error within 1e-12
+    relative (the summation order differs); split-dimension histogram identical unless
+    the problem has exactly tied error estimates (the documented tie rule differs from the JDK heap).
+"""
+import ctypes
+import json
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+NAN = float("nan")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PINS = json.load(open(os.path.join(GOLD, "oracle_pins.json")))
+SYMMETRIC = {"kat_gauss3d_sigma0.5_rel1e-4", "c1_gauss3d_sigma1_rel1e-6", "gauss3d_sigma0.5_rel1e-6", "gauss_d2_inf",
+             "reftest_2_dim2", "reftest_4_dim3", "reftest_4_dim4", "reftest_6_dim3", "reftest_6_dim4", "reftest_7_dim4"}
+
+
+def run_pin(cb, c, select, **kw):
+    rel = NAN if c["relTol"] is None else c["relTol"]
+    ab = NAN if c["absTol"] is None else c["absTol"]
+    ig = cb.Integrand.builtin(c["family"], c["dim"], c["fdim"], c["params"])
+    return cb.Cubature.integrate_ex(ig, [float(v) for v in c["xmin"]], [float(v) for v in c["xmax"]], rel, ab, c["norm"],
+                                    c["maxEval"], transform=c["transform"], select=select, trace_batches=8192,
+                                    trace_regions=c["regions"] + 8, **kw)
+
+
+def test_fp64_peak_is_plausible(cb):
+    t = cb.fp64_peak_tflops()
+    assert 20.0 < t < 50.0, t  # B200: 148 SM x 64 DFMA/clk x 2 x ~1.8 GHz
+
+
+@pytest.mark.parametrize("name", sorted(cases.GENZ))
+def test_integrand_bits(cb, oracle, name):
+    rng = np.random.default_rng(1)
+    for dim in (1, 2, 3, 5, 6, 8):
+        p = cases.genz_params(name, dim)
+        x = rng.uniform(-0.25, 1.25, (dim, 5000))
+        g = cb.Integrand.builtin(cases.GENZ[name], dim, 1, p).eval_points(x)
+        c = oracle.eval_points(cases.GENZ[name], dim, 1, p, x)
+        assert cases.bit_equal(g, c), (name, dim, cases.ulp_diff(g, c))
+
+
+def test_integrand_bits_other_families(cb, oracle):
+    rng = np.random.default_rng(2)
+    for dim in (1, 2, 3, 4):
+        x = rng.uniform(-0.5, 2.0, (dim, 3000))
+        which = [0, 1, 2, 3, 4, 5, 6, 7] + ([8] if dim == 3 else [])
+        for fam, fdim, p in [(10, 1, [0.5]), (20, len(which), which), (30, 33, []), (31, 8, [0.5, 1.0, 2.0, 3.0])]:
+            g = cb.Integrand.builtin(fam, dim, fdim, p).eval_points(x)
+            c = oracle.eval_points(fam, dim, fdim, p, x)
+            same = (g.view(np.uint64) == c.view(np.uint64)) | (np.isnan(g) & np.isnan(c))
+            assert same.all(), (fam, dim)
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4, 5, 6, 7])
+def test_genz_malik_rule_bit_exact(cb, oracle, dim):
+    for name, fam in cases.GENZ.items():
+        p = cases.genz_params(name, dim)
+        c, h = cases.random_boxes(dim, 777, 100 + dim)
+        gv, ge, gs, st = cb.Integrand.builtin(fam, dim, 1, p).eval_regions(c, h)
+        cv, ce, cs = oracle.eval_regions(fam, dim, 1, p, c, h)
+        assert cases.bit_equal(gv, cv) and cases.bit_equal(ge, ce), (name, cases.ulp_diff(gv, cv), cases.ulp_diff(ge, ce))
+        assert np.array_equal(gs, cs), name
+        assert st.num_eval == 777 * cb.points_per_region(dim)
+
+
+def test_gauss_kronrod_rule_bit_exact(cb, oracle):
+    c, h = cases.random_boxes(1, 1001, 5, 0.0, 3.0)
+    for fam, fdim, p in [(20, 8, list(range(8))), (30, 1, []), (30, 64, []), (30, 1024, []), (10, 1, [2.0]), (31, 6, [0.3, 1.0, 4.0])]:
+        gv, ge, gs, _ = cb.Integrand.builtin(fam, 1, fdim, p).eval_regions(c, h)
+        cv, ce, cs = oracle.eval_regions(fam, 1, fdim, p, c, h)
+        assert cases.bit_equal(gv, cv) and cases.bit_equal(ge, ce), (fam, fdim, cases.ulp_diff(gv, cv), cases.ulp_diff(ge, ce))
+        assert np.array_equal(gs, cs)
+
+
+def test_vector_rule_and_transforms_bit_exact(cb, oracle):
+    for dim, fam, fdim, p in [(2, 20, 3, [0, 4, 6]), (3, 31, 8, [0.5, 1.0, 2.0, 3.0]), (4, 31, 32, [0.25 * (m + 1) for m in range(16)]),
+                              (2, 30, 5, []), (5, 30, 3, [])]:
+        c, h = cases.random_boxes(dim, 300, 40 + dim, 0.05, 0.95)
+        for tr, sh in [(None, None), ([1] * dim, [0.5] * dim), ([3, 2] + [1] * (dim - 2), [0.0, 1.0] + [0.25] * (dim - 2))]:
+            gv, ge, gs, _ = cb.Integrand.builtin(fam, dim, fdim, p).eval_regions(c, h, tr, sh)
+            cv, ce, cs = oracle.eval_regions(fam, dim, fdim, p, c, h, tr, sh)
+            assert cases.bit_equal(gv, cv) and cases.bit_equal(ge, ce), (dim, fam, tr, cases.ulp_diff(gv, cv), cases.ulp_diff(ge, ce))
+            assert np.array_equal(gs, cs)
+
+
+@pytest.mark.parametrize("c", PINS, ids=[c["name"] for c in PINS])
+def test_golden_heap_exact(cb, oracle, c):
+    r, st, tr = run_pin(cb, c, cb.Select.HEAP_EXACT)
+    assert [float(v).hex() for v in r[0]] == c["val_hex"]
+    assert [float(v).hex() for v in r[1]] == c["err_hex"]
+    assert (st.num_eval, st.num_regions, st.iterations, bool(st.converged)) == (c["numEval"], c["regions"], c["iterations"], c["converged"])
+    assert tr.batches == c["batches"]
+    assert tr.split_hist(c["dim"]) == c["split_hist"]
+    assert st.gpu_launches >= 1
+
+
+@pytest.mark.parametrize("c", PINS, ids=[c["name"] for c in PINS])
+def test_golden_device(cb, oracle, c):
+    r, st, tr = run_pin(cb, c, cb.Select.DEVICE)
+    if st.ambiguous_decisions:
+        pytest.skip("a batch size was decided inside the rounding band of the reference's running sums")
+    assert (st.num_eval, st.num_regions, st.iterations, bool(st.converged)) == (c["numEval"], c["regions"], c["iterations"], c["converged"])
+    assert tr.batches == c["batches"]
+    val = np.array([float.fromhex(v) for v in c["val_hex"]])
+    err = np.array([float.fromhex(v) for v in c["err_hex"]])
+    scale = max(np.max(np.abs(val)), 1e-300)
+    assert np.max(np.abs(r[0] - val)) <= 1e-12 * scale       # north_star: within 1e-12 relative
+    assert np.max(np.abs(r[1] - err)) <= 1e-12 * max(np.max(np.abs(err)), scale * 1e-4)
+    if c["name"] not in SYMMETRIC:
+        assert tr.split_hist(c["dim"]) == c["split_hist"]
+    else:
+        assert sum(tr.split_hist(c["dim"])) == sum(c["split_hist"])
+
+
+def test_final_region_list_is_the_reference_partition(cb, oracle):
+    for c in (PINS[0], PINS[1], [p for p in PINS if p["name"] == "genz_gaussian_d3"][0], [p for p in PINS if p["name"] == "cexp_d3_f8_paired_semiinf"][0]):
+        rel = NAN if c["relTol"] is None else c["relTol"]
+        ab = NAN if c["absTol"] is None else c["absTol"]
+        o = oracle.integrate(c["family"], c["dim"], c["fdim"], c["params"], [float(v) for v in c["xmin"]], [float(v) for v in c["xmax"]],
+                             rel, ab, c["norm"], c["maxEval"], transform=c["transform"])
+        r, st, tr = run_pin(cb, c, cb.Select.HEAP_EXACT)
+        # heap ARRAY order is reproduced, so the lists agree row by row
+        assert cases.bit_equal(tr.centers, o.centers) and cases.bit_equal(tr.halfwidths, o.halfwidths)
+        assert np.array_equal(tr.split_dim, o.split_dim)
+        assert cases.bit_equal(tr.val, o.region_val) and cases.bit_equal(tr.err, o.region_err)
+        # DEVICE mode: same partition as a set (slot order differs) when no ties are involved
+        if c["name"] == "genz_gaussian_d3":
+            r2, st2, tr2 = run_pin(cb, c, cb.Select.DEVICE)
+            key = lambda cc, hh, sd: sorted(zip(map(tuple, cc.tolist()), map(tuple, hh.tolist()), sd.tolist()))
+            assert key(tr2.centers, tr2.halfwidths, tr2.split_dim) == key(o.centers, o.halfwidths, o.split_dim)
+
+
+USER_SRC = r"""
+__device__ void user_f(const double* x, double* f, const double* p) {
+    double s = 0.0, q = 1.0;
+    for (int i = 0; i < CUB_DIM; ++i) {
+        s = dm_fma(p[i], x[i] * x[i], s);
+        q = q * dm_cos(p[i] * x[i]);
+    }
+    f[0] = dm_exp(-s);
+    f[1] = q;
+    f[2] = 1.0 / (1.0 + s);
+}
+"""
+
+
+def test_nvrtc_user_plugin_matches_host_build_of_same_source(cb, oracle):
+    """The SAME source string: NVRTC -> device plugin, g++ -> host plugin for the oracle; results bit-exact."""
+    dim, fdim, p = 3, 3, [0.9, 1.7, 0.4]
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cubature_b200", "csrc")
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "user.cpp")
+        with open(src, "w") as f:
+            f.write('#define CUB_DIM %d\n#define CUB_FDIM %d\n#define __device__\n#include "detmath.h"\nextern "C" {\n%s\n}\n' % (dim, fdim, USER_SRC))
+        so = os.path.join(td, "user.so")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-march=x86-64-v3", "-I", csrc, "-o", so, src])
+        host = ctypes.CDLL(so)
+        addr = ctypes.cast(host.user_f, ctypes.c_void_p).value
+        ig = cb.Integrand.from_source(USER_SRC, "user_f", dim, fdim, p)
+        for norm in (cb.CubatureError.L2, cb.CubatureError.INDIVIDUAL, cb.CubatureError.LINF):
+            o = oracle.integrate_user(addr, dim, fdim, p, [0, -1, 0.5], [1, 1, 2], 1e-5, NAN, int(norm), 500000)
+            r, st, tr = cb.Cubature.integrate_ex(ig, [0, -1, 0.5], [1, 1, 2], 1e-5, NAN, norm, 500000, select=cb.Select.HEAP_EXACT,
+                                                 trace_batches=4096)
+            assert cases.bit_equal(r[0], o.val) and cases.bit_equal(r[1], o.err)
+            assert (st.num_eval, st.num_regions, tr.batches) == (o.num_eval, o.num_regions, o.batches)
+            r2, st2, tr2 = cb.Cubature.integrate_ex(ig, [0, -1, 0.5], [1, 1, 2], 1e-5, NAN, norm, 500000, trace_batches=4096)
+            assert (st2.num_eval, st2.num_regions, tr2.batches) == (o.num_eval, o.num_regions, o.batches)
+            assert np.allclose(r2[0], o.val, rtol=1e-12, atol=0)
+
+
+def test_nan_and_degenerate_inputs_match_reference(cb, oracle):
+    # Morokoff-Caflisch over a box reaching x < 0: pow(negative, 1/d) = NaN poisons the sums (App. C: mirrored)
+    for sel in (cb.Select.HEAP_EXACT,):
+        o = oracle.integrate(20, 2, 1, [7], [-0.5, 0.0], [1.0, 1.0], 1e-3, NAN, 0, 5000)
+        ig = cb.Integrand.builtin(20, 2, 1, [7])
+        r, st, tr = cb.Cubature.integrate_ex(ig, [-0.5, 0.0], [1.0, 1.0], 1e-3, NAN, 0, 5000, select=sel, trace_batches=4096)
+        assert math.isnan(r[0][0]) == math.isnan(o.val[0])
+        assert (st.num_eval, st.num_regions, tr.batches) == (o.num_eval, o.num_regions, o.batches)
+    # zero-width box: val = err = 0 never converges (strict <), maxEval stops it
+    ig = cb.Integrand.builtin(10, 2, 1, [1.0])
+    for sel in (cb.Select.HEAP_EXACT, cb.Select.DEVICE):
+        o = oracle.integrate(10, 2, 1, [1.0], [0.0, 0.3], [1.0, 0.3], 1e-3, NAN, 0, 300)
+        r, st, tr = cb.Cubature.integrate_ex(ig, [0.0, 0.3], [1.0, 0.3], 1e-3, NAN, 0, 300, select=sel, trace_batches=64)
+        assert r[0][0] == 0.0 and not st.converged and st.num_eval == o.num_eval and tr.batches == o.batches
+    # maxEval below one rule application: only the root box is evaluated (Rule.java:64-72)
+    for sel in (cb.Select.HEAP_EXACT, cb.Select.DEVICE):
+        r, st, _ = cb.Cubature.integrate_ex(ig, [0, 0], [1, 1], 1e-12, NAN, 0, 5, select=sel)
+        assert st.num_eval == 17 and st.num_regions == 1 and not st.converged
+    # xmin > xmax: negative half-widths, as in the reference (no check there)
+    o = oracle.integrate(10, 2, 1, [1.0], [1, 0], [0, 1], 1e-4, NAN, 0, 100000)
+    r, st, _ = cb.Cubature.integrate_ex(ig, [1, 0], [0, 1], 1e-4, NAN, 0, 100000, select=cb.Select.HEAP_EXACT)
+    assert cases.bit_equal(r[0], o.val) and st.num_eval == o.num_eval
+
+
+def test_pool_growth_does_not_change_results(cb):
+    c = [p for p in PINS if p["name"] == "genz_gaussian_d5"][0]
+    base, st0, _ = run_pin(cb, c, cb.Select.DEVICE)
+    small, st1, _ = run_pin(cb, c, cb.Select.DEVICE, pool_capacity=64)
+    assert cases.bit_equal(base, small) and st0.num_regions == st1.num_regions
+    ex0, _, _ = run_pin(cb, c, cb.Select.HEAP_EXACT)
+    ex1, _, _ = run_pin(cb, c, cb.Select.HEAP_EXACT, pool_capacity=16)
+    assert cases.bit_equal(ex0, ex1)
+
+
+def test_device_mode_is_deterministic(cb):
+    c = [p for p in PINS if p["name"] == "genz_product_peak_d5"][0]
+    a, sa, ta = run_pin(cb, c, cb.Select.DEVICE)
+    b, sb, tb = run_pin(cb, c, cb.Select.DEVICE)
+    assert cases.bit_equal(a, b) and ta.batches == tb.batches
+    assert cases.bit_equal(ta.centers, tb.centers) and np.array_equal(ta.split_dim, tb.split_dim)
+
+
+def test_full_size_properties_corner_peak_6d(cb):
+    """BASELINE config C5 at a size the oracle cannot follow: invariants of the loop itself."""
+    dim = 6
+    P = cb.points_per_region(dim)
+    p = cases.genz_params("corner_peak", dim)
+    ig = cb.Integrand.builtin(cb.Family.GENZ_CORNER_PEAK, dim, 1, p)
+    max_eval = 2_000_000_000
+    r, st, tr = cb.Cubature.integrate_ex(ig, [0] * dim, [1] * dim, 1e-13, NAN, 0, max_eval, trace_batches=256)
+    # numEval accounting of Rule.java:69,127 and one new region per pop
+    assert st.num_eval == P * (1 + sum(tr.batches)) and st.num_regions == 1 + sum(tr.batches) // 2
+    assert max_eval <= st.num_eval < max_eval + 2 * P and not st.converged
+    # every iteration but the last pops the whole heap (unreachable tolerance): batches double
+    assert tr.batches[:-1] == [2 << i for i in range(len(tr.batches) - 1)]
+    exact = cases.genz_exact("corner_peak", dim, p)
+    assert abs(r[0][0] - exact) <= r[1][0]
+    assert r[1][0] < 1e-6 * abs(exact)
+    # additivity: the two halves of the box integrate to the whole (each to its own error estimate)
+    lo, _, _ = cb.Cubature.integrate_ex(ig, [0] * dim, [0.5] + [1] * (dim - 1), 1e-13, NAN, 0, 200_000_000)
+    hi, _, _ = cb.Cubature.integrate_ex(ig, [0.5] + [0] * (dim - 1), [1] * dim, 1e-13, NAN, 0, 200_000_000)
+    assert abs(lo[0][0] + hi[0][0] - exact) <= lo[1][0] + hi[1][0]
+
+
+def test_linearity_of_vector_integrands(cb):
+    """f = (g, 2g-ish by construction): components of CEXP with equal w integrate to equal values."""
+    inf = float("inf")
+    ig = cb.Integrand.builtin(cb.Family.CEXP, 4, 8, [1.0, 1.0, 2.0, 2.0])
+    r, st, _ = cb.Cubature.integrate_ex(ig, [0] * 4, [inf] * 4, 1e-6, NAN, cb.CubatureError.L2, 30_000_000)
+    assert r[0][0] == r[0][2] and r[0][1] == r[0][3] and r[0][4] == r[0][6]
+    z = (1 / complex(1, 1.0)) ** 4
+    assert abs(r[0][0] - z.real) < 1e-5 and abs(r[0][1] - z.imag) < 1e-5
