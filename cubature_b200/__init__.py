@@ -187,6 +187,13 @@ class Comm:
         _check(_ffi.lib().cubature_cuda_comm_init(unique_id, nranks, rank, device, C.byref(h)))
         return cls(h, nranks, rank)
 
+    @classmethod
+    def init_local(cls, group_key, nranks, rank, device=-1):
+        """Ranks as threads of one process (exchange through host memory)."""
+        h = C.c_void_p()
+        _check(_ffi.lib().cubature_cuda_comm_init_local(group_key, nranks, rank, device, C.byref(h)))
+        return cls(h, nranks, rank)
+
     def close(self):
         if self._h:
             _ffi.lib().cubature_cuda_comm_free(self._h)

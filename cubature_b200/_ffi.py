@@ -84,6 +84,9 @@ SIGNATURES = {
     "cubature_cuda_fp64_peak": (C.c_int, [C.c_int, c_double_p, c_double_p]),
     "cubature_cuda_comm_unique_id": (C.c_int, [C.c_void_p]),
     "cubature_cuda_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cubature_cuda_shard_count": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "cubature_cuda_tie_share": (C.c_int64, [C.c_int64, c_int64_p, C.c_int, C.c_int]),
+    "cubature_cuda_comm_init_local": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cubature_cuda_comm_free": (None, [C.c_void_p]),
 }
 

@@ -65,13 +65,14 @@ int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, Rul
 std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transform);
 
 // nccl_dyn.cpp
+struct cub_local_group;
 struct cub_comm {
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0, device = 0;
+    cub_local_group* local = nullptr;  // in-process (thread-per-rank) communicator, else NCCL
+    unsigned long long local_key = 0;
 };
-int cub_comm_allreduce_sum_f64(cub_comm* comm, double* dev_buf, size_t count, cudaStream_t stream);
-int cub_comm_allreduce_max_u64(cub_comm* comm, unsigned long long* dev_buf, size_t count, cudaStream_t stream);
-int cub_comm_allreduce_sum_u64(cub_comm* comm, unsigned long long* dev_buf, size_t count, cudaStream_t stream);
+int cub_comm_allgather(cub_comm* comm, const void* dev_send, size_t bytes, void* dev_recv, cudaStream_t stream);
 
 int64_t cub_points_per_region(int dim);
 

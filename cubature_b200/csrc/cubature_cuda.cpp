@@ -26,6 +26,23 @@
 #include "integrands.h"
 #include "pool_kernels.h"
 
+// ---- host-side sharding arithmetic of the multi-GPU path (also exported for CPU-only tests) --------
+extern "C" int64_t cubature_cuda_shard_count(int64_t n, int nranks, int rank) {
+    // rank r keeps slots r, r + R, r + 2R, ... of a replicated pool of n regions
+    if (nranks < 1 || rank < 0 || rank >= nranks || n < 0) return CUB_ERR_BAD_ARGS;
+    return n > rank ? (n - rank + nranks - 1) / nranks : 0;
+}
+extern "C" int64_t cubature_cuda_tie_share(int64_t tie_take, const int64_t* ties_per_rank, int nranks, int rank) {
+    // regions whose errmax equals the selection threshold are popped in (rank, slot) order:
+    // rank r takes what is left of the global budget after the lower ranks, at most its own tie count
+    if (nranks < 1 || rank < 0 || rank >= nranks || !ties_per_rank) return CUB_ERR_BAD_ARGS;
+    int64_t before = 0;
+    for (int r = 0; r < rank; ++r) before += ties_per_rank[r];
+    const int64_t left = tie_take - before;
+    if (left <= 0) return 0;
+    return left < ties_per_rank[rank] ? left : ties_per_rank[rank];
+}
+
 int64_t cub_points_per_region(int dim) {
     if (dim == 1) return 15;
     if (dim < 1 || dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
@@ -221,6 +238,13 @@ struct SelectBuffers {
     DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
     long long cap = 0;
     int fdim = 0;
+    cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list + tile counters + state
+        cudaError_t e;
+        if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
+        if ((e = small.ensure(8192)) != cudaSuccess) return e;
+        if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
     cudaError_t ensure(long long n, int f) {
         if (n <= cap && f == fdim) return cudaSuccess;
         const long long c = std::max<long long>(n, 1024);
@@ -301,6 +325,7 @@ struct Session {
     bool rule_pending = false;
     Workspace* ws = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int64_t local_regions_evaluated = 1;  // regions this rank evaluated (the root box counts for everyone)
 
     ~Session() {
         release_workspace(ws);
@@ -522,6 +547,7 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
     DevBuf &d_list = W.d_list, &d_stage_val = W.d_stage_val, &d_stage_err = W.d_stage_err;
     PinnedBuf &h_list = W.h_list, &h_stage = W.h_stage;
     long long& stage_stride = W.stage_stride;
+    stage_stride = 0;  // the cached buffers may have been sized for another fdim: re-derive the stride
     auto ensure_stage = [&](long long n_items) -> int {
         if (n_items <= stage_stride) return CUB_OK;
         long long ns = std::max<long long>(n_items * 2, 1024);
@@ -680,32 +706,49 @@ int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int
 }
 
 // ---- DEVICE mode ------------------------------------------------------------------------------------
+// The pool can be sharded over the ranks of a communicator (options->comm).  Until the pool holds
+// shard_min_regions regions every rank runs the same deterministic iterations on a full copy (no
+// communication, identical bits everywhere); then rank r keeps the regions in slots r, r+R, r+2R, ...
+// and from there on refines only its own regions.  Per iteration the ranks exchange one small block
+// (local sums of val/err, the smallest-errmax region, the local region count) with ONE all-gather and
+// add the blocks in rank order, so every rank takes the same decision; the distributed batch selection
+// exchanges one 4 KB histogram per radix pass.  Children stay with the rank that owns the parent.
 int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                      LoopResult* res) {
     const int f = S.fdim;
     const int64_t P = S.P;
     cub_trace_t* trace = opt ? opt->trace : nullptr;
+    cub_comm* comm = opt ? opt->comm : nullptr;
+    const int R = comm ? comm->nranks : 1, rank = comm ? comm->rank : 0;
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 4096LL * R;
+    if (R > 1 && !(opt && opt->pool_capacity > 0) && maxEval > 0) {
+        // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
+        const long long total = maxEval / (2 * P) + 8;
+        cap = std::min(cap, std::max<long long>(total / R + total / (4 * R) + 1024, 4 * shard_min));
+    }
     CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
 
     SelectBuffers& sel = W.sel;
-    DevBuf &d_partial = W.d_partial, &d_small = W.d_small;  // d_small: totals[2f] | minvec[2f] | u64 scratch[8]
+    DevBuf &d_partial = W.d_partial, &d_small = W.d_small;
     PinnedBuf& h_small = W.h_small;
-    const size_t small_doubles = (size_t)4 * f;
+    // exchange block (doubles): totals[2f] | minvec[2f] | u64: min key, max key, argmin slot, local N
+    const size_t blk = (size_t)4 * f + 4;
     CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * 1184), S.msg);
-    CUB_CUDA_CHECK(d_small.ensure(small_doubles * 8 + 64), S.msg);
-    CUB_CUDA_CHECK(h_small.ensure(small_doubles * 8 + 64), S.msg);
+    CUB_CUDA_CHECK(d_small.ensure(blk * 8 * (size_t)(R + 1) + 64 + (size_t)R * 4096), S.msg);
+    CUB_CUDA_CHECK(h_small.ensure(blk * 8 * (size_t)(R + 1) + 64), S.msg);
     double* d_totals = d_small.as<double>();
     double* d_minvec = d_totals + 2 * f;
-    unsigned long long* d_u64 = (unsigned long long*)(d_minvec + 2 * f);
-    double* h_totals = h_small.as<double>();
-    double* h_minvec = h_totals + 2 * f;
-    unsigned long long* h_u64 = (unsigned long long*)(h_minvec + 2 * f);
+    unsigned long long* d_u64 = (unsigned long long*)(d_minvec + 2 * f);  // [0..3] part of the block, [4..7] scratch
+    double* d_gather = d_totals + blk + 8;                                 // [R][blk]
+    unsigned char* d_histgather = (unsigned char*)(d_gather + blk * R);    // [R][4096]
+    double* h_block = h_small.as<double>();                                // [R][blk] after the exchange
+    unsigned long long* h_u64 = (unsigned long long*)(h_block + blk * R);  // scratch [8]
 
     {
         HostWork w{};
@@ -715,25 +758,81 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         rc = S.launch_rule(pool.view(), w);
         if (rc != CUB_OK) return rc;
     }
-    long long N = 1;
+    long long N = 1;          // regions held by this rank
+    long long Nglobal = 1;    // regions of the whole partition
+    bool sharded = false;
     int64_t numEval = P;
     bool conv = false;
     double ops = 1.0;  // additions the reference's running sums have seen so far (rounding band)
-    std::vector<double> tmp_err(f);
+    std::vector<double> tmp_err(f), tot(2 * f), minvec(2 * f);
     const double eps = 2.220446049250313e-16;
 
     while (numEval < maxEval || maxEval == 0) {
+        if (R > 1 && !sharded && N >= shard_min) {
+            // deal the replicated pool out: rank r keeps slots r, r+R, ...
+            const long long n_local = cubature_cuda_shard_count(N, R, rank);
+            Pool np;
+            CUB_CUDA_CHECK(np.alloc(S.dim, f, pool.cap), S.msg);
+            pk_shard_gather(pool.view(), np.view(), S.dim, f, n_local, R, rank, S.stream);
+            S.launches += 1;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            std::swap(pool.center, np.center);
+            std::swap(pool.halfw, np.halfw);
+            std::swap(pool.val, np.val);
+            std::swap(pool.err, np.err);
+            std::swap(pool.errmax, np.errmax);
+            std::swap(pool.splitdim, np.splitdim);
+            N = n_local;
+            sharded = true;
+        }
         const PoolView pv = pool.view();
         pk_totals(pv, f, N, d_partial.as<double>(), d_totals, S.stream);
         pk_min_region(pv, f, N, d_u64, d_minvec, S.stream);
         S.launches += 5;
-        CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, small_doubles * 8 + 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
-        S.d2h_bytes += (int64_t)small_doubles * 8 + 24;
         S.h2d_bytes += 24;
-        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        unsigned long long min_key = 0;
+        if (!sharded) {
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_block, d_totals, blk * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += (int64_t)blk * 8;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            for (int j = 0; j < 2 * f; ++j) {
+                tot[j] = h_block[j];
+                minvec[j] = h_block[2 * f + j];
+            }
+            min_key = ((unsigned long long*)(h_block + 4 * f))[0];
+        } else {
+            const unsigned long long nloc = (unsigned long long)N;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(d_u64 + 3, &nloc, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+            rc = cub_comm_allgather(comm, d_totals, blk * 8, d_gather, S.stream);
+            if (rc != CUB_OK) return rc;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_block, d_gather, blk * 8 * R, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += (int64_t)blk * 8 * R;
+            S.h2d_bytes += 8;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            // add the per-rank blocks in rank order: identical bits on every rank
+            for (int j = 0; j < 2 * f; ++j) tot[j] = 0.0;
+            Nglobal = 0;
+            int best = -1;
+            for (int r = 0; r < R; ++r) {
+                const double* b = h_block + (size_t)r * blk;
+                const unsigned long long* u = (const unsigned long long*)(b + 4 * f);
+                if (u[3] == 0) continue;  // a rank without regions contributes nothing
+                for (int j = 0; j < 2 * f; ++j) tot[j] += b[j];
+                Nglobal += (long long)u[3];
+                if (best < 0 || u[0] <= min_key) {  // ties: the highest rank pops last
+                    best = r;
+                    min_key = u[0];
+                }
+            }
+            for (int j = 0; j < 2 * f; ++j) minvec[j] = h_block[(size_t)best * blk + 2 * f + j];
+            // the selection kernels read the GLOBAL totals
+            CUB_CUDA_CHECK(cudaMemcpyAsync(d_totals, tot.data(), (size_t)16 * f, cudaMemcpyHostToDevice, S.stream), S.msg);
+            S.h2d_bytes += 16 * f;
+        }
+        if (!sharded) Nglobal = N;
         const double band = 4.0 * eps * std::sqrt(ops);
-        const double* tv = h_totals;
-        const double* te = h_totals + f;
+        const double* tv = tot.data();
+        const double* te = tot.data() + f;
         {
             const bool c0 = cub_converged(f, VecAcc{tv, te}, absTol, relTol, norm);
             for (int j = 0; j < f; ++j) tmp_err[j] = te[j] * (1.0 + band);
@@ -746,14 +845,14 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 break;
             }
         }
-        long long Kcap = N;
+        long long Kcap = Nglobal;  // pops allowed by maxEval (Rule.java:133), over all ranks
         if (maxEval > 0) {
             const int64_t room = maxEval - numEval;  // > 0 here
-            Kcap = std::min<long long>(N, std::max<int64_t>(1, (room + 2 * P - 1) / (2 * P)));
+            Kcap = std::min<long long>(Nglobal, std::max<int64_t>(1, (room + 2 * P - 1) / (2 * P)));
         }
         // select-all shortcut: the residual after popping all but the smallest-errmax region is that
         // region's own error vector; if that is not converged, no smaller k is (monotone predicate).
-        const double* last_err = h_minvec + f;
+        const double* last_err = minvec.data() + f;
         bool all = !cub_converged(f, VecAcc{tv, last_err}, absTol, relTol, norm);
         {
             for (int j = 0; j < f; ++j) tmp_err[j] = last_err[j] + band * te[j];
@@ -762,19 +861,75 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             const bool a2 = !cub_converged(f, VecAcc{tv, tmp_err.data()}, absTol, relTol, norm);
             if (a1 != all || a2 != all) res->ambiguous += 1;
         }
-        if (N == 1) all = true;
-        long long K = N;
+        if (Nglobal == 1) all = true;
+        long long K = N;            // pops of this rank
+        long long Kglobal = Nglobal;
         const int* list = nullptr;
-        if (!(all && Kcap == N)) {
+        if (!(all && Kcap == Nglobal) && f == 1) {
+            // scalar integrand: weighted radix select on the device (no sort), then a stable compaction
+            CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+            unsigned char* sm = sel.small.as<unsigned char>();
+            unsigned long long* cnt = (unsigned long long*)(sm + 256);
+            double* sum = (double*)(sm + 256 + 2048);
+            unsigned long long* tl = sel.hist.as<unsigned long long>();
+            unsigned long long* tq = tl + pk_sel_tiles(pool.cap);
+            if (!sharded) {
+                S.launches += pk_select_scalar(pv, N, d_totals, Kcap, absTol, relTol, norm, band, sm, cnt, sum, tl, tq, sel.idxA.as<int>(), S.stream);
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, sm + 24, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                S.d2h_bytes += 24;
+                CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                K = Kglobal = (long long)h_u64[0];  // SelState::K ; [1] = tie_take ; [2] = ambiguous
+                if (h_u64[2]) res->ambiguous += 1;
+            } else {
+                // distributed: local histogram -> all-gather -> rank-ordered sum -> identical pick on every rank
+                pk_sel_init(sm, cnt, sum, S.stream);
+                for (int shift = 56; shift >= 0; shift -= 8) {
+                    pk_sel_hist(pv, N, sm, shift, cnt, sum, S.stream);
+                    rc = cub_comm_allgather(comm, cnt, 4096, d_histgather, S.stream);
+                    if (rc != CUB_OK) return rc;
+                    pk_sum_hist_ranks(d_histgather, R, cnt, sum, S.stream);
+                    pk_sel_pick(sm, cnt, sum, shift, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
+                    S.launches += 3;
+                }
+                // regions equal to the threshold key are taken in (rank, slot) order
+                pk_sel_tile_counts(pv, N, sm, tl, tq, d_u64 + 4, S.stream);
+                S.launches += 2;
+                rc = cub_comm_allgather(comm, d_u64 + 4, 16, d_histgather, S.stream);
+                if (rc != CUB_OK) return rc;
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_block, d_histgather, (size_t)16 * R, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, sm + 24, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                S.d2h_bytes += 16 * R + 24;
+                CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                Kglobal = (long long)h_u64[0];
+                const long long tie_take_global = (long long)h_u64[1];
+                if (h_u64[2]) res->ambiguous += 1;
+                const unsigned long long* le = (const unsigned long long*)h_block;  // [R][2]: less, equal
+                std::vector<int64_t> ties((size_t)R);
+                for (int r = 0; r < R; ++r) ties[(size_t)r] = (int64_t)le[2 * r + 1];
+                const long long take = cubature_cuda_tie_share(tie_take_global, ties.data(), R, rank);
+                K = (long long)le[2 * rank] + take;
+                pk_sel_compact(pv, N, sm, tl, tq, take, sel.idxA.as<int>(), S.stream);
+                S.launches += 1;
+            }
+            list = sel.idxA.as<int>();
+            if (Kglobal < 1 || Kglobal > Nglobal || K < 0 || K > N) {
+                cub_set_message(S.msg, "internal: device selection returned K=%lld of N=%lld (global %lld of %lld)", K, N, Kglobal, Nglobal);
+                return CUB_ERR_CUDA;
+            }
+        } else if (!(all && Kcap == Nglobal)) {
+            if (sharded) {
+                cub_set_message(S.msg, "multi-GPU batch selection is implemented for scalar integrands (fdim == 1) only");
+                return CUB_ERR_UNSUPPORTED;
+            }
             // sort by errmax (descending, ties by ascending slot), then prefix sums and the residual test
             CUB_CUDA_CHECK(sel.ensure(pool.cap, f), S.msg);
             pk_sort_prepare(pv.errmax, N, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64 + 4, S.stream);
             S.launches += 1;
-            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
             S.d2h_bytes += 16;
             S.h2d_bytes += 16;
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
-            const unsigned long long vary = h_u64[4] ^ h_u64[5];  // bits that differ between keys
+            const unsigned long long vary = h_u64[0] ^ h_u64[1];  // bits that differ between keys
             unsigned long long* ka = sel.keysA.as<unsigned long long>();
             unsigned long long* kb = sel.keysB.as<unsigned long long>();
             int* ia = sel.idxA.as<int>();
@@ -795,30 +950,26 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 pk_find_k(d_totals, sel.prefix.as<double>(), sel.tile_tot.as<double>(), N, f, absTol, relTol, norm, band, d_u64 + 4,
                           S.stream);
                 S.launches += 3;
-                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64 + 4, d_u64 + 4, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
                 S.d2h_bytes += 24;
                 S.h2d_bytes += 24;
                 CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
-                long long k0 = (long long)h_u64[4], k1 = (long long)h_u64[5], k2 = (long long)h_u64[6];
+                long long k0 = (long long)h_u64[0], k1 = (long long)h_u64[1], k2 = (long long)h_u64[2];
                 if (k0 > N) k0 = N;  // never converged: pop until the heap is empty (Rule.java:133)
                 if (k1 > N) k1 = N;
                 if (k2 > N) k2 = N;
                 if (std::min(k1, Kcap) != std::min(k0, Kcap) || std::min(k2, Kcap) != std::min(k0, Kcap)) res->ambiguous += 1;
                 K = std::min(k0, Kcap);
             }
+            Kglobal = K;
         }
         if (N + K > pool.cap) {
             long long nc = std::max<long long>(pool.cap * 2, N + K);
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
             cudaError_t e = pool.grow(nc, N, S.stream);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
                 return CUB_ERR_POOL_EXHAUSTED;
-            }
-            if (list) {
-                cub_set_message(S.msg, "internal: pool grew while a selection list was live");
             }
         }
         if (N + K > (long long)std::numeric_limits<int>::max()) {
@@ -833,25 +984,41 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         rc = S.launch_rule(pool.view(), w);
         if (rc != CUB_OK) return rc;
         N += K;
-        numEval += 2 * P * K;
-        ops += 3.0 * (double)K;
+        Nglobal += Kglobal;
+        numEval += 2 * P * Kglobal;
+        S.local_regions_evaluated += 2 * K;
+        ops += 3.0 * (double)Kglobal;
         res->iterations += 1;
-        push_batch(trace, 2 * K);
+        push_batch(trace, 2 * Kglobal);
         if (res->iterations >= kMaxIterations) {
             cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)res->iterations);
             break;
         }
     }
+    // final result: K5 over the pool (rank-ordered sum of the shards)
     pk_totals(pool.view(), f, N, d_partial.as<double>(), d_totals, S.stream);
     S.launches += 2;
-    CUB_CUDA_CHECK(cudaMemcpyAsync(h_small.p, d_small.p, (size_t)16 * f, cudaMemcpyDeviceToHost, S.stream), S.msg);
-    S.d2h_bytes += 16 * f;
-    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
-    for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
+    if (!sharded) {
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_block, d_totals, (size_t)16 * f, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += 16 * f;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        for (int j = 0; j < 2 * f; ++j) out[j] = h_block[j];
+    } else {
+        rc = cub_comm_allgather(comm, d_totals, (size_t)16 * f, d_gather, S.stream);
+        if (rc != CUB_OK) return rc;
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_block, d_gather, (size_t)16 * f * R, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += 16 * f * R;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        for (int j = 0; j < 2 * f; ++j) {
+            double s = 0.0;
+            for (int r = 0; r < R; ++r) s += h_block[(size_t)r * 2 * f + j];
+            out[j] = s;
+        }
+    }
     S.flush_rule_timer();
     res->converged = conv ? 1 : 0;
     res->num_eval = numEval;
-    res->num_regions = N;
+    res->num_regions = Nglobal;
     fill_trace_regions(S, pool, nullptr, N, trace);
     return CUB_OK;
 }
@@ -1036,7 +1203,7 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
         stats->num_eval = res.num_eval;
         stats->num_regions = res.num_regions;
         stats->iterations = res.iterations;
-        stats->regions_evaluated = S.P > 0 ? res.num_eval / S.P : 0;
+        stats->regions_evaluated = select == CUB_SELECT_DEVICE ? S.local_regions_evaluated : (S.P > 0 ? res.num_eval / S.P : 0);
         stats->ambiguous_decisions = res.ambiguous;
         stats->gpu_launches = S.launches;
         stats->h2d_bytes = S.h2d_bytes;

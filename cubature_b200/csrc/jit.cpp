@@ -133,6 +133,7 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     tu << "#define CUB_FDIM " << integ->fdim << "\n";
     tu << "#define CUB_NPARAMS " << integ->params.size() << "\n";
     tu << "#define CUB_HAS_TRANSFORM " << (has_transform ? 1 : 0) << "\n";
+    tu << "#define CUB_SEPARABLE " << (integ->separable ? 1 : 0) << "\n";
     tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
     if (integ->family == CUB_FAM_USER) {
         tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";
@@ -158,6 +159,12 @@ int cub_jit_compile(cub_integrand* integ, int has_transform, std::string* log) {
     const std::string tu = cub_jit_translation_unit(integ, has_transform);
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
                                      "-default-device"};
+    // tuning hook: extra -D flags for the JIT (e.g. CUBATURE_JIT_DEFINES="-DCUB_GM_MIN_BLOCKS=5"); part of the cache key
+    if (const char* extra = getenv("CUBATURE_JIT_DEFINES")) {
+        std::istringstream is(extra);
+        std::string tok;
+        while (is >> tok) opts.push_back(tok);
+    }
     // cache key: translation unit + embedded headers + options
     uint64_t h = fnv1a(tu);
     for (int i = 0; i < kNumEmbedded; ++i) h = fnv1a(kEmbeddedSources[i], h);

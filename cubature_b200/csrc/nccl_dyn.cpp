@@ -7,11 +7,14 @@
 // (torchrun) or separate threads of one host process (the Java host of BASELINE.json).
 #include <dlfcn.h>
 
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "cub_internal.h"
 
@@ -25,6 +28,7 @@ struct Nccl {
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     std::string error;
 };
@@ -53,6 +57,7 @@ Nccl* nccl() {
         LOAD(CommInitRank, "ncclCommInitRank")
         LOAD(CommDestroy, "ncclCommDestroy")
         LOAD(AllReduce, "ncclAllReduce")
+        LOAD(AllGather, "ncclAllGather")
         LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     });
@@ -60,23 +65,62 @@ Nccl* nccl() {
 }
 }  // namespace
 
-int cub_comm_allreduce_sum_f64(cub_comm* comm, double* dev_buf, size_t count, cudaStream_t stream) {
-    if (!comm || comm->nranks == 1) return CUB_OK;
+// In-process communicator: the ranks are threads of one host process (the single-process Java host of
+// BASELINE.json, or the multi-rank tests on one GPU).  The exchange goes through host memory with two
+// barriers; no kernel ever waits for another rank.
+struct cub_local_group {
+    std::mutex mu;
+    std::condition_variable cv;
+    int nranks = 0, arrived = 0, refs = 0;
+    unsigned long long generation = 0;
+    std::vector<std::vector<char>> slots;
+    void barrier() {
+        std::unique_lock<std::mutex> lock(mu);
+        const unsigned long long gen = generation;
+        if (++arrived == nranks) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lock, [&] { return generation != gen; });
+        }
+    }
+};
+namespace {
+std::mutex g_groups_mu;
+std::map<unsigned long long, cub_local_group*> g_groups;
+}  // namespace
+
+// The one collective the driver needs: every rank contributes `bytes` and receives nranks*bytes in rank
+// order.  Reductions are done afterwards by a device kernel that adds the blocks in rank order, so the
+// result is bit-identical on every rank and independent of NCCL's choice of algorithm.
+int cub_comm_allgather(cub_comm* comm, const void* dev_send, size_t bytes, void* dev_recv, cudaStream_t stream) {
+    if (!comm || comm->nranks == 1) {
+        return cudaMemcpyAsync(dev_recv, dev_send, bytes, cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? CUB_OK : CUB_ERR_CUDA;
+    }
+    if (comm->local) {
+        cub_local_group* g = comm->local;
+        std::vector<char>& mine = g->slots[(size_t)comm->rank];
+        mine.resize(bytes);
+        if (cudaMemcpyAsync(mine.data(), dev_send, bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return CUB_ERR_CUDA;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return CUB_ERR_CUDA;
+        g->barrier();
+        for (int r = 0; r < comm->nranks; ++r) {
+            if (g->slots[(size_t)r].size() != bytes) return CUB_ERR_NCCL;
+            if (cudaMemcpyAsync((char*)dev_recv + (size_t)r * bytes, g->slots[(size_t)r].data(), bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+                return CUB_ERR_CUDA;
+        }
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return CUB_ERR_CUDA;
+        g->barrier();
+        return CUB_OK;
+    }
     Nccl* n = nccl();
-    int rc = n->AllReduce(dev_buf, dev_buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm->nccl_comm, stream);
-    return rc == 0 ? CUB_OK : CUB_ERR_NCCL;
-}
-int cub_comm_allreduce_max_u64(cub_comm* comm, unsigned long long* dev_buf, size_t count, cudaStream_t stream) {
-    if (!comm || comm->nranks == 1) return CUB_OK;
-    Nccl* n = nccl();
-    int rc = n->AllReduce(dev_buf, dev_buf, count, /*ncclUint64*/ 5, /*ncclMax*/ 2, comm->nccl_comm, stream);
-    return rc == 0 ? CUB_OK : CUB_ERR_NCCL;
-}
-int cub_comm_allreduce_sum_u64(cub_comm* comm, unsigned long long* dev_buf, size_t count, cudaStream_t stream) {
-    if (!comm || comm->nranks == 1) return CUB_OK;
-    Nccl* n = nccl();
-    int rc = n->AllReduce(dev_buf, dev_buf, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, comm->nccl_comm, stream);
-    return rc == 0 ? CUB_OK : CUB_ERR_NCCL;
+    const int rc = n->AllGather(dev_send, dev_recv, bytes, /*ncclChar*/ 0, comm->nccl_comm, stream);
+    if (rc != 0) {
+        fprintf(stderr, "cubature_cuda: ncclAllGather: %s\n", n->GetErrorString(rc));
+        return CUB_ERR_NCCL;
+    }
+    return CUB_OK;
 }
 
 extern "C" {
@@ -134,9 +178,41 @@ int cubature_cuda_comm_init(const void* id, int nranks, int rank, int device, cu
     return CUB_OK;
 }
 
+int cubature_cuda_comm_init_local(uint64_t group_key, int nranks, int rank, int device, cub_comm_t** out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return CUB_ERR_BAD_ARGS;
+    *out = nullptr;
+    cub_comm* c = new cub_comm();
+    c->nranks = nranks;
+    c->rank = rank;
+    c->device = device;
+    std::lock_guard<std::mutex> lock(g_groups_mu);
+    cub_local_group*& g = g_groups[group_key];
+    if (!g) {
+        g = new cub_local_group();
+        g->nranks = nranks;
+        g->slots.resize((size_t)nranks);
+    }
+    if (g->nranks != nranks) {
+        delete c;
+        return CUB_ERR_BAD_ARGS;
+    }
+    g->refs += 1;
+    c->local = g;
+    c->local_key = group_key;
+    *out = c;
+    return CUB_OK;
+}
+
 void cubature_cuda_comm_free(cub_comm_t* comm) {
     if (!comm) return;
     if (comm->nccl_comm) nccl()->CommDestroy(comm->nccl_comm);
+    if (comm->local) {
+        std::lock_guard<std::mutex> lock(g_groups_mu);
+        if (--comm->local->refs == 0) {
+            g_groups.erase(comm->local_key);
+            delete comm->local;
+        }
+    }
     delete comm;
 }
 

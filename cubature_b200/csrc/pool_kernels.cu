@@ -356,6 +356,253 @@ __global__ void k_find_k(const double* totals, const double* prefix, const doubl
     if (cub_converged(fdim, acc, absTol, relTol, norm)) atomicMin(&out[2], (unsigned long long)(k + 1));
 }
 
+// ---- K3 for scalar integrands: weighted radix select (no sort) ------------------------------------
+// With fdim == 1 the residual test depends on ONE running sum, so the batch size K (Rule.java:109-133)
+// can be found by descending the 64-bit key space 8 bits at a time: every pass histograms the still
+// undecided regions by their next digit (count and sum of err per bucket, largest errmax first), a
+// one-thread kernel walks the 256 buckets accumulating the popped error until either the residual
+// test passes inside a bucket or the pop budget Kcap (maxEval, Rule.java:133) runs out inside it, and
+// descends into that bucket.  After 8 passes the threshold key is exact; regions with exactly that
+// errmax are taken in ascending slot order.  8 light passes over errmax/err (16 B per region) replace
+// a full sort (~250 B per region); the list of popped slots is then produced by a stable compaction.
+struct SelState {
+    unsigned long long prefix;     // decided high bits of the threshold key (key = ~bits(errmax))
+    unsigned long long mask;       // which bits are decided
+    unsigned long long count_cum;  // regions strictly ahead of the current bucket (all popped)
+    unsigned long long K;          // result: number of regions to pop
+    unsigned long long tie_take;   // how many of the regions with key == prefix are popped
+    unsigned long long ambiguous;  // decision within the rounding band
+    double P_cum;                  // sum of err of the count_cum regions
+};
+
+struct ScalarAcc {
+    double v, e;
+    __device__ double val(int) const { return v; }
+    __device__ double err(int) const { return e; }
+};
+
+constexpr int SEL_THREADS = 256;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_hist(const double* errmax, const double* err, long long n, const SelState* st, int shift, unsigned long long* cnt, double* sum) {
+    __shared__ unsigned int scnt[256];
+    __shared__ double ssum[256];
+    scnt[threadIdx.x] = 0;
+    ssum[threadIdx.x] = 0.0;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix, mask = st->mask;
+    // run-length aggregation in registers: in the early passes nearly every region shares the digit
+    // (same exponent), so a thread touches shared memory only when its digit changes
+    unsigned cur = 0xffffffffu, run_c = 0;
+    double run_s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = ~dbits(errmax[i]);
+        if ((k & mask) == prefix) {
+            const unsigned d = (unsigned)(k >> shift) & 255u;
+            if (d != cur) {
+                if (run_c) {
+                    atomicAdd(&scnt[cur], run_c);
+                    atomicAdd(&ssum[cur], run_s);
+                }
+                cur = d;
+                run_c = 0;
+                run_s = 0.0;
+            }
+            ++run_c;
+            run_s += err[i];
+        }
+    }
+    if (run_c) {
+        atomicAdd(&scnt[cur], run_c);
+        atomicAdd(&ssum[cur], run_s);
+    }
+    __syncthreads();
+    if (scnt[threadIdx.x]) {
+        atomicAdd(&cnt[threadIdx.x], (unsigned long long)scnt[threadIdx.x]);
+        atomicAdd(&sum[threadIdx.x], ssum[threadIdx.x]);
+    }
+}
+
+__global__ void k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, const double* totals /*[val, err]*/,
+                           unsigned long long Kcap, double absTol, double relTol, int norm, double band) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double V = totals[0], E = totals[1];
+    unsigned long long count_cum = st->count_cum;
+    double P = st->P_cum;
+    int chosen = -1;
+    for (int d = 0; d < 256; ++d) {
+        const unsigned long long c = cnt[d];
+        if (c == 0) continue;
+        const double s = sum[d];
+        chosen = d;  // the last non-empty bucket is chosen if nothing stops earlier
+        const bool stop = (count_cum + c >= Kcap) || cub_converged(1, ScalarAcc{V, E - (P + s)}, absTol, relTol, norm);
+        if (stop) break;
+        count_cum += c;
+        P += s;
+    }
+    const unsigned long long c_b = chosen >= 0 ? cnt[chosen] : 0ULL;
+    const double s_b = chosen >= 0 ? sum[chosen] : 0.0;
+    for (int d = 0; d < 256; ++d) {
+        cnt[d] = 0ULL;
+        sum[d] = 0.0;
+    }
+    if (chosen < 0) {  // cannot happen for n >= 1
+        st->K = 0;
+        return;
+    }
+    st->prefix |= (unsigned long long)chosen << shift;
+    st->mask |= 255ULL << shift;
+    st->count_cum = count_cum;
+    st->P_cum = P;
+    if (shift == 0) {
+        // the bucket is a single key: c_b regions with identical errmax; each carries e = s_b / c_b
+        const double e = s_b / (double)c_b;
+        unsigned long long room = Kcap - count_cum;  // >= 1
+        unsigned long long mmax = c_b < room ? c_b : room;
+        // smallest m in [1, mmax] whose residual passes (monotone), else mmax
+        unsigned long long lo = 1, hi = mmax;
+        if (cub_converged(1, ScalarAcc{V, E - (P + (double)mmax * e)}, absTol, relTol, norm)) {
+            while (lo < hi) {
+                const unsigned long long mid = lo + (hi - lo) / 2;
+                if (cub_converged(1, ScalarAcc{V, E - (P + (double)mid * e)}, absTol, relTol, norm))
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+        } else {
+            lo = mmax;
+        }
+        st->tie_take = lo;
+        st->K = count_cum + lo;
+        // sensitivity of the decision to the rounding of the reference's running sums
+        const double rK = E - (P + (double)lo * e), rKm1 = rK + e, b = band * E;
+        const bool a0 = cub_converged(1, ScalarAcc{V, rK + b}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rK - b}, absTol, relTol, norm);
+        const bool a1 = cub_converged(1, ScalarAcc{V, rKm1 + b}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rKm1 - b}, absTol, relTol, norm);
+        st->ambiguous = (a0 || a1) ? 1ULL : 0ULL;
+    }
+}
+
+// stable compaction of the popped slots: slot i is popped iff key_i < thr, or key_i == thr and it is
+// among the first tie_take such slots.  Tiles of SEL_TILE slots; two counts per tile, scanned by one block.
+constexpr int SEL_ITEMS = 8;
+constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_tile_counts(const double* errmax, long long n, const SelState* st, unsigned long long* tile_less, unsigned long long* tile_eq) {
+    const unsigned long long thr = st->prefix;
+    const long long lo = (long long)blockIdx.x * SEL_TILE;
+    unsigned less = 0, eq = 0;
+    for (int t = 0; t < SEL_ITEMS; ++t) {
+        const long long i = lo + (long long)t * SEL_THREADS + threadIdx.x;
+        if (i < n) {
+            const unsigned long long k = ~dbits(errmax[i]);
+            less += k < thr;
+            eq += k == thr;
+        }
+    }
+    __shared__ unsigned sl[SEL_THREADS], se[SEL_THREADS];
+    sl[threadIdx.x] = less;
+    se[threadIdx.x] = eq;
+    __syncthreads();
+    for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            sl[threadIdx.x] += sl[threadIdx.x + w];
+            se[threadIdx.x] += se[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tile_less[blockIdx.x] = sl[0];
+        tile_eq[blockIdx.x] = se[0];
+    }
+}
+
+__global__ void k_sel_tile_scan(unsigned long long* tile_less, unsigned long long* tile_eq, long long ntiles,
+                                unsigned long long* totals_out /*[2]: regions below the threshold key, regions equal to it*/) {
+    // exclusive scans in place, one block, 256 threads
+    __shared__ unsigned long long sh[2][256];
+    __shared__ unsigned long long carry[2];
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long base = 0; base < ntiles; base += 256) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long a = i < ntiles ? tile_less[i] : 0ULL, b = i < ntiles ? tile_eq[i] : 0ULL;
+        sh[0][threadIdx.x] = a;
+        sh[1][threadIdx.x] = b;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const unsigned long long ta = threadIdx.x >= o ? sh[0][threadIdx.x - o] : 0ULL;
+            const unsigned long long tb = threadIdx.x >= o ? sh[1][threadIdx.x - o] : 0ULL;
+            __syncthreads();
+            sh[0][threadIdx.x] += ta;
+            sh[1][threadIdx.x] += tb;
+            __syncthreads();
+        }
+        if (i < ntiles) {
+            tile_less[i] = carry[0] + sh[0][threadIdx.x] - a;
+            tile_eq[i] = carry[1] + sh[1][threadIdx.x] - b;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) {
+            carry[0] += sh[0][255];
+            carry[1] += sh[1][255];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && totals_out) {
+        totals_out[0] = carry[0];
+        totals_out[1] = carry[1];
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_compact(const double* errmax, long long n, const SelState* st, const unsigned long long* tile_less,
+              const unsigned long long* tile_eq, long long tie_take_arg, int* list) {
+    // tie_take_arg < 0: take SelState::tie_take (single GPU); else this rank's share of the tied regions
+    const unsigned long long thr = st->prefix, tie_take = tie_take_arg < 0 ? st->tie_take : (unsigned long long)tie_take_arg;
+    // thread owns SEL_ITEMS CONSECUTIVE slots so that positions follow slot order
+    const long long lo = (long long)blockIdx.x * SEL_TILE + (long long)threadIdx.x * SEL_ITEMS;
+    unsigned fl = 0, fe = 0;  // bit t set: slot lo+t is less / equal
+    unsigned less = 0, eq = 0;
+#pragma unroll
+    for (int t = 0; t < SEL_ITEMS; ++t) {
+        const long long i = lo + t;
+        if (i < n) {
+            const unsigned long long k = ~dbits(errmax[i]);
+            if (k < thr) {
+                fl |= 1u << t;
+                ++less;
+            } else if (k == thr) {
+                fe |= 1u << t;
+                ++eq;
+            }
+        }
+    }
+    __shared__ unsigned sl[SEL_THREADS], se[SEL_THREADS];
+    sl[threadIdx.x] = less;
+    se[threadIdx.x] = eq;
+    __syncthreads();
+    for (int o = 1; o < SEL_THREADS; o <<= 1) {
+        const unsigned ta = threadIdx.x >= o ? sl[threadIdx.x - o] : 0u, tb = threadIdx.x >= o ? se[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sl[threadIdx.x] += ta;
+        se[threadIdx.x] += tb;
+        __syncthreads();
+    }
+    unsigned long long less_before = tile_less[blockIdx.x] + (sl[threadIdx.x] - less);
+    unsigned long long eq_before = tile_eq[blockIdx.x] + (se[threadIdx.x] - eq);
+#pragma unroll
+    for (int t = 0; t < SEL_ITEMS; ++t) {
+        const bool is_less = (fl >> t) & 1u, is_eq = (fe >> t) & 1u;
+        if (is_less || (is_eq && eq_before < tie_take)) {
+            const unsigned long long pos = less_before + (eq_before < tie_take ? eq_before : tie_take);
+            list[pos] = (int)(lo + t);
+        }
+        less_before += is_less;
+        eq_before += is_eq;
+    }
+}
+
 // ---- FP64 peak microbenchmark: independent DFMA chains, no memory traffic --------------------------
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -435,6 +682,90 @@ void pk_find_k(const double* totals, const double* prefix, const double* tile_of
     cudaMemcpyAsync(out, init, sizeof init, cudaMemcpyHostToDevice, s);
     k_find_k<<<nblocks(n, 128), 128, 0, s>>>(totals, prefix, tile_off, n, pk_scan_tiles(n), fdim, absTol, relTol, norm, band, out);
 }
+long long pk_sel_tiles(long long n) { return (n + SEL_TILE - 1) / SEL_TILE; }
+size_t pk_sel_state_bytes() { return sizeof(SelState); }
+
+// Weighted radix select + compaction (fdim == 1), in pieces so that the multi-GPU driver can put a
+// collective between them.  scratch (device): state: SelState | cnt: u64[256] | sum: double[256] ;
+// tile_less / tile_eq: u64[pk_sel_tiles(n)] each.  SelState: K at byte 24, tie_take at 32, ambiguous at 40.
+void pk_sel_init(void* state, unsigned long long* cnt, double* sum, cudaStream_t s) {
+    cudaMemsetAsync(state, 0, sizeof(SelState), s);
+    cudaMemsetAsync(cnt, 0, 256 * 8, s);
+    cudaMemsetAsync(sum, 0, 256 * 8, s);
+}
+void pk_sel_hist(const PoolView& pool, long long n, const void* state, int shift, unsigned long long* cnt, double* sum, cudaStream_t s) {
+    long long b = (n + SEL_THREADS - 1) / SEL_THREADS;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    k_sel_hist<<<(unsigned)b, SEL_THREADS, 0, s>>>(pool.errmax, pool.err, n, (const SelState*)state, shift, cnt, sum);
+}
+void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int shift, const double* totals, long long Kcap, double absTol,
+                 double relTol, int norm, double band, cudaStream_t s) {
+    k_sel_pick<<<1, 32, 0, s>>>((SelState*)state, cnt, sum, shift, totals, (unsigned long long)Kcap, absTol, relTol, norm, band);
+}
+void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
+                        unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s) {
+    const long long ntiles = pk_sel_tiles(n);
+    if (ntiles > 0) k_sel_tile_counts<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq);
+    k_sel_tile_scan<<<1, 256, 0, s>>>(tile_less, tile_eq, ntiles, totals_out);
+}
+void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
+                    const unsigned long long* tile_eq, long long tie_take, int* list, cudaStream_t s) {
+    const long long ntiles = pk_sel_tiles(n);
+    if (ntiles > 0)
+        k_sel_compact<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq, tie_take, list);
+}
+int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
+                     int norm, double band, void* state, unsigned long long* cnt, double* sum, unsigned long long* tile_less,
+                     unsigned long long* tile_eq, int* list, cudaStream_t s) {
+    pk_sel_init(state, cnt, sum, s);
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        pk_sel_hist(pool, n, state, shift, cnt, sum, s);
+        pk_sel_pick(state, cnt, sum, shift, totals, Kcap, absTol, relTol, norm, band, s);
+    }
+    pk_sel_tile_counts(pool, n, state, tile_less, tile_eq, nullptr, s);
+    pk_sel_compact(pool, n, state, tile_less, tile_eq, -1, list, s);
+    return 19;
+}
+
+// adds the per-rank histogram blocks [R][cnt u64 x256 | sum f64 x256] in rank order
+__global__ void k_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum) {
+    const int b = threadIdx.x;  // 256 threads
+    unsigned long long c = 0;
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) {
+        const unsigned long long* pc = (const unsigned long long*)(gathered + (size_t)r * 4096);
+        const double* ps = (const double*)(gathered + (size_t)r * 4096 + 2048);
+        c += pc[b];
+        s += ps[b];
+    }
+    cnt[b] = c;
+    sum[b] = s;
+}
+void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s) {
+    k_sum_hist_ranks<<<1, 256, 0, s>>>(gathered, R, cnt, sum);
+}
+
+// keeps every R-th region (slot = j*R + rank -> j) when the replicated pool is dealt out to the ranks
+__global__ void k_shard_gather(PoolView src, PoolView dst, int dim, int fdim, long long n_local, int R, int rank) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_local) return;
+    const long long s = j * R + rank;
+    for (int d = 0; d < dim; ++d) {
+        dst.center[(long long)d * dst.cap + j] = src.center[(long long)d * src.cap + s];
+        dst.halfw[(long long)d * dst.cap + j] = src.halfw[(long long)d * src.cap + s];
+    }
+    for (int k = 0; k < fdim; ++k) {
+        dst.val[(long long)k * dst.cap + j] = src.val[(long long)k * src.cap + s];
+        dst.err[(long long)k * dst.cap + j] = src.err[(long long)k * src.cap + s];
+    }
+    dst.errmax[j] = src.errmax[s];
+    dst.splitdim[j] = src.splitdim[s];
+}
+void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, cudaStream_t s) {
+    if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank);
+}
+
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s) {
     k_dfma_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-6);
 }

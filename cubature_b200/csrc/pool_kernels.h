@@ -31,6 +31,21 @@ void pk_sort_pass(const unsigned long long* keys_in, const int* idx_in, unsigned
 void pk_prefix(const PoolView& pool, int fdim, const int* perm, long long n, double* prefix, double* tile_tot, cudaStream_t s);
 void pk_find_k(const double* totals, const double* prefix, const double* tile_off, long long n, int fdim, double absTol,
                double relTol, int norm, double band, unsigned long long* out, cudaStream_t s);
+long long pk_sel_tiles(long long n);
+size_t pk_sel_state_bytes();
+void pk_sel_init(void* state, unsigned long long* cnt, double* sum, cudaStream_t s);
+void pk_sel_hist(const PoolView& pool, long long n, const void* state, int shift, unsigned long long* cnt, double* sum, cudaStream_t s);
+void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int shift, const double* totals, long long Kcap, double absTol,
+                 double relTol, int norm, double band, cudaStream_t s);
+void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
+                        unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s);
+void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
+                    const unsigned long long* tile_eq, long long tie_take, int* list, cudaStream_t s);
+void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s);
+void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, cudaStream_t s);
+int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
+                     int norm, double band, void* state, unsigned long long* cnt, double* sum, unsigned long long* tile_less,
+                     unsigned long long* tile_eq, int* list, cudaStream_t s);
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s);
 
 #endif

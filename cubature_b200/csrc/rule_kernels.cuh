@@ -172,7 +172,10 @@ __device__ __forceinline__ void cub_eval_point(const F& fn, const CubTransform& 
 
 #if CUB_FDIM == 1
 // K1, scalar integrand: one thread per region.
-extern "C" __global__ void __launch_bounds__(128)
+#ifndef CUB_GM_MIN_BLOCKS
+#define CUB_GM_MIN_BLOCKS 5
+#endif
+extern "C" __global__ void __launch_bounds__(128, CUB_GM_MIN_BLOCKS)
 cub_gm_scalar(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr) {
     const long long n = cub_n_items(work);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +386,10 @@ __device__ __forceinline__ double cub_gk15_node(int k, double c, double h) {
     return (k & 1) ? c - w : c + w;
 }
 
+#ifndef CUB_SEPARABLE
+#define CUB_SEPARABLE 0
+#endif
+#if CUB_FDIM == 1 || CUB_SEPARABLE
 // K2, separable integrand (or fdim == 1): one thread per (component, region); regions fastest, so
 // lanes of a warp hold consecutive regions and all stores are coalesced.  With fdim > 1 the host
 // uses mode CHILDREN (several threads share a region), with fdim == 1 the fused BISECT mode.
@@ -436,6 +443,7 @@ cub_gk_separable(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr)
         work.stage_err[(long long)j * work.stage_stride + i] = err;
     }
 }
+#endif  // CUB_FDIM == 1 || CUB_SEPARABLE
 #endif  // CUB_DIM == 1
 
 

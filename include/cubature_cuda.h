@@ -193,6 +193,17 @@ int cubature_cuda_fp64_peak(int device, double* tflops, double* ms);
 #define CUB_COMM_ID_BYTES 128
 int cubature_cuda_comm_unique_id(void* id_out);
 int cubature_cuda_comm_init(const void* id, int nranks, int rank, int device, cub_comm_t** out);
+/* Host-side sharding arithmetic of the multi-GPU path (pure functions; exported so that the N > 1
+ * logic can be tested without GPUs):
+ *   shard_count: how many of n replicated regions rank keeps (slots rank, rank+nranks, ...)
+ *   tie_share:   how many of its regions tied at the selection threshold rank pops, given the global
+ *                budget tie_take and every rank's tie count (ties are popped in (rank, slot) order)   */
+int64_t cubature_cuda_shard_count(int64_t n, int nranks, int rank);
+int64_t cubature_cuda_tie_share(int64_t tie_take, const int64_t* ties_per_rank, int nranks, int rank);
+
+/* Ranks as threads of ONE process (a single-process host driving several GPUs, or several shards on one
+ * GPU for testing): every rank calls this with the same group_key; the exchange goes through host memory. */
+int cubature_cuda_comm_init_local(uint64_t group_key, int nranks, int rank, int device, cub_comm_t** out);
 void cubature_cuda_comm_free(cub_comm_t* comm);
 
 #ifdef __cplusplus

@@ -21,7 +21,13 @@ NAN = float("nan")
 
 def record(name, family, dim, fdim, params, xmin, xmax, rel, ab, norm=0, max_eval=0, transform=None):
     r = O.integrate(family, dim, fdim, params, xmin, xmax, rel, ab, norm, max_eval, transform=transform)
+    # exact ties between the error estimates of distinct final regions: the order in which the JDK heap
+    # pops tied regions is not reproduced by the device-side selection, so tests relax there
+    import numpy as np
+    em = r.errmax[r.errmax > 0]
+    ties = int(len(em) - len(np.unique(em)))
     return {
+        "exact_ties": ties,
         "name": name, "family": family, "dim": dim, "fdim": fdim, "params": [float(p) for p in params],
         "xmin": [repr(float(v)) for v in xmin], "xmax": [repr(float(v)) for v in xmax],  # strings: +-inf allowed
         "relTol": None if rel != rel else rel, "absTol": None if ab != ab else ab, "norm": norm, "maxEval": max_eval,
