@@ -212,6 +212,11 @@ def main():
         ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(ln)
         launches = int(ln.item())
+        per_rank = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(per_rank, torch.tensor([local_regions, sum(rule_ms) / len(rule_ms), sum(dev_ms) / len(dev_ms)], dtype=torch.float64, device="cuda"))
+        per_rank = [[float(v) for v in t.cpu()] for t in per_rank]
+    else:
+        per_rank = [[float(local_regions), sum(rule_ms) / len(rule_ms), sum(dev_ms) / len(dev_ms)]]
     tot_dev_ms, tot_wall_ms, tot_rule_ms = [float(v) for v in t_dev.cpu()]
     if rank != 0:
         if comm is not None:
@@ -252,6 +257,7 @@ def main():
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
                              "frac": rule_regions_per_s * BYTES_REGION / 1e9 / hbm_peak}},
         "clocks": clocks,
+        "per_rank": [{"regions_evaluated": int(p[0]), "rule_ms": p[1], "device_ms": p[2]} for p in per_rank],
     }
     if not args.no_cpu_baseline:
         v, ne, dt = cpu_port(args.cpu_sample)

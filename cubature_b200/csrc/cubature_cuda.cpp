@@ -724,7 +724,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
-    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 4096LL * R;
+    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
     if (R > 1 && !(opt && opt->pool_capacity > 0) && maxEval > 0) {
         // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
         const long long total = maxEval / (2 * P) + 8;
@@ -771,17 +771,37 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         if (R > 1 && !sharded && N >= shard_min) {
             // deal the replicated pool out: rank r keeps slots r, r+R, ...
             const long long n_local = cubature_cuda_shard_count(N, R, rank);
-            Pool np;
-            CUB_CUDA_CHECK(np.alloc(S.dim, f, pool.cap), S.msg);
-            pk_shard_gather(pool.view(), np.view(), S.dim, f, n_local, R, rank, S.stream);
-            S.launches += 1;
+            // gather into a small temporary (the pool is still tiny here), then copy the rows back in place
+            Pool tmp;
+            CUB_CUDA_CHECK(tmp.alloc(S.dim, f, std::max<long long>(n_local, 1)), S.msg);
+            // rank the regions by errmax (stable radix sort, identical on every rank) and deal round robin
+            CUB_CUDA_CHECK(sel.ensure(N, f), S.msg);
+            unsigned long long* ka = sel.keysA.as<unsigned long long>();
+            unsigned long long* kb = sel.keysB.as<unsigned long long>();
+            int* ia = sel.idxA.as<int>();
+            int* ib = sel.idxB.as<int>();
+            pk_sort_prepare(pool.view().errmax, N, ka, ia, d_u64 + 4, S.stream);
+            for (int shift = 0; shift < 64; shift += 8) {
+                pk_sort_pass(ka, ia, kb, ib, N, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
+                             sel.binbase.as<unsigned long long>(), S.stream);
+                std::swap(ka, kb);
+                std::swap(ia, ib);
+            }
+            pk_shard_gather(pool.view(), tmp.view(), S.dim, f, n_local, R, rank, ia, S.stream);
+            S.launches += 34;
+            auto rows = [&](DevBuf& dst, DevBuf& src, int nrows, size_t elt) {
+                return cudaMemcpy2DAsync(dst.p, (size_t)pool.cap * elt, src.p, (size_t)tmp.cap * elt, (size_t)n_local * elt, nrows,
+                                         cudaMemcpyDeviceToDevice, S.stream);
+            };
+            if (n_local > 0) {
+                CUB_CUDA_CHECK(rows(pool.center, tmp.center, S.dim, 8), S.msg);
+                CUB_CUDA_CHECK(rows(pool.halfw, tmp.halfw, S.dim, 8), S.msg);
+                CUB_CUDA_CHECK(rows(pool.val, tmp.val, f, 8), S.msg);
+                CUB_CUDA_CHECK(rows(pool.err, tmp.err, f, 8), S.msg);
+                CUB_CUDA_CHECK(rows(pool.errmax, tmp.errmax, 1, 8), S.msg);
+                CUB_CUDA_CHECK(rows(pool.splitdim, tmp.splitdim, 1, 4), S.msg);
+            }
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
-            std::swap(pool.center, np.center);
-            std::swap(pool.halfw, np.halfw);
-            std::swap(pool.val, np.val);
-            std::swap(pool.err, np.err);
-            std::swap(pool.errmax, np.errmax);
-            std::swap(pool.splitdim, np.splitdim);
             N = n_local;
             sharded = true;
         }

