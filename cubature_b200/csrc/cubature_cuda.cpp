@@ -238,12 +238,27 @@ struct SelectBuffers {
     DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
     long long cap = 0;
     int fdim = 0;
-    cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list + tile counters + state
+    cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list, candidates, tile counters, state
         cudaError_t e;
         if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
-        if ((e = small.ensure(8192)) != cudaSuccess) return e;
+        if ((e = keysA.ensure((size_t)8 * n)) != cudaSuccess) return e;
+        if ((e = keysB.ensure((size_t)8 * n)) != cudaSuccess) return e;
+        if ((e = small.ensure(512 + PK_SEL_HIST_BYTES)) != cudaSuccess) return e;
         if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
         return cudaSuccess;
+    }
+    SelScratch scratch(long long n) const {
+        SelScratch sc;
+        unsigned char* sm = small.as<unsigned char>();
+        sc.state = sm;
+        sc.cand_count = (unsigned long long*)(sm + 128);
+        sc.cnt = (unsigned long long*)(sm + 512);
+        sc.sum = (double*)(sm + 512 + 2048 * 8);
+        sc.cand_key = keysA.as<unsigned long long>();
+        sc.cand_err = keysB.as<double>();
+        sc.tile_less = hist.as<unsigned long long>();
+        sc.tile_eq = sc.tile_less + pk_sel_tiles(n);
+        return sc;
     }
     cudaError_t ensure(long long n, int f) {
         if (n <= cap && f == fdim) return cudaSuccess;
@@ -740,13 +755,13 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     // exchange block (doubles): totals[2f] | minvec[2f] | u64: min key, max key, argmin slot, local N
     const size_t blk = (size_t)4 * f + 4;
     CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * 1184), S.msg);
-    CUB_CUDA_CHECK(d_small.ensure(blk * 8 * (size_t)(R + 1) + 64 + (size_t)R * 4096), S.msg);
+    CUB_CUDA_CHECK(d_small.ensure(blk * 8 * (size_t)(R + 1) + 64 + (size_t)R * PK_SEL_HIST_BYTES), S.msg);
     CUB_CUDA_CHECK(h_small.ensure(blk * 8 * (size_t)(R + 1) + 64), S.msg);
     double* d_totals = d_small.as<double>();
     double* d_minvec = d_totals + 2 * f;
     unsigned long long* d_u64 = (unsigned long long*)(d_minvec + 2 * f);  // [0..3] part of the block, [4..7] scratch
     double* d_gather = d_totals + blk + 8;                                 // [R][blk]
-    unsigned char* d_histgather = (unsigned char*)(d_gather + blk * R);    // [R][4096]
+    unsigned char* d_histgather = (unsigned char*)(d_gather + blk * R);    // [R][PK_SEL_HIST_BYTES]
     double* h_block = h_small.as<double>();                                // [R][blk] after the exchange
     unsigned long long* h_u64 = (unsigned long long*)(h_block + blk * R);  // scratch [8]
 
@@ -888,13 +903,10 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         if (!(all && Kcap == Nglobal) && f == 1) {
             // scalar integrand: weighted radix select on the device (no sort), then a stable compaction
             CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
-            unsigned char* sm = sel.small.as<unsigned char>();
-            unsigned long long* cnt = (unsigned long long*)(sm + 256);
-            double* sum = (double*)(sm + 256 + 2048);
-            unsigned long long* tl = sel.hist.as<unsigned long long>();
-            unsigned long long* tq = tl + pk_sel_tiles(pool.cap);
+            const SelScratch sc = sel.scratch(pool.cap);
+            unsigned char* sm = (unsigned char*)sc.state;
             if (!sharded) {
-                S.launches += pk_select_scalar(pv, N, d_totals, Kcap, absTol, relTol, norm, band, sm, cnt, sum, tl, tq, sel.idxA.as<int>(), S.stream);
+                S.launches += pk_select_scalar(pv, N, d_totals, Kcap, absTol, relTol, norm, band, sc, sel.idxA.as<int>(), S.stream);
                 CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, sm + 24, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
                 S.d2h_bytes += 24;
                 CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
@@ -902,17 +914,17 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 if (h_u64[2]) res->ambiguous += 1;
             } else {
                 // distributed: local histogram -> all-gather -> rank-ordered sum -> identical pick on every rank
-                pk_sel_init(sm, cnt, sum, S.stream);
-                for (int shift = 56; shift >= 0; shift -= 8) {
-                    pk_sel_hist(pv, N, sm, shift, cnt, sum, S.stream);
-                    rc = cub_comm_allgather(comm, cnt, 4096, d_histgather, S.stream);
+                pk_sel_init(sc.state, sc.cnt, sc.sum, sc.cand_count, S.stream);
+                for (int pass = 0; pass < pk_sel_passes(); ++pass) {
+                    pk_sel_hist(pv, N, sc.state, pass, sc.cnt, sc.sum, sc.cand_key, sc.cand_err, sc.cand_count, N, S.stream);
+                    rc = cub_comm_allgather(comm, sc.cnt, PK_SEL_HIST_BYTES, d_histgather, S.stream);
                     if (rc != CUB_OK) return rc;
-                    pk_sum_hist_ranks(d_histgather, R, cnt, sum, S.stream);
-                    pk_sel_pick(sm, cnt, sum, shift, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
+                    pk_sum_hist_ranks(d_histgather, R, sc.cnt, sc.sum, S.stream);
+                    pk_sel_pick(sc.state, sc.cnt, sc.sum, pass, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
                     S.launches += 3;
                 }
                 // regions equal to the threshold key are taken in (rank, slot) order
-                pk_sel_tile_counts(pv, N, sm, tl, tq, d_u64 + 4, S.stream);
+                pk_sel_tile_counts(pv, N, sc.state, sc.tile_less, sc.tile_eq, d_u64 + 4, S.stream);
                 S.launches += 2;
                 rc = cub_comm_allgather(comm, d_u64 + 4, 16, d_histgather, S.stream);
                 if (rc != CUB_OK) return rc;
@@ -928,7 +940,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 for (int r = 0; r < R; ++r) ties[(size_t)r] = (int64_t)le[2 * r + 1];
                 const long long take = cubature_cuda_tie_share(tie_take_global, ties.data(), R, rank);
                 K = (long long)le[2 * rank] + take;
-                pk_sel_compact(pv, N, sm, tl, tq, take, sel.idxA.as<int>(), S.stream);
+                pk_sel_compact(pv, N, sc.state, sc.tile_less, sc.tile_eq, take, sel.idxA.as<int>(), S.stream);
                 S.launches += 1;
             }
             list = sel.idxA.as<int>();

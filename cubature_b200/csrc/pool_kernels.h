@@ -33,9 +33,23 @@ void pk_find_k(const double* totals, const double* prefix, const double* tile_of
                double relTol, int norm, double band, unsigned long long* out, cudaStream_t s);
 long long pk_sel_tiles(long long n);
 size_t pk_sel_state_bytes();
-void pk_sel_init(void* state, unsigned long long* cnt, double* sum, cudaStream_t s);
-void pk_sel_hist(const PoolView& pool, long long n, const void* state, int shift, unsigned long long* cnt, double* sum, cudaStream_t s);
-void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int shift, const double* totals, long long Kcap, double absTol,
+// device scratch of the scalar select
+struct SelScratch {
+    void* state;                    // SelState
+    unsigned long long* cnt;        // [2048]
+    double* sum;                    // [2048], directly after cnt
+    unsigned long long* cand_count; // [1]
+    unsigned long long* cand_key;   // [pool capacity]
+    double* cand_err;               // [pool capacity]
+    unsigned long long* tile_less;  // [pk_sel_tiles(capacity)]
+    unsigned long long* tile_eq;    // [pk_sel_tiles(capacity)]
+};
+#define PK_SEL_HIST_BYTES (2048 * 16)
+int pk_sel_passes();
+void pk_sel_init(void* state, unsigned long long* cnt, double* sum, unsigned long long* cand_count, cudaStream_t s);
+void pk_sel_hist(const PoolView& pool, long long n, const void* state, int pass, unsigned long long* cnt, double* sum,
+                 unsigned long long* cand_key, double* cand_err, unsigned long long* cand_count, long long cand_cap, cudaStream_t s);
+void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int pass, const double* totals, long long Kcap, double absTol,
                  double relTol, int norm, double band, cudaStream_t s);
 void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
                         unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s);
@@ -45,8 +59,7 @@ void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long*
 void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
                      cudaStream_t s);
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
-                     int norm, double band, void* state, unsigned long long* cnt, double* sum, unsigned long long* tile_less,
-                     unsigned long long* tile_eq, int* list, cudaStream_t s);
+                     int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s);
 
 #endif
