@@ -238,11 +238,9 @@ struct SelectBuffers {
     DevBuf keysA, keysB, idxA, idxB, hist, bin_totals, binbase, prefix, tile_tot, small;
     long long cap = 0;
     int fdim = 0;
-    cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list, candidates, tile counters, state
+    cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list, tile counters, state
         cudaError_t e;
         if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
-        if ((e = keysA.ensure((size_t)8 * n)) != cudaSuccess) return e;
-        if ((e = keysB.ensure((size_t)8 * n)) != cudaSuccess) return e;
         if ((e = small.ensure(512 + PK_SEL_HIST_BYTES)) != cudaSuccess) return e;
         if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
         return cudaSuccess;
@@ -251,11 +249,9 @@ struct SelectBuffers {
         SelScratch sc;
         unsigned char* sm = small.as<unsigned char>();
         sc.state = sm;
-        sc.cand_count = (unsigned long long*)(sm + 128);
+        sc.ticket = (unsigned*)(sm + 128);
         sc.cnt = (unsigned long long*)(sm + 512);
-        sc.sum = (double*)(sm + 512 + 2048 * 8);
-        sc.cand_key = keysA.as<unsigned long long>();
-        sc.cand_err = keysB.as<double>();
+        sc.sum = (double*)(sm + 512 + 256 * 8);
         sc.tile_less = hist.as<unsigned long long>();
         sc.tile_eq = sc.tile_less + pk_sel_tiles(n);
         return sc;
@@ -914,13 +910,13 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 if (h_u64[2]) res->ambiguous += 1;
             } else {
                 // distributed: local histogram -> all-gather -> rank-ordered sum -> identical pick on every rank
-                pk_sel_init(sc.state, sc.cnt, sc.sum, sc.cand_count, S.stream);
+                pk_sel_init(sc, S.stream);
                 for (int pass = 0; pass < pk_sel_passes(); ++pass) {
-                    pk_sel_hist(pv, N, sc.state, pass, sc.cnt, sc.sum, sc.cand_key, sc.cand_err, sc.cand_count, N, S.stream);
+                    pk_sel_pass(pv, N, sc, pass, 0, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
                     rc = cub_comm_allgather(comm, sc.cnt, PK_SEL_HIST_BYTES, d_histgather, S.stream);
                     if (rc != CUB_OK) return rc;
                     pk_sum_hist_ranks(d_histgather, R, sc.cnt, sc.sum, S.stream);
-                    pk_sel_pick(sc.state, sc.cnt, sc.sum, pass, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
+                    pk_sel_pick(sc, pass, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
                     S.launches += 3;
                 }
                 // regions equal to the threshold key are taken in (rank, slot) order

@@ -33,6 +33,28 @@
 
 #define CUB_TWO_PI 6.283185307179586
 
+// ---- building blocks with a FIXED association (part of each family's definition) -----------------
+// Two interleaved accumulation chains (even / odd coordinates) halve the dependent-FMA depth of a
+// d-term sum on the GPU; x^N by square-and-multiply needs ~2 log2 N multiplications instead of N-1.
+template <int DIM>
+DM_HD double cub_dot2(const double* a, const double* x, double init) {
+    double s0 = init, s1 = 0.0;
+    for (int i = 0; i < DIM; i += 2) s0 = dm_fma(a[i], x[i], s0);
+    for (int i = 1; i < DIM; i += 2) s1 = dm_fma(a[i], x[i], s1);
+    return DIM > 1 ? s0 + s1 : s0;
+}
+template <int N>
+struct CubPow {  // x^N, N >= 1: p = x^(N/2); N even -> p*p, N odd -> (p*p)*x
+    DM_HD static double of(double x) {
+        const double p = CubPow<N / 2>::of(x);
+        return (N & 1) ? (p * p) * x : p * p;
+    }
+};
+template <>
+struct CubPow<1> {
+    DM_HD static double of(double x) { return x; }
+};
+
 // ---- Genz family --------------------------------------------------------------------------------
 
 template <int DIM>
@@ -43,11 +65,7 @@ struct GenzOscillatory {  // cos(2 pi u_0 + sum a_i x_i)
         for (int i = 0; i < DIM; ++i) a[i] = p[i];
         phase = CUB_TWO_PI * p[DIM];
     }
-    DM_HD void eval(const double* x, double* f) const {
-        double s = phase;
-        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
-        f[0] = dm_cos(s);
-    }
+    DM_HD void eval(const double* x, double* f) const { f[0] = dm_cos(cub_dot2<DIM>(a, x, phase)); }
 };
 
 template <int DIM>
@@ -61,12 +79,16 @@ struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 /
         }
     }
     DM_HD void eval(const double* x, double* f) const {
-        double den = 1.0;
-        for (int i = 0; i < DIM; ++i) {
+        double d0 = 1.0, d1 = 1.0;  // two interleaved product chains (even / odd coordinates)
+        for (int i = 0; i < DIM; i += 2) {
             double t = x[i] - u[i];
-            den = den * dm_fma(t, t, c[i]);
+            d0 = d0 * dm_fma(t, t, c[i]);
         }
-        f[0] = 1.0 / den;
+        for (int i = 1; i < DIM; i += 2) {
+            double t = x[i] - u[i];
+            d1 = d1 * dm_fma(t, t, c[i]);
+        }
+        f[0] = 1.0 / (d0 * d1);
     }
 };
 
@@ -78,11 +100,8 @@ struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
         for (int i = 0; i < DIM; ++i) a[i] = p[i];
     }
     DM_HD void eval(const double* x, double* f) const {
-        double s = 1.0;
-        for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
-        double r = s;
-        for (int i = 0; i < DIM; ++i) r = r * s;  // s^(d+1), left to right
-        f[0] = 1.0 / r;
+        const double s = cub_dot2<DIM>(a, x, 1.0);
+        f[0] = 1.0 / CubPow<DIM + 1>::of(s);  // s^(d+1) by square-and-multiply (fixed association)
     }
 };
 
@@ -97,12 +116,16 @@ struct GenzGaussian {  // exp(-sum a_i^2 (x_i - u_i)^2)
         }
     }
     DM_HD void eval(const double* x, double* f) const {
-        double s = 0.0;
-        for (int i = 0; i < DIM; ++i) {
+        double s0 = 0.0, s1 = 0.0;  // two interleaved chains (even / odd coordinates)
+        for (int i = 0; i < DIM; i += 2) {
             double t = a[i] * (x[i] - u[i]);
-            s = dm_fma(t, t, s);
+            s0 = dm_fma(t, t, s0);
         }
-        f[0] = dm_exp(-s);
+        for (int i = 1; i < DIM; i += 2) {
+            double t = a[i] * (x[i] - u[i]);
+            s1 = dm_fma(t, t, s1);
+        }
+        f[0] = dm_exp(-(s0 + s1));
     }
 };
 

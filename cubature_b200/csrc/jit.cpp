@@ -134,6 +134,12 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     tu << "#define CUB_NPARAMS " << integ->params.size() << "\n";
     tu << "#define CUB_HAS_TRANSFORM " << (has_transform ? 1 : 0) << "\n";
     tu << "#define CUB_SEPARABLE " << (integ->separable ? 1 : 0) << "\n";
+    // CTAs per SM the scalar Genz-Malik kernel is compiled for (register budget 65536 / (128 * n)); measured on
+    // B200 (profiles/r01_tuning.md): rational integrands like 6 (80 registers), cos-heavy ones 4, the rest 5
+    int min_blocks = 5;
+    if (integ->family == CUB_FAM_GENZ_CORNER_PEAK || integ->family == CUB_FAM_GENZ_PRODUCT_PEAK || integ->family == CUB_FAM_GENZ_GAUSSIAN) min_blocks = 6;
+    if (integ->family == CUB_FAM_GENZ_OSCILLATORY) min_blocks = 4;
+    tu << "#ifndef CUB_GM_MIN_BLOCKS\n#define CUB_GM_MIN_BLOCKS " << min_blocks << "\n#endif\n";
     tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
     if (integ->family == CUB_FAM_USER) {
         tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";

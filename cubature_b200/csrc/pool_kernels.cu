@@ -382,12 +382,13 @@ struct ScalarAcc {
 };
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_MAXB = 2048;  // buckets of the widest digit (the 11 exponent bits)
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SEL_UNROLL = 4;
 
 // Digit schedule of the descent over key = ~bits(errmax): eight 8-bit digits, most significant first.
-// Every pass scans errmax of the whole pool (8 B per region) but only the regions inside the bucket
-// chosen so far take part in the histogram (after two passes: about 1 % of the pool), so passes 2..7
-// are pure streaming reads.  (kSelCompactPass >= 0 switches to a compacted candidate list instead.)
+// Every pass streams errmax of the whole pool (8 B per region, SEL_UNROLL independent loads in flight
+// per thread) but only the regions inside the bucket chosen so far take part in the histogram (after
+// two passes: about 1 % of the pool), so passes 2..7 are pure streaming reads.
 __device__ __forceinline__ void sel_flush(unsigned* scnt, double* ssum, unsigned cur, unsigned run_c, double run_s) {
     if (run_c) {
         atomicAdd(&scnt[cur], run_c);
@@ -395,131 +396,14 @@ __device__ __forceinline__ void sel_flush(unsigned* scnt, double* ssum, unsigned
     }
 }
 
-// histogram of the pool regions that match the decided prefix, by the digit (key >> shift) & (nb - 1);
-// when cand_key != nullptr the matching regions are also appended to the candidate list.
-// Every warp owns a private copy of the histogram in shared memory (double atomicAdd on shared memory
-// is a compare-and-swap loop: with one copy per CTA the 256 threads fight over the ~20 hot buckets).
-constexpr int SEL_WARPS = SEL_THREADS / 32;
-__global__ void __launch_bounds__(SEL_THREADS)
-k_sel_hist_pool(const double* errmax, const double* err, long long n, const SelState* st, int shift, int nb,
-                unsigned long long* cnt, double* sum, unsigned long long* cand_key, double* cand_err, unsigned long long* cand_count) {
-    __shared__ unsigned scnt[SEL_WARPS][256];
-    __shared__ double ssum[SEL_WARPS][256];
-    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    for (int b = lane; b < 256; b += 32) {
-        scnt[w][b] = 0;
-        ssum[w][b] = 0.0;
-    }
-    __syncwarp();
-    const unsigned long long prefix = st->prefix, mask = st->mask;
-    const unsigned dmask = (unsigned)nb - 1u;
-    // run-length aggregation in registers: in the first pass nearly every region shares the digit, so a
-    // thread touches shared memory only when its digit changes
-    unsigned cur = 0, run_c = 0;
-    double run_s = 0.0;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + threadIdx.x;
-        bool match = false;
-        unsigned long long k = 0;
-        double e = 0.0;
-        if (i < n) {
-            k = ~dbits(errmax[i]);
-            match = (k & mask) == prefix;
-            if (match) e = err[i];
-        }
-        if (match) {
-            const unsigned d = (unsigned)(k >> shift) & dmask;
-            if (d != cur) {
-                sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
-                cur = d;
-                run_c = 0;
-                run_s = 0.0;
-            }
-            ++run_c;
-            run_s += e;
-        }
-        if (cand_key) {  // warp-aggregated append
-            const unsigned ballot = __ballot_sync(0xffffffffu, match);
-            if (ballot) {
-                unsigned long long pos = 0;
-                if (lane == (unsigned)(__ffs(ballot) - 1)) pos = atomicAdd(cand_count, (unsigned long long)__popc(ballot));
-                pos = __shfl_sync(0xffffffffu, pos, __ffs(ballot) - 1);
-                if (match) {
-                    const unsigned long long at = pos + (unsigned long long)__popc(ballot & ((1u << lane) - 1u));
-                    cand_key[at] = k;
-                    cand_err[at] = e;
-                }
-            }
-        }
-    }
-    sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
-    __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += SEL_THREADS) {
-        unsigned c = 0;
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < SEL_WARPS; ++q) {
-            c += scnt[q][b];
-            s += ssum[q][b];
-        }
-        if (c) {
-            atomicAdd(&cnt[b], (unsigned long long)c);
-            atomicAdd(&sum[b], s);
-        }
-    }
-}
-
-// the same over the candidate list
-__global__ void __launch_bounds__(SEL_THREADS)
-k_sel_hist_list(const unsigned long long* cand_key, const double* cand_err, const unsigned long long* cand_count,
-                const SelState* st, int shift, int nb, unsigned long long* cnt, double* sum) {
-    __shared__ unsigned scnt[SEL_MAXB];
-    __shared__ double ssum[SEL_MAXB];
-    for (int b = threadIdx.x; b < nb; b += SEL_THREADS) {
-        scnt[b] = 0;
-        ssum[b] = 0.0;
-    }
-    __syncthreads();
-    const unsigned long long prefix = st->prefix, mask = st->mask;
-    const unsigned dmask = (unsigned)nb - 1u;
-    const long long n = (long long)*cand_count;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long k = cand_key[i];
-        if ((k & mask) == prefix) {
-            const unsigned d = (unsigned)(k >> shift) & dmask;
-            atomicAdd(&scnt[d], 1u);
-            atomicAdd(&ssum[d], cand_err[i]);
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += SEL_THREADS) {
-        if (scnt[b]) {
-            atomicAdd(&cnt[b], (unsigned long long)scnt[b]);
-            atomicAdd(&sum[b], ssum[b]);
-        }
-    }
-}
-
-// one block: stages the histogram in shared memory, thread 0 walks the buckets (largest errmax first),
-// all threads clear the global histogram for the next pass
-__global__ void __launch_bounds__(SEL_THREADS)
-k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, int nb, int last, const double* totals /*[val, err]*/,
-           unsigned long long Kcap, double absTol, double relTol, int norm, double band) {
-    __shared__ unsigned long long scnt[SEL_MAXB];
-    __shared__ double ssum[SEL_MAXB];
-    for (int b = threadIdx.x; b < nb; b += SEL_THREADS) {
-        scnt[b] = cnt[b];
-        ssum[b] = sum[b];
-        cnt[b] = 0ULL;
-        sum[b] = 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    const double V = totals[0], E = totals[1];
+// Walks the 256 buckets of one pass (largest errmax first), accumulating the popped error until the
+// residual test passes inside a bucket or the pop budget runs out inside it; descends into that bucket.
+__device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, const double* ssum, int shift, int last, double V, double E,
+                              unsigned long long Kcap, double absTol, double relTol, int norm, double band) {
     unsigned long long count_cum = st->count_cum;
     double P = st->P_cum;
     int chosen = -1;
-    for (int d = 0; d < nb; ++d) {
+    for (int d = 0; d < 256; ++d) {
         const unsigned long long c = scnt[d];
         if (c == 0) continue;
         const double s = ssum[d];
@@ -536,7 +420,7 @@ k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, int nb
     const unsigned long long c_b = scnt[chosen];
     const double s_b = ssum[chosen];
     st->prefix |= (unsigned long long)chosen << shift;
-    st->mask |= (unsigned long long)(nb - 1) << shift;
+    st->mask |= 255ULL << shift;
     st->count_cum = count_cum;
     st->P_cum = P;
     if (last) {
@@ -565,6 +449,103 @@ k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, int nb
         const bool a1 = cub_converged(1, ScalarAcc{V, rKm1 + b}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rKm1 - b}, absTol, relTol, norm);
         st->ambiguous = (a0 || a1) ? 1ULL : 0ULL;
     }
+}
+
+// One pass: histogram of the pool regions that match the decided prefix by the digit (key >> shift) & 255.
+// Every warp owns a private copy of the histogram in shared memory (double atomicAdd on shared memory is
+// a compare-and-swap loop; with one copy per CTA 256 threads fight over the ~20 hot buckets).
+// With fuse_pick the CTA that finishes last (ticket counter) also runs the pick, so a pass is one launch;
+// the multi-GPU driver passes fuse_pick = 0 and puts the all-gather between histogram and pick.
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_pass(const double* __restrict__ errmax, const double* __restrict__ err, long long n, SelState* st, int shift, int last,
+           unsigned long long* cnt, double* sum, unsigned* ticket, int fuse_pick, const double* totals, unsigned long long Kcap,
+           double absTol, double relTol, int norm, double band) {
+    __shared__ unsigned scnt[SEL_WARPS][256];
+    __shared__ double ssum[SEL_WARPS][256];
+    __shared__ bool s_last;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (int b = lane; b < 256; b += 32) {
+        scnt[w][b] = 0;
+        ssum[w][b] = 0.0;
+    }
+    __syncwarp();
+    const unsigned long long prefix = st->prefix, mask = st->mask;
+    // run-length aggregation in registers: in the first pass nearly every region shares the digit, so a
+    // thread touches shared memory only when its digit changes
+    unsigned cur = 0, run_c = 0;
+    double run_s = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * SEL_UNROLL) {
+        unsigned long long k[SEL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SEL_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            k[u] = i < n ? ~dbits(errmax[i]) : 0ULL;  // key 0 never matches: bit 63 of a real key is 1
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_UNROLL; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < n && (k[u] & mask) == prefix) {
+                const unsigned d = (unsigned)(k[u] >> shift) & 255u;
+                if (d != cur) {
+                    sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
+                    cur = d;
+                    run_c = 0;
+                    run_s = 0.0;
+                }
+                ++run_c;
+                run_s += err[i];
+            }
+        }
+    }
+    sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
+    __syncthreads();
+    {
+        const int b = threadIdx.x;
+        unsigned c = 0;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < SEL_WARPS; ++q) {
+            c += scnt[q][b];
+            s += ssum[q][b];
+        }
+        if (c) {
+            atomicAdd(&cnt[b], (unsigned long long)c);
+            atomicAdd(&sum[b], s);
+        }
+    }
+    if (!fuse_pick) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA: stage the global histogram (L2 loads), clear it for the next pass, thread 0 picks
+    unsigned long long* pc = (unsigned long long*)&ssum[0][0];  // reuse shared memory: 256 u64 + 256 f64
+    double* ps = &ssum[2][0];
+    pc[threadIdx.x] = __ldcg(&cnt[threadIdx.x]);
+    ps[threadIdx.x] = __ldcg(&sum[threadIdx.x]);
+    cnt[threadIdx.x] = 0ULL;
+    sum[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        sel_pick_body(st, pc, ps, shift, last, __ldcg(&totals[0]), __ldcg(&totals[1]), Kcap, absTol, relTol, norm, band);
+    }
+}
+
+// stand-alone pick (multi-GPU: after the all-gather and the rank-ordered sum of the histograms)
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, int last, const double* totals, unsigned long long Kcap,
+           double absTol, double relTol, int norm, double band) {
+    __shared__ unsigned long long pc[256];
+    __shared__ double ps[256];
+    pc[threadIdx.x] = cnt[threadIdx.x];
+    ps[threadIdx.x] = sum[threadIdx.x];
+    cnt[threadIdx.x] = 0ULL;
+    sum[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) sel_pick_body(st, pc, ps, shift, last, totals[0], totals[1], Kcap, absTol, relTol, norm, band);
 }
 
 // stable compaction of the popped slots: slot i is popped iff key_i < thr, or key_i == thr and it is
@@ -774,39 +755,23 @@ size_t pk_sel_state_bytes() { return sizeof(SelState); }
 // collective between them.  scratch: see SelScratch (pool_kernels.h); cnt and sum are contiguous
 // (u64[2048] then double[2048]) so that one all-gather ships both.
 // SelState: K at byte 24, tie_take at 32, ambiguous at 40.
-void pk_sel_init(void* state, unsigned long long* cnt, double* sum, unsigned long long* cand_count, cudaStream_t s) {
-    cudaMemsetAsync(state, 0, sizeof(SelState), s);
-    cudaMemsetAsync(cnt, 0, SEL_MAXB * 8, s);
-    cudaMemsetAsync(sum, 0, SEL_MAXB * 8, s);
-    cudaMemsetAsync(cand_count, 0, 8, s);
+void pk_sel_init(const SelScratch& sc, cudaStream_t s) {
+    cudaMemsetAsync(sc.state, 0, 512 + PK_SEL_HIST_BYTES, s);  // SelState, ticket, cnt[256], sum[256]
 }
-// digit schedule: see k_sel_hist_pool
-static const int kSelPasses = 8;
-static const int kSelShift[kSelPasses] = {56, 48, 40, 32, 24, 16, 8, 0};
-static const int kSelBuckets[kSelPasses] = {256, 256, 256, 256, 256, 256, 256, 256};
-static const int kSelCompactPass = -1;  // >= 0: pass that builds the candidate list (later passes scan only that list)
-int pk_sel_passes() { return kSelPasses; }
-void pk_sel_hist(const PoolView& pool, long long n, const void* state, int pass, unsigned long long* cnt, double* sum,
-                 unsigned long long* cand_key, double* cand_err, unsigned long long* cand_count, long long cand_cap, cudaStream_t s) {
-    if (kSelCompactPass < 0 || pass <= kSelCompactPass) {
-        long long b = (n + SEL_THREADS - 1) / SEL_THREADS;
-        if (b > 148 * 8) b = 148 * 8;
-        if (b < 1) b = 1;
-        const bool compact = pass == kSelCompactPass;
-        k_sel_hist_pool<<<(unsigned)b, SEL_THREADS, 0, s>>>(pool.errmax, pool.err, n, (const SelState*)state, kSelShift[pass], kSelBuckets[pass], cnt,
-                                                          sum, compact ? cand_key : nullptr, cand_err, cand_count);
-    } else {
-        long long b = (cand_cap + SEL_THREADS - 1) / SEL_THREADS;
-        if (b > 148 * 2) b = 148 * 2;
-        if (b < 1) b = 1;
-        k_sel_hist_list<<<(unsigned)b, SEL_THREADS, 0, s>>>(cand_key, cand_err, cand_count, (const SelState*)state, kSelShift[pass],
-                                                          kSelBuckets[pass], cnt, sum);
-    }
+int pk_sel_passes() { return 8; }
+// pass p decides bits [63 - 8p, 56 - 8p]; fuse_pick = 1: histogram + pick in one launch (single GPU)
+void pk_sel_pass(const PoolView& pool, long long n, const SelScratch& sc, int pass, int fuse_pick, const double* totals, long long Kcap,
+                 double absTol, double relTol, int norm, double band, cudaStream_t s) {
+    long long b = (n + (long long)SEL_THREADS * SEL_UNROLL - 1) / ((long long)SEL_THREADS * SEL_UNROLL);
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    k_sel_pass<<<(unsigned)b, SEL_THREADS, 0, s>>>(pool.errmax, pool.err, n, (SelState*)sc.state, 56 - 8 * pass, pass == 7, sc.cnt, sc.sum,
+                                                  sc.ticket, fuse_pick, totals, (unsigned long long)Kcap, absTol, relTol, norm, band);
 }
-void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int pass, const double* totals, long long Kcap, double absTol,
-                 double relTol, int norm, double band, cudaStream_t s) {
-    k_sel_pick<<<1, SEL_THREADS, 0, s>>>((SelState*)state, cnt, sum, kSelShift[pass], kSelBuckets[pass], pass == kSelPasses - 1, totals,
-                                        (unsigned long long)Kcap, absTol, relTol, norm, band);
+void pk_sel_pick(const SelScratch& sc, int pass, const double* totals, long long Kcap, double absTol, double relTol, int norm,
+                 double band, cudaStream_t s) {
+    k_sel_pick<<<1, SEL_THREADS, 0, s>>>((SelState*)sc.state, sc.cnt, sc.sum, 56 - 8 * pass, pass == 7, totals, (unsigned long long)Kcap,
+                                        absTol, relTol, norm, band);
 }
 void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
                         unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s) {
@@ -822,24 +787,21 @@ void pk_sel_compact(const PoolView& pool, long long n, const void* state, const 
 }
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s) {
-    pk_sel_init(sc.state, sc.cnt, sc.sum, sc.cand_count, s);
-    for (int pass = 0; pass < kSelPasses; ++pass) {
-        pk_sel_hist(pool, n, sc.state, pass, sc.cnt, sc.sum, sc.cand_key, sc.cand_err, sc.cand_count, n, s);
-        pk_sel_pick(sc.state, sc.cnt, sc.sum, pass, totals, Kcap, absTol, relTol, norm, band, s);
-    }
+    pk_sel_init(sc, s);
+    for (int pass = 0; pass < 8; ++pass) pk_sel_pass(pool, n, sc, pass, 1, totals, Kcap, absTol, relTol, norm, band, s);
     pk_sel_tile_counts(pool, n, sc.state, sc.tile_less, sc.tile_eq, nullptr, s);
     pk_sel_compact(pool, n, sc.state, sc.tile_less, sc.tile_eq, -1, list, s);
-    return 2 * kSelPasses + 3;
+    return 8 + 3;
 }
 
-// adds the per-rank histogram blocks [R][cnt u64 x2048 | sum f64 x2048] in rank order
+// adds the per-rank histogram blocks [R][cnt u64 x256 | sum f64 x256] in rank order
 __global__ void k_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;  // SEL_MAXB threads in total
+    const int b = threadIdx.x;  // 256 threads
     unsigned long long c = 0;
     double s = 0.0;
     for (int r = 0; r < R; ++r) {
-        const unsigned long long* pc = (const unsigned long long*)(gathered + (size_t)r * (SEL_MAXB * 16));
-        const double* ps = (const double*)(gathered + (size_t)r * (SEL_MAXB * 16) + SEL_MAXB * 8);
+        const unsigned long long* pc = (const unsigned long long*)(gathered + (size_t)r * PK_SEL_HIST_BYTES);
+        const double* ps = (const double*)(gathered + (size_t)r * PK_SEL_HIST_BYTES + 2048);
         c += pc[b];
         s += ps[b];
     }
@@ -847,7 +809,7 @@ __global__ void k_sum_hist_ranks(const unsigned char* gathered, int R, unsigned 
     sum[b] = s;
 }
 void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s) {
-    k_sum_hist_ranks<<<SEL_MAXB / 256, 256, 0, s>>>(gathered, R, cnt, sum);
+    k_sum_hist_ranks<<<1, 256, 0, s>>>(gathered, R, cnt, sum);
 }
 
 // deals the replicated pool out to the ranks: with `perm` = the regions in descending-errmax order,

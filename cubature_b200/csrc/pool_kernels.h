@@ -35,22 +35,20 @@ long long pk_sel_tiles(long long n);
 size_t pk_sel_state_bytes();
 // device scratch of the scalar select
 struct SelScratch {
-    void* state;                    // SelState
-    unsigned long long* cnt;        // [2048]
-    double* sum;                    // [2048], directly after cnt
-    unsigned long long* cand_count; // [1]
-    unsigned long long* cand_key;   // [pool capacity]
-    double* cand_err;               // [pool capacity]
+    void* state;                    // SelState (56 B) at byte 0 of a zero-initialised 512 B header
+    unsigned* ticket;               // last-CTA ticket counter (byte 128 of the header)
+    unsigned long long* cnt;        // [256] at byte 512
+    double* sum;                    // [256] directly after cnt (one all-gather ships both)
     unsigned long long* tile_less;  // [pk_sel_tiles(capacity)]
     unsigned long long* tile_eq;    // [pk_sel_tiles(capacity)]
 };
-#define PK_SEL_HIST_BYTES (2048 * 16)
+#define PK_SEL_HIST_BYTES (256 * 16)
 int pk_sel_passes();
-void pk_sel_init(void* state, unsigned long long* cnt, double* sum, unsigned long long* cand_count, cudaStream_t s);
-void pk_sel_hist(const PoolView& pool, long long n, const void* state, int pass, unsigned long long* cnt, double* sum,
-                 unsigned long long* cand_key, double* cand_err, unsigned long long* cand_count, long long cand_cap, cudaStream_t s);
-void pk_sel_pick(void* state, unsigned long long* cnt, double* sum, int pass, const double* totals, long long Kcap, double absTol,
-                 double relTol, int norm, double band, cudaStream_t s);
+void pk_sel_init(const SelScratch& sc, cudaStream_t s);
+void pk_sel_pass(const PoolView& pool, long long n, const SelScratch& sc, int pass, int fuse_pick, const double* totals, long long Kcap,
+                 double absTol, double relTol, int norm, double band, cudaStream_t s);
+void pk_sel_pick(const SelScratch& sc, int pass, const double* totals, long long Kcap, double absTol, double relTol, int norm,
+                 double band, cudaStream_t s);
 void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
                         unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s);
 void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
