@@ -27,7 +27,7 @@ struct HostPoolView {
 };
 struct HostWork {
     const int* list;
-    const long long* n_items_dev;
+    const long long* dyn;  // device-resident {n_items, use_list, base} or null
     long long n_items;
     long long base;
     int mode;

@@ -241,7 +241,7 @@ struct SelectBuffers {
     cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list, tile counters, state
         cudaError_t e;
         if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
-        if ((e = small.ensure(512 + PK_SEL_HIST_BYTES)) != cudaSuccess) return e;
+        if ((e = small.ensure(512 + PK_COOP_HIST_BYTES)) != cudaSuccess) return e;
         if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
         return cudaSuccess;
     }
@@ -254,6 +254,7 @@ struct SelectBuffers {
         sc.sum = (double*)(sm + 512 + 256 * 8);
         sc.tile_less = hist.as<unsigned long long>();
         sc.tile_eq = sc.tile_less + pk_sel_tiles(n);
+        sc.ctl = nullptr;
         return sc;
     }
     cudaError_t ensure(long long n, int f) {
@@ -330,6 +331,7 @@ struct Session {
     std::vector<unsigned char> tr_arg;   // device-side CubTransform bytes
     std::vector<double> prm_arg;         // device-side CubParams
     int64_t launches = 0;
+    int n_sms = 148;
     double rule_ms = 0.0;
     char* msg = nullptr;
     char msgbuf[256];
@@ -368,6 +370,7 @@ struct Session {
             CUB_CUDA_CHECK(cudaSetDevice(device), msg);
         }
         ws = acquire_workspace(device);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
         CUB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev0), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev1), msg);
@@ -529,6 +532,7 @@ void fill_trace_regions(Session& S, Pool& pool, const std::vector<int>* order, l
 // the reference loops forever.  Every iteration at least doubles nothing, so the
 // guard is generous; hitting it returns the best estimate with converged = 0.
 const int64_t kMaxIterations = 100000;
+const long long kDeviceSizedMaxRegions = 1 << 20;  // below this the rule kernel is sized on the device (no round trip)
 
 struct LoopResult {
     int converged = 0;
@@ -912,7 +916,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 // distributed: local histogram -> all-gather -> rank-ordered sum -> identical pick on every rank
                 pk_sel_init(sc, S.stream);
                 for (int pass = 0; pass < pk_sel_passes(); ++pass) {
-                    pk_sel_pass(pv, N, sc, pass, 0, d_totals, Kcap, absTol, relTol, norm, band, S.stream);
+                    pk_sel_pass(pv, N, sc, pass, 0, d_totals, Kcap, absTol, relTol, norm, band, nullptr, S.stream);
                     rc = cub_comm_allgather(comm, sc.cnt, PK_SEL_HIST_BYTES, d_histgather, S.stream);
                     if (rc != CUB_OK) return rc;
                     pk_sum_hist_ranks(d_histgather, R, sc.cnt, sc.sum, S.stream);
@@ -920,7 +924,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                     S.launches += 3;
                 }
                 // regions equal to the threshold key are taken in (rank, slot) order
-                pk_sel_tile_counts(pv, N, sc.state, sc.tile_less, sc.tile_eq, d_u64 + 4, S.stream);
+                pk_sel_tile_counts(pv, N, sc.state, sc.tile_less, sc.tile_eq, d_u64 + 4, nullptr, S.stream);
                 S.launches += 2;
                 rc = cub_comm_allgather(comm, d_u64 + 4, 16, d_histgather, S.stream);
                 if (rc != CUB_OK) return rc;
@@ -936,7 +940,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 for (int r = 0; r < R; ++r) ties[(size_t)r] = (int64_t)le[2 * r + 1];
                 const long long take = cubature_cuda_tie_share(tie_take_global, ties.data(), R, rank);
                 K = (long long)le[2 * rank] + take;
-                pk_sel_compact(pv, N, sc.state, sc.tile_less, sc.tile_eq, take, sel.idxA.as<int>(), S.stream);
+                pk_sel_compact(pv, N, sc.state, sc.tile_less, sc.tile_eq, take, sel.idxA.as<int>(), nullptr, S.stream);
                 S.launches += 1;
             }
             list = sel.idxA.as<int>();
@@ -1047,6 +1051,226 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     res->converged = conv ? 1 : 0;
     res->num_eval = numEval;
     res->num_regions = Nglobal;
+    fill_trace_regions(S, pool, nullptr, N, trace);
+    return CUB_OK;
+}
+
+// ---- DEVICE mode, one GPU: device-driven iterations -----------------------------------------------------
+// Per iteration the host enqueues, without waiting in between: k_pool_stats (totals, extreme keys,
+// convergence test, select-all shortcut -> device control block), the eight select passes + compaction
+// (scalar integrands; they retire at once when the control block says "converged" or "pop everything"),
+// and the fused bisect + rule kernel, which reads its work size from the control block (CubWork::dyn).
+// Then ONE small device->host copy tells the host how many regions were popped.  Integrands with
+// fdim > 1 use the same stats kernel and fall back to the sort-based selection when a batch has to be cut.
+int integrate_device_fused(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res) {
+    const int f = S.fdim;
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    const size_t extra = 24 + (size_t)8 * f + 1;
+    long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
+    int rc = set_root(S, pool);
+    if (rc != CUB_OK) return rc;
+
+    SelectBuffers& sel = W.sel;
+    DevBuf &d_partial = W.d_partial, &d_small = W.d_small;
+    PinnedBuf& h_small = W.h_small;
+    const int G = 1184;
+    const size_t ctl_words = PK_CTL_WORDS + (size_t)4 * f;
+    CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * 5 * G), S.msg);
+    CUB_CUDA_CHECK(d_small.ensure(ctl_words * 8 + 256), S.msg);
+    CUB_CUDA_CHECK(h_small.ensure(ctl_words * 8 + 256), S.msg);
+    double* d_part = d_partial.as<double>();
+    unsigned long long* d_blk = (unsigned long long*)(d_part + (size_t)2 * f * G);
+    long long* d_ctl = d_small.as<long long>();
+    unsigned long long* d_u64 = (unsigned long long*)(d_ctl + ctl_words) + 8;  // scratch for the fdim > 1 path
+    double* d_totals = (double*)(d_ctl + PK_CTL_WORDS);
+    long long* h_ctl = h_small.as<long long>();
+    const double* h_totals = (const double*)(h_ctl + PK_CTL_WORDS);
+    unsigned long long* h_u64 = (unsigned long long*)(h_ctl + ctl_words) + 8;
+    CUB_CUDA_CHECK(cudaMemsetAsync(d_small.p, 0, ctl_words * 8 + 256, S.stream), S.msg);
+    CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);  // selection scratch header is cleared by the stats kernel
+
+    {
+        HostWork w{};
+        w.n_items = 1;
+        w.base = 0;
+        w.mode = MODE_PLAIN;
+        rc = S.launch_rule(pool.view(), w);
+        if (rc != CUB_OK) return rc;
+    }
+    long long N = 1;
+    int64_t numEval = P;
+    bool conv = false, have_totals = false;
+    double ops = 1.0;
+    const double eps = 2.220446049250313e-16;
+
+    while (numEval < maxEval || maxEval == 0) {
+        long long Kcap = N;
+        if (maxEval > 0) {
+            const int64_t room = maxEval - numEval;  // > 0 here
+            Kcap = std::min<long long>(N, std::max<int64_t>(1, (room + 2 * P - 1) / (2 * P)));
+        }
+        // the rule kernel is sized on the device: make room for the largest batch this iteration can pop
+        if (N + Kcap > pool.cap) {
+            long long nc = std::max<long long>(pool.cap * 2, N + Kcap);
+            cudaError_t e = pool.grow(nc, N, S.stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+            CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+        }
+        if (N + Kcap > (long long)std::numeric_limits<int>::max()) {
+            cub_set_message(S.msg, "region pool exceeds 2^31 slots");
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+        const PoolView pv = pool.view();
+        const double band = 4.0 * eps * std::sqrt(ops);
+        SelScratch sc = sel.scratch(pool.cap);
+        sc.ctl = d_ctl;
+        // ONE cooperative launch: totals, loop decisions and (scalar integrands) the whole batch selection
+        {
+            cudaError_t e = pk_iter_coop(pv, f, N, Kcap, absTol, relTol, norm, band, f == 1 ? 1 : 0, d_part, d_blk, d_ctl, sc.state,
+                                         (unsigned char*)sc.state + 512, sel.idxA.as<int>(), S.n_sms, S.stream);
+            if (e != cudaSuccess) {
+                cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
+                return CUB_ERR_CUDA;
+            }
+        }
+        S.launches += 1;
+        long long K = 0;
+        if (f == 1) {
+            // small pools: the rule kernel is sized on the device (grid for the largest possible batch, surplus
+            // CTAs retire at once) and the host learns K afterwards; large pools: one extra round trip buys an
+            // exactly sized launch
+            const bool device_sized = N <= kDeviceSizedMaxRegions;
+            HostWork w{};
+            w.list = sel.idxA.as<int>();
+            w.base = N;
+            w.mode = MODE_BISECT;
+            if (device_sized) {
+                w.dyn = d_ctl;
+                w.n_items = 2 * Kcap;  // upper bound: sizes the grid only
+                rc = S.launch_rule(pool.view(), w);
+                if (rc != CUB_OK) return rc;
+            }
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += (int64_t)ctl_words * 8;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            res->ambiguous += h_ctl[6];
+            if (h_ctl[4]) {
+                conv = true;
+                have_totals = true;
+                break;
+            }
+            K = h_ctl[3];
+            if (!device_sized && K >= 1 && K <= Kcap) {
+                if (h_ctl[5]) w.list = nullptr;  // pop-all: identity list, coalesced parent reads
+                w.n_items = 2 * K;
+                rc = S.launch_rule(pool.view(), w);
+                if (rc != CUB_OK) return rc;
+            }
+            if (K < 1 || K > Kcap) {
+                cub_set_message(S.msg, "internal: device selection returned K=%lld of N=%lld (cap %lld)", K, N, Kcap);
+                return CUB_ERR_CUDA;
+            }
+        } else {
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += (int64_t)ctl_words * 8;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            res->ambiguous += h_ctl[6];
+            if (h_ctl[4]) {
+                conv = true;
+                have_totals = true;
+                break;
+            }
+            const int* list = nullptr;
+            if (h_ctl[5]) {
+                K = N;
+            } else {
+                // the batch has to be cut: stable sort by errmax, prefix sums, residual test for every k
+                const bool all = (!cub_converged(f, VecAcc{h_totals, h_totals + 3 * f}, absTol, relTol, norm)) || N == 1;
+                CUB_CUDA_CHECK(sel.ensure(pool.cap, f), S.msg);
+                pk_sort_prepare(pv.errmax, N, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64, S.stream);
+                S.launches += 1;
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                S.d2h_bytes += 16;
+                S.h2d_bytes += 16;
+                CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                const unsigned long long vary = h_u64[0] ^ h_u64[1];
+                unsigned long long* ka = sel.keysA.as<unsigned long long>();
+                unsigned long long* kb = sel.keysB.as<unsigned long long>();
+                int* ia = sel.idxA.as<int>();
+                int* ib = sel.idxB.as<int>();
+                for (int shift = 0; shift < 64; shift += 8) {
+                    if (((vary >> shift) & 0xffULL) == 0) continue;
+                    pk_sort_pass(ka, ia, kb, ib, N, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
+                                 sel.binbase.as<unsigned long long>(), S.stream);
+                    S.launches += 4;
+                    std::swap(ka, kb);
+                    std::swap(ia, ib);
+                }
+                list = ia;
+                if (all) {
+                    K = Kcap;
+                } else {
+                    pk_prefix(pv, f, ia, N, sel.prefix.as<double>(), sel.tile_tot.as<double>(), S.stream);
+                    pk_find_k(d_totals, sel.prefix.as<double>(), sel.tile_tot.as<double>(), N, f, absTol, relTol, norm, band, d_u64, S.stream);
+                    S.launches += 3;
+                    CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                    S.d2h_bytes += 24;
+                    S.h2d_bytes += 24;
+                    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                    long long k0 = (long long)h_u64[0], k1 = (long long)h_u64[1], k2 = (long long)h_u64[2];
+                    if (k0 > N) k0 = N;
+                    if (k1 > N) k1 = N;
+                    if (k2 > N) k2 = N;
+                    if (std::min(k1, Kcap) != std::min(k0, Kcap) || std::min(k2, Kcap) != std::min(k0, Kcap)) res->ambiguous += 1;
+                    K = std::min(k0, Kcap);
+                }
+            }
+            HostWork w{};
+            w.list = list;
+            w.n_items = 2 * K;
+            w.base = N;
+            w.mode = MODE_BISECT;
+            rc = S.launch_rule(pool.view(), w);
+            if (rc != CUB_OK) return rc;
+        }
+        N += K;
+        numEval += 2 * P * K;
+        S.local_regions_evaluated += 2 * K;
+        ops += 3.0 * (double)K;
+        res->iterations += 1;
+        push_batch(trace, 2 * K);
+        if (res->iterations >= kMaxIterations) {
+            cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)res->iterations);
+            break;
+        }
+    }
+    if (!have_totals) {  // stopped by maxEval: K5 over the final pool
+        SelScratch sc = sel.scratch(pool.cap);
+        cudaError_t e = pk_iter_coop(pool.view(), f, N, N, absTol, relTol, norm, 0.0, 0, d_part, d_blk, d_ctl, sc.state,
+                                     (unsigned char*)sc.state + 512, sel.idxA.as<int>(), S.n_sms, S.stream);
+        if (e != cudaSuccess) {
+            cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        S.launches += 1;
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += (int64_t)ctl_words * 8;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    }
+    for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
+    S.flush_rule_timer();
+    res->converged = conv ? 1 : 0;
+    res->num_eval = numEval;
+    res->num_regions = N;
     fill_trace_regions(S, pool, nullptr, N, trace);
     return CUB_OK;
 }
@@ -1220,8 +1444,10 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
     cudaEventRecord(S.ev0, S.stream);
     if (select == CUB_SELECT_HEAP_EXACT)
         rc = integrate_heap_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
-    else
+    else if (options && options->comm && options->comm->nranks > 1)
         rc = integrate_device(S, relTol, absTol, norm, maxEval, options, out, &res);
+    else
+        rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, options, out, &res);
     cudaEventRecord(S.ev1, S.stream);
     cudaEventSynchronize(S.ev1);
     if (stats) {

@@ -12,6 +12,7 @@
 //   Rule.errMax                 Rule.java:281-289           -> k_errmax_rows
 //   RegionHeap running sums     RegionHeap.java:21-36       -> k_totals_* (recomputed, not incremental)
 //   Gladwell batch pop          Rule.java:101-133           -> k_sort_*, k_scan_*, k_find_k
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -142,6 +143,169 @@ __global__ void k_gather_slot(PoolView pool, int fdim, const unsigned long long*
     const long long s = (long long)*slot_ptr;
     out[j] = pool.val[(long long)j * pool.cap + s];
     out[fdim + j] = pool.err[(long long)j * pool.cap + s];
+}
+
+// ---- K5 fused: one launch per iteration computes everything the loop control needs ------------------
+// Every CTA reduces a contiguous chunk (same fixed shape as k_totals_partial: bit-reproducible) and its
+// min / max errmax key; the CTA that finishes last (ticket) adds the partials in CTA order, finds the
+// smallest-errmax region (highest slot among ties: the region popped last), gathers its val/err column,
+// evaluates the reference's convergence test (Rule.java:73) and the select-all shortcut, writes the
+// device control block and clears the scratch of the selection kernels.  Control block (8-byte words):
+//   [0] n_items  [1] use_list  [2] base        <- read by the rule kernel (CubWork::dyn)
+//   [3] K        [4] done      [5] all   [6] ambiguous   [8] min key  [9] max key  [10] argmin slot
+//   [16 ..) totals val[f], err[f], then the smallest region's val[f], err[f]
+struct BandAcc {  // err_j * scale + add * base_j
+    const double* v;
+    const double* e;
+    const double* base;
+    double scale, add;
+    __device__ double val(int j) const { return v[j]; }
+    __device__ double err(int j) const { return e[j] * scale + add * base[j]; }
+};
+
+__global__ void __launch_bounds__(TOT_THREADS)
+k_pool_stats(PoolView pool, int fdim, long long n, double* partial /*[2f][G]*/, unsigned long long* blk /*[3][G]: min key, its slot, max key*/,
+             unsigned* ticket, long long* ctl, long long Kcap, double absTol, double relTol, int norm, double band,
+             unsigned long long* sel_zero, int sel_zero_words) {
+    __shared__ double sh[TOT_THREADS];
+    __shared__ unsigned long long shk[TOT_THREADS], shs[TOT_THREADS], shm[TOT_THREADS];
+    __shared__ bool s_last;
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const long long per = (n + G - 1) / G;
+    const long long lo = per * b;
+    long long hi = lo + per;
+    if (hi > n) hi = n;
+    for (int row = 0; row < 2 * fdim; ++row) {
+        const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
+        double s = 0.0;
+        for (long long i = lo + tid; i < hi; i += TOT_THREADS) s += src[i];
+        sh[tid] = s;
+        __syncthreads();
+        for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) sh[tid] += sh[tid + w];
+            __syncthreads();
+        }
+        if (tid == 0) partial[(long long)row * G + b] = sh[0];
+        __syncthreads();
+    }
+    {
+        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+        for (long long i = lo + tid; i < hi; i += TOT_THREADS) {
+            const unsigned long long k = dbits(pool.errmax[i]);
+            if (k <= mn) {  // ascending i: among equal keys the highest slot wins
+                mn = k;
+                ms = (unsigned long long)i;
+            }
+            mx = k > mx ? k : mx;
+        }
+        shk[tid] = mn;
+        shs[tid] = ms;
+        shm[tid] = mx;
+        __syncthreads();
+        for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) {
+                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+                if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
+                    shk[tid] = k2;
+                    shs[tid] = s2;
+                }
+                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            blk[b] = shk[0];
+            blk[G + b] = shs[0];
+            blk[2 * G + b] = shm[0];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)G - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // ---- last CTA -------------------------------------------------------------------------------
+    double* totals = (double*)(ctl + 16);
+    double* minvec = totals + 2 * fdim;
+    for (int row = 0; row < 2 * fdim; ++row) {
+        double s = 0.0;
+        for (int i = tid; i < G; i += TOT_THREADS) s += __ldcg(&partial[(long long)row * G + i]);
+        sh[tid] = s;
+        __syncthreads();
+        for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) sh[tid] += sh[tid + w];
+            __syncthreads();
+        }
+        if (tid == 0) totals[row] = sh[0];
+        __syncthreads();
+    }
+    {
+        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+        for (int i = tid; i < G; i += TOT_THREADS) {
+            const unsigned long long k = __ldcg(&blk[i]), sl = __ldcg(&blk[G + i]), m2 = __ldcg(&blk[2 * G + i]);
+            if (k < mn || (k == mn && sl > ms)) {
+                mn = k;
+                ms = sl;
+            }
+            mx = m2 > mx ? m2 : mx;
+        }
+        shk[tid] = mn;
+        shs[tid] = ms;
+        shm[tid] = mx;
+        __syncthreads();
+        for (int w = TOT_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) {
+                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+                if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
+                    shk[tid] = k2;
+                    shs[tid] = s2;
+                }
+                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+            }
+            __syncthreads();
+        }
+    }
+    const long long argmin = (long long)shs[0];
+    for (int j = tid; j < fdim; j += TOT_THREADS) {
+        minvec[j] = pool.val[(long long)j * pool.cap + argmin];
+        minvec[fdim + j] = pool.err[(long long)j * pool.cap + argmin];
+    }
+    for (int i = tid; i < sel_zero_words; i += TOT_THREADS) sel_zero[i] = 0ULL;
+    __syncthreads();
+    if (tid != 0) return;
+    *ticket = 0u;
+    ((unsigned long long*)ctl)[8] = shk[0];
+    ((unsigned long long*)ctl)[9] = shm[0];
+    ctl[10] = argmin;
+    const double* tv = totals;
+    const double* te = totals + fdim;
+    long long amb = 0;
+    const bool c0 = cub_converged(fdim, BandAcc{tv, te, te, 1.0, 0.0}, absTol, relTol, norm);
+    const bool c1 = cub_converged(fdim, BandAcc{tv, te, te, 1.0 + band, 0.0}, absTol, relTol, norm);
+    const bool c2 = cub_converged(fdim, BandAcc{tv, te, te, 1.0 - band, 0.0}, absTol, relTol, norm);
+    if (c0 != c1 || c0 != c2) amb += 1;
+    ctl[0] = 0;
+    ctl[1] = 0;
+    ctl[2] = n;
+    ctl[3] = 0;
+    ctl[4] = c0 ? 1 : 0;
+    ctl[5] = 0;
+    if (!c0) {
+        // select-all shortcut: the residual after popping all but the smallest-errmax region is that
+        // region's own error vector; if that is not converged, no smaller k is (monotone predicate)
+        const double* le = minvec + fdim;
+        bool all = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, 0.0}, absTol, relTol, norm);
+        const bool a1 = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, band}, absTol, relTol, norm);
+        const bool a2 = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, -band}, absTol, relTol, norm);
+        if (a1 != all || a2 != all) amb += 1;
+        if (n == 1) all = true;
+        if (all && Kcap >= n) {
+            ctl[0] = 2 * n;
+            ctl[3] = n;
+            ctl[5] = 1;
+        }
+    }
+    ctl[6] = amb;
 }
 
 // ---- K3a: stable LSD radix sort of (key = ~bits(errmax), slot), 8 bits per pass --------------------
@@ -398,20 +562,26 @@ __device__ __forceinline__ void sel_flush(unsigned* scnt, double* ssum, unsigned
 
 // Walks the 256 buckets of one pass (largest errmax first), accumulating the popped error until the
 // residual test passes inside a bucket or the pop budget runs out inside it; descends into that bucket.
-__device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, const double* ssum, int shift, int last, double V, double E,
-                              unsigned long long Kcap, double absTol, double relTol, int norm, double band) {
+__device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, const double* ssum, const unsigned* nonzero /*[8] bit masks*/,
+                              int shift, int last, double V, double E, unsigned long long Kcap, double absTol, double relTol, int norm,
+                              double band) {
     unsigned long long count_cum = st->count_cum;
     double P = st->P_cum;
     int chosen = -1;
-    for (int d = 0; d < 256; ++d) {
-        const unsigned long long c = scnt[d];
-        if (c == 0) continue;
-        const double s = ssum[d];
-        chosen = d;  // the last non-empty bucket is chosen if nothing stops earlier
-        const bool stop = (count_cum + c >= Kcap) || cub_converged(1, ScalarAcc{V, E - (P + s)}, absTol, relTol, norm);
-        if (stop) break;
-        count_cum += c;
-        P += s;
+    bool stop = false;
+    for (int w = 0; w < 8 && !stop; ++w) {  // only the non-empty buckets, in ascending order
+        unsigned m = nonzero[w];
+        while (m) {
+            const int d = w * 32 + (__ffs(m) - 1);
+            m &= m - 1;
+            const unsigned long long c = scnt[d];
+            const double s = ssum[d];
+            chosen = d;  // the last non-empty bucket is chosen if nothing stops earlier
+            stop = (count_cum + c >= Kcap) || cub_converged(1, ScalarAcc{V, E - (P + s)}, absTol, relTol, norm);
+            if (stop) break;
+            count_cum += c;
+            P += s;
+        }
     }
     if (chosen < 0) {  // cannot happen for n >= 1
         st->K = 0;
@@ -459,7 +629,8 @@ __device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, cons
 __global__ void __launch_bounds__(SEL_THREADS)
 k_sel_pass(const double* __restrict__ errmax, const double* __restrict__ err, long long n, SelState* st, int shift, int last,
            unsigned long long* cnt, double* sum, unsigned* ticket, int fuse_pick, const double* totals, unsigned long long Kcap,
-           double absTol, double relTol, int norm, double band) {
+           double absTol, double relTol, int norm, double band, const long long* ctl) {
+    if (ctl && (ctl[4] | ctl[5])) return;  // converged, or the whole pool is popped: nothing to select
     __shared__ unsigned scnt[SEL_WARPS][256];
     __shared__ double ssum[SEL_WARPS][256];
     __shared__ bool s_last;
@@ -523,14 +694,20 @@ k_sel_pass(const double* __restrict__ errmax, const double* __restrict__ err, lo
     // last CTA: stage the global histogram (L2 loads), clear it for the next pass, thread 0 picks
     unsigned long long* pc = (unsigned long long*)&ssum[0][0];  // reuse shared memory: 256 u64 + 256 f64
     double* ps = &ssum[2][0];
-    pc[threadIdx.x] = __ldcg(&cnt[threadIdx.x]);
-    ps[threadIdx.x] = __ldcg(&sum[threadIdx.x]);
-    cnt[threadIdx.x] = 0ULL;
-    sum[threadIdx.x] = 0.0;
+    unsigned* nzm = &scnt[0][0];
+    {
+        const unsigned long long c = __ldcg(&cnt[threadIdx.x]);
+        pc[threadIdx.x] = c;
+        ps[threadIdx.x] = __ldcg(&sum[threadIdx.x]);
+        cnt[threadIdx.x] = 0ULL;
+        sum[threadIdx.x] = 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, c != 0ULL);
+        if (lane == 0) nzm[w] = m;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         *ticket = 0u;
-        sel_pick_body(st, pc, ps, shift, last, __ldcg(&totals[0]), __ldcg(&totals[1]), Kcap, absTol, relTol, norm, band);
+        sel_pick_body(st, pc, ps, nzm, shift, last, __ldcg(&totals[0]), __ldcg(&totals[1]), Kcap, absTol, relTol, norm, band);
     }
 }
 
@@ -540,12 +717,16 @@ k_sel_pick(SelState* st, unsigned long long* cnt, double* sum, int shift, int la
            double absTol, double relTol, int norm, double band) {
     __shared__ unsigned long long pc[256];
     __shared__ double ps[256];
-    pc[threadIdx.x] = cnt[threadIdx.x];
+    __shared__ unsigned nzm[8];
+    const unsigned long long c = cnt[threadIdx.x];
+    pc[threadIdx.x] = c;
     ps[threadIdx.x] = sum[threadIdx.x];
     cnt[threadIdx.x] = 0ULL;
     sum[threadIdx.x] = 0.0;
+    const unsigned m = __ballot_sync(0xffffffffu, c != 0ULL);
+    if ((threadIdx.x & 31) == 0) nzm[threadIdx.x >> 5] = m;
     __syncthreads();
-    if (threadIdx.x == 0) sel_pick_body(st, pc, ps, shift, last, totals[0], totals[1], Kcap, absTol, relTol, norm, band);
+    if (threadIdx.x == 0) sel_pick_body(st, pc, ps, nzm, shift, last, totals[0], totals[1], Kcap, absTol, relTol, norm, band);
 }
 
 // stable compaction of the popped slots: slot i is popped iff key_i < thr, or key_i == thr and it is
@@ -554,7 +735,9 @@ constexpr int SEL_ITEMS = 8;
 constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
 
 __global__ void __launch_bounds__(SEL_THREADS)
-k_sel_tile_counts(const double* errmax, long long n, const SelState* st, unsigned long long* tile_less, unsigned long long* tile_eq) {
+k_sel_tile_counts(const double* errmax, long long n, const SelState* st, unsigned long long* tile_less, unsigned long long* tile_eq,
+                  const long long* ctl) {
+    if (ctl && (ctl[4] | ctl[5])) return;
     const unsigned long long thr = st->prefix;
     const long long lo = (long long)blockIdx.x * SEL_TILE;
     unsigned less = 0, eq = 0;
@@ -584,7 +767,9 @@ k_sel_tile_counts(const double* errmax, long long n, const SelState* st, unsigne
 }
 
 __global__ void k_sel_tile_scan(unsigned long long* tile_less, unsigned long long* tile_eq, long long ntiles,
-                                unsigned long long* totals_out /*[2]: regions below the threshold key, regions equal to it*/) {
+                                unsigned long long* totals_out /*[2]: regions below the threshold key, regions equal to it*/,
+                                const SelState* st, long long* ctl, long long n) {
+    if (ctl && (ctl[4] | ctl[5])) return;
     // exclusive scans in place, one block, 256 threads
     __shared__ unsigned long long sh[2][256];
     __shared__ unsigned long long carry[2];
@@ -619,11 +804,19 @@ __global__ void k_sel_tile_scan(unsigned long long* tile_less, unsigned long lon
         totals_out[0] = carry[0];
         totals_out[1] = carry[1];
     }
+    if (threadIdx.x == 0 && ctl) {  // hand the batch to the rule kernel without a host round trip
+        ctl[0] = 2 * (long long)st->K;
+        ctl[1] = 1;
+        ctl[2] = n;
+        ctl[3] = (long long)st->K;
+        ctl[6] += (long long)st->ambiguous;
+    }
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_sel_compact(const double* errmax, long long n, const SelState* st, const unsigned long long* tile_less,
-              const unsigned long long* tile_eq, long long tie_take_arg, int* list) {
+              const unsigned long long* tile_eq, long long tie_take_arg, int* list, const long long* ctl) {
+    if (ctl && (ctl[4] | ctl[5])) return;
     // tie_take_arg < 0: take SelState::tie_take (single GPU); else this rank's share of the tied regions
     const unsigned long long thr = st->prefix, tie_take = tie_take_arg < 0 ? st->tie_take : (unsigned long long)tie_take_arg;
     // thread owns SEL_ITEMS CONSECUTIVE slots so that positions follow slot order
@@ -666,6 +859,404 @@ k_sel_compact(const double* errmax, long long n, const SelState* st, const unsig
         }
         less_before += is_less;
         eq_before += is_eq;
+    }
+}
+
+// ---- one cooperative launch per iteration: K5 + loop control + K3 (scalar integrands) ----------------
+// The whole host-free part of an iteration in ONE kernel, phases separated by grid-wide barriers
+// (cooperative launch, every CTA co-resident):
+//   A  every CTA reduces its contiguous chunk: partial sums of val/err per component, min/max errmax key
+//   B  (after barrier 1) every CTA redundantly adds the partials in CTA order -- identical bits in every
+//      CTA, no second barrier -- and takes the loop decisions: converged? pop everything? (control block)
+//   C  eight radix passes of the weighted select; each pass = per-warp shared-memory histograms flushed
+//      to that pass's own global histogram, one barrier, then every CTA redundantly walks the 256 buckets
+//      (same inputs, same result), so a pass costs one barrier
+//   D  stable compaction of the popped slots: CTA totals, one barrier, CTA offsets, compaction
+// = 10 barriers instead of 12 kernel launches.  The fdim > 1 path stops after B.
+namespace cg = cooperative_groups;
+
+struct IterParams {
+    PoolView pool;
+    int fdim, norm, do_select;
+    long long n, Kcap;
+    double absTol, relTol, band;
+    double* partial;             // [2f][G]
+    unsigned long long* blk;     // [3][G] min key, its slot, max key ; then [2][G] less / equal counts
+    long long* ctl;              // control block (see k_pool_stats)
+    SelState* st;                // final selection state (written by CTA 0)
+    unsigned long long* hcnt;    // [8][256], zero on entry
+    double* hsum;                // [8][256], zero on entry
+    int* list;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[SEL_THREADS];
+    __shared__ unsigned long long shk[SEL_THREADS], shs[SEL_THREADS], shm[SEL_THREADS];
+    __shared__ unsigned scnt[SEL_WARPS][256];
+    __shared__ double ssum[SEL_WARPS][256];
+    __shared__ unsigned long long pc[256];
+    __shared__ double ps[256];
+    __shared__ SelState lst;
+    __shared__ long long s_flags[2];
+    __shared__ unsigned s_nzm[8];
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, fdim = p.fdim;
+    // the per-pass histograms are cleared here; pass 0 accumulates only after the first grid barrier
+    if (p.do_select)
+        for (int q = b * SEL_THREADS + tid; q < 8 * 256; q += G * SEL_THREADS) {
+            p.hcnt[q] = 0ULL;
+            p.hsum[q] = 0.0;
+        }
+    const long long n = p.n;
+    const PoolView& pool = p.pool;
+    // ---- A: chunk partials -----------------------------------------------------------------------
+    const long long per = (n + G - 1) / G;
+    const long long lo = per * b;
+    long long hi = lo + per;
+    if (hi > n) hi = n;
+    for (int row = 0; row < 2 * fdim; ++row) {
+        const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
+        double s = 0.0;
+        for (long long i = lo + tid; i < hi; i += SEL_THREADS) s += src[i];
+        sh[tid] = s;
+        __syncthreads();
+        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) sh[tid] += sh[tid + w];
+            __syncthreads();
+        }
+        if (tid == 0) p.partial[(long long)row * G + b] = sh[0];
+        __syncthreads();
+    }
+    {
+        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+        for (long long i = lo + tid; i < hi; i += SEL_THREADS) {
+            const unsigned long long k = dbits(pool.errmax[i]);
+            if (k <= mn) {
+                mn = k;
+                ms = (unsigned long long)i;
+            }
+            mx = k > mx ? k : mx;
+        }
+        shk[tid] = mn;
+        shs[tid] = ms;
+        shm[tid] = mx;
+        __syncthreads();
+        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) {
+                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+                if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
+                    shk[tid] = k2;
+                    shs[tid] = s2;
+                }
+                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            p.blk[b] = shk[0];
+            p.blk[G + b] = shs[0];
+            p.blk[2 * G + b] = shm[0];
+        }
+    }
+    grid.sync();
+    // ---- B: totals and decisions, redundantly in every CTA --------------------------------------------
+    double* totals = (double*)(p.ctl + 16);  // CTA 0 publishes; every CTA keeps V, E for fdim == 1 in registers
+    double* minvec = totals + 2 * fdim;
+    double V = 0.0, E = 0.0;
+    for (int row = 0; row < 2 * fdim; ++row) {
+        double s = 0.0;
+        for (int i = tid; i < G; i += SEL_THREADS) s += __ldcg(&p.partial[(long long)row * G + i]);
+        sh[tid] = s;
+        __syncthreads();
+        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) sh[tid] += sh[tid + w];
+            __syncthreads();
+        }
+        if (row == 0) V = sh[0];
+        if (row == fdim) E = sh[0];
+        if (b == 0 && tid == 0) totals[row] = sh[0];
+        __syncthreads();
+    }
+    {
+        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+        for (int i = tid; i < G; i += SEL_THREADS) {
+            const unsigned long long k = __ldcg(&p.blk[i]), sl = __ldcg(&p.blk[G + i]), m2 = __ldcg(&p.blk[2 * G + i]);
+            if (k < mn || (k == mn && sl > ms)) {
+                mn = k;
+                ms = sl;
+            }
+            mx = m2 > mx ? m2 : mx;
+        }
+        shk[tid] = mn;
+        shs[tid] = ms;
+        shm[tid] = mx;
+        __syncthreads();
+        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
+            if (tid < w) {
+                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+                if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
+                    shk[tid] = k2;
+                    shs[tid] = s2;
+                }
+                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+            }
+            __syncthreads();
+        }
+    }
+    const long long argmin = (long long)shs[0];
+    if (fdim == 1) {
+        // scalar: every CTA decides on its own registers (no dependence on CTA 0's stores)
+        if (tid == 0) {
+            const double e_last = pool.err[argmin];
+            long long amb = 0;
+            const bool c0 = cub_converged(1, ScalarAcc{V, E}, p.absTol, p.relTol, p.norm);
+            const bool c1 = cub_converged(1, ScalarAcc{V, E * (1.0 + p.band)}, p.absTol, p.relTol, p.norm);
+            const bool c2 = cub_converged(1, ScalarAcc{V, E * (1.0 - p.band)}, p.absTol, p.relTol, p.norm);
+            if (c0 != c1 || c0 != c2) amb += 1;
+            bool all = false;
+            if (!c0) {
+                all = !cub_converged(1, ScalarAcc{V, e_last}, p.absTol, p.relTol, p.norm);
+                const bool a1 = !cub_converged(1, ScalarAcc{V, e_last + p.band * E}, p.absTol, p.relTol, p.norm);
+                const bool a2 = !cub_converged(1, ScalarAcc{V, e_last - p.band * E}, p.absTol, p.relTol, p.norm);
+                if (a1 != all || a2 != all) amb += 1;
+                if (n == 1) all = true;
+                all = all && p.Kcap >= n;
+            }
+            s_flags[0] = c0 ? 1 : 0;
+            s_flags[1] = all ? 1 : 0;
+            if (b == 0) {
+                minvec[0] = pool.val[argmin];
+                minvec[1] = e_last;
+                ((unsigned long long*)p.ctl)[8] = shk[0];
+                ((unsigned long long*)p.ctl)[9] = shm[0];
+                p.ctl[10] = argmin;
+                p.ctl[0] = all ? 2 * n : 0;
+                p.ctl[1] = 0;
+                p.ctl[2] = n;
+                p.ctl[3] = all ? n : 0;
+                p.ctl[4] = c0 ? 1 : 0;
+                p.ctl[5] = all ? 1 : 0;
+                p.ctl[6] = amb;
+            }
+        }
+        __syncthreads();
+    } else {
+        // vector integrands: CTA 0 alone publishes the decisions; the host continues (sort-based selection)
+        if (b == 0) {
+            for (int j = tid; j < fdim; j += SEL_THREADS) {
+                minvec[j] = pool.val[(long long)j * pool.cap + argmin];
+                minvec[fdim + j] = pool.err[(long long)j * pool.cap + argmin];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const double* tv = totals;
+                const double* te = totals + fdim;
+                long long amb = 0;
+                const bool c0 = cub_converged(fdim, BandAcc{tv, te, te, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                const bool c1 = cub_converged(fdim, BandAcc{tv, te, te, 1.0 + p.band, 0.0}, p.absTol, p.relTol, p.norm);
+                const bool c2 = cub_converged(fdim, BandAcc{tv, te, te, 1.0 - p.band, 0.0}, p.absTol, p.relTol, p.norm);
+                if (c0 != c1 || c0 != c2) amb += 1;
+                bool all = false;
+                if (!c0) {
+                    const double* le = minvec + fdim;
+                    all = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                    const bool a1 = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, p.band}, p.absTol, p.relTol, p.norm);
+                    const bool a2 = !cub_converged(fdim, BandAcc{tv, le, te, 1.0, -p.band}, p.absTol, p.relTol, p.norm);
+                    if (a1 != all || a2 != all) amb += 1;
+                    if (n == 1) all = true;
+                    all = all && p.Kcap >= n;
+                }
+                ((unsigned long long*)p.ctl)[8] = shk[0];
+                ((unsigned long long*)p.ctl)[9] = shm[0];
+                p.ctl[10] = argmin;
+                p.ctl[0] = all ? 2 * n : 0;
+                p.ctl[1] = 0;
+                p.ctl[2] = n;
+                p.ctl[3] = all ? n : 0;
+                p.ctl[4] = c0 ? 1 : 0;
+                p.ctl[5] = all ? 1 : 0;
+                p.ctl[6] = amb;
+            }
+        }
+        return;
+    }
+    if (s_flags[0] | s_flags[1]) return;  // converged, or the whole pool is popped (uniform over the grid)
+    if (!p.do_select) return;
+    // ---- C: weighted radix select ------------------------------------------------------------------
+    if (tid == 0) {
+        lst.prefix = lst.mask = lst.count_cum = lst.K = lst.tie_take = lst.ambiguous = 0ULL;
+        lst.P_cum = 0.0;
+    }
+    const unsigned lane = tid & 31u, w = tid >> 5;
+    const long long stride = (long long)G * SEL_THREADS;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int q = lane; q < 256; q += 32) {
+            scnt[w][q] = 0;
+            ssum[w][q] = 0.0;
+        }
+        __syncthreads();
+        const unsigned long long prefix = lst.prefix, mask = lst.mask;
+        unsigned cur = 0, run_c = 0;
+        double run_s = 0.0;
+        for (long long i0 = (long long)b * SEL_THREADS + tid; i0 < n; i0 += stride * SEL_UNROLL) {
+            unsigned long long k[SEL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) {
+                const long long i = i0 + u * stride;
+                k[u] = i < n ? ~dbits(pool.errmax[i]) : 0ULL;
+            }
+#pragma unroll
+            for (int u = 0; u < SEL_UNROLL; ++u) {
+                const long long i = i0 + u * stride;
+                if (i < n && (k[u] & mask) == prefix) {
+                    const unsigned d = (unsigned)(k[u] >> shift) & 255u;
+                    if (d != cur) {
+                        sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
+                        cur = d;
+                        run_c = 0;
+                        run_s = 0.0;
+                    }
+                    ++run_c;
+                    run_s += pool.err[i];
+                }
+            }
+        }
+        sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
+        __syncthreads();
+        {
+            unsigned c = 0;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < SEL_WARPS; ++q) {
+                c += scnt[q][tid];
+                s += ssum[q][tid];
+            }
+            if (c) {
+                atomicAdd(&p.hcnt[pass * 256 + tid], (unsigned long long)c);
+                atomicAdd(&p.hsum[pass * 256 + tid], s);
+            }
+        }
+        grid.sync();
+        {
+            const unsigned long long c = __ldcg(&p.hcnt[pass * 256 + tid]);
+            pc[tid] = c;
+            ps[tid] = __ldcg(&p.hsum[pass * 256 + tid]);
+            const unsigned m = __ballot_sync(0xffffffffu, c != 0ULL);
+            if (lane == 0) s_nzm[w] = m;
+        }
+        __syncthreads();
+        if (tid == 0)
+            sel_pick_body(&lst, pc, ps, s_nzm, shift, pass == 7, V, E, (unsigned long long)p.Kcap, p.absTol, p.relTol, p.norm, p.band);
+        __syncthreads();
+    }
+    // ---- D: stable compaction of the popped slots -----------------------------------------------------
+    const unsigned long long thr = lst.prefix, tie_take = lst.tie_take;
+    const long long ntiles = (n + SEL_TILE - 1) / SEL_TILE;
+    const long long tper = (ntiles + G - 1) / G;
+    const long long t_lo = tper * b;
+    long long t_hi = t_lo + tper;
+    if (t_hi > ntiles) t_hi = ntiles;
+    unsigned long long my_less = 0, my_eq = 0;
+    for (long long t = t_lo; t < t_hi; ++t) {
+        const long long base = t * SEL_TILE;
+#pragma unroll
+        for (int u = 0; u < SEL_ITEMS; ++u) {
+            const long long i = base + (long long)u * SEL_THREADS + tid;
+            if (i < n) {
+                const unsigned long long k = ~dbits(pool.errmax[i]);
+                my_less += k < thr;
+                my_eq += k == thr;
+            }
+        }
+    }
+    shk[tid] = my_less;
+    shs[tid] = my_eq;
+    __syncthreads();
+    for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+        if (tid < q) {
+            shk[tid] += shk[tid + q];
+            shs[tid] += shs[tid + q];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.blk[3 * G + b] = shk[0];
+        p.blk[4 * G + b] = shs[0];
+    }
+    grid.sync();
+    {
+        unsigned long long a = 0, c = 0;
+        for (int i = tid; i < b; i += SEL_THREADS) {
+            a += __ldcg(&p.blk[3 * G + i]);
+            c += __ldcg(&p.blk[4 * G + i]);
+        }
+        shk[tid] = a;
+        shs[tid] = c;
+        __syncthreads();
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) {
+                shk[tid] += shk[tid + q];
+                shs[tid] += shs[tid + q];
+            }
+            __syncthreads();
+        }
+    }
+    unsigned long long less_base = shk[0], eq_base = shs[0];
+    __syncthreads();
+    for (long long t = t_lo; t < t_hi; ++t) {
+        const long long i_lo = t * SEL_TILE + (long long)tid * SEL_ITEMS;  // SEL_ITEMS consecutive slots per thread
+        unsigned fl = 0, fe = 0, less = 0, eq = 0;
+#pragma unroll
+        for (int u = 0; u < SEL_ITEMS; ++u) {
+            const long long i = i_lo + u;
+            if (i < n) {
+                const unsigned long long k = ~dbits(pool.errmax[i]);
+                if (k < thr) {
+                    fl |= 1u << u;
+                    ++less;
+                } else if (k == thr) {
+                    fe |= 1u << u;
+                    ++eq;
+                }
+            }
+        }
+        unsigned* sl = (unsigned*)&scnt[0][0];
+        unsigned* se = sl + SEL_THREADS;
+        sl[tid] = less;
+        se[tid] = eq;
+        __syncthreads();
+        for (int o = 1; o < SEL_THREADS; o <<= 1) {
+            const unsigned ta = tid >= o ? sl[tid - o] : 0u, tb = tid >= o ? se[tid - o] : 0u;
+            __syncthreads();
+            sl[tid] += ta;
+            se[tid] += tb;
+            __syncthreads();
+        }
+        unsigned long long less_before = less_base + (sl[tid] - less);
+        unsigned long long eq_before = eq_base + (se[tid] - eq);
+        const unsigned tile_less = sl[SEL_THREADS - 1], tile_eq = se[SEL_THREADS - 1];
+#pragma unroll
+        for (int u = 0; u < SEL_ITEMS; ++u) {
+            const bool is_less = (fl >> u) & 1u, is_eq = (fe >> u) & 1u;
+            if (is_less || (is_eq && eq_before < tie_take)) {
+                const unsigned long long pos = less_before + (eq_before < tie_take ? eq_before : tie_take);
+                p.list[pos] = (int)(i_lo + u);
+            }
+            less_before += is_less;
+            eq_before += is_eq;
+        }
+        less_base += tile_less;
+        eq_base += tile_eq;
+        __syncthreads();
+    }
+    if (b == 0 && tid == 0) {
+        *p.st = lst;
+        p.ctl[0] = 2 * (long long)lst.K;
+        p.ctl[1] = 1;
+        p.ctl[2] = n;
+        p.ctl[3] = (long long)lst.K;
+        p.ctl[6] += (long long)lst.ambiguous;
     }
 }
 
@@ -761,12 +1352,12 @@ void pk_sel_init(const SelScratch& sc, cudaStream_t s) {
 int pk_sel_passes() { return 8; }
 // pass p decides bits [63 - 8p, 56 - 8p]; fuse_pick = 1: histogram + pick in one launch (single GPU)
 void pk_sel_pass(const PoolView& pool, long long n, const SelScratch& sc, int pass, int fuse_pick, const double* totals, long long Kcap,
-                 double absTol, double relTol, int norm, double band, cudaStream_t s) {
+                 double absTol, double relTol, int norm, double band, const long long* ctl, cudaStream_t s) {
     long long b = (n + (long long)SEL_THREADS * SEL_UNROLL - 1) / ((long long)SEL_THREADS * SEL_UNROLL);
     if (b > 148 * 8) b = 148 * 8;
     if (b < 1) b = 1;
     k_sel_pass<<<(unsigned)b, SEL_THREADS, 0, s>>>(pool.errmax, pool.err, n, (SelState*)sc.state, 56 - 8 * pass, pass == 7, sc.cnt, sc.sum,
-                                                  sc.ticket, fuse_pick, totals, (unsigned long long)Kcap, absTol, relTol, norm, band);
+                                                  sc.ticket, fuse_pick, totals, (unsigned long long)Kcap, absTol, relTol, norm, band, ctl);
 }
 void pk_sel_pick(const SelScratch& sc, int pass, const double* totals, long long Kcap, double absTol, double relTol, int norm,
                  double band, cudaStream_t s) {
@@ -774,23 +1365,32 @@ void pk_sel_pick(const SelScratch& sc, int pass, const double* totals, long long
                                         absTol, relTol, norm, band);
 }
 void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
-                        unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s) {
+                        unsigned long long* tile_eq, unsigned long long* totals_out, long long* ctl, cudaStream_t s) {
     const long long ntiles = pk_sel_tiles(n);
-    if (ntiles > 0) k_sel_tile_counts<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq);
-    k_sel_tile_scan<<<1, 256, 0, s>>>(tile_less, tile_eq, ntiles, totals_out);
+    if (ntiles > 0) k_sel_tile_counts<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq, ctl);
+    k_sel_tile_scan<<<1, 256, 0, s>>>(tile_less, tile_eq, ntiles, totals_out, (const SelState*)state, ctl, n);
 }
 void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
-                    const unsigned long long* tile_eq, long long tie_take, int* list, cudaStream_t s) {
+                    const unsigned long long* tile_eq, long long tie_take, int* list, const long long* ctl, cudaStream_t s) {
     const long long ntiles = pk_sel_tiles(n);
     if (ntiles > 0)
-        k_sel_compact<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq, tie_take, list);
+        k_sel_compact<<<(unsigned)ntiles, SEL_THREADS, 0, s>>>(pool.errmax, n, (const SelState*)state, tile_less, tile_eq, tie_take, list, ctl);
+}
+// One launch: totals, extreme keys, convergence test, select-all shortcut -> device control block.
+// scratch: partial [2f][G] doubles, blk [3][G] u64, ticket; the selection scratch header is cleared.
+void pk_pool_stats(const PoolView& pool, int fdim, long long n, double* partial, unsigned long long* blk, unsigned* ticket, long long* ctl,
+                   long long Kcap, double absTol, double relTol, int norm, double band, unsigned long long* sel_zero, int sel_zero_words,
+                   cudaStream_t s) {
+    const int G = pk_totals_blocks(n);
+    k_pool_stats<<<G, TOT_THREADS, 0, s>>>(pool, fdim, n, partial, blk, ticket, ctl, Kcap, absTol, relTol, norm, band, sel_zero, sel_zero_words);
 }
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s) {
-    pk_sel_init(sc, s);
-    for (int pass = 0; pass < 8; ++pass) pk_sel_pass(pool, n, sc, pass, 1, totals, Kcap, absTol, relTol, norm, band, s);
-    pk_sel_tile_counts(pool, n, sc.state, sc.tile_less, sc.tile_eq, nullptr, s);
-    pk_sel_compact(pool, n, sc.state, sc.tile_less, sc.tile_eq, -1, list, s);
+    // (the selection scratch header was cleared by k_pool_stats when ctl != nullptr)
+    if (!sc.ctl) pk_sel_init(sc, s);
+    for (int pass = 0; pass < 8; ++pass) pk_sel_pass(pool, n, sc, pass, 1, totals, Kcap, absTol, relTol, norm, band, sc.ctl, s);
+    pk_sel_tile_counts(pool, n, sc.state, sc.tile_less, sc.tile_eq, nullptr, sc.ctl, s);
+    pk_sel_compact(pool, n, sc.state, sc.tile_less, sc.tile_eq, -1, list, sc.ctl, s);
     return 8 + 3;
 }
 
@@ -834,6 +1434,43 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
                      cudaStream_t s) {
     if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank, perm);
 }
+
+// Cooperative launch of one whole iteration (everything but the rule kernel).  hist: [8][256] u64 then
+// [8][256] double, zeroed here.  Returns cudaSuccess or the launch error.
+static int g_coop_blocks_per_sm = -1;
+cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
+                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hist, int* list,
+                         int n_sms, cudaStream_t s) {
+    if (g_coop_blocks_per_sm < 0) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_iter_coop, SEL_THREADS, 0);
+        g_coop_blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    const int per_sm = g_coop_blocks_per_sm < 4 ? g_coop_blocks_per_sm : 4;
+    long long G = (n + (long long)SEL_THREADS * 16 - 1) / ((long long)SEL_THREADS * 16);
+    if (G > (long long)n_sms * per_sm) G = (long long)n_sms * per_sm;
+    if (G < 1) G = 1;
+    IterParams p;
+    p.pool = pool;
+    p.fdim = fdim;
+    p.norm = norm;
+    p.do_select = do_select;
+    p.n = n;
+    p.Kcap = Kcap;
+    p.absTol = absTol;
+    p.relTol = relTol;
+    p.band = band;
+    p.partial = partial;
+    p.blk = blk;
+    p.ctl = ctl;
+    p.st = (SelState*)state;
+    p.hcnt = (unsigned long long*)hist;
+    p.hsum = (double*)((unsigned char*)hist + 8 * 256 * 8);
+    p.list = list;
+    void* args[1] = {&p};
+    return cudaLaunchCooperativeKernel((const void*)k_iter_coop, dim3((unsigned)G), dim3(SEL_THREADS), args, 0, s);
+}
+int pk_iter_coop_max_blocks(int n_sms) { return n_sms * 4; }
 
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s) {
     k_dfma_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-6);

@@ -41,23 +41,33 @@ struct SelScratch {
     double* sum;                    // [256] directly after cnt (one all-gather ships both)
     unsigned long long* tile_less;  // [pk_sel_tiles(capacity)]
     unsigned long long* tile_eq;    // [pk_sel_tiles(capacity)]
+    long long* ctl;                 // device control block of the fused loop, or null
 };
+#define PK_CTL_WORDS 16  // 8-byte header words of the control block; totals[2f] and minvec[2f] follow
 #define PK_SEL_HIST_BYTES (256 * 16)
 int pk_sel_passes();
 void pk_sel_init(const SelScratch& sc, cudaStream_t s);
 void pk_sel_pass(const PoolView& pool, long long n, const SelScratch& sc, int pass, int fuse_pick, const double* totals, long long Kcap,
-                 double absTol, double relTol, int norm, double band, cudaStream_t s);
+                 double absTol, double relTol, int norm, double band, const long long* ctl, cudaStream_t s);
+void pk_pool_stats(const PoolView& pool, int fdim, long long n, double* partial, unsigned long long* blk, unsigned* ticket, long long* ctl,
+                   long long Kcap, double absTol, double relTol, int norm, double band, unsigned long long* sel_zero, int sel_zero_words,
+                   cudaStream_t s);
 void pk_sel_pick(const SelScratch& sc, int pass, const double* totals, long long Kcap, double absTol, double relTol, int norm,
                  double band, cudaStream_t s);
 void pk_sel_tile_counts(const PoolView& pool, long long n, const void* state, unsigned long long* tile_less,
-                        unsigned long long* tile_eq, unsigned long long* totals_out, cudaStream_t s);
+                        unsigned long long* tile_eq, unsigned long long* totals_out, long long* ctl, cudaStream_t s);
 void pk_sel_compact(const PoolView& pool, long long n, const void* state, const unsigned long long* tile_less,
-                    const unsigned long long* tile_eq, long long tie_take, int* list, cudaStream_t s);
+                    const unsigned long long* tile_eq, long long tie_take, int* list, const long long* ctl, cudaStream_t s);
 void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s);
 void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
                      cudaStream_t s);
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
+cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
+                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hist, int* list,
+                         int n_sms, cudaStream_t s);
+int pk_iter_coop_max_blocks(int n_sms);
+#define PK_COOP_HIST_BYTES (8 * 256 * 16)
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s);
 
 #endif

@@ -52,13 +52,16 @@ struct CubPoolView {
 //   mode 2 CHILDREN: same slot arithmetic as mode 1, but the child boxes were already written by
 //                    the stand-alone bisect kernel (pool_kernels.cu) -- used when several threads
 //                    share one region (fdim > 1), where the in-place update would race.
-// n_items is read from *n_items_dev when that pointer is non-null (device-resident loop control).
+// When `dyn` is non-null the launch is sized by the DEVICE (no host round trip between the selection
+// kernels and the rule kernel): dyn[0] = n_items, dyn[1] = 0 drops the list (pop-all iteration),
+// dyn[2] = base.  The host then launches a grid for the largest possible batch and CTAs beyond the actual
+// one retire at once.
 #define CUB_MODE_PLAIN 0
 #define CUB_MODE_BISECT 1
 #define CUB_MODE_CHILDREN 2
 struct CubWork {
     const int* list;
-    const long long* n_items_dev;
+    const long long* dyn;
     long long n_items;
     long long base;
     int mode;
@@ -83,8 +86,14 @@ struct CubTransform {
 
 #define CUB_GM_POINTS (1 + 4 * CUB_DIM + 2 * CUB_DIM * (CUB_DIM - 1) + (1 << CUB_DIM))
 
-__device__ __forceinline__ long long cub_n_items(const CubWork& w) {
-    return w.n_items_dev ? *w.n_items_dev : w.n_items;
+__device__ __forceinline__ CubWork cub_resolve(const CubWork& w) {
+    CubWork r = w;
+    if (w.dyn) {
+        r.n_items = w.dyn[0];
+        if (!w.dyn[1]) r.list = nullptr;
+        r.base = w.dyn[2];
+    }
+    return r;
 }
 
 __device__ __forceinline__ long long cub_item_slot(const CubWork& w, long long i) {
@@ -176,9 +185,11 @@ __device__ __forceinline__ void cub_eval_point(const F& fn, const CubTransform& 
 #define CUB_GM_MIN_BLOCKS 5
 #endif
 extern "C" __global__ void __launch_bounds__(128, CUB_GM_MIN_BLOCKS)
-cub_gm_scalar(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr) {
-    const long long n = cub_n_items(work);
+cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
+    const CubWork work = cub_resolve(work_in);
+    const long long n = work.n_items;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)blockIdx.x * blockDim.x >= n) return;  // device-sized launch: CTAs beyond the batch retire at once
     const bool active = i < n;
     double c[CUB_DIM], h[CUB_DIM];
 #pragma unroll
@@ -394,9 +405,11 @@ __device__ __forceinline__ double cub_gk15_node(int k, double c, double h) {
 // lanes of a warp hold consecutive regions and all stores are coalesced.  With fdim > 1 the host
 // uses mode CHILDREN (several threads share a region), with fdim == 1 the fused BISECT mode.
 extern "C" __global__ void __launch_bounds__(128)
-cub_gk_separable(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr) {
-    const long long n = cub_n_items(work);
+cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
+    const CubWork work = cub_resolve(work_in);
+    const long long n = work.n_items;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)blockIdx.x * blockDim.x >= n * CUB_FDIM) return;
     const bool active = t < n * CUB_FDIM;
     const long long i = active ? t % n : 0;
     const int j = active ? (int)(t / n) : 0;
@@ -513,7 +526,8 @@ __device__ __forceinline__ void cub_gm_point(int k, const double* c, const doubl
 #define CUB_FS ((CUB_FDIM) | 1)
 
 extern "C" __global__ void __launch_bounds__(256)
-cub_rule_staged(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr, int rpb) {
+cub_rule_staged(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr, int rpb) {
+    const CubWork work = cub_resolve(work_in);
     extern __shared__ double cub_smem[];
     double* sval = cub_smem;                                        // [rpb][P][FS]
     double* sc = sval + (long long)rpb * CUB_RULE_POINTS * CUB_FS;  // [rpb][DIM]
@@ -522,7 +536,7 @@ cub_rule_staged(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr, 
     double* serr = sdiff + rpb * CUB_DIM;                           // [rpb][FDIM]
     long long* sslot = (long long*)(serr + (long long)rpb * CUB_FDIM);  // [rpb]
 
-    const long long n = cub_n_items(work);
+    const long long n = work.n_items;
     const CUB_INTEGRAND fn(prm.v, CUB_FDIM);
     const int tid = threadIdx.x, nt = blockDim.x;
 
@@ -632,7 +646,8 @@ cub_rule_staged(CubPoolView pool, CubWork work, CubParams prm, CubTransform tr, 
 
 // Integrand alone at caller-supplied points x[dim][n] -> out[fdim][n] (bit-parity tests of detmath
 // and of the built-in families against the g++ build of the same header).
-extern "C" __global__ void cub_eval_points(const double* x, double* out, long long n, CubParams prm, CubTransform tr) {
+extern "C" __global__ void cub_eval_points(const double* x, double* out, long long n, const __grid_constant__ CubParams prm,
+                                           const __grid_constant__ CubTransform tr) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const CUB_INTEGRAND fn(prm.v, CUB_FDIM);
