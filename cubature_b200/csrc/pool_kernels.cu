@@ -562,9 +562,11 @@ __device__ __forceinline__ void sel_flush(unsigned* scnt, double* ssum, unsigned
 
 // Walks the 256 buckets of one pass (largest errmax first), accumulating the popped error until the
 // residual test passes inside a bucket or the pop budget runs out inside it; descends into that bucket.
-__device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, const double* ssum, const unsigned* nonzero /*[8] bit masks*/,
-                              int shift, int last, double V, double E, unsigned long long Kcap, double absTol, double relTol, int norm,
-                              double band) {
+// returns 1 when the batch size is final (last pass, or the chosen bucket holds a single region: then only
+// that region's complete key is still missing, see k_iter_coop), else 0
+__device__ int sel_pick_body(SelState* st, const unsigned long long* scnt, const double* ssum, const unsigned* nonzero /*[8] bit masks*/,
+                             int shift, int last, double V, double E, unsigned long long Kcap, double absTol, double relTol, int norm,
+                             double band, int early_exit = 0) {
     unsigned long long count_cum = st->count_cum;
     double P = st->P_cum;
     int chosen = -1;
@@ -585,7 +587,7 @@ __device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, cons
     }
     if (chosen < 0) {  // cannot happen for n >= 1
         st->K = 0;
-        return;
+        return 1;
     }
     const unsigned long long c_b = scnt[chosen];
     const double s_b = ssum[chosen];
@@ -593,7 +595,7 @@ __device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, cons
     st->mask |= 255ULL << shift;
     st->count_cum = count_cum;
     st->P_cum = P;
-    if (last) {
+    if (last || (early_exit && c_b == 1)) {
         // the bucket is a single key: c_b regions with identical errmax; each carries e = s_b / c_b
         const double e = s_b / (double)c_b;
         unsigned long long room = Kcap - count_cum;  // >= 1
@@ -618,7 +620,9 @@ __device__ void sel_pick_body(SelState* st, const unsigned long long* scnt, cons
         const bool a0 = cub_converged(1, ScalarAcc{V, rK + b}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rK - b}, absTol, relTol, norm);
         const bool a1 = cub_converged(1, ScalarAcc{V, rKm1 + b}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rKm1 - b}, absTol, relTol, norm);
         st->ambiguous = (a0 || a1) ? 1ULL : 0ULL;
+        return 1;
     }
+    return 0;
 }
 
 // One pass: histogram of the pool regions that match the decided prefix by the digit (key >> shift) & 255.
@@ -881,7 +885,7 @@ struct IterParams {
     long long n, Kcap;
     double absTol, relTol, band;
     double* partial;             // [2f][G]
-    unsigned long long* blk;     // [3][G] min key, its slot, max key ; then [2][G] less / equal counts
+    unsigned long long* blk;     // [3][G] min key, its slot, max key ; [2][G] less / equal counts ; [1] unique key
     long long* ctl;              // control block (see k_pool_stats)
     SelState* st;                // final selection state (written by CTA 0)
     unsigned long long* hcnt;    // [8][256], zero on entry
@@ -1132,13 +1136,18 @@ __global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
                 c += scnt[q][tid];
                 s += ssum[q][tid];
             }
-            if (c) {
+            if (G == 1) {  // one CTA holds the whole pool: no global histogram, no grid barrier
+                pc[tid] = c;
+                ps[tid] = s;
+                const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
+                if (lane == 0) s_nzm[w] = m;
+            } else if (c) {
                 atomicAdd(&p.hcnt[pass * 256 + tid], (unsigned long long)c);
                 atomicAdd(&p.hsum[pass * 256 + tid], s);
             }
         }
-        grid.sync();
-        {
+        if (G > 1) {
+            grid.sync();
             const unsigned long long c = __ldcg(&p.hcnt[pass * 256 + tid]);
             pc[tid] = c;
             ps[tid] = __ldcg(&p.hsum[pass * 256 + tid]);
@@ -1147,8 +1156,31 @@ __global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
         }
         __syncthreads();
         if (tid == 0)
-            sel_pick_body(&lst, pc, ps, s_nzm, shift, pass == 7, V, E, (unsigned long long)p.Kcap, p.absTol, p.relTol, p.norm, p.band);
+            s_flags[0] = sel_pick_body(&lst, pc, ps, s_nzm, shift, pass == 7, V, E, (unsigned long long)p.Kcap, p.absTol, p.relTol, p.norm,
+                                       p.band, 1);
         __syncthreads();
+        if (s_flags[0] && pass < 7) {
+            // the chosen bucket holds ONE region: the batch size is final, only the low bits of the threshold
+            // key are missing.  Whoever owns that region publishes its key (one more barrier instead of the
+            // remaining passes).
+            const unsigned long long prefix2 = lst.prefix, mask2 = lst.mask;
+            for (long long i = (long long)b * SEL_THREADS + tid; i < n; i += stride) {
+                const unsigned long long k = ~dbits(pool.errmax[i]);
+                if ((k & mask2) == prefix2) p.blk[5 * G] = k;
+            }
+            if (G > 1) {
+                __threadfence();
+                grid.sync();
+            } else {
+                __syncthreads();
+            }
+            if (tid == 0) {
+                lst.prefix = __ldcg(&p.blk[5 * G]);
+                lst.mask = ~0ULL;
+            }
+            __syncthreads();
+            break;
+        }
     }
     // ---- D: stable compaction of the popped slots -----------------------------------------------------
     const unsigned long long thr = lst.prefix, tie_take = lst.tie_take;
