@@ -539,6 +539,16 @@ struct LoopResult {
     int64_t num_eval = 0, num_regions = 0, iterations = 0, ambiguous = 0;
 };
 
+// state handed from the replicated (single-GPU style) phase to the sharded phase of a multi-GPU run
+struct LoopState {
+    long long N = 1;
+    int64_t numEval = 0;
+    double ops = 1.0;
+    bool handoff = false;
+};
+int integrate_device_fused(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, long long stop_at_regions = 0, LoopState* state_out = nullptr, long long cap_override = 0);
+
 void push_batch(cub_trace_t* tr, int64_t nR) {
     if (!tr) return;
     if (tr->batches && tr->n_batches < tr->batch_cap) tr->batches[tr->n_batches] = nR;
@@ -745,9 +755,11 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         const long long total = maxEval / (2 * P) + 8;
         cap = std::min(cap, std::max<long long>(total / R + total / (4 * R) + 1024, 4 * shard_min));
     }
-    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
-    int rc = set_root(S, pool);
-    if (rc != CUB_OK) return rc;
+    // replicated phase: every rank runs the single-GPU device-driven loop on a full copy until the pool is
+    // large enough to be dealt out (identical, deterministic kernels => identical pools on every rank)
+    LoopState st0;
+    int rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
+    if (rc != CUB_OK || !st0.handoff) return rc;  // finished (converged / maxEval) before sharding: result already complete
 
     SelectBuffers& sel = W.sel;
     DevBuf &d_partial = W.d_partial, &d_small = W.d_small;
@@ -765,24 +777,24 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     double* h_block = h_small.as<double>();                                // [R][blk] after the exchange
     unsigned long long* h_u64 = (unsigned long long*)(h_block + blk * R);  // scratch [8]
 
-    {
-        HostWork w{};
-        w.n_items = 1;
-        w.base = 0;
-        w.mode = MODE_PLAIN;
-        rc = S.launch_rule(pool.view(), w);
-        if (rc != CUB_OK) return rc;
-    }
-    long long N = 1;          // regions held by this rank
-    long long Nglobal = 1;    // regions of the whole partition
+    long long N = st0.N;          // regions held by this rank
+    long long Nglobal = st0.N;    // regions of the whole partition
     bool sharded = false;
-    int64_t numEval = P;
+    int64_t numEval = st0.numEval;
     bool conv = false;
-    double ops = 1.0;  // additions the reference's running sums have seen so far (rounding band)
+    double ops = st0.ops;  // additions the reference's running sums have seen so far (rounding band)
     std::vector<double> tmp_err(f), tot(2 * f), minvec(2 * f);
     const double eps = 2.220446049250313e-16;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    double t_stats = 0, t_select = 0, t_rule = 0, t_shard = 0;
+    int n_sel_iters = 0, n_iters = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
 
     while (numEval < maxEval || maxEval == 0) {
+        auto t_iter = now();
         if (R > 1 && !sharded && N >= shard_min) {
             // deal the replicated pool out: rank r keeps slots r, r+R, ...
             const long long n_local = cubature_cuda_shard_count(N, R, rank);
@@ -819,6 +831,8 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
             N = n_local;
             sharded = true;
+            t_shard += ms_since(t_iter);
+            t_iter = now();
         }
         const PoolView pv = pool.view();
         pk_totals(pv, f, N, d_partial.as<double>(), d_totals, S.stream);
@@ -865,6 +879,9 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             S.h2d_bytes += 16 * f;
         }
         if (!sharded) Nglobal = N;
+        t_stats += ms_since(t_iter);
+        t_iter = now();
+        ++n_iters;
         const double band = 4.0 * eps * std::sqrt(ops);
         const double* tv = tot.data();
         const double* te = tot.data() + f;
@@ -1008,6 +1025,9 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             cub_set_message(S.msg, "region pool exceeds 2^31 slots");
             return CUB_ERR_POOL_EXHAUSTED;
         }
+        if (list) ++n_sel_iters;
+        t_select += ms_since(t_iter);
+        t_iter = now();
         HostWork w{};
         w.list = list;
         w.n_items = 2 * K;
@@ -1015,6 +1035,8 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         w.mode = MODE_BISECT;
         rc = S.launch_rule(pool.view(), w);
         if (rc != CUB_OK) return rc;
+        if (timing) cudaStreamSynchronize(S.stream);
+        t_rule += ms_since(t_iter);
         N += K;
         Nglobal += Kglobal;
         numEval += 2 * P * Kglobal;
@@ -1048,6 +1070,9 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
         }
     }
     S.flush_rule_timer();
+    if (timing)
+        fprintf(stderr, "[cubature rank %d] sharded phase: %d iterations (%d with selection): shard %.2f ms, stats+exchange %.2f ms, select %.2f ms, rule %.2f ms\n",
+                rank, n_iters, n_sel_iters, t_shard, t_stats, t_select, t_rule);
     res->converged = conv ? 1 : 0;
     res->num_eval = numEval;
     res->num_regions = Nglobal;
@@ -1063,14 +1088,14 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
 // Then ONE small device->host copy tells the host how many regions were popped.  Integrands with
 // fdim > 1 use the same stats kernel and fall back to the sort-based selection when a batch has to be cut.
 int integrate_device_fused(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
-                           LoopResult* res) {
+                           LoopResult* res, long long stop_at_regions, LoopState* state_out, long long cap_override) {
     const int f = S.fdim;
     const int64_t P = S.P;
     cub_trace_t* trace = opt ? opt->trace : nullptr;
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;
-    long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
     CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
@@ -1109,6 +1134,13 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     const double eps = 2.220446049250313e-16;
 
     while (numEval < maxEval || maxEval == 0) {
+        if (stop_at_regions > 0 && N >= stop_at_regions) {  // multi-GPU: time to deal the pool out to the ranks
+            state_out->N = N;
+            state_out->numEval = numEval;
+            state_out->ops = ops;
+            state_out->handoff = true;
+            return CUB_OK;
+        }
         long long Kcap = N;
         if (maxEval > 0) {
             const int64_t room = maxEval - numEval;  // > 0 here
