@@ -211,7 +211,7 @@ class Cubature:
     @staticmethod
     def integrate_ex(integrand, xmin, xmax, relTol, absTol, norm=CubatureError.INDIVIDUAL, maxEval=0, transform=None,
                      select=Select.DEVICE, device=-1, pool_capacity=0, trace_regions=0, trace_batches=0, comm=None,
-                     shard_min_regions=0):
+                     shard_min_regions=0, strict_all=False):
         """-> (result[2][fdim], Stats, Trace or None)."""
         L = _ffi.lib()
         if xmin is None or len(xmin) == 0:
@@ -231,6 +231,7 @@ class Cubature:
         opt.pool_capacity = pool_capacity
         opt.comm = comm._h if comm is not None else None
         opt.shard_min_regions = shard_min_regions
+        opt.strict_all = 1 if strict_all else 0
         tr = None
         keep = []
         if trace_regions or trace_batches:

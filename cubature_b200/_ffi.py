@@ -35,7 +35,7 @@ class CubOptions(C.Structure):
         ("struct_size", C.c_int32),
         ("select", C.c_int32),
         ("device", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("strict_all", C.c_int32),
         ("pool_capacity", C.c_int64),
         ("trace", C.POINTER(CubTrace)),
         ("comm", C.c_void_p),

@@ -749,7 +749,10 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
-    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
+    // A sharded iteration costs about a millisecond of exchange and host round trips, a replicated one about
+    // 0.1 ms plus the redundant rule evaluations (2N regions at ~6e9/s): sharding pays off from a few million
+    // regions on, whatever the number of ranks.
+    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : std::max<long long>(32768LL * R, 1LL << 21);
     if (R > 1 && !(opt && opt->pool_capacity > 0) && maxEval > 0) {
         // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
         const long long total = maxEval / (2 * P) + 8;
@@ -808,7 +811,11 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             int* ia = sel.idxA.as<int>();
             int* ib = sel.idxB.as<int>();
             pk_sort_prepare(pool.view().errmax, N, ka, ia, d_u64 + 4, S.stream);
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            const unsigned long long vary0 = h_u64[0] ^ h_u64[1];  // digits shared by every key need no pass
             for (int shift = 0; shift < 64; shift += 8) {
+                if (((vary0 >> shift) & 0xffULL) == 0) continue;
                 pk_sort_pass(ka, ia, kb, ib, N, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
                              sel.binbase.as<unsigned long long>(), S.stream);
                 std::swap(ka, kb);
@@ -1344,7 +1351,7 @@ int64_t cubature_cuda_points_per_region(int dim) { return cub_points_per_region(
 int cubature_cuda_converged(int fdim, const double* val, const double* err, double absTol, double relTol, int norm) {
     if (fdim < 1 || !val || !err) return CUB_ERR_BAD_ARGS;
     if (std::isnan(relTol) && std::isnan(absTol)) return CUB_ERR_BAD_TOL;
-    if (norm < 0 || norm > 4) return CUB_ERR_BAD_NORM;
+    if ((norm & ~8) < 0 || (norm & ~8) > 4 || ((norm & 8) && (norm & 7) > 1)) return CUB_ERR_BAD_NORM;
     return cub_converged(fdim, VecAcc{val, err}, absTol, relTol, norm) ? 1 : 0;
 }
 
@@ -1465,6 +1472,7 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
     if (rc != CUB_OK) return rc;
     const int select = options ? options->select : CUB_SELECT_DEVICE;
     if (select != CUB_SELECT_DEVICE && select != CUB_SELECT_HEAP_EXACT) return CUB_ERR_BAD_ARGS;
+    if (options && options->strict_all && norm <= CUB_NORM_PAIRED) norm |= CUB_NORM_STRICT;  // section 8f-3 extension
     if (options && options->trace) {
         options->trace->n_batches = 0;
         options->trace->n_regions = 0;

@@ -920,8 +920,18 @@ __global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
     if (hi > n) hi = n;
     for (int row = 0; row < 2 * fdim; ++row) {
         const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
+        // same summation order as the plain loop (thread tid adds elements tid, tid+256, ... in order);
+        // the loads of four consecutive steps are issued together
         double s = 0.0;
-        for (long long i = lo + tid; i < hi; i += SEL_THREADS) s += src[i];
+        long long i = lo + tid;
+        for (; i + 3 * SEL_THREADS < hi; i += 4 * SEL_THREADS) {
+            const double a0 = src[i], a1 = src[i + SEL_THREADS], a2 = src[i + 2 * SEL_THREADS], a3 = src[i + 3 * SEL_THREADS];
+            s += a0;
+            s += a1;
+            s += a2;
+            s += a3;
+        }
+        for (; i < hi; i += SEL_THREADS) s += src[i];
         sh[tid] = s;
         __syncthreads();
         for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
@@ -933,7 +943,21 @@ __global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
     }
     {
         unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
-        for (long long i = lo + tid; i < hi; i += SEL_THREADS) {
+        long long i = lo + tid;
+        for (; i + 3 * SEL_THREADS < hi; i += 4 * SEL_THREADS) {
+            unsigned long long k[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) k[u] = dbits(pool.errmax[i + u * SEL_THREADS]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k[u] <= mn) {
+                    mn = k[u];
+                    ms = (unsigned long long)(i + u * SEL_THREADS);
+                }
+                mx = k[u] > mx ? k[u] : mx;
+            }
+        }
+        for (; i < hi; i += SEL_THREADS) {
             const unsigned long long k = dbits(pool.errmax[i]);
             if (k <= mn) {
                 mn = k;

@@ -51,6 +51,7 @@ extern "C" {
 #define CUB_NORM_L2 2
 #define CUB_NORM_L1 3
 #define CUB_NORM_LINF 4
+#define CUB_NORM_STRICT 8   /* flag for cubature_cuda_converged: INDIVIDUAL|STRICT, PAIRED|STRICT (see cub_options_t.strict_all) */
 
 /* ---- built-in integrand families (cubature_b200/csrc/integrands.h) ---------------------------- */
 #define CUB_FAMILY_GENZ_OSCILLATORY 1   /* params: a[dim], u[dim]               */
@@ -99,12 +100,13 @@ typedef struct cub_options {
     int32_t struct_size;    /* = sizeof(cub_options_t)                                              */
     int32_t select;         /* CUB_SELECT_*                                                         */
     int32_t device;         /* CUDA device ordinal; -1 = current device                             */
-    int32_t reserved0;
+    int32_t strict_all;     /* 1: INDIVIDUAL / PAIRED converge only when EVERY component (pair) meets a tolerance
+                               (what README.md:112-122 documents); 0: the reference's ANY semantics (Rule.java:172-213) */
     int64_t pool_capacity;  /* regions; 0 = derive from maxEval and free memory                     */
     cub_trace_t* trace;     /* NULL = no trace                                                      */
     cub_comm_t* comm;       /* NULL = single GPU; else shard the pool over comm's ranks (DEVICE mode)*/
     int64_t shard_min_regions; /* replicate the loop on every rank until the pool holds this many
-                                  regions, then shard (0 = default 32768 * nranks)                   */
+                                  regions, then shard (0 = default max(32768 * nranks, 2^21))                   */
 } cub_options_t;
 
 typedef struct cub_stats {

@@ -168,11 +168,44 @@ static double errMax(int fdim, const std::vector<ErrorEstimate>& ee) {  // Rule.
 }
 
 // Rule.java:162-279.  Returns -1 for "both tolerances NaN" (the Java code throws).
+// EXTENSION, not reference behaviour: norm | 8 on INDIVIDUAL / PAIRED requires EVERY
+// component (pair) to meet a tolerance, as README.md:112-122 documents and upstream C cubature implements.
 static int converged(int fdim, const std::vector<ErrorEstimate>& ee, double absTol, double relTol, int norm) {
     if (std::isnan(relTol) && std::isnan(absTol)) return -1;
     bool conv = false;
     int j;
-    switch (norm) {
+    if ((norm & 8) && (norm & 7) <= 1) {
+        conv = true;
+        if ((norm & 7) == 0) {
+            for (j = 0; j < fdim; ++j) {
+                bool cj = false;
+                if (!std::isnan(absTol)) cj |= ee[j].err < absTol;
+                if (!std::isnan(relTol)) cj |= ee[j].err < std::fabs(ee[j].val) * relTol;
+                conv &= cj;
+            }
+        } else {
+            for (j = 0; j + 1 < fdim; j += 2) {
+                double maxerr = ee[j].err > ee[j + 1].err ? ee[j].err : ee[j + 1].err;
+                double maxval = ee[j].val > ee[j + 1].val ? ee[j].val : ee[j + 1].val;
+                double serr = maxerr > 0 ? 1 / maxerr : 1;
+                double sval = maxval > 0 ? 1 / maxval : 1;
+                double err = std::sqrt((ee[j].err * serr) * (ee[j].err * serr) + (ee[j + 1].err * serr) * (ee[j + 1].err * serr)) * maxerr;
+                double val = std::sqrt((ee[j].val * sval) * (ee[j].val * sval) + (ee[j + 1].val * sval) * (ee[j + 1].val * sval)) * maxval;
+                bool cj = false;
+                if (!std::isnan(absTol)) cj |= err < absTol;
+                if (!std::isnan(relTol)) cj |= err < std::fabs(val) * relTol;
+                conv &= cj;
+            }
+            if (j < fdim) {
+                bool cj = false;
+                if (!std::isnan(absTol)) cj |= ee[j].err < absTol;
+                if (!std::isnan(relTol)) cj |= ee[j].err < std::fabs(ee[j].val) * relTol;
+                conv &= cj;
+            }
+        }
+        return conv ? 1 : 0;
+    }
+    switch (norm & 7) {
         case NORM_INDIVIDUAL:
             for (j = 0; j < fdim; ++j) {
                 if (!std::isnan(absTol)) conv |= ee[j].err < absTol;

@@ -126,11 +126,12 @@ def test_convergence_predicate_matches_oracle(cb, oracle):
         rel = [1e-3, NAN, 1e-6, 1e-1][(trial // 4) % 4]
         if ab != ab and rel != rel:
             continue
-        for norm in range(5):
+        for norm in (0, 1, 2, 3, 4, 8, 9):  # 8, 9: the strict-ALL extension of INDIVIDUAL / PAIRED (section 8f-3)
             a = L.cubature_cuda_converged(f, val.ctypes.data_as(dp), err.ctypes.data_as(dp), ab, rel, norm)
             b = oracle.converged(val, err, ab, rel, norm)
             assert a == b, (f, norm, ab, rel, val, err)
             n += 1
     assert n > 10000
     v = np.zeros(2)
+    assert L.cubature_cuda_converged(2, v.ctypes.data_as(dp), v.ctypes.data_as(dp), 1e-3, NAN, 10) == -4  # L2|strict: no such norm
     assert L.cubature_cuda_converged(2, v.ctypes.data_as(dp), v.ctypes.data_as(dp), NAN, NAN, 0) == -2

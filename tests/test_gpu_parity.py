@@ -320,3 +320,28 @@ def test_sharded_pool_matches_single_gpu(cb, R):
         key = lambda cc, hh: sorted(zip(map(tuple, cc.tolist()), map(tuple, hh.tolist())))
         union = key(np.concatenate([t.centers for t in parts]), np.concatenate([t.halfwidths for t in parts]))
         assert union == key(t1.centers, t1.halfwidths)
+
+
+def test_strict_all_option_matches_oracle_extension(cb, oracle):
+    """cub_options_t.strict_all (section 8f-3): every component must converge; parity with the oracle's extension."""
+    inf = float("inf")
+    for fam, dim, fdim, p, xmin, xmax, rel, norm, tr in [
+            (20, 2, 2, [0, 4], [0, 0], [1, 1], 1e-3, 0, None),
+            (20, 2, 3, [0, 4, 6], [0, 0], [1, 1], 1e-4, 1, None),
+            (31, 3, 8, [0.5, 1.0, 2.0, 3.0], [0] * 3, [inf] * 3, 1e-3, 1, [1, 1, 1]),
+            (30, 1, 16, [], [0], [2], 1e-10, 0, None)]:
+        o = oracle.integrate(fam, dim, fdim, p, xmin, xmax, rel, NAN, norm | 8, 3000000, transform=tr)
+        ig = cb.Integrand.builtin(fam, dim, fdim, p)
+        r, st, t = cb.Cubature.integrate_ex(ig, xmin, xmax, rel, NAN, norm, 3000000, transform=tr, select=cb.Select.HEAP_EXACT,
+                                            strict_all=True, trace_batches=4096)
+        assert cases.bit_equal(r[0], o.val) and cases.bit_equal(r[1], o.err)
+        assert (st.num_eval, st.num_regions, t.batches, bool(st.converged)) == (o.num_eval, o.num_regions, o.batches, o.converged)
+        r2, st2, t2 = cb.Cubature.integrate_ex(ig, xmin, xmax, rel, NAN, norm, 3000000, transform=tr, strict_all=True, trace_batches=4096)
+        if not st2.ambiguous_decisions and t2.batches == o.batches:
+            assert st2.num_eval == o.num_eval and np.allclose(r2[0], o.val, rtol=1e-12, atol=1e-300)
+        else:
+            assert bool(st2.converged) == o.converged and np.all(np.abs(r2[0] - o.val) <= r2[1] + o.err)
+    # the ANY semantics stay the default
+    ig = cb.Integrand.builtin(20, 2, 2, [0, 4])
+    r, st, _ = cb.Cubature.integrate_ex(ig, [0, 0], [1, 1], 1e-3, NAN, 0, 0)
+    assert st.num_regions == 1

@@ -141,3 +141,17 @@ def test_max_eval_and_edge_cases(oracle):
     # absTol as the stopping rule
     r = oracle.integrate(10, 2, 1, [1.0], [0, 0], [1, 1], NAN, 1e-7)
     assert r.converged and r.err[0] < 1e-7
+
+
+def test_strict_all_extension(oracle):
+    """Section 8f-3 (NOT reference behaviour): with norm | 8, INDIVIDUAL stops only when EVERY component meets the
+    tolerance (README.md:112-122), so the garbage second component of Appendix E.3 gets refined."""
+    any_ = oracle.integrate(20, 2, 2, [0, 4], [0, 0], [1, 1], 1e-3, NAN, 0)
+    all_ = oracle.integrate(20, 2, 2, [0, 4], [0, 0], [1, 1], 1e-3, NAN, 8)
+    assert any_.num_regions == 1 and all_.num_regions > 1
+    assert np.all(all_.err < np.abs(all_.val) * 1e-3)
+    assert all_.val[1] == pytest.approx(1.0, rel=2e-3)
+    # a single component: ANY == ALL
+    a = oracle.integrate(4, 3, 1, cases.genz_params("gaussian", 3), [0] * 3, [1] * 3, 1e-5, NAN, 0)
+    b = oracle.integrate(4, 3, 1, cases.genz_params("gaussian", 3), [0] * 3, [1] * 3, 1e-5, NAN, 8)
+    assert a.num_eval == b.num_eval and a.val[0] == b.val[0]
