@@ -74,6 +74,15 @@ def points_per_region(dim):
     return int(n)
 
 
+def rule_points(center, halfwidth):
+    """The rule points of one box in the reference's order -> [P][dim] (for plotting evaluation positions)."""
+    c = np.ascontiguousarray(center, dtype=np.float64)
+    h = np.ascontiguousarray(halfwidth, dtype=np.float64)
+    out = np.zeros((points_per_region(len(c)), len(c)))
+    _check(_ffi.lib().cubature_cuda_rule_points(len(c), _dp(c), _dp(h), _dp(out)))
+    return out
+
+
 class Integrand:
     """A device-side integrand plugin: dim inputs -> fdim outputs (Cubature.java:98-99, moved to the GPU)."""
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "cubature_cuda_strerror": (C.c_char_p, [C.c_int]),
     "cubature_cuda_points_per_region": (C.c_int64, [C.c_int]),
     "cubature_cuda_converged": (C.c_int, [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int]),
+    "cubature_cuda_rule_points": (C.c_int, [C.c_int, c_double_p, c_double_p, c_double_p]),
     "cubature_cuda_integrand_builtin": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "cubature_cuda_integrand_nvrtc": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_size_t,
                                                 C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),

@@ -1355,6 +1355,65 @@ int cubature_cuda_converged(int fdim, const double* val, const double* err, doub
     return cub_converged(fdim, VecAcc{val, err}, absTol, relTol, norm) ? 1 : 0;
 }
 
+int cubature_cuda_rule_points(int dim, const double* c, const double* h, double* pts) {
+    if (!c || !h || !pts) return CUB_ERR_BAD_ARGS;
+    if (dim < 1 || dim > CUB_MAX_DIM) return CUB_ERR_BAD_DIM;
+    auto put = [&](int64_t k, const std::vector<double>& x) {
+        for (int d = 0; d < dim; ++d) pts[k * dim + d] = x[(size_t)d];
+    };
+    std::vector<double> x(c, c + dim);
+    int64_t k = 0;
+    if (dim == 1) {  // RuleGaussKronrod_1d.java:60-84: centre, Gauss nodes 1,3,5, then Kronrod nodes 0,2,4,6
+        static const double xgk[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+                                      0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
+                                      0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+                                      0.207784955007898467600689403773245, 0.0};
+        pts[k++] = c[0];
+        for (int j = 1; j < 7; j += 2) {
+            const double w = h[0] * xgk[j];
+            pts[k++] = c[0] - w;
+            pts[k++] = c[0] + w;
+        }
+        for (int j = 0; j < 8; j += 2) {
+            const double w = h[0] * xgk[j];
+            pts[k++] = c[0] - w;
+            pts[k++] = c[0] + w;
+        }
+        return CUB_OK;
+    }
+    const double l2 = 0.3585685828003180919906451539079374954541, l4 = 0.9486832980505137995996680633298155601160,
+                 l5 = 0.6882472016116852977216287342936235251269;
+    put(k++, x);
+    for (int i = 0; i < dim; ++i) {  // Rule75GenzMalik.java:307-325
+        const double r2 = h[i] * l2, r4 = h[i] * l4;
+        x[(size_t)i] = c[i] - r2; put(k++, x);
+        x[(size_t)i] = c[i] + r2; put(k++, x);
+        x[(size_t)i] = c[i] - r4; put(k++, x);
+        x[(size_t)i] = c[i] + r4; put(k++, x);
+        x[(size_t)i] = c[i];
+    }
+    for (int i = 0; i < dim - 1; ++i) {  // Rule75GenzMalik.java:274-296
+        for (int j = i + 1; j < dim; ++j) {
+            const double ri = h[i] * l4, rj = h[j] * l4;
+            x[(size_t)i] = c[i] - ri; x[(size_t)j] = c[j] - rj; put(k++, x);
+            x[(size_t)i] = c[i] + ri; put(k++, x);
+            x[(size_t)j] = c[j] + rj; put(k++, x);
+            x[(size_t)i] = c[i] - ri; put(k++, x);
+            x[(size_t)j] = c[j];
+        }
+        x[(size_t)i] = c[i];
+    }
+    for (unsigned n = 0; n < (1u << dim); ++n) {  // Gray-code order, Rule75GenzMalik.java:237-269
+        const unsigned g = n ^ (n >> 1);
+        for (int d = 0; d < dim; ++d) {
+            const double r = h[d] * l5;
+            x[(size_t)d] = ((g >> d) & 1u) ? c[d] - r : c[d] + r;
+        }
+        put(k++, x);
+    }
+    return CUB_OK;
+}
+
 int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams, cub_integrand_t** out) {
     if (!out) return CUB_ERR_BAD_ARGS;
     *out = nullptr;

@@ -893,7 +893,7 @@ struct IterParams {
     int* list;
 };
 
-__global__ void __launch_bounds__(SEL_THREADS) k_iter_coop(IterParams p) {
+__global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[SEL_THREADS];
     __shared__ unsigned long long shk[SEL_THREADS], shs[SEL_THREADS], shm[SEL_THREADS];

@@ -141,6 +141,11 @@ int64_t cubature_cuda_points_per_region(int dim);
  * err[fdim]: returns 1 (converged), 0, or CUB_ERR_BAD_TOL / CUB_ERR_BAD_NORM.  Host-only utility. */
 int cubature_cuda_converged(int fdim, const double* val, const double* err, double absTol, double relTol, int norm);
 
+/* The rule points of one box in the reference's order (Rule75GenzMalik.java:237-326,
+ * RuleGaussKronrod_1d.java:60-84): points[P][dim] row-major, P = cubature_cuda_points_per_region(dim).  Host-only utility
+ * for plotting evaluation positions (the reference's examples/PlotEvalPositions.java) from a cub_trace_t region dump. */
+int cubature_cuda_rule_points(int dim, const double* center, const double* halfwidth, double* points);
+
 /* Built-in integrand family -> device plugin. */
 int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams,
                                     cub_integrand_t** out);

@@ -60,6 +60,7 @@ def main():
     out.append(record("genz_corner_d6_maxeval", 3, 6, 1, cases.genz_params("corner_peak", 6), [0] * 6, [1] * 6, 1e-12, NAN,
                       max_eval=3000000))
     out.append(record("oscvec_d1_f64_L2", 30, 1, 64, [], [0], [1], 1e-8, NAN, 2))
+    out.append(record("c2_oscvec_d1_f1024_L2", 30, 1, 1024, [], [0], [1], 1e-8, NAN, 2))   # BASELINE config C2
     out.append(record("oscvec_d1_f7_LINF", 30, 1, 7, [], [0], [3], 1e-9, NAN, 4))
     out.append(record("oscvec_d2_f5_L1", 30, 2, 5, [], [0, 0], [1, 2], 1e-6, NAN, 3))
     out.append(record("cexp_d3_f8_paired_semiinf", 31, 3, 8, [0.5, 1.0, 2.0, 3.0], [0] * 3, [inf] * 3, 1e-4, NAN, 1,

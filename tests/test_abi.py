@@ -135,3 +135,22 @@ def test_convergence_predicate_matches_oracle(cb, oracle):
     v = np.zeros(2)
     assert L.cubature_cuda_converged(2, v.ctypes.data_as(dp), v.ctypes.data_as(dp), 1e-3, NAN, 10) == -4  # L2|strict: no such norm
     assert L.cubature_cuda_converged(2, v.ctypes.data_as(dp), v.ctypes.data_as(dp), NAN, NAN, 0) == -2
+
+
+def test_rule_points_follow_the_reference_order(cb):
+    """Point order of SURVEY.md Appendix A (Rule75GenzMalik.java:237-326, RuleGaussKronrod_1d.java:60-84)."""
+    pts = cb.rule_points([0.0, 0.0, 0.0], [1.0, 2.0, 4.0])
+    l2, l4, l5 = 0.3585685828003180919906451539079374954541, 0.9486832980505137995996680633298155601160, 0.6882472016116852977216287342936235251269
+    assert pts.shape == (33, 3)
+    assert pts[0].tolist() == [0, 0, 0]
+    assert pts[1].tolist() == [-l2, 0, 0] and pts[2].tolist() == [l2, 0, 0] and pts[3].tolist() == [-l4, 0, 0] and pts[4].tolist() == [l4, 0, 0]
+    assert pts[5].tolist() == [0, -2 * l2, 0]
+    # (lambda4, lambda4, 0) orbit: (-,-) (+,-) (+,+) (-,+) for the pair (0,1)
+    assert [p[:2].tolist() for p in pts[13:17]] == [[-l4, -2 * l4], [l4, -2 * l4], [l4, 2 * l4], [-l4, 2 * l4]]
+    # Gray code: +++, -++, --+, +-+, +--, ---, -+-, ++-
+    signs = np.sign(pts[25:33]).astype(int).tolist()
+    assert signs == [[1, 1, 1], [-1, 1, 1], [-1, -1, 1], [1, -1, 1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1], [1, 1, -1]]
+    assert np.allclose(np.abs(pts[25:33]), [l5, 2 * l5, 4 * l5])
+    gk = cb.rule_points([0.5], [0.5])
+    assert gk.shape == (15, 1) and gk[0, 0] == 0.5 and gk[1, 0] < 0.5 < gk[2, 0]
+    assert abs(gk[7, 0] - (0.5 - 0.5 * 0.991455371120812639)) < 1e-16

@@ -345,3 +345,4 @@ def test_strict_all_option_matches_oracle_extension(cb, oracle):
     ig = cb.Integrand.builtin(20, 2, 2, [0, 4])
     r, st, _ = cb.Cubature.integrate_ex(ig, [0, 0], [1, 1], 1e-3, NAN, 0, 0)
     assert st.num_regions == 1
+
