@@ -201,6 +201,7 @@ def main():
         rule_ms.append(st.rule_ms)
         launches += st.gpu_launches
         regions = st.num_eval // P          # all ranks (global numEval)
+        iterations_last = st.iterations
         local_regions = st.regions_evaluated
         h2d += st.h2d_bytes
         d2h += st.d2h_bytes
@@ -230,6 +231,7 @@ def main():
     e2e = regions * steps / (tot_wall_ms * 1e-3)
     # rule kernel (cub_gm_scalar): regions per launch-set = this rank's share; time = summed launch durations
     rule_regions_per_s = (regions / world) * steps / (tot_rule_ms * 1e-3)
+    rule_launches_per_step = iterations_last + 1  # one fused bisect+rule launch per iteration, plus the root box
     achieved_tflops = rule_regions_per_s * F_REGION / 1e12
     peaks = {}
     try:
@@ -250,7 +252,10 @@ def main():
                 "ms_per_step": tot_wall_ms / steps},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "kernel": "cub_gm_scalar", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / fp64_peak, "traffic": None,
+                     "frac": achieved_tflops / fp64_peak,
+                     # DRAM bytes per average rule launch: 207 B per evaluated region measured with `ncu --set full`
+                     # (dram__bytes_read.sum + dram__bytes_write.sum of one 5.99e7-region launch, profiles/r01_summary.md)
+                     "traffic": 207.0 * regions / max(1, rule_launches_per_step),
                      "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                      "flops_per_region": F_REGION, "rule_kernel_ms_per_step": tot_rule_ms / steps,
                      "rule_regions_per_s_per_gpu": rule_regions_per_s,
