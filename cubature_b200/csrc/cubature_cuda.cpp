@@ -749,10 +749,9 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;  // sort keys/indices + prefix sums per region
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
-    // A sharded iteration costs about a millisecond of exchange and host round trips, a replicated one about
-    // 0.1 ms plus the redundant rule evaluations (2N regions at ~6e9/s): sharding pays off from a few million
-    // regions on, whatever the number of ranks.
-    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : std::max<long long>(32768LL * R, 1LL << 21);
+    // (measured on 4 and 8 B200: sharding later, at 2^21 regions, is slower -- ranking 2^21 regions for the
+    // deal costs more than the cheaper replicated iterations save)
+    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
     if (R > 1 && !(opt && opt->pool_capacity > 0) && maxEval > 0) {
         // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
         const long long total = maxEval / (2 * P) + 8;

@@ -106,7 +106,7 @@ typedef struct cub_options {
     cub_trace_t* trace;     /* NULL = no trace                                                      */
     cub_comm_t* comm;       /* NULL = single GPU; else shard the pool over comm's ranks (DEVICE mode)*/
     int64_t shard_min_regions; /* replicate the loop on every rank until the pool holds this many
-                                  regions, then shard (0 = default max(32768 * nranks, 2^21))                   */
+                                  regions, then shard (0 = default 32768 * nranks)                   */
 } cub_options_t;
 
 typedef struct cub_stats {
