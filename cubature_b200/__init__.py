@@ -282,6 +282,13 @@ def fp64_peak_tflops(device=-1):
     return t.value
 
 
+def fp64_peak_sustained_tflops(device=-1, window_ms=400.0):
+    """(burst, sustained) FP64 FMA peak: the DFMA probe launched back to back for window_ms (power-capped clocks)."""
+    b, s = C.c_double(), C.c_double()
+    _check(_ffi.lib().cubature_cuda_fp64_peak_sustained(device, float(window_ms), C.byref(b), C.byref(s)))
+    return b.value, s.value
+
+
 def bench_rule(integrand, xmin, xmax, n_regions, repeats=5):
     """Rule kernel alone on n_regions boxes resident in HBM -> (ms per launch, checksum)."""
     xmin = np.ascontiguousarray(xmin, dtype=np.float64)

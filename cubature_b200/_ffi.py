@@ -83,6 +83,7 @@ SIGNATURES = {
     "cubature_cuda_bench_rule": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p]),
     "cubature_cuda_release_workspace": (None, []),
     "cubature_cuda_fp64_peak": (C.c_int, [C.c_int, c_double_p, c_double_p]),
+    "cubature_cuda_fp64_peak_sustained": (C.c_int, [C.c_int, C.c_double, c_double_p, c_double_p]),
     "cubature_cuda_comm_unique_id": (C.c_int, [C.c_void_p]),
     "cubature_cuda_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cubature_cuda_shard_count": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),

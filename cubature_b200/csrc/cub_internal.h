@@ -45,6 +45,7 @@ struct RuleKernels {
     cudaKernel_t staged = nullptr;        // any
     cudaKernel_t eval_points = nullptr;
     int staged_max_smem = 0;
+    int gm_threads = 128;                 // block size gm_scalar was compiled for
 };
 
 struct cub_integrand {
@@ -66,11 +67,19 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
 
 // nccl_dyn.cpp
 struct cub_local_group;
+#define CUB_MAX_RANKS 16
+#define CUB_XBUF_BYTES (128 * 1024)
 struct cub_comm {
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0, device = 0;
     cub_local_group* local = nullptr;  // in-process (thread-per-rank) communicator, else NCCL
     unsigned long long local_key = 0;
+    // NVLink peer exchange (NCCL communicators only): every rank owns one exchange buffer in its HBM, mapped
+    // into all peers with CUDA IPC; the sharded iteration kernel publishes and gathers through these
+    // directly (pool_kernels.cu: k_iter_coop_sharded), so the refinement loop itself makes no NCCL call.
+    bool peer_ok = false;
+    void* xbuf[CUB_MAX_RANKS] = {nullptr};  // xbuf[rank] = own buffer, others = IPC mappings
+    unsigned long long seq = 1;             // next exchange sequence number (monotonic over the comm's life)
 };
 int cub_comm_allgather(cub_comm* comm, const void* dev_send, size_t bytes, void* dev_recv, cudaStream_t stream);
 

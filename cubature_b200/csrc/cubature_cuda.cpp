@@ -408,8 +408,9 @@ struct Session {
         cudaEventRecord(evr0, stream);
         cudaError_t e;
         if (dim >= 2 && fdim == 1) {
-            const unsigned grid = (unsigned)((work.n_items + 127) / 128);
-            e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(128), args, 0, stream);
+            const int threads = kern->gm_threads;  // the kernel's __launch_bounds__ (CUB_GM_THREADS)
+            const unsigned grid = (unsigned)((work.n_items + threads - 1) / threads);
+            e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(threads), args, 0, stream);
             ++launches;
         } else if (dim == 1 && (fdim == 1 || integ->separable)) {
             const long long threads = work.n_items * fdim;
@@ -1673,7 +1674,11 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
     }
     const int f = S.fdim;
     Pool& pool = S.ws->pool;
-    CUB_CUDA_CHECK(pool.alloc(dim, f, n_regions), S.msg);
+    // CUBATURE_BENCH_MODE=bisect: time the fused bisect + rule launch the adaptive loop uses (n_regions parents ->
+    // 2 n_regions children per launch, every launch halves the boxes again) instead of the plain evaluation
+    const char* bm = getenv("CUBATURE_BENCH_MODE");
+    const bool bisect = bm && strcmp(bm, "bisect") == 0 && f == 1 && dim >= 2;
+    CUB_CUDA_CHECK(pool.alloc(dim, f, bisect ? 2 * n_regions : n_regions), S.msg);
     // uniform slabs along dimension 0: region i covers [xmin0 + i*w, xmin0 + (i+1)*w] x the full box elsewhere
     {
         std::vector<double> row((size_t)n_regions);
@@ -1687,9 +1692,9 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
                     row[(size_t)i] = 0.5 * (lo + hi);
                 }
             }
-            CUB_CUDA_CHECK(cudaMemcpy(pool.center.as<double>() + (size_t)d * n_regions, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
+            CUB_CUDA_CHECK(cudaMemcpy(pool.center.as<double>() + (size_t)d * pool.cap, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
             for (int64_t i = 0; i < n_regions; ++i) row[(size_t)i] = d == 0 ? 0.5 * (hi - lo) / (double)n_regions : 0.5 * (hi - lo);
-            CUB_CUDA_CHECK(cudaMemcpy(pool.halfw.as<double>() + (size_t)d * n_regions, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
+            CUB_CUDA_CHECK(cudaMemcpy(pool.halfw.as<double>() + (size_t)d * pool.cap, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
         }
     }
     HostWork w{};
@@ -1700,13 +1705,18 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
     CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
     S.flush_rule_timer();
     S.rule_ms = 0.0;
+    if (bisect) {
+        w.n_items = 2 * n_regions;
+        w.base = n_regions;
+        w.mode = MODE_BISECT;
+    }
     for (int r = 0; r < repeats; ++r) {
         rc = S.launch_rule(pool.view(), w);
         if (rc != CUB_OK) return rc;
     }
     CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
     S.flush_rule_timer();
-    *ms_per_launch = S.rule_ms / repeats;
+    *ms_per_launch = S.rule_ms / repeats / (bisect ? 2.0 : 1.0);  // per n_regions evaluated
     if (checksum) {
         DevBuf part, tot;
         CUB_CUDA_CHECK(part.ensure((size_t)8 * 2 * f * 1184), S.msg);
@@ -1770,6 +1780,65 @@ int cubature_cuda_fp64_peak(int device, double* tflops, double* ms_out) {
     if (ms_out) *ms_out = best;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
+    cudaStreamDestroy(s);
+    return cudaGetLastError() == cudaSuccess ? CUB_OK : CUB_ERR_CUDA;
+}
+
+// The same probe run back to back for `window_ms`: a B200 at its 1000 W power cap lowers the SM clock under a sustained
+// FP64 load, so a rule kernel timed inside a long step is bounded by the SUSTAINED rate (the second half of the window),
+// not by the burst rate of a 10 ms probe.
+int cubature_cuda_fp64_peak_sustained(int device, double window_ms, double* tflops_burst, double* tflops_sustained) {
+    if (!tflops_burst || !tflops_sustained || !(window_ms > 0)) return CUB_ERR_BAD_ARGS;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return CUB_ERR_NO_DEVICE;
+    }
+    char msg[256];
+    if (device >= 0) CUB_CUDA_CHECK(cudaSetDevice(device), msg);
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t s;
+    CUB_CUDA_CHECK(cudaStreamCreate(&s), msg);
+    DevBuf out;
+    CUB_CUDA_CHECK(out.ensure(64), msg);
+    const int blocks = sms * 8, iters = 1 << 15;  // about 5 ms per launch
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    const int max_launches = 2048;
+    std::vector<cudaEvent_t> ev;
+    pk_dfma_peak(out.as<double>(), blocks, 1024, s);  // warm-up
+    cudaStreamSynchronize(s);
+    cudaEvent_t e0;
+    cudaEventCreate(&e0);
+    cudaEventRecord(e0, s);
+    ev.push_back(e0);
+    const auto t0 = std::chrono::steady_clock::now();
+    int n = 0;
+    while (n < max_launches) {
+        pk_dfma_peak(out.as<double>(), blocks, iters, s);
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        ++n;
+        if (n % 4 == 0) {  // keep at most a few launches queued ahead of the clock
+            cudaEventSynchronize(ev[(size_t)n - 2]);
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() >= window_ms) break;
+        }
+    }
+    cudaStreamSynchronize(s);
+    double best = 1e30;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[(size_t)i], ev[(size_t)i + 1]);
+        if (ms < best) best = ms;
+    }
+    float half = 0.f;
+    cudaEventElapsedTime(&half, ev[(size_t)n / 2], ev[(size_t)n]);
+    *tflops_burst = flops / (best * 1e-3) / 1e12;
+    *tflops_sustained = flops * (double)(n - n / 2) / (half * 1e-3) / 1e12;
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(s);
     return cudaGetLastError() == cudaSuccess ? CUB_OK : CUB_ERR_CUDA;
 }

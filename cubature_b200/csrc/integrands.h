@@ -68,15 +68,18 @@ struct GenzOscillatory {  // cos(2 pi u_0 + sum a_i x_i)
     DM_HD void eval(const double* x, double* f) const { f[0] = dm_cos(cub_dot2<DIM>(a, x, phase)); }
 };
 
-template <int DIM>
+template <int DIM, bool FAST = true>
 struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 / prod(...)
     static const bool kSeparable = false;
+    typedef GenzProductPeak<DIM, false> Exact;  // always IEEE division (rule_kernels.cuh: cub_fast_failed)
     double c[DIM], u[DIM];
+    mutable int bad;
     DM_HD GenzProductPeak(const double* p, int) {
         for (int i = 0; i < DIM; ++i) {
             c[i] = 1.0 / (p[i] * p[i]);
             u[i] = p[DIM + i];
         }
+        bad = 0;
     }
     DM_HD void eval(const double* x, double* f) const {
         double d0 = 1.0, d1 = 1.0;  // two interleaved product chains (even / odd coordinates)
@@ -88,20 +91,24 @@ struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 /
             double t = x[i] - u[i];
             d1 = d1 * dm_fma(t, t, c[i]);
         }
-        f[0] = 1.0 / (d0 * d1);
+        f[0] = FAST ? dm_rcp_flag(d0 * d1, &bad) : 1.0 / (d0 * d1);
     }
 };
 
-template <int DIM>
+template <int DIM, bool FAST = true>
 struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
     static const bool kSeparable = false;
+    typedef GenzCornerPeak<DIM, false> Exact;  // always IEEE division (rule_kernels.cuh: cub_fast_failed)
     double a[DIM];
+    mutable int bad;
     DM_HD GenzCornerPeak(const double* p, int) {
         for (int i = 0; i < DIM; ++i) a[i] = p[i];
+        bad = 0;
     }
     DM_HD void eval(const double* x, double* f) const {
         const double s = cub_dot2<DIM>(a, x, 1.0);
-        f[0] = 1.0 / CubPow<DIM + 1>::of(s);  // s^(d+1) by square-and-multiply (fixed association)
+        const double p = CubPow<DIM + 1>::of(s);  // s^(d+1) by square-and-multiply (fixed association)
+        f[0] = FAST ? dm_rcp_flag(p, &bad) : 1.0 / p;
     }
 };
 

@@ -134,12 +134,18 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     tu << "#define CUB_NPARAMS " << integ->params.size() << "\n";
     tu << "#define CUB_HAS_TRANSFORM " << (has_transform ? 1 : 0) << "\n";
     tu << "#define CUB_SEPARABLE " << (integ->separable ? 1 : 0) << "\n";
-    // CTAs per SM the scalar Genz-Malik kernel is compiled for (register budget 65536 / (128 * n)); measured on
-    // B200 (profiles/r01_tuning.md): rational integrands like 6 (80 registers), cos-heavy ones 4, the rest 5
+    // CTAs per SM the scalar Genz-Malik kernel is compiled for (register budget 65536 / (128 * n)); measured on B200
+    // (profiles/r01_summary.md, "power"): the rational families run best at 4 (128 registers, next to no spills: the
+    // local-memory traffic of the 5- and 6-CTA variants drives the board into its power cap under a sustained load)
     int min_blocks = 5;
-    if (integ->family == CUB_FAM_GENZ_CORNER_PEAK || integ->family == CUB_FAM_GENZ_PRODUCT_PEAK || integ->family == CUB_FAM_GENZ_GAUSSIAN) min_blocks = 6;
+    if (integ->family == CUB_FAM_GENZ_CORNER_PEAK || integ->family == CUB_FAM_GENZ_PRODUCT_PEAK) min_blocks = 4;
+    if (integ->family == CUB_FAM_GENZ_GAUSSIAN || integ->family == CUB_FAM_GENZ_DISCONTINUOUS) min_blocks = 6;
     if (integ->family == CUB_FAM_GENZ_OSCILLATORY) min_blocks = 4;
+    if (integ->family == CUB_FAM_GENZ_C0) min_blocks = 3;
     tu << "#ifndef CUB_GM_MIN_BLOCKS\n#define CUB_GM_MIN_BLOCKS " << min_blocks << "\n#endif\n";
+    // branch-free reciprocal fast path of the rational built-in families (detmath.h: dm_rcp_flag; the kernel re-evaluates a
+    // region with the IEEE division when an argument leaves the fast path's exact range)
+    tu << "#ifndef CUB_FAST_RCP\n#define CUB_FAST_RCP 1\n#endif\n";
     tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
     if (integ->family == CUB_FAM_USER) {
         tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";
@@ -251,7 +257,12 @@ int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, Rul
         if (log) *log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e);
         return CUB_ERR_CUDA;
     }
-    if (integ->dim >= 2 && integ->fdim == 1) cudaLibraryGetKernel(&k.gm_scalar, k.lib, "cub_gm_scalar");
+    if (integ->dim >= 2 && integ->fdim == 1) {
+        cudaLibraryGetKernel(&k.gm_scalar, k.lib, "cub_gm_scalar");
+        cudaFuncAttributes fa;
+        if (k.gm_scalar && cudaFuncGetAttributes(&fa, (const void*)k.gm_scalar) == cudaSuccess && fa.maxThreadsPerBlock >= 32)
+            k.gm_threads = fa.maxThreadsPerBlock;  // = __launch_bounds__(CUB_GM_THREADS, ..) of the compiled kernel
+    }
     if (integ->dim == 1 && (integ->fdim == 1 || integ->separable)) cudaLibraryGetKernel(&k.gk_separable, k.lib, "cub_gk_separable");
     cudaLibraryGetKernel(&k.staged, k.lib, "cub_rule_staged");
     cudaLibraryGetKernel(&k.eval_points, k.lib, "cub_eval_points");

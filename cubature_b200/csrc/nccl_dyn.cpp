@@ -173,6 +173,62 @@ int cubature_cuda_comm_init(const void* id, int nranks, int rank, int device, cu
             delete c;
             return CUB_ERR_NCCL;
         }
+        // NVLink peer exchange buffers (best effort: without them the driver falls back to NCCL all-gathers).
+        // CUBATURE_PEER_EXCHANGE=0 disables.
+        const char* env = getenv("CUBATURE_PEER_EXCHANGE");
+        if (nranks <= CUB_MAX_RANKS && !(env && env[0] == '0')) {
+            bool ok = true;
+            void* mine = nullptr;
+            cudaIpcMemHandle_t h;
+            cudaIpcMemHandle_t* d_handles = nullptr;
+            std::vector<cudaIpcMemHandle_t> all((size_t)nranks);
+            ok = ok && cudaMalloc(&mine, CUB_XBUF_BYTES) == cudaSuccess;
+            ok = ok && cudaMemset(mine, 0, CUB_XBUF_BYTES) == cudaSuccess;
+            ok = ok && cudaIpcGetMemHandle(&h, mine) == cudaSuccess;
+            ok = ok && cudaMalloc((void**)&d_handles, sizeof(h) * (size_t)(nranks + 1)) == cudaSuccess;
+            // every rank takes part in the all-gather even if its own setup failed (a zero handle then)
+            if (!ok) memset(&h, 0, sizeof h);
+            if (d_handles) {
+                cudaMemcpy(d_handles + nranks, &h, sizeof h, cudaMemcpyHostToDevice);
+                int rc2 = n->AllGather(d_handles + nranks, d_handles, sizeof h, /*ncclChar*/ 0, c->nccl_comm, (cudaStream_t)0);
+                ok = ok && rc2 == 0 && cudaDeviceSynchronize() == cudaSuccess;
+                ok = ok && cudaMemcpy(all.data(), d_handles, sizeof(h) * (size_t)nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+                cudaFree(d_handles);
+            }
+            cudaIpcMemHandle_t zero;
+            memset(&zero, 0, sizeof zero);
+            for (int r = 0; ok && r < nranks; ++r) {
+                if (memcmp(&all[(size_t)r], &zero, sizeof zero) == 0) ok = false;
+            }
+            for (int r = 0; ok && r < nranks; ++r) {
+                if (r == rank) {
+                    c->xbuf[r] = mine;
+                } else if (cudaIpcOpenMemHandle(&c->xbuf[r], all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    ok = false;
+                }
+            }
+            cudaGetLastError();
+            // all ranks must agree: exchange the outcome (min over ranks) through one more all-gather
+            int* d_ok = nullptr;
+            std::vector<int> oks((size_t)nranks, 0);
+            if (cudaMalloc((void**)&d_ok, sizeof(int) * (size_t)(nranks + 1)) == cudaSuccess) {
+                const int mine_ok = ok ? 1 : 0;
+                cudaMemcpy(d_ok + nranks, &mine_ok, sizeof(int), cudaMemcpyHostToDevice);
+                if (n->AllGather(d_ok + nranks, d_ok, sizeof(int), 0, c->nccl_comm, (cudaStream_t)0) == 0 && cudaDeviceSynchronize() == cudaSuccess)
+                    cudaMemcpy(oks.data(), d_ok, sizeof(int) * (size_t)nranks, cudaMemcpyDeviceToHost);
+                cudaFree(d_ok);
+            }
+            bool all_ok = true;
+            for (int r = 0; r < nranks; ++r) all_ok = all_ok && oks[(size_t)r] == 1;
+            c->peer_ok = all_ok;
+            if (!all_ok) {
+                for (int r = 0; r < nranks; ++r)
+                    if (r != rank && c->xbuf[r]) cudaIpcCloseMemHandle(c->xbuf[r]);
+                if (mine) cudaFree(mine);
+                for (int r = 0; r < nranks; ++r) c->xbuf[r] = nullptr;
+                cudaGetLastError();
+            }
+        }
     }
     *out = c;
     return CUB_OK;
@@ -205,6 +261,16 @@ int cubature_cuda_comm_init_local(uint64_t group_key, int nranks, int rank, int 
 
 void cubature_cuda_comm_free(cub_comm_t* comm) {
     if (!comm) return;
+    if (comm->peer_ok) {
+        for (int r = 0; r < comm->nranks; ++r) {
+            if (!comm->xbuf[r]) continue;
+            if (r == comm->rank)
+                cudaFree(comm->xbuf[r]);
+            else
+                cudaIpcCloseMemHandle(comm->xbuf[r]);
+        }
+        cudaGetLastError();
+    }
     if (comm->nccl_comm) nccl()->CommDestroy(comm->nccl_comm);
     if (comm->local) {
         std::lock_guard<std::mutex> lock(g_groups_mu);

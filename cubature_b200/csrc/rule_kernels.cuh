@@ -84,6 +84,14 @@ struct CubTransform {
     double shift[CUB_DIM];
 };
 
+// The always-exact variant of an integrand type: F::Exact where the family has a flagged fast path (integrands.h),
+// F itself otherwise.  Only cub_gm_scalar runs the fast variant (it checks the flag and re-evaluates).
+template <class F>
+__device__ auto cub_exact_probe(int) -> typename F::Exact;
+template <class F>
+__device__ F cub_exact_probe(long);
+typedef decltype(cub_exact_probe<CUB_INTEGRAND>(0)) CubExactIntegrand;
+
 #define CUB_GM_POINTS (1 + 4 * CUB_DIM + 2 * CUB_DIM * (CUB_DIM - 1) + (1 << CUB_DIM))
 
 __device__ __forceinline__ CubWork cub_resolve(const CubWork& w) {
@@ -180,24 +188,11 @@ __device__ __forceinline__ void cub_eval_point(const F& fn, const CubTransform& 
 #define CUB_E4 (25.0 / 729.0)
 
 #if CUB_FDIM == 1
-// K1, scalar integrand: one thread per region.
-#ifndef CUB_GM_MIN_BLOCKS
-#define CUB_GM_MIN_BLOCKS 5
-#endif
-extern "C" __global__ void __launch_bounds__(128, CUB_GM_MIN_BLOCKS)
-cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
-    const CubWork work = cub_resolve(work_in);
-    const long long n = work.n_items;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((long long)blockIdx.x * blockDim.x >= n) return;  // device-sized launch: CTAs beyond the batch retire at once
-    const bool active = i < n;
-    double c[CUB_DIM], h[CUB_DIM];
-#pragma unroll
-    for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
-    const long long slot = cub_load_item(pool, work, i, active, c, h);
-    if (!active) return;
-
-    const CUB_INTEGRAND fn(prm.v, 1);
+// One region of the scalar Genz-Malik rule: all P integrand values are consumed as they are produced, sums in
+// registers in reference order.  F is the integrand functor (fast or exact variant, see cub_fast_failed).
+template <class F>
+__device__ __forceinline__ void cub_gm_region(const F& fn, const CubTransform& tr, const double (&c)[CUB_DIM], const double (&h)[CUB_DIM],
+                                              double& result, double& err, int& split_out) {
     const double ratio = (CUB_L2 * CUB_L2) / (CUB_L4 * CUB_L4);
 
     double vol = 1.0;  // Hypercube.java:36-41
@@ -308,9 +303,74 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
     }
 
     // Rule75GenzMalik.java:163-167
-    const double result = vol * (CUB_W1 * val0 + CUB_W2 * sum2 + CUB_W3 * sum3 + CUB_W4 * sum4 + CUB_W5 * sum5);
+    result = vol * (CUB_W1 * val0 + CUB_W2 * sum2 + CUB_W3 * sum3 + CUB_W4 * sum4 + CUB_W5 * sum5);
     const double res5th = vol * (CUB_E1 * val0 + CUB_E2 * sum2 + CUB_E3 * sum3 + CUB_E4 * sum4);
-    const double err = dm_abs(res5th - result);
+    err = dm_abs(res5th - result);
+    split_out = split;
+}
+
+// Integrands may carry a branch-free fast path that is exact only on a stated argument range (detmath.h:
+// dm_rcp_flag); they record leaving it in a member `bad` and name their always-exact variant `Exact`.  The kernel
+// then re-evaluates that region with the exact variant (out of line: never fetched unless needed).
+template <class F>
+__device__ __forceinline__ auto cub_fast_failed(const F& f, int) -> decltype(f.bad != 0) { return f.bad != 0; }
+template <class F>
+__device__ __forceinline__ bool cub_fast_failed(const F&, long) { return false; }
+struct CubRegionResult {
+    double result, err;
+    int split;
+};
+template <class F, class E = typename F::Exact>
+__device__ __noinline__ CubRegionResult cub_gm_region_exact(const CubPoolView& pool, long long slot, const CubParams& prm,
+                                                            const CubTransform& tr, int) {
+    double c[CUB_DIM], h[CUB_DIM];
+#pragma unroll
+    for (int d = 0; d < CUB_DIM; ++d) {
+        c[d] = pool.center[(long long)d * pool.cap + slot];
+        h[d] = pool.halfw[(long long)d * pool.cap + slot];
+    }
+    const E fe(prm.v, 1);
+    CubRegionResult r;
+    cub_gm_region(fe, tr, c, h, r.result, r.err, r.split);
+    return r;
+}
+template <class F>
+__device__ __forceinline__ CubRegionResult cub_gm_region_exact(const CubPoolView&, long long, const CubParams&, const CubTransform&, long) {
+    return CubRegionResult();
+}
+
+// K1, scalar integrand: one thread per region.
+#ifndef CUB_GM_MIN_BLOCKS
+#define CUB_GM_MIN_BLOCKS 5
+#endif
+// (tried and dropped: per-thread coordinate tables in shared memory to raise occupancy -- slower at every
+//  CTA count, profiles/r01_summary.md)
+#ifndef CUB_GM_THREADS
+#define CUB_GM_THREADS 128
+#endif
+extern "C" __global__ void __launch_bounds__(CUB_GM_THREADS, CUB_GM_MIN_BLOCKS)
+cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
+    const CubWork work = cub_resolve(work_in);
+    const long long n = work.n_items;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)blockIdx.x * blockDim.x >= n) return;  // device-sized launch: CTAs beyond the batch retire at once
+    const bool active = i < n;
+    double c[CUB_DIM], h[CUB_DIM];
+#pragma unroll
+    for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
+    const long long slot = cub_load_item(pool, work, i, active, c, h);
+    if (!active) return;
+
+    const CUB_INTEGRAND fn(prm.v, 1);
+    double result, err;
+    int split;
+    cub_gm_region(fn, tr, c, h, result, err, split);
+    if (cub_fast_failed(fn, 0)) {  // an argument left the fast path's exact range: redo with IEEE division
+        const CubRegionResult r = cub_gm_region_exact<CUB_INTEGRAND>(pool, slot, prm, tr, 0);
+        result = r.result;
+        err = r.err;
+        split = r.split;
+    }
     double emax = 0.0;  // Rule.java:281-289
     if (err > emax) emax = err;
 
@@ -418,7 +478,7 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
     if (!active) return;
     const double c = cc[0], h = hh[0];
 
-    const CUB_INTEGRAND fn(prm.v, CUB_FDIM);
+    const CubExactIntegrand fn(prm.v, CUB_FDIM);
     double q[15];
 #pragma unroll
     for (int k = 0; k < 15; ++k) {
@@ -537,7 +597,7 @@ cub_rule_staged(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPa
     long long* sslot = (long long*)(serr + (long long)rpb * CUB_FDIM);  // [rpb]
 
     const long long n = work.n_items;
-    const CUB_INTEGRAND fn(prm.v, CUB_FDIM);
+    const CubExactIntegrand fn(prm.v, CUB_FDIM);
     const int tid = threadIdx.x, nt = blockDim.x;
 
     for (long long first = (long long)blockIdx.x * rpb; first < n; first += (long long)gridDim.x * rpb) {
@@ -650,7 +710,7 @@ extern "C" __global__ void cub_eval_points(const double* x, double* out, long lo
                                            const __grid_constant__ CubTransform tr) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const CUB_INTEGRAND fn(prm.v, CUB_FDIM);
+    const CubExactIntegrand fn(prm.v, CUB_FDIM);
     double t[CUB_DIM];
 #pragma unroll
     for (int d = 0; d < CUB_DIM; ++d) t[d] = x[(long long)d * n + i];

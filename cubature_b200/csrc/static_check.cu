@@ -16,4 +16,7 @@
 #ifndef CUB_INTEGRAND
 #define CUB_INTEGRAND GenzCornerPeak<CUB_DIM>
 #endif
+#ifndef CUB_FAST_RCP
+#define CUB_FAST_RCP 1
+#endif
 #include "rule_kernels.cuh"

@@ -194,6 +194,9 @@ void cubature_cuda_release_workspace(void);
 
 /* Measured FP64 FMA peak of the current device (dependent-chain DFMA microbenchmark), TFLOP/s. */
 int cubature_cuda_fp64_peak(int device, double* tflops, double* ms);
+/* The same probe launched back to back for window_ms: burst = best single launch, sustained = rate over the second half of
+ * the window (the SM clock drops under a sustained FP64 load once the board reaches its power cap). */
+int cubature_cuda_fp64_peak_sustained(int device, double window_ms, double* tflops_burst, double* tflops_sustained);
 
 /* Multi-GPU: one rank per process (or per thread).  Rank 0 creates the id and ships the 128 bytes to
  * the other ranks by any means (torch.distributed, MPI, a file); every rank then calls comm_init. */
