@@ -241,6 +241,8 @@ struct SelectBuffers {
     cudaError_t ensure_scalar(long long n) {  // fdim == 1 select path: list, tile counters, state
         cudaError_t e;
         if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
+        if ((e = keysA.ensure((size_t)8 * n)) != cudaSuccess) return e;  // candidate keys / slots of the cooperative select
+        if ((e = idxB.ensure((size_t)4 * n)) != cudaSuccess) return e;
         if ((e = small.ensure(512 + PK_COOP_HIST_BYTES)) != cudaSuccess) return e;
         if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
         return cudaSuccess;
@@ -1112,7 +1114,7 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     PinnedBuf& h_small = W.h_small;
     const int G = 1184;
     const size_t ctl_words = PK_CTL_WORDS + (size_t)4 * f;
-    CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * 5 * G), S.msg);
+    CUB_CUDA_CHECK(d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * (5 * G + 8)), S.msg);
     CUB_CUDA_CHECK(d_small.ensure(ctl_words * 8 + 256), S.msg);
     CUB_CUDA_CHECK(h_small.ensure(ctl_words * 8 + 256), S.msg);
     double* d_part = d_partial.as<double>();
@@ -1124,7 +1126,10 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     const double* h_totals = (const double*)(h_ctl + PK_CTL_WORDS);
     unsigned long long* h_u64 = (unsigned long long*)(h_ctl + ctl_words) + 8;
     CUB_CUDA_CHECK(cudaMemsetAsync(d_small.p, 0, ctl_words * 8 + 256, S.stream), S.msg);
-    CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);  // selection scratch header is cleared by the stats kernel
+    CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+    // both histogram sets of the cooperative kernel start out zero; launch k then clears the set of launch k + 1
+    CUB_CUDA_CHECK(cudaMemsetAsync(sel.small.p, 0, 512 + PK_COOP_HIST_BYTES, S.stream), S.msg);
+    int coop_parity = 0;
 
     {
         HostWork w{};
@@ -1175,7 +1180,8 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
         // ONE cooperative launch: totals, loop decisions and (scalar integrands) the whole batch selection
         {
             cudaError_t e = pk_iter_coop(pv, f, N, Kcap, absTol, relTol, norm, band, f == 1 ? 1 : 0, d_part, d_blk, d_ctl, sc.state,
-                                         (unsigned char*)sc.state + 512, sel.idxA.as<int>(), S.n_sms, S.stream);
+                                         (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
+                                         sel.idxA.as<int>(), S.n_sms, S.stream);
             if (e != cudaSuccess) {
                 cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
                 return CUB_ERR_CUDA;
@@ -1295,7 +1301,8 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     if (!have_totals) {  // stopped by maxEval: K5 over the final pool
         SelScratch sc = sel.scratch(pool.cap);
         cudaError_t e = pk_iter_coop(pool.view(), f, N, N, absTol, relTol, norm, 0.0, 0, d_part, d_blk, d_ctl, sc.state,
-                                     (unsigned char*)sc.state + 512, sel.idxA.as<int>(), S.n_sms, S.stream);
+                                     (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
+                                     sel.idxA.as<int>(), S.n_sms, S.stream);
         if (e != cudaSuccess) {
             cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
             return CUB_ERR_CUDA;

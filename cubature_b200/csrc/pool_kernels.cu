@@ -868,16 +868,29 @@ k_sel_compact(const double* errmax, long long n, const SelState* st, const unsig
 
 // ---- one cooperative launch per iteration: K5 + loop control + K3 (scalar integrands) ----------------
 // The whole host-free part of an iteration in ONE kernel, phases separated by grid-wide barriers
-// (cooperative launch, every CTA co-resident):
-//   A  every CTA reduces its contiguous chunk: partial sums of val/err per component, min/max errmax key
+// (cooperative launch, every CTA co-resident).  Every CTA owns one contiguous chunk of the pool.
+//   A  chunk partial sums of val/err per component, min/max errmax key, and (scalar integrands) the level-0
+//      histogram of the weighted select (top 8 key bits), fused into the same read
 //   B  (after barrier 1) every CTA redundantly adds the partials in CTA order -- identical bits in every
 //      CTA, no second barrier -- and takes the loop decisions: converged? pop everything? (control block)
-//   C  eight radix passes of the weighted select; each pass = per-warp shared-memory histograms flushed
-//      to that pass's own global histogram, one barrier, then every CTA redundantly walks the 256 buckets
-//      (same inputs, same result), so a pass costs one barrier
-//   D  stable compaction of the popped slots: CTA totals, one barrier, CTA offsets, compaction
-// = 10 barriers instead of 12 kernel launches.  The fdim > 1 path stops after B.
+//   C  weighted radix select, coarse to fine.  key = ~bits(errmax); digits: 8 bits, then 11 bits per level.
+//      Level 1 and level 2 stream the chunk again (8 B per region); the level-2 scan also copies the regions
+//      that match the 19 key bits decided so far (about 0.2 % of the pool) into a candidate list and counts
+//      the regions that are certainly popped; all further levels, and the per-CTA offsets of the compaction,
+//      only touch the candidates.  After each level's barrier every CTA picks the bucket redundantly with a
+//      block-wide prefix scan over the buckets (no serial walk).
+//   D  stable compaction of the popped slots (one more read of the chunk, 4 B written per popped region)
+// HBM traffic per active region and iteration: 16 B (A) + 8 B + 8 B (C) + 12 B (D) instead of one 8 B read per
+// radix pass (8) plus two compaction reads.  For scalar integrands errmax is derived from err (errmax ==
+// max(0, err) bit for bit in every rule kernel, Rule.java:281-289), so errmax[] is not read at all.
+// The fdim > 1 path stops after B.
 namespace cg = cooperative_groups;
+
+constexpr int SEL_LEVELS = 7;
+constexpr int SEL_LB = 2048;  // buckets of levels 1..5
+__device__ __forceinline__ int sel_shift(int level) { return level == 0 ? 56 : (level <= 5 ? 56 - 11 * level : 0); }
+__device__ __forceinline__ int sel_nbuckets(int level) { return level == 0 ? 256 : (level <= 5 ? SEL_LB : 2); }
+__device__ __forceinline__ unsigned long long sel_key_of_err(double e) { return ~dbits(e > 0.0 ? e : 0.0); }
 
 struct IterParams {
     PoolView pool;
@@ -885,64 +898,240 @@ struct IterParams {
     long long n, Kcap;
     double absTol, relTol, band;
     double* partial;             // [2f][G]
-    unsigned long long* blk;     // [3][G] min key, its slot, max key ; [2][G] less / equal counts ; [1] unique key
+    unsigned long long* blk;     // [3][G] min key, its slot, max key ; [2][G] less / equal counts ; [5G] unique key
     long long* ctl;              // control block (see k_pool_stats)
     SelState* st;                // final selection state (written by CTA 0)
-    unsigned long long* hcnt;    // [8][256], zero on entry
-    double* hsum;                // [8][256], zero on entry
+    unsigned long long* hset;    // this launch's histogram set (PK_COOP_SET_WORDS words, zero on entry)
+    unsigned long long* hzero;   // the other set: cleared by this launch for the next one
+    unsigned long long* cand_key;  // [n] candidates of the level-2 scan
+    int* cand_idx;                 // [n]
     int* list;
 };
+// histogram set layout (8-byte words): cnt[SEL_LEVELS][SEL_LB] | sum[SEL_LEVELS][SEL_LB] | misc[8] ([0] candidate count)
+__device__ __forceinline__ unsigned long long* set_cnt(unsigned long long* set, int level) { return set + (size_t)level * SEL_LB; }
+__device__ __forceinline__ double* set_sum(unsigned long long* set, int level) {
+    return (double*)(set + (size_t)SEL_LEVELS * SEL_LB) + (size_t)level * SEL_LB;
+}
+__device__ __forceinline__ unsigned long long* set_misc(unsigned long long* set) { return set + (size_t)2 * SEL_LEVELS * SEL_LB; }
+
+// Block-wide pick of one level (all SEL_THREADS threads): the first bucket (ascending key = descending errmax)
+// at which the pop budget runs out or the residual test passes, found with a prefix scan over the buckets.
+// pc / ps: this level's global histogram staged in shared memory.  Returns 1 when the batch size is final
+// (last level, or the chosen bucket holds a single region: then only that region's full key is still missing).
+__device__ int sel_pick_parallel(SelState* lst, const unsigned long long* pc, const double* ps, int NB, int shift, int last, double V, double E,
+                                 unsigned long long Kcap, double absTol, double relTol, int norm, double band, double* sh,
+                                 unsigned long long* shk, unsigned long long* shs, double* s_dbl /*[2]*/, long long* s_ll /*[2]*/) {
+    const int tid = threadIdx.x;
+    const int per_t = NB >= SEL_THREADS ? NB / SEL_THREADS : 1;
+    const int first = tid * per_t;
+    const unsigned long long count_cum = lst->count_cum;
+    const double P_cum = lst->P_cum;
+    unsigned long long c_loc[8];
+    double s_loc[8];
+    unsigned long long ct = 0;
+    double stt = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < per_t && first + j < NB) {
+            ct += pc[first + j];
+            stt += ps[first + j];
+        }
+        c_loc[j] = ct;
+        s_loc[j] = stt;
+    }
+    __syncthreads();  // everybody has read lst
+    shk[tid] = ct;
+    sh[tid] = stt;
+    __syncthreads();
+    for (int o = 1; o < SEL_THREADS; o <<= 1) {  // inclusive scan over the threads, fixed order
+        const unsigned long long ta = tid >= o ? shk[tid - o] : 0ULL;
+        const double tb = tid >= o ? sh[tid - o] : 0.0;
+        __syncthreads();
+        shk[tid] += ta;
+        if (tid >= o) sh[tid] = tb + sh[tid];
+        __syncthreads();
+    }
+    const unsigned long long c_off = shk[tid] - ct;
+    const double s_off = tid > 0 ? sh[tid - 1] : 0.0;
+    unsigned long long first_stop = ~0ULL, last_nz = 0ULL;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < per_t && first + j < NB) {
+            const unsigned long long c = pc[first + j];
+            if (c) {
+                last_nz = (unsigned long long)(first + j) + 1ULL;
+                const unsigned long long Cincl = count_cum + c_off + c_loc[j];
+                const double Sincl = P_cum + (s_off + s_loc[j]);
+                const bool stop = Cincl >= Kcap || cub_converged(1, ScalarAcc{V, E - Sincl}, absTol, relTol, norm);
+                if (stop && first_stop == ~0ULL) first_stop = (unsigned long long)(first + j);
+            }
+        }
+    }
+    __syncthreads();
+    shk[tid] = first_stop;
+    shs[tid] = last_nz;
+    __syncthreads();
+    for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+        if (tid < q) {
+            if (shk[tid + q] < shk[tid]) shk[tid] = shk[tid + q];
+            if (shs[tid + q] > shs[tid]) shs[tid] = shs[tid + q];
+        }
+        __syncthreads();
+    }
+    const unsigned long long any_stop = shk[0], nz = shs[0];
+    __syncthreads();
+    if (nz == 0ULL) {  // cannot happen for n >= 1
+        if (tid == 0) lst->K = 0;
+        __syncthreads();
+        return 1;
+    }
+    const int chosen = any_stop != ~0ULL ? (int)any_stop : (int)(nz - 1ULL);
+    if (chosen >= first && chosen < first + per_t) {  // the owner publishes the descent
+        const int j = chosen - first;
+        unsigned long long c_prev = 0;
+        double s_prev = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q == j - 1) {
+                c_prev = c_loc[q];
+                s_prev = s_loc[q];
+            }
+        lst->prefix |= (unsigned long long)chosen << shift;
+        lst->mask |= (unsigned long long)(NB - 1) << shift;
+        lst->count_cum = count_cum + c_off + c_prev;
+        lst->P_cum = j > 0 || tid > 0 ? P_cum + (s_off + s_prev) : P_cum;
+        s_ll[0] = (long long)pc[chosen];
+        s_dbl[0] = ps[chosen];
+    }
+    __syncthreads();
+    const unsigned long long c_b = (unsigned long long)s_ll[0];
+    int fin = 0;
+    if (last || c_b == 1ULL) {
+        fin = 1;
+        if (tid == 0) {
+            // the bucket is a single key: c_b regions with identical errmax; each carries e = s_b / c_b
+            const double s_b = s_dbl[0], P = lst->P_cum;
+            const unsigned long long cc = lst->count_cum;
+            const double e = s_b / (double)c_b;
+            const unsigned long long room = Kcap - cc;  // >= 1
+            const unsigned long long mmax = c_b < room ? c_b : room;
+            unsigned long long lo = 1, hi = mmax;  // smallest m in [1, mmax] whose residual passes (monotone), else mmax
+            if (cub_converged(1, ScalarAcc{V, E - (P + (double)mmax * e)}, absTol, relTol, norm)) {
+                while (lo < hi) {
+                    const unsigned long long mid = lo + (hi - lo) / 2;
+                    if (cub_converged(1, ScalarAcc{V, E - (P + (double)mid * e)}, absTol, relTol, norm))
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+            } else {
+                lo = mmax;
+            }
+            lst->tie_take = lo;
+            lst->K = cc + lo;
+            // sensitivity of the decision to the rounding of the reference's running sums
+            const double rK = E - (P + (double)lo * e), rKm1 = rK + e, bb = band * E;
+            const bool a0 = cub_converged(1, ScalarAcc{V, rK + bb}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rK - bb}, absTol, relTol, norm);
+            const bool a1 = cub_converged(1, ScalarAcc{V, rKm1 + bb}, absTol, relTol, norm) != cub_converged(1, ScalarAcc{V, rKm1 - bb}, absTol, relTol, norm);
+            lst->ambiguous = (a0 || a1) ? 1ULL : 0ULL;
+        }
+    }
+    __syncthreads();
+    return fin;
+}
 
 __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[SEL_THREADS];
     __shared__ unsigned long long shk[SEL_THREADS], shs[SEL_THREADS], shm[SEL_THREADS];
-    __shared__ unsigned scnt[SEL_WARPS][256];
-    __shared__ double ssum[SEL_WARPS][256];
-    __shared__ unsigned long long pc[256];
-    __shared__ double ps[256];
+    __shared__ unsigned long long pc[SEL_LB];  // staged global counts; its first half doubles as the CTA histogram counts
+    __shared__ double ps[SEL_LB];              // staged global sums; doubles as the CTA histogram sums
     __shared__ SelState lst;
     __shared__ long long s_flags[2];
-    __shared__ unsigned s_nzm[8];
+    __shared__ double s_dbl[2];
+    __shared__ long long s_ll[2];
+    unsigned* const scnt = (unsigned*)pc;  // [SEL_WARPS][256] at level 0, [SEL_LB] at levels >= 1
+    double* const ssum = ps;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, fdim = p.fdim;
-    // the per-pass histograms are cleared here; pass 0 accumulates only after the first grid barrier
-    if (p.do_select)
-        for (int q = b * SEL_THREADS + tid; q < 8 * 256; q += G * SEL_THREADS) {
-            p.hcnt[q] = 0ULL;
-            p.hsum[q] = 0.0;
-        }
+    const unsigned lane = tid & 31u, w = tid >> 5;
     const long long n = p.n;
     const PoolView& pool = p.pool;
-    // ---- A: chunk partials -----------------------------------------------------------------------
+    const bool scalar_select = fdim == 1 && p.do_select;
+    // clear the OTHER histogram set for the next launch (nobody reads or writes it during this one)
+    if (p.hzero)
+        for (long long q = (long long)b * SEL_THREADS + tid; q < PK_COOP_SET_WORDS; q += (long long)G * SEL_THREADS) p.hzero[q] = 0ULL;
+    // ---- A: chunk partials (+ level-0 histogram) -----------------------------------------------------
     const long long per = (n + G - 1) / G;
     const long long lo = per * b;
     long long hi = lo + per;
     if (hi > n) hi = n;
+    if (scalar_select) {
+        for (int q = tid; q < SEL_WARPS * 256; q += SEL_THREADS) {
+            scnt[q] = 0u;
+            ssum[q] = 0.0;
+        }
+        __syncthreads();
+    }
+    unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;  // smallest errmax bits (highest slot among ties), largest
     for (int row = 0; row < 2 * fdim; ++row) {
         const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
-        // same summation order as the plain loop (thread tid adds elements tid, tid+256, ... in order);
-        // the loads of four consecutive steps are issued together
+        // fixed summation order (thread tid adds elements tid, tid+256, ... in order); the loads of four
+        // consecutive steps are issued together
         double s = 0.0;
         long long i = lo + tid;
-        for (; i + 3 * SEL_THREADS < hi; i += 4 * SEL_THREADS) {
-            const double a0 = src[i], a1 = src[i + SEL_THREADS], a2 = src[i + 2 * SEL_THREADS], a3 = src[i + 3 * SEL_THREADS];
-            s += a0;
-            s += a1;
-            s += a2;
-            s += a3;
+        if (scalar_select && row == 1) {
+            // err row of a scalar integrand: the same read also feeds min/max and the level-0 histogram
+            unsigned cur = 0, run_c = 0;
+            double run_s = 0.0;
+            unsigned* const myc = scnt + w * 256;
+            double* const mys = ssum + w * 256;
+            for (; i < hi; i += 4 * SEL_THREADS) {
+                double a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = i + u * SEL_THREADS < hi ? src[i + u * SEL_THREADS] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i + u * SEL_THREADS < hi) {
+                        s += a[u];
+                        const unsigned long long kb = dbits(a[u] > 0.0 ? a[u] : 0.0);
+                        if (kb <= mn) {
+                            mn = kb;
+                            ms = (unsigned long long)(i + u * SEL_THREADS);
+                        }
+                        mx = kb > mx ? kb : mx;
+                        const unsigned d = (unsigned)((~kb) >> 56);
+                        if (d != cur) {
+                            sel_flush(myc, mys, cur, run_c, run_s);
+                            cur = d;
+                            run_c = 0;
+                            run_s = 0.0;
+                        }
+                        ++run_c;
+                        run_s += a[u];
+                    }
+                }
+            }
+            sel_flush(myc, mys, cur, run_c, run_s);
+        } else {
+            for (; i + 3 * SEL_THREADS < hi; i += 4 * SEL_THREADS) {
+                const double a0 = src[i], a1 = src[i + SEL_THREADS], a2 = src[i + 2 * SEL_THREADS], a3 = src[i + 3 * SEL_THREADS];
+                s += a0;
+                s += a1;
+                s += a2;
+                s += a3;
+            }
+            for (; i < hi; i += SEL_THREADS) s += src[i];
         }
-        for (; i < hi; i += SEL_THREADS) s += src[i];
         sh[tid] = s;
         __syncthreads();
-        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
-            if (tid < w) sh[tid] += sh[tid + w];
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) sh[tid] += sh[tid + q];
             __syncthreads();
         }
         if (tid == 0) p.partial[(long long)row * G + b] = sh[0];
         __syncthreads();
     }
-    {
-        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+    if (!scalar_select) {  // vector integrands (and plain totals): errmax[] holds max over the components
         long long i = lo + tid;
         for (; i + 3 * SEL_THREADS < hi; i += 4 * SEL_THREADS) {
             unsigned long long k[4];
@@ -965,18 +1154,33 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
             }
             mx = k > mx ? k : mx;
         }
+    } else {
+        // flush the level-0 histogram (per-warp copies) to the global one
+        unsigned c = 0;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < SEL_WARPS; ++q) {
+            c += scnt[q * 256 + tid];
+            s += ssum[q * 256 + tid];
+        }
+        if (c) {
+            atomicAdd(&set_cnt(p.hset, 0)[tid], (unsigned long long)c);
+            atomicAdd(&set_sum(p.hset, 0)[tid], s);
+        }
+    }
+    {
         shk[tid] = mn;
         shs[tid] = ms;
         shm[tid] = mx;
         __syncthreads();
-        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
-            if (tid < w) {
-                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) {
+                const unsigned long long k2 = shk[tid + q], s2 = shs[tid + q];
                 if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
                     shk[tid] = k2;
                     shs[tid] = s2;
                 }
-                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+                if (shm[tid + q] > shm[tid]) shm[tid] = shm[tid + q];
             }
             __syncthreads();
         }
@@ -996,8 +1200,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         for (int i = tid; i < G; i += SEL_THREADS) s += __ldcg(&p.partial[(long long)row * G + i]);
         sh[tid] = s;
         __syncthreads();
-        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
-            if (tid < w) sh[tid] += sh[tid + w];
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) sh[tid] += sh[tid + q];
             __syncthreads();
         }
         if (row == 0) V = sh[0];
@@ -1006,7 +1210,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         __syncthreads();
     }
     {
-        unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
+        mn = ~0ULL, ms = 0ULL, mx = 0ULL;
         for (int i = tid; i < G; i += SEL_THREADS) {
             const unsigned long long k = __ldcg(&p.blk[i]), sl = __ldcg(&p.blk[G + i]), m2 = __ldcg(&p.blk[2 * G + i]);
             if (k < mn || (k == mn && sl > ms)) {
@@ -1019,14 +1223,14 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         shs[tid] = ms;
         shm[tid] = mx;
         __syncthreads();
-        for (int w = SEL_THREADS / 2; w > 0; w >>= 1) {
-            if (tid < w) {
-                const unsigned long long k2 = shk[tid + w], s2 = shs[tid + w];
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) {
+                const unsigned long long k2 = shk[tid + q], s2 = shs[tid + q];
                 if (k2 < shk[tid] || (k2 == shk[tid] && s2 > shs[tid])) {
                     shk[tid] = k2;
                     shs[tid] = s2;
                 }
-                if (shm[tid + w] > shm[tid]) shm[tid] = shm[tid + w];
+                if (shm[tid + q] > shm[tid]) shm[tid] = shm[tid + q];
             }
             __syncthreads();
         }
@@ -1110,137 +1314,222 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     }
     if (s_flags[0] | s_flags[1]) return;  // converged, or the whole pool is popped (uniform over the grid)
     if (!p.do_select) return;
-    // ---- C: weighted radix select ------------------------------------------------------------------
+    // ---- C: weighted radix select, coarse to fine -----------------------------------------------------
     if (tid == 0) {
         lst.prefix = lst.mask = lst.count_cum = lst.K = lst.tie_take = lst.ambiguous = 0ULL;
         lst.P_cum = 0.0;
     }
-    const unsigned lane = tid & 31u, w = tid >> 5;
-    const long long stride = (long long)G * SEL_THREADS;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        for (int q = lane; q < 256; q += 32) {
-            scnt[w][q] = 0;
-            ssum[w][q] = 0.0;
-        }
-        __syncthreads();
-        const unsigned long long prefix = lst.prefix, mask = lst.mask;
-        unsigned cur = 0, run_c = 0;
-        double run_s = 0.0;
-        for (long long i0 = (long long)b * SEL_THREADS + tid; i0 < n; i0 += stride * SEL_UNROLL) {
-            unsigned long long k[SEL_UNROLL];
-#pragma unroll
-            for (int u = 0; u < SEL_UNROLL; ++u) {
-                const long long i = i0 + u * stride;
-                k[u] = i < n ? ~dbits(pool.errmax[i]) : 0ULL;
+    __syncthreads();
+    const double* err = pool.err;
+    bool have_cand = false;
+    unsigned long long less_def = 0;  // (thread-local) regions of this chunk that are certainly popped
+    long long M = 0;                  // candidates
+    int fin = 0;
+    for (int level = 0; level < SEL_LEVELS; ++level) {
+        const int shift = sel_shift(level), NB = sel_nbuckets(level);
+        if (level >= 1) {
+            for (int q = tid; q < NB; q += SEL_THREADS) {
+                scnt[q] = 0u;
+                ssum[q] = 0.0;
             }
+            __syncthreads();
+            const unsigned long long prefix = lst.prefix, mask = lst.mask;
+            unsigned cur = 0, run_c = 0;
+            double run_s = 0.0;
+            if (level <= 2) {
+                // full scan of the chunk; level 2 also extracts the candidates and counts the certain pops
+                unsigned long long* const cand_count = set_misc(p.hset);
+                // (loop bounds are warp-uniform: the level-2 body votes with the full mask)
+                for (long long w0 = lo + (long long)(tid - (int)lane); w0 < hi; w0 += 4 * SEL_THREADS) {
+                    const long long i0 = w0 + lane;
+                    double a[4];
 #pragma unroll
-            for (int u = 0; u < SEL_UNROLL; ++u) {
-                const long long i = i0 + u * stride;
-                if (i < n && (k[u] & mask) == prefix) {
-                    const unsigned d = (unsigned)(k[u] >> shift) & 255u;
-                    if (d != cur) {
-                        sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
-                        cur = d;
-                        run_c = 0;
-                        run_s = 0.0;
+                    for (int u = 0; u < 4; ++u) a[u] = i0 + u * SEL_THREADS < hi ? err[i0 + u * SEL_THREADS] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long i = i0 + u * SEL_THREADS;
+                        const bool in = i < hi;
+                        const unsigned long long k = sel_key_of_err(a[u]);
+                        const bool match = in && (k & mask) == prefix;
+                        if (level == 2) {
+                            less_def += (in && (k & mask) < prefix) ? 1ULL : 0ULL;
+                            // warp-aggregated append
+                            const unsigned bal = __ballot_sync(0xffffffffu, match);
+                            if (bal) {
+                                unsigned long long base = 0;
+                                if (lane == (unsigned)(__ffs(bal) - 1)) base = atomicAdd(cand_count, (unsigned long long)__popc(bal));
+                                base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                                if (match) {
+                                    const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+                                    p.cand_key[pos] = k;
+                                    p.cand_idx[pos] = (int)i;
+                                }
+                            }
+                        }
+                        if (match) {
+                            const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                            if (d != cur) {
+                                sel_flush(scnt, ssum, cur, run_c, run_s);
+                                cur = d;
+                                run_c = 0;
+                                run_s = 0.0;
+                            }
+                            ++run_c;
+                            run_s += a[u];
+                        }
                     }
-                    ++run_c;
-                    run_s += pool.err[i];
+                }
+                if (level == 2) have_cand = true;
+            } else {
+                // candidates only
+                for (long long q = (long long)b * SEL_THREADS + tid; q < M; q += (long long)G * SEL_THREADS) {
+                    const unsigned long long k = p.cand_key[q];
+                    if ((k & mask) == prefix) {
+                        const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                        if (d != cur) {
+                            sel_flush(scnt, ssum, cur, run_c, run_s);
+                            cur = d;
+                            run_c = 0;
+                            run_s = 0.0;
+                        }
+                        ++run_c;
+                        run_s += __longlong_as_double((long long)~k);  // err == errmax for a candidate (errmax > 0 or both 0)
+                    }
+                }
+            }
+            sel_flush(scnt, ssum, cur, run_c, run_s);
+            __syncthreads();
+            if (G > 1) {
+                unsigned long long* gc = set_cnt(p.hset, level);
+                double* gs = set_sum(p.hset, level);
+                for (int q = tid; q < NB; q += SEL_THREADS) {
+                    const unsigned c = scnt[q];
+                    if (c) {
+                        atomicAdd(&gc[q], (unsigned long long)c);
+                        atomicAdd(&gs[q], ssum[q]);
+                    }
+                }
+                if (level == 2) {  // certain pops of this chunk -> per-CTA counters of the compaction
+                    shk[tid] = less_def;
+                    __syncthreads();
+                    for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+                        if (tid < q) shk[tid] += shk[tid + q];
+                        __syncthreads();
+                    }
+                    if (tid == 0) {
+                        p.blk[3 * G + b] = shk[0];
+                        p.blk[4 * G + b] = 0ULL;
+                    }
+                }
+                grid.sync();
+            }
+        }
+        // stage this level's global histogram and pick (every CTA, same inputs, same result)
+        if (G > 1 || level == 0) {
+            const unsigned long long* gc = set_cnt(p.hset, level);
+            const double* gs = set_sum(p.hset, level);
+            __syncthreads();
+            for (int q = tid; q < NB; q += SEL_THREADS) {
+                pc[q] = __ldcg(&gc[q]);
+                ps[q] = __ldcg(&gs[q]);
+            }
+        } else {
+            // one CTA holds the whole pool: its own histogram is the global one (widen the counts in place, top down)
+            unsigned cc[SEL_LB / SEL_THREADS];
+#pragma unroll
+            for (int j = 0; j < SEL_LB / SEL_THREADS; ++j) cc[j] = tid + j * SEL_THREADS < NB ? scnt[tid + j * SEL_THREADS] : 0u;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < SEL_LB / SEL_THREADS; ++j)
+                if (tid + j * SEL_THREADS < NB) pc[tid + j * SEL_THREADS] = cc[j];
+            if (level == 2) {
+                shk[tid] = less_def;
+                __syncthreads();
+                for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+                    if (tid < q) shk[tid] += shk[tid + q];
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    p.blk[3 * G + b] = shk[0];
+                    p.blk[4 * G + b] = 0ULL;
                 }
             }
         }
-        sel_flush(scnt[w], ssum[w], cur, run_c, run_s);
         __syncthreads();
-        {
-            unsigned c = 0;
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < SEL_WARPS; ++q) {
-                c += scnt[q][tid];
-                s += ssum[q][tid];
-            }
-            if (G == 1) {  // one CTA holds the whole pool: no global histogram, no grid barrier
-                pc[tid] = c;
-                ps[tid] = s;
-                const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
-                if (lane == 0) s_nzm[w] = m;
-            } else if (c) {
-                atomicAdd(&p.hcnt[pass * 256 + tid], (unsigned long long)c);
-                atomicAdd(&p.hsum[pass * 256 + tid], s);
-            }
-        }
-        if (G > 1) {
-            grid.sync();
-            const unsigned long long c = __ldcg(&p.hcnt[pass * 256 + tid]);
-            pc[tid] = c;
-            ps[tid] = __ldcg(&p.hsum[pass * 256 + tid]);
-            const unsigned m = __ballot_sync(0xffffffffu, c != 0ULL);
-            if (lane == 0) s_nzm[w] = m;
-        }
-        __syncthreads();
-        if (tid == 0)
-            s_flags[0] = sel_pick_body(&lst, pc, ps, s_nzm, shift, pass == 7, V, E, (unsigned long long)p.Kcap, p.absTol, p.relTol, p.norm,
-                                       p.band, 1);
-        __syncthreads();
-        if (s_flags[0] && pass < 7) {
-            // the chosen bucket holds ONE region: the batch size is final, only the low bits of the threshold
-            // key are missing.  Whoever owns that region publishes its key (one more barrier instead of the
-            // remaining passes).
-            const unsigned long long prefix2 = lst.prefix, mask2 = lst.mask;
-            for (long long i = (long long)b * SEL_THREADS + tid; i < n; i += stride) {
-                const unsigned long long k = ~dbits(pool.errmax[i]);
-                if ((k & mask2) == prefix2) p.blk[5 * G] = k;
-            }
-            if (G > 1) {
-                __threadfence();
-                grid.sync();
-            } else {
+        if (level == 2) M = (long long)__ldcg(set_misc(p.hset));
+        fin = sel_pick_parallel(&lst, pc, ps, NB, shift, level == SEL_LEVELS - 1, V, E, (unsigned long long)p.Kcap, p.absTol, p.relTol, p.norm,
+                                p.band, sh, shk, shs, s_dbl, s_ll);
+        if (fin) {
+            if (level < SEL_LEVELS - 1) {
+                // the chosen bucket holds ONE region: the batch size is final, only the low bits of the threshold
+                // key are missing.  Whoever sees that region publishes its key (one more barrier instead of the
+                // remaining levels).
+                const unsigned long long prefix2 = lst.prefix, mask2 = lst.mask;
+                if (have_cand) {
+                    for (long long q = (long long)b * SEL_THREADS + tid; q < M; q += (long long)G * SEL_THREADS) {
+                        const unsigned long long k = p.cand_key[q];
+                        if ((k & mask2) == prefix2) p.blk[5 * G] = k;
+                    }
+                } else {
+                    for (long long i = lo + tid; i < hi; i += SEL_THREADS) {
+                        const unsigned long long k = sel_key_of_err(err[i]);
+                        if ((k & mask2) == prefix2) p.blk[5 * G] = k;
+                    }
+                }
+                if (G > 1) {
+                    __threadfence();
+                    grid.sync();
+                } else {
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    lst.prefix = __ldcg(&p.blk[5 * G]);
+                    lst.mask = ~0ULL;
+                }
                 __syncthreads();
             }
-            if (tid == 0) {
-                lst.prefix = __ldcg(&p.blk[5 * G]);
-                lst.mask = ~0ULL;
-            }
-            __syncthreads();
             break;
         }
     }
     // ---- D: stable compaction of the popped slots -----------------------------------------------------
     const unsigned long long thr = lst.prefix, tie_take = lst.tie_take;
-    const long long ntiles = (n + SEL_TILE - 1) / SEL_TILE;
-    const long long tper = (ntiles + G - 1) / G;
-    const long long t_lo = tper * b;
-    long long t_hi = t_lo + tper;
-    if (t_hi > ntiles) t_hi = ntiles;
-    unsigned long long my_less = 0, my_eq = 0;
-    for (long long t = t_lo; t < t_hi; ++t) {
-        const long long base = t * SEL_TILE;
-#pragma unroll
-        for (int u = 0; u < SEL_ITEMS; ++u) {
-            const long long i = base + (long long)u * SEL_THREADS + tid;
-            if (i < n) {
-                const unsigned long long k = ~dbits(pool.errmax[i]);
-                my_less += k < thr;
-                my_eq += k == thr;
+    if (have_cand) {
+        // per-CTA counts: certain pops (level-2 scan) + the candidates below / at the threshold key
+        for (long long q = (long long)b * SEL_THREADS + tid; q < M; q += (long long)G * SEL_THREADS) {
+            const unsigned long long k = p.cand_key[q];
+            if (k <= thr) {
+                const long long owner = (long long)p.cand_idx[q] / per;
+                atomicAdd(&p.blk[(k < thr ? 3 : 4) * (long long)G + owner], 1ULL);
             }
         }
-    }
-    shk[tid] = my_less;
-    shs[tid] = my_eq;
-    __syncthreads();
-    for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
-        if (tid < q) {
-            shk[tid] += shk[tid + q];
-            shs[tid] += shs[tid + q];
+    } else {
+        unsigned long long my_less = 0, my_eq = 0;
+        for (long long i = lo + tid; i < hi; i += SEL_THREADS) {
+            const unsigned long long k = sel_key_of_err(err[i]);
+            my_less += k < thr;
+            my_eq += k == thr;
         }
+        shk[tid] = my_less;
+        shs[tid] = my_eq;
+        __syncthreads();
+        for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+            if (tid < q) {
+                shk[tid] += shk[tid + q];
+                shs[tid] += shs[tid + q];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            p.blk[3 * G + b] = shk[0];
+            p.blk[4 * G + b] = shs[0];
+        }
+    }
+    if (G > 1) {
+        __threadfence();
+        grid.sync();
+    } else {
         __syncthreads();
     }
-    if (tid == 0) {
-        p.blk[3 * G + b] = shk[0];
-        p.blk[4 * G + b] = shs[0];
-    }
-    grid.sync();
     {
         unsigned long long a = 0, c = 0;
         for (int i = tid; i < b; i += SEL_THREADS) {
@@ -1260,14 +1549,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     }
     unsigned long long less_base = shk[0], eq_base = shs[0];
     __syncthreads();
-    for (long long t = t_lo; t < t_hi; ++t) {
-        const long long i_lo = t * SEL_TILE + (long long)tid * SEL_ITEMS;  // SEL_ITEMS consecutive slots per thread
+    unsigned* const sl = (unsigned*)pc;
+    unsigned* const se = sl + SEL_THREADS;
+    for (long long t_lo = lo; t_lo < hi; t_lo += SEL_TILE) {
+        const long long i_lo = t_lo + (long long)tid * SEL_ITEMS;  // SEL_ITEMS consecutive slots per thread
         unsigned fl = 0, fe = 0, less = 0, eq = 0;
 #pragma unroll
         for (int u = 0; u < SEL_ITEMS; ++u) {
             const long long i = i_lo + u;
-            if (i < n) {
-                const unsigned long long k = ~dbits(pool.errmax[i]);
+            if (i < hi) {
+                const unsigned long long k = sel_key_of_err(err[i]);
                 if (k < thr) {
                     fl |= 1u << u;
                     ++less;
@@ -1277,8 +1568,6 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                 }
             }
         }
-        unsigned* sl = (unsigned*)&scnt[0][0];
-        unsigned* se = sl + SEL_THREADS;
         sl[tid] = less;
         se[tid] = eq;
         __syncthreads();
@@ -1491,12 +1780,14 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
     if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank, perm);
 }
 
-// Cooperative launch of one whole iteration (everything but the rule kernel).  hist: [8][256] u64 then
-// [8][256] double, zeroed here.  Returns cudaSuccess or the launch error.
+// Cooperative launch of one whole iteration (everything but the rule kernel).  hsets: two histogram sets of
+// PK_COOP_SET_BYTES each (both zero before the first launch of a loop; launch k uses set k & 1 and clears the other
+// one for launch k + 1).  cand_key / cand_idx: candidate scratch of the select, n entries each.
+// Returns cudaSuccess or the launch error.
 static int g_coop_blocks_per_sm = -1;
 cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
-                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hist, int* list,
-                         int n_sms, cudaStream_t s) {
+                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hsets, int parity,
+                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s) {
     if (g_coop_blocks_per_sm < 0) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_iter_coop, SEL_THREADS, 0);
@@ -1520,8 +1811,10 @@ cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long 
     p.blk = blk;
     p.ctl = ctl;
     p.st = (SelState*)state;
-    p.hcnt = (unsigned long long*)hist;
-    p.hsum = (double*)((unsigned char*)hist + 8 * 256 * 8);
+    p.hset = (unsigned long long*)((unsigned char*)hsets + (size_t)(parity & 1) * PK_COOP_SET_BYTES);
+    p.hzero = (unsigned long long*)((unsigned char*)hsets + (size_t)((parity + 1) & 1) * PK_COOP_SET_BYTES);
+    p.cand_key = cand_key;
+    p.cand_idx = cand_idx;
     p.list = list;
     void* args[1] = {&p};
     return cudaLaunchCooperativeKernel((const void*)k_iter_coop, dim3((unsigned)G), dim3(SEL_THREADS), args, 0, s);

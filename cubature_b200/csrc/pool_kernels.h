@@ -64,10 +64,13 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
 cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
-                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hist, int* list,
-                         int n_sms, cudaStream_t s);
+                         int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hsets, int parity,
+                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s);
 int pk_iter_coop_max_blocks(int n_sms);
-#define PK_COOP_HIST_BYTES (8 * 256 * 16)
+// one histogram set of the cooperative iteration kernel: cnt[7][2048] u64 | sum[7][2048] f64 | misc[8]
+#define PK_COOP_SET_WORDS (2 * 7 * 2048 + 8)
+#define PK_COOP_SET_BYTES (PK_COOP_SET_WORDS * 8)
+#define PK_COOP_HIST_BYTES (2 * PK_COOP_SET_BYTES)
 void pk_dfma_peak(double* out, int blocks, int iters, cudaStream_t s);
 
 #endif
