@@ -67,8 +67,9 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
 
 // nccl_dyn.cpp
 struct cub_local_group;
-#define CUB_MAX_RANKS 16
-#define CUB_XBUF_BYTES (128 * 1024)
+#include "pool_kernels.h"
+#define CUB_MAX_RANKS PK_MAX_RANKS
+#define CUB_XBUF_BYTES PK_XB_BYTES
 struct cub_comm {
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0, device = 0;
@@ -76,10 +77,10 @@ struct cub_comm {
     unsigned long long local_key = 0;
     // NVLink peer exchange (NCCL communicators only): every rank owns one exchange buffer in its HBM, mapped
     // into all peers with CUDA IPC; the sharded iteration kernel publishes and gathers through these
-    // directly (pool_kernels.cu: k_iter_coop_sharded), so the refinement loop itself makes no NCCL call.
+    // directly (pool_kernels.cu: k_iter_coop with R > 1), so the refinement loop itself makes no NCCL call.
+    // The exchange sequence number lives in the buffer itself (PK_XB_SEQ).
     bool peer_ok = false;
     void* xbuf[CUB_MAX_RANKS] = {nullptr};  // xbuf[rank] = own buffer, others = IPC mappings
-    unsigned long long seq = 1;             // next exchange sequence number (monotonic over the comm's life)
 };
 int cub_comm_allgather(cub_comm* comm, const void* dev_send, size_t bytes, void* dev_recv, cudaStream_t stream);
 

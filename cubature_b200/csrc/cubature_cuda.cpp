@@ -124,6 +124,15 @@ struct Pool {
         if ((e = err.ensure((size_t)8 * fdim * cap)) != cudaSuccess) return e;
         if ((e = errmax.ensure((size_t)8 * cap)) != cudaSuccess) return e;
         if ((e = splitdim.ensure((size_t)4 * cap)) != cudaSuccess) return e;
+        // buffers cached from an earlier call may hold more: use all of it (saves the re-striding growth steps, and
+        // cudaMalloc / cudaFree are slow once peer mappings exist)
+        size_t fit = center.bytes / ((size_t)8 * dim);
+        fit = std::min(fit, halfw.bytes / ((size_t)8 * dim));
+        fit = std::min(fit, val.bytes / ((size_t)8 * fdim));
+        fit = std::min(fit, err.bytes / ((size_t)8 * fdim));
+        fit = std::min(fit, errmax.bytes / 8);
+        fit = std::min(fit, splitdim.bytes / 4);
+        if ((long long)fit > cap) cap = (long long)std::min<size_t>(fit, (size_t)std::numeric_limits<int>::max());
         return cudaSuccess;
     }
     // re-stride every row into a pool of larger capacity (n live regions)
@@ -476,7 +485,8 @@ int set_root(Session& S, Pool& pool) {
 
 long long auto_capacity(int dim, int fdim, int64_t P, int64_t maxEval, long long requested, size_t extra_per_region) {
     if (requested > 0) return requested;
-    long long cap = 1 << 16;
+    // unknown amount of work: start with about 256 MB of pool (at least 4 096, at most 2^21 regions) and grow on demand
+    long long cap = std::min<long long>(1 << 21, std::max<long long>(1 << 12, (long long)(((size_t)256 << 20) / Pool::bytes_per_region(dim, fdim))));
     if (maxEval > 0) {
         const long long need = maxEval / (2 * P) + 8;
         cap = std::max<long long>(need, 1024);
@@ -551,6 +561,9 @@ struct LoopState {
 };
 int integrate_device_fused(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                            LoopResult* res, long long stop_at_regions = 0, LoopState* state_out = nullptr, long long cap_override = 0);
+
+int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, const LoopState& st0);
 
 void push_batch(cub_trace_t* tr, int64_t nR) {
     if (!tr) return;
@@ -765,6 +778,11 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     LoopState st0;
     int rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
     if (rc != CUB_OK || !st0.handoff) return rc;  // finished (converged / maxEval) before sharding: result already complete
+    {
+        const char* env = getenv("CUBATURE_PEER_LOOP");
+        if (R > 1 && comm->peer_ok && f == 1 && !(env && env[0] == '0'))
+            return integrate_sharded_peer(S, relTol, absTol, norm, maxEval, opt, out, res, st0);
+    }
 
     SelectBuffers& sel = W.sel;
     DevBuf &d_partial = W.d_partial, &d_small = W.d_small;
@@ -1082,6 +1100,231 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     if (timing)
         fprintf(stderr, "[cubature rank %d] sharded phase: %d iterations (%d with selection): shard %.2f ms, stats+exchange %.2f ms, select %.2f ms, rule %.2f ms\n",
                 rank, n_iters, n_sel_iters, t_shard, t_stats, t_select, t_rule);
+    res->converged = conv ? 1 : 0;
+    res->num_eval = numEval;
+    res->num_regions = Nglobal;
+    fill_trace_regions(S, pool, nullptr, N, trace);
+    return CUB_OK;
+}
+
+// ---- DEVICE mode, sharded pool, scalar integrand, NVLink peer exchange ---------------------------------------
+// After the replicated phase every rank ranks the (identical) pool by errmax, keeps every R-th region and then
+// runs the same device-driven loop as a single GPU: per iteration ONE cooperative kernel (k_iter_coop with R > 1:
+// shard totals and histograms, exchanged with the other ranks through peer-mapped buffers inside the kernel,
+// identical decisions on every rank, compaction of this rank's share of the batch) and the fused bisect + rule
+// kernel on the rank's own regions, then one 200-byte read-back.  No NCCL call and no host-side exchange in the loop.
+int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, const LoopState& st0) {
+    const int f = S.fdim;  // == 1
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    cub_comm* comm = opt->comm;
+    const int R = comm->nranks, rank = comm->rank;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    SelectBuffers& sel = W.sel;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+
+    long long N = st0.N;
+    long long Nglobal = st0.N;
+    int64_t numEval = st0.numEval;
+    double ops = st0.ops;
+    const double eps = 2.220446049250313e-16;
+
+    const int G = 1184;
+    const size_t ctl_words = PK_CTL_WORDS + (size_t)4 * f;
+    CUB_CUDA_CHECK(W.d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * (5 * G + 8)), S.msg);
+    CUB_CUDA_CHECK(W.d_small.ensure(ctl_words * 8 + 256 + 128), S.msg);
+    CUB_CUDA_CHECK(W.h_small.ensure(ctl_words * 8 + 256), S.msg);
+    double* d_part = W.d_partial.as<double>();
+    unsigned long long* d_blk = (unsigned long long*)(d_part + (size_t)2 * f * G);
+    long long* d_ctl = W.d_small.as<long long>();
+    unsigned long long* d_u64 = (unsigned long long*)(d_ctl + ctl_words) + 8;
+    unsigned long long* d_gblock = (unsigned long long*)((unsigned char*)W.d_small.p + ctl_words * 8 + 256);
+    long long* h_ctl = W.h_small.as<long long>();
+    const double* h_totals = (const double*)(h_ctl + PK_CTL_WORDS);
+    unsigned long long* h_u64 = (unsigned long long*)(h_ctl + ctl_words) + 8;
+
+    // ---- deal the replicated pool out: rank the regions by errmax (stable radix sort, identical on every rank), rank r
+    // keeps ranks r, r + R, ... of that order.  Gathered into the free upper part of the pool, then moved down.
+    const long long n_local = cubature_cuda_shard_count(N, R, rank);
+    {
+        if (N + n_local > pool.cap) {
+            cudaError_t e = pool.grow(std::max<long long>(pool.cap * 2, N + n_local), N, S.stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+        }
+        CUB_CUDA_CHECK(sel.ensure(N, f), S.msg);
+        unsigned long long* ka = sel.keysA.as<unsigned long long>();
+        unsigned long long* kb = sel.keysB.as<unsigned long long>();
+        int* ia = sel.idxA.as<int>();
+        int* ib = sel.idxB.as<int>();
+        pk_sort_prepare(pool.view().errmax, N, ka, ia, d_u64, S.stream);
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        const unsigned long long vary0 = h_u64[0] ^ h_u64[1];  // digits shared by every key need no pass
+        S.launches += 1;
+        for (int shift = 0; shift < 64; shift += 8) {
+            if (((vary0 >> shift) & 0xffULL) == 0) continue;
+            pk_sort_pass(ka, ia, kb, ib, N, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
+                         sel.binbase.as<unsigned long long>(), S.stream);
+            std::swap(ka, kb);
+            std::swap(ia, ib);
+            S.launches += 4;
+        }
+        const PoolView src = pool.view();
+        PoolView dst = src;  // same arrays, shifted by N slots
+        dst.center += N;
+        dst.halfw += N;
+        dst.val += N;
+        dst.err += N;
+        dst.errmax += N;
+        dst.splitdim += N;
+        pk_shard_gather(src, dst, S.dim, f, n_local, R, rank, ia, S.stream);
+        S.launches += 1;
+        auto rows = [&](DevBuf& buf, int nrows, size_t elt) {
+            return cudaMemcpy2DAsync(buf.p, (size_t)pool.cap * elt, (const unsigned char*)buf.p + (size_t)N * elt, (size_t)pool.cap * elt,
+                                     (size_t)n_local * elt, nrows, cudaMemcpyDeviceToDevice, S.stream);
+        };
+        if (n_local > 0) {
+            CUB_CUDA_CHECK(rows(pool.center, S.dim, 8), S.msg);
+            CUB_CUDA_CHECK(rows(pool.halfw, S.dim, 8), S.msg);
+            CUB_CUDA_CHECK(rows(pool.val, f, 8), S.msg);
+            CUB_CUDA_CHECK(rows(pool.err, f, 8), S.msg);
+            CUB_CUDA_CHECK(rows(pool.errmax, 1, 8), S.msg);
+            CUB_CUDA_CHECK(rows(pool.splitdim, 1, 4), S.msg);
+        }
+        N = n_local;
+    }
+    const double t_shard = ms_since(t_begin);
+
+    PkShard shard;
+    shard.R = R;
+    shard.rank = rank;
+    for (int r = 0; r < PK_MAX_RANKS; ++r) shard.xbuf[r] = r < R ? comm->xbuf[r] : nullptr;
+    shard.gblock = d_gblock;
+    CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+    CUB_CUDA_CHECK(cudaMemsetAsync(sel.small.p, 0, 512 + PK_COOP_HIST_BYTES, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaMemsetAsync(W.d_small.p, 0, ctl_words * 8 + 256 + 128, S.stream), S.msg);
+    int coop_parity = 0;
+    bool conv = false, have_totals = false;
+    int n_iters = 0;
+
+    while (numEval < maxEval || maxEval == 0) {
+        long long Kcap = Nglobal;  // pops allowed by maxEval (Rule.java:133), over all ranks
+        if (maxEval > 0) {
+            const int64_t room = maxEval - numEval;  // > 0 here
+            Kcap = std::min<long long>(Nglobal, std::max<int64_t>(1, (room + 2 * P - 1) / (2 * P)));
+        }
+        const long long Klocal_max = std::min<long long>(N, Kcap);
+        if (N + Klocal_max > pool.cap) {
+            long long nc = std::max<long long>(pool.cap * 2, N + Klocal_max);
+            cudaError_t e = pool.grow(nc, N, S.stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+            CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+        }
+        if (N + Klocal_max > (long long)std::numeric_limits<int>::max()) {
+            cub_set_message(S.msg, "region pool exceeds 2^31 slots");
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+        const PoolView pv = pool.view();
+        const double band = 4.0 * eps * std::sqrt(ops);
+        SelScratch sc = sel.scratch(pool.cap);
+        {
+            cudaError_t e = pk_iter_coop(pv, f, N, Kcap, absTol, relTol, norm, band, 1, d_part, d_blk, d_ctl, sc.state,
+                                         (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
+                                         sel.idxA.as<int>(), S.n_sms, S.stream, &shard);
+            if (e != cudaSuccess) {
+                cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
+                return CUB_ERR_CUDA;
+            }
+        }
+        S.launches += 1;
+        const bool device_sized = N <= kDeviceSizedMaxRegions;
+        HostWork w{};
+        w.list = sel.idxA.as<int>();
+        w.base = N;
+        w.mode = MODE_BISECT;
+        int rc;
+        if (device_sized && N > 0) {
+            w.dyn = d_ctl;
+            w.n_items = 2 * Klocal_max;  // upper bound: sizes the grid only
+            rc = S.launch_rule(pool.view(), w);
+            if (rc != CUB_OK) return rc;
+        }
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += (int64_t)ctl_words * 8;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        if (h_ctl[11]) {
+            cub_set_message(S.msg, "peer exchange timed out: a rank of the communicator did not take part in the iteration");
+            return CUB_ERR_NCCL;
+        }
+        res->ambiguous += h_ctl[6];
+        Nglobal = h_ctl[12];
+        ++n_iters;
+        if (h_ctl[4]) {
+            conv = true;
+            have_totals = true;
+            break;
+        }
+        const long long K = h_ctl[3], Kglobal = h_ctl[7];
+        if (K < 0 || K > Klocal_max || Kglobal < 1 || Kglobal > Kcap) {
+            cub_set_message(S.msg, "internal: sharded selection returned K=%lld of N=%lld (global %lld of %lld, cap %lld)", K, N, Kglobal,
+                            Nglobal, Kcap);
+            return CUB_ERR_CUDA;
+        }
+        if (!(device_sized && N > 0) && K >= 1) {
+            if (h_ctl[5]) w.list = nullptr;  // pop-all: identity list, coalesced parent reads
+            w.n_items = 2 * K;
+            rc = S.launch_rule(pool.view(), w);
+            if (rc != CUB_OK) return rc;
+        }
+        N += K;
+        Nglobal += Kglobal;
+        numEval += 2 * P * Kglobal;
+        S.local_regions_evaluated += 2 * K;
+        ops += 3.0 * (double)Kglobal;
+        res->iterations += 1;
+        push_batch(trace, 2 * Kglobal);
+        if (res->iterations >= kMaxIterations) {
+            cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)res->iterations);
+            break;
+        }
+    }
+    if (!have_totals) {  // stopped by maxEval: K5 over the final shards, exchanged and added in rank order
+        SelScratch sc = sel.scratch(pool.cap);
+        cudaError_t e = pk_iter_coop(pool.view(), f, N, Nglobal, absTol, relTol, norm, 0.0, 0, d_part, d_blk, d_ctl, sc.state,
+                                     (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
+                                     sel.idxA.as<int>(), S.n_sms, S.stream, &shard);
+        if (e != cudaSuccess) {
+            cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        S.launches += 1;
+        CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        S.d2h_bytes += (int64_t)ctl_words * 8;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        if (h_ctl[11]) {
+            cub_set_message(S.msg, "peer exchange timed out: a rank of the communicator did not take part in the final sum");
+            return CUB_ERR_NCCL;
+        }
+    }
+    for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
+    S.flush_rule_timer();
+    if (timing)
+        fprintf(stderr, "[cubature rank %d] sharded peer loop: %d iterations, deal %.2f ms, total %.2f ms, rule %.2f ms\n", rank, n_iters, t_shard,
+                ms_since(t_begin), S.rule_ms);
     res->converged = conv ? 1 : 0;
     res->num_eval = numEval;
     res->num_regions = Nglobal;

@@ -906,6 +906,11 @@ struct IterParams {
     unsigned long long* cand_key;  // [n] candidates of the level-2 scan
     int* cand_idx;                 // [n]
     int* list;
+    // sharded pool (R > 1): this launch handles one shard; the per-level histograms, the totals and the tie
+    // counts of the R ranks are exchanged through peer-mapped buffers over NVLink (no NCCL call, no host)
+    int R, rank;
+    unsigned long long* xbuf[PK_MAX_RANKS];  // [rank] = own buffer, others = peer mappings (layout: pool_kernels.h)
+    unsigned long long* gblock;              // [16] local global scratch: combined totals / decisions of CTA 0
 };
 // histogram set layout (8-byte words): cnt[SEL_LEVELS][SEL_LB] | sum[SEL_LEVELS][SEL_LB] | misc[8] ([0] candidate count)
 __device__ __forceinline__ unsigned long long* set_cnt(unsigned long long* set, int level) { return set + (size_t)level * SEL_LB; }
@@ -913,6 +918,86 @@ __device__ __forceinline__ double* set_sum(unsigned long long* set, int level) {
     return (double*)(set + (size_t)SEL_LEVELS * SEL_LB) + (size_t)level * SEL_LB;
 }
 __device__ __forceinline__ unsigned long long* set_misc(unsigned long long* set) { return set + (size_t)2 * SEL_LEVELS * SEL_LB; }
+
+// ---- exchange between the ranks of a sharded pool (CTA 0 only, all SEL_THREADS threads) ---------------------
+// Push model: every rank writes its payload into slot [parity][rank] of EVERY rank's buffer (plain stores over
+// NVLink), fences, then raises flag [parity][rank] = seq in every buffer; it then waits for the R flags of its own
+// buffer and reads the R payloads locally (L2, __ldcg).  seq counts the exchanges of the communicator's life (kept
+// in the own buffer), parity = seq & 1: a rank can run at most one exchange ahead of its slowest peer (it needs the
+// peer's flag of exchange e to finish e), so two payload slots suffice.  All ranks execute the same exchanges in
+// the same order (their control flow depends on combined data only).  A wait that lasts longer than
+// PK_XCHG_TIMEOUT_NS marks the launch failed instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned long long* ptr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* ptr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long* xb_payload(unsigned long long* buf, unsigned long long seq, int src_rank) {
+    return buf + PK_XB_DATA + ((size_t)(seq & 1ULL) * PK_MAX_RANKS + (size_t)src_rank) * PK_XB_PAY;
+}
+// payload = hdr[0..16) from shared memory `hdr`, then n_cnt words from cnt, then n_cnt words from sum (either may be null)
+// returns the sequence number used (0 on timeout); on return the R payloads are readable with xb_payload(own, seq, r)
+__device__ unsigned long long xchg_all(const IterParams& p, const unsigned long long* hdr, const unsigned long long* cnt, const double* sum,
+                                       int n_cnt, long long* s_ll) {
+    const int tid = threadIdx.x;
+    unsigned long long* own = p.xbuf[p.rank];
+    const unsigned long long seq = *(volatile unsigned long long*)&own[PK_XB_SEQ] + 1ULL;  // thread 0 advances it below
+    __syncthreads();
+    for (int r = 0; r < p.R; ++r) {
+        unsigned long long* dst = xb_payload(p.xbuf[r], seq, p.rank);
+        if (tid < 16) dst[tid] = hdr[tid];
+        if (cnt)
+            for (int q = tid; q < n_cnt; q += SEL_THREADS) {
+                dst[16 + q] = __ldcg(&cnt[q]);
+                dst[16 + n_cnt + q] = (unsigned long long)__double_as_longlong(__ldcg(&sum[q]));
+            }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        own[PK_XB_SEQ] = seq;
+        s_ll[1] = 1;
+    }
+    if (tid < p.R) st_release_sys(p.xbuf[tid] + PK_XB_FLAGS + (size_t)(seq & 1ULL) * PK_MAX_RANKS + p.rank, seq);
+    __syncthreads();
+    if (tid < p.R) {
+        const unsigned long long* f = own + PK_XB_FLAGS + (size_t)(seq & 1ULL) * PK_MAX_RANKS + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < seq) {
+            if (global_timer_ns() - t0 > PK_XCHG_TIMEOUT_NS) {
+                s_ll[1] = 0;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return s_ll[1] ? seq : 0ULL;
+}
+// adds the R histograms of an exchange in rank order and stores the result as this rank's "global" histogram
+__device__ void xchg_combine_hist(const IterParams& p, unsigned long long seq, unsigned long long* cnt, double* sum, int n_cnt) {
+    unsigned long long* own = p.xbuf[p.rank];
+    for (int q = threadIdx.x; q < n_cnt; q += SEL_THREADS) {
+        unsigned long long c = 0ULL;
+        double sacc = 0.0;
+        for (int r = 0; r < p.R; ++r) {
+            const unsigned long long* pay = xb_payload(own, seq, r);
+            c += __ldcg(&pay[16 + q]);
+            sacc += __longlong_as_double((long long)__ldcg(&pay[16 + n_cnt + q]));
+        }
+        cnt[q] = c;
+        sum[q] = sacc;
+    }
+}
 
 // Block-wide pick of one level (all SEL_THREADS threads): the first bucket (ascending key = descending errmax)
 // at which the pop budget runs out or the residual test passes, found with a prefix scan over the buckets.
@@ -1057,6 +1142,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     const long long n = p.n;
     const PoolView& pool = p.pool;
     const bool scalar_select = fdim == 1 && p.do_select;
+    const bool sharded = p.R > 1;
+    __shared__ unsigned long long s_hdr[16];
+    if (b == 0 && tid == 0) p.blk[5 * G] = 0ULL;  // "unique key not found here" (a real key has bit 63 set)
     // clear the OTHER histogram set for the next launch (nobody reads or writes it during this one)
     if (p.hzero)
         for (long long q = (long long)b * SEL_THREADS + tid; q < PK_COOP_SET_WORDS; q += (long long)G * SEL_THREADS) p.hzero[q] = 0ULL;
@@ -1236,10 +1324,81 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         }
     }
     const long long argmin = (long long)shs[0];
+    long long n_glob = n;  // regions of the whole partition
     if (fdim == 1) {
+        double e_last = 0.0, v_last = 0.0;
+        unsigned long long kmin = shk[0], kmax = shm[0];
+        if (sharded) {
+            // CTA 0 exchanges {V, E, smallest-errmax region, N} and the level-0 histogram with the other ranks, adds the
+            // blocks in rank order (identical bits on every rank) and publishes the result to the other CTAs
+            if (b == 0) {
+                if (tid == 0) {
+                    s_hdr[0] = dbits(V);
+                    s_hdr[1] = dbits(E);
+                    s_hdr[2] = n > 0 ? shk[0] : ~0ULL;
+                    s_hdr[3] = shm[0];
+                    s_hdr[4] = dbits(n > 0 ? pool.val[argmin] : 0.0);
+                    s_hdr[5] = dbits(n > 0 ? pool.err[argmin] : 0.0);
+                    s_hdr[6] = (unsigned long long)n;
+                    for (int q = 7; q < 16; ++q) s_hdr[q] = 0ULL;
+                }
+                __syncthreads();
+                const unsigned long long seq = xchg_all(p, s_hdr, scalar_select ? set_cnt(p.hset, 0) : nullptr,
+                                                        scalar_select ? set_sum(p.hset, 0) : nullptr, 256, s_ll);
+                if (seq && scalar_select) xchg_combine_hist(p, seq, set_cnt(p.hset, 0), set_sum(p.hset, 0), 256);
+                if (tid == 0) {
+                    unsigned long long* own = p.xbuf[p.rank];
+                    double gV = 0.0, gE = 0.0, gvl = 0.0, gel = 0.0;
+                    unsigned long long gmin = ~0ULL, gmax = 0ULL, gN = 0ULL;
+                    bool any = false;
+                    for (int r = 0; seq && r < p.R; ++r) {
+                        const unsigned long long* pay = xb_payload(own, seq, r);
+                        const unsigned long long nr = __ldcg(&pay[6]);
+                        if (nr == 0ULL) continue;  // a rank without regions contributes nothing
+                        gV += __longlong_as_double((long long)__ldcg(&pay[0]));
+                        gE += __longlong_as_double((long long)__ldcg(&pay[1]));
+                        gN += nr;
+                        const unsigned long long km = __ldcg(&pay[2]), kx = __ldcg(&pay[3]);
+                        if (!any || km <= gmin) {  // ties: the highest rank pops last
+                            gmin = km;
+                            gvl = __longlong_as_double((long long)__ldcg(&pay[4]));
+                            gel = __longlong_as_double((long long)__ldcg(&pay[5]));
+                            any = true;
+                        }
+                        gmax = kx > gmax ? kx : gmax;
+                    }
+                    p.gblock[0] = dbits(gV);
+                    p.gblock[1] = dbits(gE);
+                    p.gblock[2] = gmin;
+                    p.gblock[3] = gmax;
+                    p.gblock[4] = dbits(gvl);
+                    p.gblock[5] = dbits(gel);
+                    p.gblock[6] = gN;
+                    p.gblock[7] = seq ? 0ULL : 1ULL;  // exchange failed (timeout)
+                    totals[0] = gV;
+                    totals[1] = gE;
+                }
+                __threadfence();
+            }
+            grid.sync();
+            if (__ldcg(&p.gblock[7])) {
+                if (b == 0 && tid == 0) p.ctl[11] = 1;  // a peer did not answer
+                return;
+            }
+            V = __longlong_as_double((long long)__ldcg(&p.gblock[0]));
+            E = __longlong_as_double((long long)__ldcg(&p.gblock[1]));
+            kmin = __ldcg(&p.gblock[2]);
+            kmax = __ldcg(&p.gblock[3]);
+            v_last = __longlong_as_double((long long)__ldcg(&p.gblock[4]));
+            e_last = __longlong_as_double((long long)__ldcg(&p.gblock[5]));
+            n_glob = (long long)__ldcg(&p.gblock[6]);
+        }
         // scalar: every CTA decides on its own registers (no dependence on CTA 0's stores)
         if (tid == 0) {
-            const double e_last = pool.err[argmin];
+            if (!sharded) {
+                e_last = pool.err[argmin];
+                v_last = pool.val[argmin];
+            }
             long long amb = 0;
             const bool c0 = cub_converged(1, ScalarAcc{V, E}, p.absTol, p.relTol, p.norm);
             const bool c1 = cub_converged(1, ScalarAcc{V, E * (1.0 + p.band)}, p.absTol, p.relTol, p.norm);
@@ -1251,16 +1410,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                 const bool a1 = !cub_converged(1, ScalarAcc{V, e_last + p.band * E}, p.absTol, p.relTol, p.norm);
                 const bool a2 = !cub_converged(1, ScalarAcc{V, e_last - p.band * E}, p.absTol, p.relTol, p.norm);
                 if (a1 != all || a2 != all) amb += 1;
-                if (n == 1) all = true;
-                all = all && p.Kcap >= n;
+                if (n_glob == 1) all = true;
+                all = all && p.Kcap >= n_glob;
             }
             s_flags[0] = c0 ? 1 : 0;
             s_flags[1] = all ? 1 : 0;
             if (b == 0) {
-                minvec[0] = pool.val[argmin];
+                minvec[0] = v_last;
                 minvec[1] = e_last;
-                ((unsigned long long*)p.ctl)[8] = shk[0];
-                ((unsigned long long*)p.ctl)[9] = shm[0];
+                ((unsigned long long*)p.ctl)[8] = kmin;
+                ((unsigned long long*)p.ctl)[9] = kmax;
                 p.ctl[10] = argmin;
                 p.ctl[0] = all ? 2 * n : 0;
                 p.ctl[1] = 0;
@@ -1269,6 +1428,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                 p.ctl[4] = c0 ? 1 : 0;
                 p.ctl[5] = all ? 1 : 0;
                 p.ctl[6] = amb;
+                p.ctl[7] = all ? n_glob : 0;  // pops of the whole partition
+                p.ctl[12] = n_glob;
             }
         }
         __syncthreads();
@@ -1399,7 +1560,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
             }
             sel_flush(scnt, ssum, cur, run_c, run_s);
             __syncthreads();
-            if (G > 1) {
+            if (G > 1 || sharded) {
                 unsigned long long* gc = set_cnt(p.hset, level);
                 double* gs = set_sum(p.hset, level);
                 for (int q = tid; q < NB; q += SEL_THREADS) {
@@ -1421,11 +1582,27 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                         p.blk[4 * G + b] = 0ULL;
                     }
                 }
+                __threadfence();
                 grid.sync();
+                if (sharded) {  // this level's histogram of the whole partition: rank-ordered sum of the R local ones
+                    if (b == 0) {
+                        if (tid < 16) s_hdr[tid] = 0ULL;
+                        __syncthreads();
+                        const unsigned long long seq = xchg_all(p, s_hdr, gc, gs, NB, s_ll);
+                        if (seq) xchg_combine_hist(p, seq, gc, gs, NB);
+                        if (tid == 0) p.gblock[7] = seq ? 0ULL : 1ULL;
+                        __threadfence();
+                    }
+                    grid.sync();
+                    if (__ldcg(&p.gblock[7])) {
+                        if (b == 0 && tid == 0) p.ctl[11] = 1;
+                        return;
+                    }
+                }
             }
         }
         // stage this level's global histogram and pick (every CTA, same inputs, same result)
-        if (G > 1 || level == 0) {
+        if (G > 1 || sharded || level == 0) {
             const unsigned long long* gc = set_cnt(p.hset, level);
             const double* gs = set_sum(p.hset, level);
             __syncthreads();
@@ -1476,11 +1653,33 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                         if ((k & mask2) == prefix2) p.blk[5 * G] = k;
                     }
                 }
-                if (G > 1) {
+                if (G > 1 || sharded) {
                     __threadfence();
                     grid.sync();
                 } else {
                     __syncthreads();
+                }
+                if (sharded) {  // exactly one rank owns that region
+                    if (b == 0) {
+                        if (tid < 16) s_hdr[tid] = tid == 0 ? __ldcg(&p.blk[5 * G]) : 0ULL;
+                        __syncthreads();
+                        const unsigned long long seq = xchg_all(p, s_hdr, nullptr, nullptr, 0, s_ll);
+                        if (tid == 0) {
+                            unsigned long long key = 0ULL;
+                            for (int r = 0; seq && r < p.R; ++r) {
+                                const unsigned long long k = __ldcg(&xb_payload(p.xbuf[p.rank], seq, r)[0]);
+                                if (k) key = k;
+                            }
+                            p.blk[5 * G] = key;
+                            p.gblock[7] = seq ? 0ULL : 1ULL;
+                        }
+                        __threadfence();
+                    }
+                    grid.sync();
+                    if (__ldcg(&p.gblock[7])) {
+                        if (b == 0 && tid == 0) p.ctl[11] = 1;
+                        return;
+                    }
                 }
                 if (tid == 0) {
                     lst.prefix = __ldcg(&p.blk[5 * G]);
@@ -1524,11 +1723,60 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
             p.blk[4 * G + b] = shs[0];
         }
     }
-    if (G > 1) {
+    if (G > 1 || sharded) {
         __threadfence();
         grid.sync();
     } else {
         __syncthreads();
+    }
+    unsigned long long tie_take_local = tie_take, K_local = lst.K;
+    if (sharded) {
+        // regions equal to the threshold key are taken in (rank, slot) order: every rank publishes how many of its
+        // regions are below / at the threshold and takes its share of the global tie budget
+        if (b == 0) {
+            unsigned long long a = 0, c = 0;
+            for (int i = tid; i < G; i += SEL_THREADS) {
+                a += __ldcg(&p.blk[3 * G + i]);
+                c += __ldcg(&p.blk[4 * G + i]);
+            }
+            shk[tid] = a;
+            shs[tid] = c;
+            __syncthreads();
+            for (int q = SEL_THREADS / 2; q > 0; q >>= 1) {
+                if (tid < q) {
+                    shk[tid] += shk[tid + q];
+                    shs[tid] += shs[tid + q];
+                }
+                __syncthreads();
+            }
+            if (tid < 16) s_hdr[tid] = tid == 0 ? shk[0] : (tid == 1 ? shs[0] : 0ULL);
+            __syncthreads();
+            const unsigned long long seq = xchg_all(p, s_hdr, nullptr, nullptr, 0, s_ll);
+            if (tid == 0) {
+                unsigned long long eq_before = 0ULL, my_less = 0ULL, my_eq = 0ULL;
+                for (int r = 0; seq && r < p.R; ++r) {
+                    const unsigned long long* pay = xb_payload(p.xbuf[p.rank], seq, r);
+                    if (r < p.rank) eq_before += __ldcg(&pay[1]);
+                    if (r == p.rank) {
+                        my_less = __ldcg(&pay[0]);
+                        my_eq = __ldcg(&pay[1]);
+                    }
+                }
+                unsigned long long share = tie_take > eq_before ? tie_take - eq_before : 0ULL;
+                if (share > my_eq) share = my_eq;
+                p.gblock[8] = share;
+                p.gblock[9] = my_less + share;
+                p.gblock[7] = seq ? 0ULL : 1ULL;
+            }
+            __threadfence();
+        }
+        grid.sync();
+        if (__ldcg(&p.gblock[7])) {
+            if (b == 0 && tid == 0) p.ctl[11] = 1;
+            return;
+        }
+        tie_take_local = __ldcg(&p.gblock[8]);
+        K_local = __ldcg(&p.gblock[9]);
     }
     {
         unsigned long long a = 0, c = 0;
@@ -1584,8 +1832,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
 #pragma unroll
         for (int u = 0; u < SEL_ITEMS; ++u) {
             const bool is_less = (fl >> u) & 1u, is_eq = (fe >> u) & 1u;
-            if (is_less || (is_eq && eq_before < tie_take)) {
-                const unsigned long long pos = less_before + (eq_before < tie_take ? eq_before : tie_take);
+            if (is_less || (is_eq && eq_before < tie_take_local)) {
+                const unsigned long long pos = less_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
                 p.list[pos] = (int)(i_lo + u);
             }
             less_before += is_less;
@@ -1597,11 +1845,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     }
     if (b == 0 && tid == 0) {
         *p.st = lst;
-        p.ctl[0] = 2 * (long long)lst.K;
+        p.ctl[0] = 2 * (long long)K_local;
         p.ctl[1] = 1;
         p.ctl[2] = n;
-        p.ctl[3] = (long long)lst.K;
+        p.ctl[3] = (long long)K_local;
         p.ctl[6] += (long long)lst.ambiguous;
+        p.ctl[7] = (long long)lst.K;  // pops of the whole partition
     }
 }
 
@@ -1787,7 +2036,7 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
 static int g_coop_blocks_per_sm = -1;
 cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
                          int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hsets, int parity,
-                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s) {
+                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s, const PkShard* shard) {
     if (g_coop_blocks_per_sm < 0) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_iter_coop, SEL_THREADS, 0);
@@ -1816,6 +2065,16 @@ cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long 
     p.cand_key = cand_key;
     p.cand_idx = cand_idx;
     p.list = list;
+    p.R = 1;
+    p.rank = 0;
+    for (int r = 0; r < PK_MAX_RANKS; ++r) p.xbuf[r] = nullptr;
+    p.gblock = nullptr;
+    if (shard && shard->R > 1) {
+        p.R = shard->R;
+        p.rank = shard->rank;
+        for (int r = 0; r < shard->R; ++r) p.xbuf[r] = (unsigned long long*)shard->xbuf[r];
+        p.gblock = shard->gblock;
+    }
     void* args[1] = {&p};
     return cudaLaunchCooperativeKernel((const void*)k_iter_coop, dim3((unsigned)G), dim3(SEL_THREADS), args, 0, s);
 }

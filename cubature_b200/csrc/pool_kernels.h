@@ -63,9 +63,27 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
                      cudaStream_t s);
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
+// peer exchange buffer of a sharded pool (one per rank, mapped into every peer; 8-byte words):
+//   [PK_XB_FLAGS + parity * PK_MAX_RANKS + src]  flag: sequence number of src's latest exchange of that parity
+//   [PK_XB_SEQ]                                  exchanges this rank has started (kept across launches and calls)
+//   [PK_XB_DATA + (parity * PK_MAX_RANKS + src) * PK_XB_PAY ..]  payload of src: header[16] | cnt[n] | sum[n]
+#define PK_MAX_RANKS 16
+#define PK_XB_FLAGS 0
+#define PK_XB_SEQ 32
+#define PK_XB_DATA 64
+#define PK_XB_PAY (16 + 2 * 2048 + 48)
+#define PK_XB_WORDS (PK_XB_DATA + 2 * PK_MAX_RANKS * PK_XB_PAY)
+#define PK_XB_BYTES (PK_XB_WORDS * 8)
+#define PK_XCHG_TIMEOUT_NS 8000000000ULL
+// sharded pool: this rank's view of the peer exchange buffers (nullptr / R == 1: single GPU)
+struct PkShard {
+    int R, rank;
+    void* xbuf[PK_MAX_RANKS];
+    unsigned long long* gblock;  // [16] words of local device scratch
+};
 cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
                          int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hsets, int parity,
-                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s);
+                         unsigned long long* cand_key, int* cand_idx, int* list, int n_sms, cudaStream_t s, const PkShard* shard = nullptr);
 int pk_iter_coop_max_blocks(int n_sms);
 // one histogram set of the cooperative iteration kernel: cnt[7][2048] u64 | sum[7][2048] f64 | misc[8]
 #define PK_COOP_SET_WORDS (2 * 7 * 2048 + 8)

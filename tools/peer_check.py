@@ -1,0 +1,68 @@
+"""Multi-GPU check of the sharded device loop (run under torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/peer_check.py
+Every case is integrated on one GPU (each rank does that on its own device: identical bits) and on the pool sharded
+over all ranks; the batches, numEval and region counts must be identical and value / error agree to 1e-12."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+import cubature_b200 as cb
+import cases
+
+rank = int(os.environ.get("RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+id_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    id_t = torch.frombuffer(bytearray(cb.Comm.unique_id()), dtype=torch.uint8).cuda()
+dist.broadcast(id_t, 0)
+comm = cb.Comm.init(bytes(id_t.cpu().numpy().tobytes()), world, rank, local_rank)
+NAN = float("nan")
+CASES = [
+    # name, dim, relTol, maxEval, shard_min
+    ("corner_peak", 6, 1e-13, int(3e9), 0),
+    ("corner_peak", 6, 1e-13, int(2e8), 4096),
+    ("corner_peak", 5, 1e-8, 0, 0),
+    ("product_peak", 5, 1e-8, 0, 1024),
+    ("gaussian", 4, 1e-7, 0, 256),
+    ("oscillatory", 3, 1e-9, 0, 64),
+    ("discontinuous", 3, 1e-3, int(4e7), 64),
+    ("c0", 4, 1e-5, int(2e8), 128),
+]
+bad = 0
+for name, dim, rel, max_eval, smin in CASES:
+    p = cases.genz_params(name, dim)
+    ig = cb.Integrand.builtin(cases.GENZ[name], dim, 1, p)
+    args = ([0.0] * dim, [1.0] * dim, rel, NAN, cb.CubatureError.INDIVIDUAL, max_eval)
+    r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, trace_batches=4096)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r2, s2, t2 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm, shard_min_regions=smin, trace_batches=4096)
+    dt = time.perf_counter() - t0
+    same = (t1.batches == t2.batches and s1.num_eval == s2.num_eval and s1.num_regions == s2.num_regions and s1.converged == s2.converged)
+    rel_v = abs(r1[0][0] - r2[0][0]) / max(abs(r1[0][0]), 1e-300)
+    rel_e = abs(r1[1][0] - r2[1][0]) / max(abs(r1[1][0]), 1e-300)
+    ok = same and rel_v <= 1e-12 and rel_e <= 1e-9
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("%-14s d=%d rel=%g maxEval=%d shard_min=%d: %s  regions=%d iters=%d conv=%d  |dv|/v=%.1e |de|/e=%.1e  single %.2f ms  sharded(%d) %.2f ms (wall %.2f)  ambiguous %d/%d"
+              % (name, dim, rel, max_eval, smin, "OK" if flag.item() == 0 else "MISMATCH", s2.num_regions, s2.iterations, s2.converged, rel_v, rel_e,
+                 s1.device_ms, world, s2.device_ms, dt * 1e3, s1.ambiguous_decisions, s2.ambiguous_decisions), flush=True)
+        if not same:
+            for i, (a, b) in enumerate(zip(t1.batches, t2.batches)):
+                if a != b:
+                    print("   first batch difference at iteration", i, a, b, "of", len(t1.batches), len(t2.batches))
+                    break
+    bad += int(flag.item())
+comm.close()
+dist.destroy_process_group()
+sys.exit(1 if bad else 0)
