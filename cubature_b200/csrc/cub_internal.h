@@ -78,8 +78,8 @@ struct cub_comm {
     // NVLink peer exchange (NCCL communicators only): every rank owns one exchange buffer in its HBM, mapped
     // into all peers with CUDA IPC; the sharded iteration kernel publishes and gathers through these
     // directly (pool_kernels.cu: k_iter_coop with R > 1), so the refinement loop itself makes no NCCL call.
-    // The exchange sequence number lives in the buffer itself (PK_XB_SEQ).
     bool peer_ok = false;
+    unsigned long long seq = 1;  // sequence number of the next exchange (every launch reports how many it ran)
     void* xbuf[CUB_MAX_RANKS] = {nullptr};  // xbuf[rank] = own buffer, others = IPC mappings
 };
 int cub_comm_allgather(cub_comm* comm, const void* dev_send, size_t bytes, void* dev_recv, cudaStream_t stream);

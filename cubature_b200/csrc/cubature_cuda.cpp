@@ -1124,6 +1124,7 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
     Pool& pool = W.pool;
     SelectBuffers& sel = W.sel;
     const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    const bool debug_peer = getenv("CUBATURE_DEBUG_PEER") != nullptr;
     auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
@@ -1242,6 +1243,7 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
         const double band = 4.0 * eps * std::sqrt(ops);
         SelScratch sc = sel.scratch(pool.cap);
         {
+            shard.seq0 = comm->seq;
             cudaError_t e = pk_iter_coop(pv, f, N, Kcap, absTol, relTol, norm, band, 1, d_part, d_blk, d_ctl, sc.state,
                                          (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
                                          sel.idxA.as<int>(), S.n_sms, S.stream, &shard);
@@ -1266,11 +1268,19 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
         CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
         S.d2h_bytes += (int64_t)ctl_words * 8;
         CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        if (debug_peer)
+            fprintf(stderr, "[peer rank %d] iter %d seq0 %llu exchanges %lld N %lld Nglobal %lld K %lld Kglobal %lld conv %lld all %lld totals %.17g %.17g disagreeing CTAs %lld\n", rank,
+                    n_iters, comm->seq, h_ctl[13], N, h_ctl[12], h_ctl[3], h_ctl[7], h_ctl[4], h_ctl[5], h_totals[0], h_totals[1], h_ctl[14]);
+        comm->seq += (unsigned long long)h_ctl[13];
         if (h_ctl[11]) {
             cub_set_message(S.msg, "peer exchange timed out: a rank of the communicator did not take part in the iteration");
             return CUB_ERR_NCCL;
         }
         res->ambiguous += h_ctl[6];
+        if (h_ctl[14]) {
+            cub_set_message(S.msg, "internal: %lld CTAs of the iteration kernel disagree on the selection state", h_ctl[14]);
+            return CUB_ERR_CUDA;
+        }
         Nglobal = h_ctl[12];
         ++n_iters;
         if (h_ctl[4]) {
@@ -1304,6 +1314,7 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
     }
     if (!have_totals) {  // stopped by maxEval: K5 over the final shards, exchanged and added in rank order
         SelScratch sc = sel.scratch(pool.cap);
+        shard.seq0 = comm->seq;
         cudaError_t e = pk_iter_coop(pool.view(), f, N, Nglobal, absTol, relTol, norm, 0.0, 0, d_part, d_blk, d_ctl, sc.state,
                                      (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
                                      sel.idxA.as<int>(), S.n_sms, S.stream, &shard);
@@ -1315,6 +1326,10 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
         CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
         S.d2h_bytes += (int64_t)ctl_words * 8;
         CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        if (debug_peer)
+            fprintf(stderr, "[peer rank %d] final seq0 %llu exchanges %lld N %lld Nglobal %lld totals %.17g %.17g\n", rank, comm->seq, h_ctl[13], N,
+                    h_ctl[12], h_totals[0], h_totals[1]);
+        comm->seq += (unsigned long long)h_ctl[13];
         if (h_ctl[11]) {
             cub_set_message(S.msg, "peer exchange timed out: a rank of the communicator did not take part in the final sum");
             return CUB_ERR_NCCL;
@@ -1451,6 +1466,10 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
             S.d2h_bytes += (int64_t)ctl_words * 8;
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
             res->ambiguous += h_ctl[6];
+            if (h_ctl[14]) {
+                cub_set_message(S.msg, "internal: %lld CTAs of the iteration kernel disagree on the selection state", h_ctl[14]);
+                return CUB_ERR_CUDA;
+            }
             if (h_ctl[4]) {
                 conv = true;
                 have_totals = true;
@@ -1841,6 +1860,7 @@ int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* t
     const int f = S.fdim;
     Pool& pool = S.ws->pool;
     CUB_CUDA_CHECK(pool.alloc(dim, f, nR), S.msg);
+    pool.cap = nR;  // dense rows: the host copies below assume stride nR (the cached buffers may be larger)
     // [nR][dim] -> [dim][nR]
     std::vector<double> tmp((size_t)nR * std::max(dim, f));
     for (int pass = 0; pass < 2; ++pass) {

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "converge.h"
 #include "pool_kernels.h"
@@ -889,7 +890,9 @@ namespace cg = cooperative_groups;
 constexpr int SEL_LEVELS = 7;
 constexpr int SEL_LB = 2048;  // buckets of levels 1..5
 __device__ __forceinline__ int sel_shift(int level) { return level == 0 ? 56 : (level <= 5 ? 56 - 11 * level : 0); }
-__device__ __forceinline__ int sel_nbuckets(int level) { return level == 0 ? 256 : (level <= 5 ? SEL_LB : 2); }
+// (the last level re-reads bits 7..1, which are already decided, so that it has one bucket per thread like level 0;
+//  only the two buckets that match the prefix can be occupied)
+__device__ __forceinline__ int sel_nbuckets(int level) { return level == 0 ? 256 : (level <= 5 ? SEL_LB : 256); }
 __device__ __forceinline__ unsigned long long sel_key_of_err(double e) { return ~dbits(e > 0.0 ? e : 0.0); }
 
 struct IterParams {
@@ -911,6 +914,8 @@ struct IterParams {
     int R, rank;
     unsigned long long* xbuf[PK_MAX_RANKS];  // [rank] = own buffer, others = peer mappings (layout: pool_kernels.h)
     unsigned long long* gblock;              // [16] local global scratch: combined totals / decisions of CTA 0
+    unsigned long long seq0;                 // sequence number of this launch's first exchange
+    int xsliced;                             // 1: the first CTAs share an exchange (one 256-bucket slice each); 0: CTA 0 alone
 };
 // histogram set layout (8-byte words): cnt[SEL_LEVELS][SEL_LB] | sum[SEL_LEVELS][SEL_LB] | misc[8] ([0] candidate count)
 __device__ __forceinline__ unsigned long long* set_cnt(unsigned long long* set, int level) { return set + (size_t)level * SEL_LB; }
@@ -919,14 +924,16 @@ __device__ __forceinline__ double* set_sum(unsigned long long* set, int level) {
 }
 __device__ __forceinline__ unsigned long long* set_misc(unsigned long long* set) { return set + (size_t)2 * SEL_LEVELS * SEL_LB; }
 
-// ---- exchange between the ranks of a sharded pool (CTA 0 only, all SEL_THREADS threads) ---------------------
-// Push model: every rank writes its payload into slot [parity][rank] of EVERY rank's buffer (plain stores over
-// NVLink), fences, then raises flag [parity][rank] = seq in every buffer; it then waits for the R flags of its own
-// buffer and reads the R payloads locally (L2, __ldcg).  seq counts the exchanges of the communicator's life (kept
-// in the own buffer), parity = seq & 1: a rank can run at most one exchange ahead of its slowest peer (it needs the
-// peer's flag of exchange e to finish e), so two payload slots suffice.  All ranks execute the same exchanges in
-// the same order (their control flow depends on combined data only).  A wait that lasts longer than
-// PK_XCHG_TIMEOUT_NS marks the launch failed instead of hanging the GPU.
+// ---- exchange between the ranks of a sharded pool ------------------------------------------------------------
+// Push model, sliced over CTAs: CTA c < nslices owns the histogram buckets [256 c, 256 c + 256) (CTA 0 also the 16-word
+// header).  It writes its slice of this rank's payload into slot [parity][rank] of EVERY rank's buffer (plain stores over
+// NVLink), fences, raises flag [parity][rank][c] = seq in every buffer, waits for the R flags [parity][*][c] of its own
+// buffer, then adds the R slices in rank order (identical bits on every rank) and stores the sum as this rank's
+// "global" histogram.  seq counts the exchanges of the communicator's life (host-tracked: cub_comm::seq), parity =
+// seq & 1: a rank can run at most one exchange ahead of its slowest peer (it needs the peer's flags of exchange e to
+// finish e, and its own CTAs meet at a grid barrier after every exchange), so two payload slots suffice.  All ranks
+// execute the same exchanges in the same order (their control flow depends on combined data only).  A wait longer
+// than PK_XCHG_TIMEOUT_NS marks the launch failed (gblock[7]) instead of hanging the GPU.
 __device__ __forceinline__ void st_release_sys(unsigned long long* ptr, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
 }
@@ -943,50 +950,57 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ unsigned long long* xb_payload(unsigned long long* buf, unsigned long long seq, int src_rank) {
     return buf + PK_XB_DATA + ((size_t)(seq & 1ULL) * PK_MAX_RANKS + (size_t)src_rank) * PK_XB_PAY;
 }
-// payload = hdr[0..16) from shared memory `hdr`, then n_cnt words from cnt, then n_cnt words from sum (either may be null)
-// returns the sequence number used (0 on timeout); on return the R payloads are readable with xb_payload(own, seq, r)
-__device__ unsigned long long xchg_all(const IterParams& p, const unsigned long long* hdr, const unsigned long long* cnt, const double* sum,
-                                       int n_cnt, long long* s_ll) {
+__device__ __forceinline__ unsigned long long* xb_flag(unsigned long long* buf, unsigned long long seq, int src_rank, int slice) {
+    return buf + PK_XB_FLAGS + ((size_t)(seq & 1ULL) * PK_MAX_RANKS + (size_t)src_rank) * PK_XB_SLICES + (size_t)slice;
+}
+// Called by every CTA (all SEL_THREADS threads); CTAs with blockIdx.x >= nslices return at once.  hdr: shared memory of
+// CTA 0 (16 words).  n_cnt buckets (0: header only); cnt/sum in: this rank's histogram, out: the partition's.
+__device__ void xchg_slice_body(const IterParams& p, unsigned long long seq, const unsigned long long* hdr, unsigned long long* cnt, double* sum,
+                                int n_cnt, int slice);
+__device__ void xchg_slice(const IterParams& p, unsigned long long seq, const unsigned long long* hdr, unsigned long long* cnt, double* sum,
+                           int n_cnt) {
+    const int nslices = n_cnt > SEL_THREADS ? n_cnt / SEL_THREADS : 1;
+    if (p.xsliced) {
+        if ((int)blockIdx.x < nslices) xchg_slice_body(p, seq, hdr, cnt, sum, n_cnt, blockIdx.x);
+    } else if (blockIdx.x == 0) {  // CTA 0 runs the slices one after the other
+        for (int sl = 0; sl < nslices; ++sl) xchg_slice_body(p, seq, hdr, cnt, sum, n_cnt, sl);
+    }
+}
+__device__ void xchg_slice_body(const IterParams& p, unsigned long long seq, const unsigned long long* hdr, unsigned long long* cnt, double* sum,
+                                int n_cnt, int slice) {
     const int tid = threadIdx.x;
     unsigned long long* own = p.xbuf[p.rank];
-    const unsigned long long seq = *(volatile unsigned long long*)&own[PK_XB_SEQ] + 1ULL;  // thread 0 advances it below
-    __syncthreads();
+    const int q = slice * SEL_THREADS + tid;
+    const bool have = q < n_cnt;
+    unsigned long long c_val = 0ULL, s_val = 0ULL;
+    if (have) {
+        c_val = __ldcg(&cnt[q]);
+        s_val = dbits(__ldcg(&sum[q]));
+    }
     for (int r = 0; r < p.R; ++r) {
         unsigned long long* dst = xb_payload(p.xbuf[r], seq, p.rank);
-        if (tid < 16) dst[tid] = hdr[tid];
-        if (cnt)
-            for (int q = tid; q < n_cnt; q += SEL_THREADS) {
-                dst[16 + q] = __ldcg(&cnt[q]);
-                dst[16 + n_cnt + q] = (unsigned long long)__double_as_longlong(__ldcg(&sum[q]));
-            }
+        if (slice == 0 && tid < 16) dst[tid] = hdr[tid];
+        if (have) {
+            dst[16 + q] = c_val;
+            dst[16 + n_cnt + q] = s_val;
+        }
     }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) {
-        own[PK_XB_SEQ] = seq;
-        s_ll[1] = 1;
-    }
-    if (tid < p.R) st_release_sys(p.xbuf[tid] + PK_XB_FLAGS + (size_t)(seq & 1ULL) * PK_MAX_RANKS + p.rank, seq);
-    __syncthreads();
     if (tid < p.R) {
-        const unsigned long long* f = own + PK_XB_FLAGS + (size_t)(seq & 1ULL) * PK_MAX_RANKS + tid;
+        st_release_sys(xb_flag(p.xbuf[tid], seq, p.rank, slice), seq);
+        const unsigned long long* f = xb_flag(own, seq, tid, slice);
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(f) < seq) {
             if (global_timer_ns() - t0 > PK_XCHG_TIMEOUT_NS) {
-                s_ll[1] = 0;
+                atomicExch(&p.gblock[7], 1ULL);
                 break;
             }
-            __nanosleep(100);
         }
     }
     __syncthreads();
     __threadfence_system();
-    return s_ll[1] ? seq : 0ULL;
-}
-// adds the R histograms of an exchange in rank order and stores the result as this rank's "global" histogram
-__device__ void xchg_combine_hist(const IterParams& p, unsigned long long seq, unsigned long long* cnt, double* sum, int n_cnt) {
-    unsigned long long* own = p.xbuf[p.rank];
-    for (int q = threadIdx.x; q < n_cnt; q += SEL_THREADS) {
+    if (have) {
         unsigned long long c = 0ULL;
         double sacc = 0.0;
         for (int r = 0; r < p.R; ++r) {
@@ -1003,9 +1017,9 @@ __device__ void xchg_combine_hist(const IterParams& p, unsigned long long seq, u
 // at which the pop budget runs out or the residual test passes, found with a prefix scan over the buckets.
 // pc / ps: this level's global histogram staged in shared memory.  Returns 1 when the batch size is final
 // (last level, or the chosen bucket holds a single region: then only that region's full key is still missing).
-__device__ int sel_pick_parallel(SelState* lst, const unsigned long long* pc, const double* ps, int NB, int shift, int last, double V, double E,
-                                 unsigned long long Kcap, double absTol, double relTol, int norm, double band, double* sh,
-                                 unsigned long long* shk, unsigned long long* shs, double* s_dbl /*[2]*/, long long* s_ll /*[2]*/) {
+__device__ int sel_pick_parallel(volatile SelState* lst, const unsigned long long* pc, const double* ps, int NB, int shift, int last, double V,
+                                 double E, unsigned long long Kcap, double absTol, double relTol, int norm, double band, double* sh,
+                                 unsigned long long* shk, unsigned long long* shs, volatile double* s_dbl /*[2]*/, volatile long long* s_ll /*[2]*/) {
     const int tid = threadIdx.x;
     const int per_t = NB >= SEL_THREADS ? NB / SEL_THREADS : 1;
     const int first = tid * per_t;
@@ -1081,12 +1095,13 @@ __device__ int sel_pick_parallel(SelState* lst, const unsigned long long* pc, co
                 c_prev = c_loc[q];
                 s_prev = s_loc[q];
             }
-        lst->prefix |= (unsigned long long)chosen << shift;
-        lst->mask |= (unsigned long long)(NB - 1) << shift;
+        lst->prefix = lst->prefix | ((unsigned long long)chosen << shift);
+        lst->mask = lst->mask | ((unsigned long long)(NB - 1) << shift);
         lst->count_cum = count_cum + c_off + c_prev;
         lst->P_cum = j > 0 || tid > 0 ? P_cum + (s_off + s_prev) : P_cum;
         s_ll[0] = (long long)pc[chosen];
         s_dbl[0] = ps[chosen];
+
     }
     __syncthreads();
     const unsigned long long c_b = (unsigned long long)s_ll[0];
@@ -1131,10 +1146,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     __shared__ unsigned long long shk[SEL_THREADS], shs[SEL_THREADS], shm[SEL_THREADS];
     __shared__ unsigned long long pc[SEL_LB];  // staged global counts; its first half doubles as the CTA histogram counts
     __shared__ double ps[SEL_LB];              // staged global sums; doubles as the CTA histogram sums
-    __shared__ SelState lst;
+    __shared__ SelState lst_storage;  // written by single threads, read by all: every access is volatile
+    volatile SelState& lst = lst_storage;
     __shared__ long long s_flags[2];
-    __shared__ double s_dbl[2];
-    __shared__ long long s_ll[2];
+    __shared__ double s_dbl_storage[2];
+    __shared__ long long s_ll_storage[2];
+    volatile double* const s_dbl = s_dbl_storage;
+    volatile long long* const s_ll = s_ll_storage;
     unsigned* const scnt = (unsigned*)pc;  // [SEL_WARPS][256] at level 0, [SEL_LB] at levels >= 1
     double* const ssum = ps;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, fdim = p.fdim;
@@ -1143,6 +1161,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     const PoolView& pool = p.pool;
     const bool scalar_select = fdim == 1 && p.do_select;
     const bool sharded = p.R > 1;
+    unsigned long long xseq = p.seq0;  // next exchange (uniform over the grid and over the ranks)
     __shared__ unsigned long long s_hdr[16];
     if (b == 0 && tid == 0) p.blk[5 * G] = 0ULL;  // "unique key not found here" (a real key has bit 63 set)
     // clear the OTHER histogram set for the next launch (nobody reads or writes it during this one)
@@ -1343,15 +1362,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                     for (int q = 7; q < 16; ++q) s_hdr[q] = 0ULL;
                 }
                 __syncthreads();
-                const unsigned long long seq = xchg_all(p, s_hdr, scalar_select ? set_cnt(p.hset, 0) : nullptr,
-                                                        scalar_select ? set_sum(p.hset, 0) : nullptr, 256, s_ll);
-                if (seq && scalar_select) xchg_combine_hist(p, seq, set_cnt(p.hset, 0), set_sum(p.hset, 0), 256);
+            }
+            const unsigned long long seq = xseq++;
+            xchg_slice(p, seq, s_hdr, set_cnt(p.hset, 0), set_sum(p.hset, 0), scalar_select ? 256 : 0);
+            if (b == 0) {
                 if (tid == 0) {
                     unsigned long long* own = p.xbuf[p.rank];
                     double gV = 0.0, gE = 0.0, gvl = 0.0, gel = 0.0;
                     unsigned long long gmin = ~0ULL, gmax = 0ULL, gN = 0ULL;
                     bool any = false;
-                    for (int r = 0; seq && r < p.R; ++r) {
+                    for (int r = 0; r < p.R; ++r) {
                         const unsigned long long* pay = xb_payload(own, seq, r);
                         const unsigned long long nr = __ldcg(&pay[6]);
                         if (nr == 0ULL) continue;  // a rank without regions contributes nothing
@@ -1374,15 +1394,17 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                     p.gblock[4] = dbits(gvl);
                     p.gblock[5] = dbits(gel);
                     p.gblock[6] = gN;
-                    p.gblock[7] = seq ? 0ULL : 1ULL;  // exchange failed (timeout)
                     totals[0] = gV;
                     totals[1] = gE;
                 }
                 __threadfence();
             }
             grid.sync();
-            if (__ldcg(&p.gblock[7])) {
-                if (b == 0 && tid == 0) p.ctl[11] = 1;  // a peer did not answer
+            if (__ldcg(&p.gblock[7])) {  // a peer did not answer (timeout)
+                if (b == 0 && tid == 0) {
+                    p.ctl[11] = 1;
+                    p.ctl[13] = (long long)(xseq - p.seq0);
+                }
                 return;
             }
             V = __longlong_as_double((long long)__ldcg(&p.gblock[0]));
@@ -1430,6 +1452,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                 p.ctl[6] = amb;
                 p.ctl[7] = all ? n_glob : 0;  // pops of the whole partition
                 p.ctl[12] = n_glob;
+                p.ctl[13] = (long long)(xseq - p.seq0);  // exchanges so far (final unless the select runs)
             }
         }
         __syncthreads();
@@ -1477,7 +1500,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     if (!p.do_select) return;
     // ---- C: weighted radix select, coarse to fine -----------------------------------------------------
     if (tid == 0) {
-        lst.prefix = lst.mask = lst.count_cum = lst.K = lst.tie_take = lst.ambiguous = 0ULL;
+        lst.prefix = 0ULL;
+        lst.mask = 0ULL;
+        lst.count_cum = 0ULL;
+        lst.K = 0ULL;
+        lst.tie_take = 0ULL;
+        lst.ambiguous = 0ULL;
         lst.P_cum = 0.0;
     }
     __syncthreads();
@@ -1588,14 +1616,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                     if (b == 0) {
                         if (tid < 16) s_hdr[tid] = 0ULL;
                         __syncthreads();
-                        const unsigned long long seq = xchg_all(p, s_hdr, gc, gs, NB, s_ll);
-                        if (seq) xchg_combine_hist(p, seq, gc, gs, NB);
-                        if (tid == 0) p.gblock[7] = seq ? 0ULL : 1ULL;
-                        __threadfence();
                     }
+                    xchg_slice(p, xseq++, s_hdr, gc, gs, NB);
+                    __threadfence();
                     grid.sync();
                     if (__ldcg(&p.gblock[7])) {
-                        if (b == 0 && tid == 0) p.ctl[11] = 1;
+                        if (b == 0 && tid == 0) {
+                            p.ctl[11] = 1;
+                            p.ctl[13] = (long long)(xseq - p.seq0);
+                        }
                         return;
                     }
                 }
@@ -1660,24 +1689,27 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                     __syncthreads();
                 }
                 if (sharded) {  // exactly one rank owns that region
+                    const unsigned long long seq = xseq++;
                     if (b == 0) {
                         if (tid < 16) s_hdr[tid] = tid == 0 ? __ldcg(&p.blk[5 * G]) : 0ULL;
                         __syncthreads();
-                        const unsigned long long seq = xchg_all(p, s_hdr, nullptr, nullptr, 0, s_ll);
+                        xchg_slice(p, seq, s_hdr, nullptr, nullptr, 0);
                         if (tid == 0) {
                             unsigned long long key = 0ULL;
-                            for (int r = 0; seq && r < p.R; ++r) {
+                            for (int r = 0; r < p.R; ++r) {
                                 const unsigned long long k = __ldcg(&xb_payload(p.xbuf[p.rank], seq, r)[0]);
                                 if (k) key = k;
                             }
                             p.blk[5 * G] = key;
-                            p.gblock[7] = seq ? 0ULL : 1ULL;
                         }
                         __threadfence();
                     }
                     grid.sync();
                     if (__ldcg(&p.gblock[7])) {
-                        if (b == 0 && tid == 0) p.ctl[11] = 1;
+                        if (b == 0 && tid == 0) {
+                            p.ctl[11] = 1;
+                            p.ctl[13] = (long long)(xseq - p.seq0);
+                        }
                         return;
                     }
                 }
@@ -1691,7 +1723,27 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         }
     }
     // ---- D: stable compaction of the popped slots -----------------------------------------------------
-    const unsigned long long thr = lst.prefix, tie_take = lst.tie_take;
+    // Every CTA has computed the selection state redundantly; CTA 0's copy is the one that counts (it publishes K):
+    // broadcast it so that the compaction below uses one threshold everywhere, and count disagreeing CTAs.
+    const volatile SelState* const vlst = &lst;  // (same object)
+    if (G > 1) {
+        if (b == 0 && tid == 0) {
+            p.blk[5 * G + 1] = vlst->prefix;
+            p.blk[5 * G + 2] = vlst->tie_take;
+            p.blk[5 * G + 3] = vlst->K;
+        }
+        __threadfence();
+        grid.sync();
+        if (tid == 0) {
+            const unsigned long long g_prefix = __ldcg(&p.blk[5 * G + 1]), g_tie = __ldcg(&p.blk[5 * G + 2]), g_K = __ldcg(&p.blk[5 * G + 3]);
+            if (g_prefix != vlst->prefix || g_tie != vlst->tie_take || g_K != vlst->K) atomicAdd((unsigned long long*)&p.ctl[14], 1ULL);
+            lst.prefix = g_prefix;
+            lst.tie_take = g_tie;
+            lst.K = g_K;
+        }
+        __syncthreads();
+    }
+    const unsigned long long thr = vlst->prefix, tie_take = vlst->tie_take;
     if (have_cand) {
         // per-CTA counts: certain pops (level-2 scan) + the candidates below / at the threshold key
         for (long long q = (long long)b * SEL_THREADS + tid; q < M; q += (long long)G * SEL_THREADS) {
@@ -1729,8 +1781,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     } else {
         __syncthreads();
     }
-    unsigned long long tie_take_local = tie_take, K_local = lst.K;
+    unsigned long long tie_take_local = tie_take, K_local = vlst->K;
     if (sharded) {
+        const unsigned long long seq = xseq++;
         // regions equal to the threshold key are taken in (rank, slot) order: every rank publishes how many of its
         // regions are below / at the threshold and takes its share of the global tie budget
         if (b == 0) {
@@ -1751,10 +1804,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
             }
             if (tid < 16) s_hdr[tid] = tid == 0 ? shk[0] : (tid == 1 ? shs[0] : 0ULL);
             __syncthreads();
-            const unsigned long long seq = xchg_all(p, s_hdr, nullptr, nullptr, 0, s_ll);
+            xchg_slice(p, seq, s_hdr, nullptr, nullptr, 0);
             if (tid == 0) {
                 unsigned long long eq_before = 0ULL, my_less = 0ULL, my_eq = 0ULL;
-                for (int r = 0; seq && r < p.R; ++r) {
+                for (int r = 0; r < p.R; ++r) {
                     const unsigned long long* pay = xb_payload(p.xbuf[p.rank], seq, r);
                     if (r < p.rank) eq_before += __ldcg(&pay[1]);
                     if (r == p.rank) {
@@ -1766,13 +1819,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
                 if (share > my_eq) share = my_eq;
                 p.gblock[8] = share;
                 p.gblock[9] = my_less + share;
-                p.gblock[7] = seq ? 0ULL : 1ULL;
+
             }
             __threadfence();
         }
         grid.sync();
         if (__ldcg(&p.gblock[7])) {
-            if (b == 0 && tid == 0) p.ctl[11] = 1;
+            if (b == 0 && tid == 0) {
+                p.ctl[11] = 1;
+                p.ctl[13] = (long long)(xseq - p.seq0);
+            }
             return;
         }
         tie_take_local = __ldcg(&p.gblock[8]);
@@ -1844,13 +1900,21 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         __syncthreads();
     }
     if (b == 0 && tid == 0) {
-        *p.st = lst;
+        p.st->prefix = lst.prefix;
+        p.st->mask = lst.mask;
+        p.st->count_cum = lst.count_cum;
+        p.st->K = lst.K;
+        p.st->tie_take = lst.tie_take;
+        p.st->ambiguous = lst.ambiguous;
+        p.st->P_cum = lst.P_cum;
         p.ctl[0] = 2 * (long long)K_local;
         p.ctl[1] = 1;
         p.ctl[2] = n;
         p.ctl[3] = (long long)K_local;
         p.ctl[6] += (long long)lst.ambiguous;
         p.ctl[7] = (long long)lst.K;  // pops of the whole partition
+        p.ctl[13] = (long long)(xseq - p.seq0);
+
     }
 }
 
@@ -2069,11 +2133,17 @@ cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long 
     p.rank = 0;
     for (int r = 0; r < PK_MAX_RANKS; ++r) p.xbuf[r] = nullptr;
     p.gblock = nullptr;
+    p.seq0 = 0;
+    p.xsliced = 0;
     if (shard && shard->R > 1) {
         p.R = shard->R;
         p.rank = shard->rank;
         for (int r = 0; r < shard->R; ++r) p.xbuf[r] = (unsigned long long*)shard->xbuf[r];
         p.gblock = shard->gblock;
+        p.seq0 = shard->seq0;
+        static const int sliced = [] { const char* e = getenv("CUBATURE_XCHG_SLICED"); return e && e[0] == '1' ? 1 : 0; }();
+        p.xsliced = sliced;
+        if (sliced && G < PK_XB_SLICES) G = PK_XB_SLICES;  // the exchange is sliced over the first CTAs
     }
     void* args[1] = {&p};
     return cudaLaunchCooperativeKernel((const void*)k_iter_coop, dim3((unsigned)G), dim3(SEL_THREADS), args, 0, s);

@@ -64,13 +64,13 @@ void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
 // peer exchange buffer of a sharded pool (one per rank, mapped into every peer; 8-byte words):
-//   [PK_XB_FLAGS + parity * PK_MAX_RANKS + src]  flag: sequence number of src's latest exchange of that parity
-//   [PK_XB_SEQ]                                  exchanges this rank has started (kept across launches and calls)
+//   [PK_XB_FLAGS + (parity * PK_MAX_RANKS + src) * PK_XB_SLICES + slice]  flag: sequence number of src's latest
+//                                                exchange of that parity, one flag per 256-bucket slice of the payload
 //   [PK_XB_DATA + (parity * PK_MAX_RANKS + src) * PK_XB_PAY ..]  payload of src: header[16] | cnt[n] | sum[n]
 #define PK_MAX_RANKS 16
 #define PK_XB_FLAGS 0
-#define PK_XB_SEQ 32
-#define PK_XB_DATA 64
+#define PK_XB_SLICES 8
+#define PK_XB_DATA 512
 #define PK_XB_PAY (16 + 2 * 2048 + 48)
 #define PK_XB_WORDS (PK_XB_DATA + 2 * PK_MAX_RANKS * PK_XB_PAY)
 #define PK_XB_BYTES (PK_XB_WORDS * 8)
@@ -80,6 +80,7 @@ struct PkShard {
     int R, rank;
     void* xbuf[PK_MAX_RANKS];
     unsigned long long* gblock;  // [16] words of local device scratch
+    unsigned long long seq0;     // sequence number of the launch's first exchange (cub_comm::seq)
 };
 cudaError_t pk_iter_coop(const PoolView& pool, int fdim, long long n, long long Kcap, double absTol, double relTol, int norm, double band,
                          int do_select, double* partial, unsigned long long* blk, long long* ctl, void* state, void* hsets, int parity,

@@ -37,6 +37,8 @@ CASES = [
     ("c0", 4, 1e-5, int(2e8), 128),
 ]
 bad = 0
+if os.environ.get("PEER_CASES"):
+    CASES = [CASES[int(i)] for i in os.environ["PEER_CASES"].split(",")]
 for name, dim, rel, max_eval, smin in CASES:
     p = cases.genz_params(name, dim)
     ig = cb.Integrand.builtin(cases.GENZ[name], dim, 1, p)
