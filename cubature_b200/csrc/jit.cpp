@@ -137,11 +137,9 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     // CTAs per SM the scalar Genz-Malik kernel is compiled for (register budget 65536 / (128 * n)); measured on B200
     // (profiles/r01_summary.md, "power"): the rational families run best at 4 (128 registers, next to no spills: the
     // local-memory traffic of the 5- and 6-CTA variants drives the board into its power cap under a sustained load)
-    int min_blocks = 5;
+    int min_blocks = 5;  // Gaussian, C0 and everything not listed (profiles/r01_summary.md, family sweep)
     if (integ->family == CUB_FAM_GENZ_CORNER_PEAK || integ->family == CUB_FAM_GENZ_PRODUCT_PEAK) min_blocks = 4;
-    if (integ->family == CUB_FAM_GENZ_GAUSSIAN || integ->family == CUB_FAM_GENZ_DISCONTINUOUS) min_blocks = 6;
-    if (integ->family == CUB_FAM_GENZ_OSCILLATORY) min_blocks = 4;
-    if (integ->family == CUB_FAM_GENZ_C0) min_blocks = 3;
+    if (integ->family == CUB_FAM_GENZ_OSCILLATORY || integ->family == CUB_FAM_GENZ_DISCONTINUOUS) min_blocks = 4;
     tu << "#ifndef CUB_GM_MIN_BLOCKS\n#define CUB_GM_MIN_BLOCKS " << min_blocks << "\n#endif\n";
     // branch-free reciprocal fast path of the rational built-in families (detmath.h: dm_rcp_flag; the kernel re-evaluates a
     // region with the IEEE division when an argument leaves the fast path's exact range)

@@ -346,3 +346,22 @@ def test_strict_all_option_matches_oracle_extension(cb, oracle):
     r, st, _ = cb.Cubature.integrate_ex(ig, [0, 0], [1, 1], 1e-3, NAN, 0, 0)
     assert st.num_regions == 1
 
+
+
+@pytest.mark.gpu
+def test_sharded_pool_over_nvlink_peers_matches_single_gpu():
+    """Section 8(e) on real peers: one process per GPU (torchrun), the sharded loop with the in-kernel NVLink exchange
+    (k_iter_coop with R > 1) against the 1-GPU run of the same cases -- identical batches and counts, values to 1e-12.
+    Needs at least two GPUs (skipped on a one-GPU box; `gpurun --gpus 2` runs it)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout and r.stdout.count("OK") + r.stdout.count("AMBIGUOUS") >= 8
