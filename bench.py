@@ -38,6 +38,7 @@ DIM = 6
 P = 149
 F_REGION = 3643.0      # algorithmic flops per evaluated 6-D corner-peak region
 BYTES_REGION = 124.0   # algorithmic HBM bytes per evaluated region
+TRAFFIC_REGION = 207.0 # DRAM bytes per evaluated region of the bisecting rule launch, ncu --set full (profiles/r01_summary.md)
 NAN = float("nan")
 
 
@@ -183,6 +184,9 @@ def main():
         torch.cuda.synchronize()
 
     fp64_peak = cb.fp64_peak_tflops(local_rank)
+    # the same probe back to back for 300 ms: on these boards the pure-DFMA probe does not reach the power cap, so
+    # burst and sustained agree; a rule kernel that spills to local memory does (profiles/r01_summary.md, "power")
+    fp64_burst, fp64_sustained = cb.fp64_peak_sustained_tflops(local_rank, 300.0) if rank == 0 else (fp64_peak, fp64_peak)
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -245,7 +249,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "genz_corner_peak_d6 [0,1]^6 relTol=1e-13 maxEval=%d total (BASELINE config C5), select=device" % max_eval,
                    "regions_per_step": regions, "points_per_region": P, "l2": "pool per step >> 126 MB L2, no flush needed",
-                   "parallelism": "pool sharded over %d GPU(s), NCCL allreduce per iteration" % world if world > 1 else "1 GPU"},
+                   "parallelism": ("pool sharded over %d GPUs, one cooperative kernel per iteration with the exchange over NVLink peer memory "
+                                   "(no NCCL call in the loop)" % world) if world > 1 else "1 GPU"},
         "fevals_per_s": value * P,
         "result": {"val": float(result[0][0]), "err": float(result[1][0])},
         "e2e": {"value": e2e, "unit": "regions/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
@@ -253,10 +258,11 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "kernel": "cub_gm_scalar", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp64_peak,
-                     # DRAM bytes per average rule launch: 207 B per evaluated region measured with `ncu --set full`
-                     # (dram__bytes_read.sum + dram__bytes_write.sum of one 5.99e7-region launch, profiles/r01_summary.md)
-                     "traffic": 207.0 * regions / max(1, rule_launches_per_step),
-                     "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                     # DRAM bytes per average rule launch: TRAFFIC_REGION per evaluated region measured with `ncu --set full`
+                     # (dram__bytes_read.sum + dram__bytes_write.sum of one 6e7-region launch, profiles/r01_summary.md)
+                     "traffic": TRAFFIC_REGION * regions / max(1, rule_launches_per_step),
+                     "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak), best 10 ms launch; MEASURED_PEAKS.json has no FP64 entry",
+                     "peak_sustained": fp64_sustained,
                      "flops_per_region": F_REGION, "rule_kernel_ms_per_step": tot_rule_ms / steps,
                      "rule_regions_per_s_per_gpu": rule_regions_per_s,
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,

@@ -113,10 +113,25 @@ struct Pool {
         return v;
     }
     static size_t bytes_per_region(int dim, int fdim) { return (size_t)8 * (2 * dim + 2 * fdim + 1) + 4; }
-    cudaError_t alloc(int dim_, int fdim_, long long cap_) {
+    static constexpr size_t kPresizeBytes = (size_t)512 << 20;
+    // cap_: capacity the caller would like (an upper bound derived from maxEval, or an explicit request when `exact`).
+    // Unless exact, at most kPresizeBytes of pool are allocated up front -- the loop grows the pool on demand -- and
+    // buffers cached from an earlier call are used as they are: a call never pays a multi-GB cudaFree / cudaMalloc
+    // because the free-memory estimate behind cap_ moved a little.
+    cudaError_t alloc(int dim_, int fdim_, long long cap_, bool exact = false) {
         dim = dim_;
         fdim = fdim_;
         cap = cap_;
+        if (!exact) {
+            size_t have = center.bytes / ((size_t)8 * dim);
+            have = std::min(have, halfw.bytes / ((size_t)8 * dim));
+            have = std::min(have, val.bytes / ((size_t)8 * fdim));
+            have = std::min(have, err.bytes / ((size_t)8 * fdim));
+            have = std::min(have, errmax.bytes / 8);
+            have = std::min(have, splitdim.bytes / 4);
+            const long long presize = std::max<long long>(1 << 12, (long long)(kPresizeBytes / bytes_per_region(dim, fdim)));
+            cap = std::min<long long>(cap_, std::max<long long>(presize, (long long)have));
+        }
         cudaError_t e;
         if ((e = center.ensure((size_t)8 * dim * cap)) != cudaSuccess) return e;
         if ((e = halfw.ensure((size_t)8 * dim * cap)) != cudaSuccess) return e;
@@ -138,7 +153,7 @@ struct Pool {
     // re-stride every row into a pool of larger capacity (n live regions)
     cudaError_t grow(long long new_cap, long long n, cudaStream_t s) {
         Pool np;
-        cudaError_t e = np.alloc(dim, fdim, new_cap);
+        cudaError_t e = np.alloc(dim, fdim, new_cap, true);
         if (e != cudaSuccess) return e;
         auto rows = [&](DevBuf& dst, DevBuf& src, int nrows, size_t elt) {
             return cudaMemcpy2DAsync(dst.p, (size_t)new_cap * elt, src.p, (size_t)cap * elt, (size_t)n * elt, nrows,
@@ -558,6 +573,7 @@ struct LoopState {
     int64_t numEval = 0;
     double ops = 1.0;
     bool handoff = false;
+    long long cap_hint = 0;  // capacity maxEval can need on this rank (upper bound for pool growth)
 };
 int integrate_device_fused(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                            LoopResult* res, long long stop_at_regions = 0, LoopState* state_out = nullptr, long long cap_override = 0);
@@ -823,7 +839,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             const long long n_local = cubature_cuda_shard_count(N, R, rank);
             // gather into a small temporary (the pool is still tiny here), then copy the rows back in place
             Pool tmp;
-            CUB_CUDA_CHECK(tmp.alloc(S.dim, f, std::max<long long>(n_local, 1)), S.msg);
+            CUB_CUDA_CHECK(tmp.alloc(S.dim, f, std::max<long long>(n_local, 1), true), S.msg);
             // rank the regions by errmax (stable radix sort, identical on every rank) and deal round robin
             CUB_CUDA_CHECK(sel.ensure(N, f), S.msg);
             unsigned long long* ka = sel.keysA.as<unsigned long long>();
@@ -1227,6 +1243,7 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
         const long long Klocal_max = std::min<long long>(N, Kcap);
         if (N + Klocal_max > pool.cap) {
             long long nc = std::max<long long>(pool.cap * 2, N + Klocal_max);
+            if (st0.cap_hint > N + Klocal_max) nc = std::min(nc, st0.cap_hint);
             cudaError_t e = pool.grow(nc, N, S.stream);
             if (e != cudaSuccess) {
                 cudaGetLastError();
@@ -1363,7 +1380,7 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     Pool& pool = W.pool;
     const size_t extra = 24 + (size_t)8 * f + 1;
     long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
-    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap), S.msg);
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
 
@@ -1402,12 +1419,21 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     bool conv = false, have_totals = false;
     double ops = 1.0;
     const double eps = 2.220446049250313e-16;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    double t_coop = 0, t_rule = 0, t_wait = 0, t_grow = 0;
+    int n_grow = 0;
+    auto tick = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    const auto t_loop = tick();
 
     while (numEval < maxEval || maxEval == 0) {
         if (stop_at_regions > 0 && N >= stop_at_regions) {  // multi-GPU: time to deal the pool out to the ranks
             state_out->N = N;
             state_out->numEval = numEval;
             state_out->ops = ops;
+            state_out->cap_hint = cap;
             state_out->handoff = true;
             return CUB_OK;
         }
@@ -1418,7 +1444,10 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
         }
         // the rule kernel is sized on the device: make room for the largest batch this iteration can pop
         if (N + Kcap > pool.cap) {
+            const auto tg = tick();
+            ++n_grow;
             long long nc = std::max<long long>(pool.cap * 2, N + Kcap);
+            if (cap > N + Kcap) nc = std::min(nc, cap);  // never beyond what maxEval can need
             cudaError_t e = pool.grow(nc, N, S.stream);
             if (e != cudaSuccess) {
                 cudaGetLastError();
@@ -1426,6 +1455,7 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
                 return CUB_ERR_POOL_EXHAUSTED;
             }
             CUB_CUDA_CHECK(sel.ensure_scalar(pool.cap), S.msg);
+            t_grow += ms_since(tg);
         }
         if (N + Kcap > (long long)std::numeric_limits<int>::max()) {
             cub_set_message(S.msg, "region pool exceeds 2^31 slots");
@@ -1437,6 +1467,7 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
         sc.ctl = d_ctl;
         // ONE cooperative launch: totals, loop decisions and (scalar integrands) the whole batch selection
         {
+            const auto tc = tick();
             cudaError_t e = pk_iter_coop(pv, f, N, Kcap, absTol, relTol, norm, band, f == 1 ? 1 : 0, d_part, d_blk, d_ctl, sc.state,
                                          (unsigned char*)sc.state + 512, coop_parity++, sel.keysA.as<unsigned long long>(), sel.idxB.as<int>(),
                                          sel.idxA.as<int>(), S.n_sms, S.stream);
@@ -1444,6 +1475,7 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
                 cub_set_message(S.msg, "cooperative launch failed: %s", cudaGetErrorString(e));
                 return CUB_ERR_CUDA;
             }
+            t_coop += ms_since(tc);
         }
         S.launches += 1;
         long long K = 0;
@@ -1457,14 +1489,18 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
             w.base = N;
             w.mode = MODE_BISECT;
             if (device_sized) {
+                const auto tr0 = tick();
                 w.dyn = d_ctl;
                 w.n_items = 2 * Kcap;  // upper bound: sizes the grid only
                 rc = S.launch_rule(pool.view(), w);
                 if (rc != CUB_OK) return rc;
+                t_rule += ms_since(tr0);
             }
+            const auto tw = tick();
             CUB_CUDA_CHECK(cudaMemcpyAsync(h_ctl, d_ctl, ctl_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
             S.d2h_bytes += (int64_t)ctl_words * 8;
             CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            t_wait += ms_since(tw);
             res->ambiguous += h_ctl[6];
             if (h_ctl[14]) {
                 cub_set_message(S.msg, "internal: %lld CTAs of the iteration kernel disagree on the selection state", h_ctl[14]);
@@ -1576,6 +1612,9 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     }
     for (int j = 0; j < 2 * f; ++j) out[j] = h_totals[j];
     S.flush_rule_timer();
+    if (timing)
+        fprintf(stderr, "[cubature] device loop: %lld iterations, %.2f ms: host time in coop launch %.2f, rule launch %.2f, read-back wait %.2f, %d pool growths %.2f ms; rule kernels %.2f ms\n",
+                (long long)res->iterations, ms_since(t_loop), t_coop, t_rule, t_wait, n_grow, t_grow, S.rule_ms);
     res->converged = conv ? 1 : 0;
     res->num_eval = numEval;
     res->num_regions = N;
@@ -1859,7 +1898,7 @@ int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* t
     if (rc != CUB_OK) return rc;
     const int f = S.fdim;
     Pool& pool = S.ws->pool;
-    CUB_CUDA_CHECK(pool.alloc(dim, f, nR), S.msg);
+    CUB_CUDA_CHECK(pool.alloc(dim, f, nR, true), S.msg);
     pool.cap = nR;  // dense rows: the host copies below assume stride nR (the cached buffers may be larger)
     // [nR][dim] -> [dim][nR]
     std::vector<double> tmp((size_t)nR * std::max(dim, f));
@@ -1948,7 +1987,7 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
     // 2 n_regions children per launch, every launch halves the boxes again) instead of the plain evaluation
     const char* bm = getenv("CUBATURE_BENCH_MODE");
     const bool bisect = bm && strcmp(bm, "bisect") == 0 && f == 1 && dim >= 2;
-    CUB_CUDA_CHECK(pool.alloc(dim, f, bisect ? 2 * n_regions : n_regions), S.msg);
+    CUB_CUDA_CHECK(pool.alloc(dim, f, bisect ? 2 * n_regions : n_regions, true), S.msg);
     // uniform slabs along dimension 0: region i covers [xmin0 + i*w, xmin0 + (i+1)*w] x the full box elsewhere
     {
         std::vector<double> row((size_t)n_regions);
