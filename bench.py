@@ -38,7 +38,7 @@ DIM = 6
 P = 149
 F_REGION = 3643.0      # algorithmic flops per evaluated 6-D corner-peak region
 BYTES_REGION = 124.0   # algorithmic HBM bytes per evaluated region
-TRAFFIC_REGION = 207.0 # DRAM bytes per evaluated region of the bisecting rule launch, ncu --set full (profiles/r01_summary.md)
+TRAFFIC_REGION = 185.0 # DRAM bytes per evaluated region of the bisecting rule launch, ncu --set full (profiles/r01_summary.md)
 NAN = float("nan")
 
 

@@ -199,7 +199,10 @@ int cubature_cuda_fp64_peak(int device, double* tflops, double* ms);
 int cubature_cuda_fp64_peak_sustained(int device, double window_ms, double* tflops_burst, double* tflops_sustained);
 
 /* Multi-GPU: one rank per process (or per thread).  Rank 0 creates the id and ships the 128 bytes to
- * the other ranks by any means (torch.distributed, MPI, a file); every rank then calls comm_init. */
+ * the other ranks by any means (torch.distributed, MPI, a file); every rank then calls comm_init.
+ * comm_init also maps one exchange buffer per rank into every peer (CUDA IPC over NVLink): with it the sharded
+ * refinement loop of a scalar integrand runs without any NCCL call (the iteration kernel exchanges through peer
+ * memory).  CUBATURE_PEER_EXCHANGE=0 / CUBATURE_PEER_LOOP=0 fall back to NCCL all-gathers driven by the host. */
 #define CUB_COMM_ID_BYTES 128
 int cubature_cuda_comm_unique_id(void* id_out);
 int cubature_cuda_comm_init(const void* id, int nranks, int rank, int device, cub_comm_t** out);
