@@ -311,6 +311,7 @@ struct Workspace {
     Pool pool;
     SelectBuffers sel;
     DevBuf d_list, d_stage_val, d_stage_err, d_partial, d_small;
+    DevBuf g_send, g_recv, g_dense;  // sharded vector select: padded send block, gathered blocks, dense [f + 1][Nglobal]
     PinnedBuf h_list, h_stage, h_small;
     long long stage_stride = 0;
 };
@@ -823,6 +824,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     bool conv = false;
     double ops = st0.ops;  // additions the reference's running sums have seen so far (rounding band)
     std::vector<double> tmp_err(f), tot(2 * f), minvec(2 * f);
+    std::vector<long long> Nr((size_t)R, 0);  // regions per rank (from the per-iteration exchange)
     const double eps = 2.220446049250313e-16;
     const bool timing = getenv("CUBATURE_TIMING") != nullptr;
     double t_stats = 0, t_select = 0, t_rule = 0, t_shard = 0;
@@ -908,6 +910,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
             for (int r = 0; r < R; ++r) {
                 const double* b = h_block + (size_t)r * blk;
                 const unsigned long long* u = (const unsigned long long*)(b + 4 * f);
+                Nr[(size_t)r] = (long long)u[3];
                 if (u[3] == 0) continue;  // a rank without regions contributes nothing
                 for (int j = 0; j < 2 * f; ++j) tot[j] += b[j];
                 Nglobal += (long long)u[3];
@@ -1008,11 +1011,96 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
                 cub_set_message(S.msg, "internal: device selection returned K=%lld of N=%lld (global %lld of %lld)", K, N, Kglobal, Nglobal);
                 return CUB_ERR_CUDA;
             }
-        } else if (!(all && Kcap == Nglobal)) {
-            if (sharded) {
-                cub_set_message(S.msg, "multi-GPU batch selection is implemented for scalar integrands (fdim == 1) only");
+        } else if (!(all && Kcap == Nglobal) && sharded) {
+            // Vector integrand, sharded pool, the batch has to be cut: every rank gathers errmax and err[f] of ALL regions
+            // (one all-gather of (f + 1) rows padded to the largest shard), runs the single-GPU selection on the gathered
+            // arrays (stable sort by errmax -- ties in (rank, slot) order --, per-component prefix sums, residual test for
+            // every k: identical inputs, identical K on every rank) and keeps its own part of the first K regions.
+            long long Nmax = 0, off = 0;
+            for (int r = 0; r < R; ++r) {
+                Nmax = std::max(Nmax, Nr[(size_t)r]);
+                if (r < rank) off += Nr[(size_t)r];
+            }
+            if (Nglobal > (long long)std::numeric_limits<int>::max()) {
+                cub_set_message(S.msg, "sharded vector selection: more than 2^31 regions in the partition");
                 return CUB_ERR_UNSUPPORTED;
             }
+            const size_t rows = (size_t)f + 1;
+            CUB_CUDA_CHECK(W.g_send.ensure(rows * (size_t)Nmax * 8), S.msg);
+            CUB_CUDA_CHECK(W.g_recv.ensure(rows * (size_t)Nmax * 8 * (size_t)R), S.msg);
+            CUB_CUDA_CHECK(W.g_dense.ensure(rows * (size_t)Nglobal * 8), S.msg);
+            if (N > 0) {
+                CUB_CUDA_CHECK(cudaMemcpy2DAsync(W.g_send.p, (size_t)Nmax * 8, pool.err.p, (size_t)pool.cap * 8, (size_t)N * 8, (size_t)f,
+                                                 cudaMemcpyDeviceToDevice, S.stream), S.msg);
+                CUB_CUDA_CHECK(cudaMemcpyAsync(W.g_send.as<double>() + (size_t)f * Nmax, pool.errmax.p, (size_t)N * 8, cudaMemcpyDeviceToDevice,
+                                               S.stream), S.msg);
+            }
+            rc = cub_comm_allgather(comm, W.g_send.p, rows * (size_t)Nmax * 8, W.g_recv.p, S.stream);
+            if (rc != CUB_OK) return rc;
+            {
+                long long o = 0;  // drop the padding: dense [f + 1][Nglobal], rank-major region numbering
+                for (int r = 0; r < R; ++r) {
+                    if (Nr[(size_t)r] > 0)
+                        CUB_CUDA_CHECK(cudaMemcpy2DAsync(W.g_dense.as<double>() + o, (size_t)Nglobal * 8,
+                                                         W.g_recv.as<double>() + (size_t)r * rows * (size_t)Nmax, (size_t)Nmax * 8,
+                                                         (size_t)Nr[(size_t)r] * 8, rows, cudaMemcpyDeviceToDevice, S.stream), S.msg);
+                    o += Nr[(size_t)r];
+                }
+            }
+            PoolView gv = pv;  // only err / errmax / cap are read by the selection kernels
+            gv.err = W.g_dense.as<double>();
+            gv.errmax = W.g_dense.as<double>() + (size_t)f * Nglobal;
+            gv.cap = Nglobal;
+            CUB_CUDA_CHECK(sel.ensure(std::max<long long>(Nglobal, pool.cap), f), S.msg);
+            pk_sort_prepare(gv.errmax, Nglobal, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64 + 4, S.stream);
+            S.launches += 1;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 16, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += 16;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            const unsigned long long vary = h_u64[0] ^ h_u64[1];
+            unsigned long long* ka = sel.keysA.as<unsigned long long>();
+            unsigned long long* kb = sel.keysB.as<unsigned long long>();
+            int* ia = sel.idxA.as<int>();
+            int* ib = sel.idxB.as<int>();
+            for (int shift = 0; shift < 64; shift += 8) {
+                if (((vary >> shift) & 0xffULL) == 0) continue;
+                pk_sort_pass(ka, ia, kb, ib, Nglobal, shift, sel.hist.as<unsigned>(), sel.bin_totals.as<unsigned long long>(),
+                             sel.binbase.as<unsigned long long>(), S.stream);
+                S.launches += 4;
+                std::swap(ka, kb);
+                std::swap(ia, ib);
+            }
+            if (all) {
+                Kglobal = Kcap;  // maxEval truncation: the Kcap largest
+            } else {
+                pk_prefix(gv, f, ia, Nglobal, sel.prefix.as<double>(), sel.tile_tot.as<double>(), S.stream);
+                pk_find_k(d_totals, sel.prefix.as<double>(), sel.tile_tot.as<double>(), Nglobal, f, absTol, relTol, norm, band, d_u64 + 4,
+                          S.stream);
+                S.launches += 3;
+                CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 24, cudaMemcpyDeviceToHost, S.stream), S.msg);
+                S.d2h_bytes += 24;
+                CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+                long long k0 = (long long)h_u64[0], k1 = (long long)h_u64[1], k2 = (long long)h_u64[2];
+                if (k0 > Nglobal) k0 = Nglobal;
+                if (k1 > Nglobal) k1 = Nglobal;
+                if (k2 > Nglobal) k2 = Nglobal;
+                if (std::min(k1, Kcap) != std::min(k0, Kcap) || std::min(k2, Kcap) != std::min(k0, Kcap)) res->ambiguous += 1;
+                Kglobal = std::min(k0, Kcap);
+            }
+            // this rank's part of the batch, in ranking order (the other sort buffer holds the list)
+            CUB_CUDA_CHECK(W.g_send.ensure((size_t)8 * (size_t)(pk_filter_tiles(Kglobal) + 8)), S.msg);
+            pk_filter_range(ia, Kglobal, off, off + N, W.g_send.as<unsigned long long>(), d_u64 + 4, ib, S.stream);
+            S.launches += 3;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(h_u64, d_u64 + 4, 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+            S.d2h_bytes += 8;
+            CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+            K = (long long)h_u64[0];
+            list = ib;
+            if (Kglobal < 1 || Kglobal > Nglobal || K < 0 || K > N) {
+                cub_set_message(S.msg, "internal: sharded vector selection returned K=%lld of N=%lld (global %lld of %lld)", K, N, Kglobal, Nglobal);
+                return CUB_ERR_CUDA;
+            }
+        } else if (!(all && Kcap == Nglobal)) {
             // sort by errmax (descending, ties by ascending slot), then prefix sums and the residual test
             CUB_CUDA_CHECK(sel.ensure(pool.cap, f), S.msg);
             pk_sort_prepare(pv.errmax, N, sel.keysA.as<unsigned long long>(), sel.idxA.as<int>(), d_u64 + 4, S.stream);

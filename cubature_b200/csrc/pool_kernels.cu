@@ -2070,6 +2070,83 @@ void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long*
     k_sum_hist_ranks<<<1, 256, 0, s>>>(gathered, R, cnt, sum);
 }
 
+// ---- sharded vector select: this rank's part of the first K entries of the global error ranking ------------------
+// sorted[i] are global region numbers (rank-major: rank r owns [lo_r, hi_r)) in descending-errmax order; the ranks'
+// local lists are the stable sub-sequences of sorted[0..K) that fall into their range.  Three small launches:
+// per-tile counts, a one-block scan of the tile counts, the stable write.
+constexpr int FLT_THREADS = 256;
+constexpr int FLT_ITEMS = 8;
+constexpr int FLT_TILE = FLT_THREADS * FLT_ITEMS;
+__global__ void __launch_bounds__(FLT_THREADS) k_filter_count(const int* sorted, long long K, long long lo, long long hi, unsigned long long* tile_cnt) {
+    const long long base = (long long)blockIdx.x * FLT_TILE + (long long)threadIdx.x * FLT_ITEMS;
+    unsigned c = 0;
+    for (int u = 0; u < FLT_ITEMS; ++u) {
+        const long long i = base + u;
+        if (i < K) {
+            const long long g = sorted[i];
+            c += (g >= lo && g < hi) ? 1u : 0u;
+        }
+    }
+    __shared__ unsigned sh[FLT_THREADS];
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int w = FLT_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = sh[0];
+}
+__global__ void k_filter_scan(unsigned long long* tile_cnt, long long ntiles, unsigned long long* total_out) {  // exclusive, in place
+    __shared__ unsigned long long sh[256];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < ntiles; base += 256) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long a = i < ntiles ? tile_cnt[i] : 0ULL;
+        sh[threadIdx.x] = a;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0ULL;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < ntiles) tile_cnt[i] = carry + sh[threadIdx.x] - a;
+        __syncthreads();
+        if (threadIdx.x == 255) carry += sh[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(FLT_THREADS) k_filter_write(const int* sorted, long long K, long long lo, long long hi,
+                                                              const unsigned long long* tile_off, int* list) {
+    const long long base = (long long)blockIdx.x * FLT_TILE + (long long)threadIdx.x * FLT_ITEMS;
+    unsigned flags = 0, c = 0;
+    for (int u = 0; u < FLT_ITEMS; ++u) {
+        const long long i = base + u;
+        if (i < K) {
+            const long long g = sorted[i];
+            if (g >= lo && g < hi) {
+                flags |= 1u << u;
+                ++c;
+            }
+        }
+    }
+    __shared__ unsigned sh[FLT_THREADS];
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < FLT_THREADS; o <<= 1) {
+        const unsigned t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long pos = tile_off[blockIdx.x] + (sh[threadIdx.x] - c);
+    for (int u = 0; u < FLT_ITEMS; ++u)
+        if ((flags >> u) & 1u) list[pos++] = (int)((long long)sorted[base + u] - lo);
+}
+
 // deals the replicated pool out to the ranks: with `perm` = the regions in descending-errmax order,
 // rank r keeps perm[r], perm[r + R], ... (round robin over the error ranking, so every rank gets the
 // same share of the regions that will be refined most); without perm, slots r, r + R, ...
@@ -2091,6 +2168,20 @@ __global__ void k_shard_gather(PoolView src, PoolView dst, int dim, int fdim, lo
 void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
                      cudaStream_t s) {
     if (n_local > 0) k_shard_gather<<<nblocks(n_local, 128), 128, 0, s>>>(src, dst, dim, fdim, n_local, R, rank, perm);
+}
+
+long long pk_filter_tiles(long long K) { return (K + FLT_TILE - 1) / FLT_TILE; }
+// list[0..*count) = local slots (g - lo) of the entries of sorted[0..K) inside [lo, hi), in their sorted order
+void pk_filter_range(const int* sorted, long long K, long long lo, long long hi, unsigned long long* tile_scratch /*[pk_filter_tiles(K)]*/,
+                     unsigned long long* count_out, int* list, cudaStream_t s) {
+    const long long nt = pk_filter_tiles(K);
+    if (nt <= 0) {
+        cudaMemsetAsync(count_out, 0, 8, s);
+        return;
+    }
+    k_filter_count<<<(unsigned)nt, FLT_THREADS, 0, s>>>(sorted, K, lo, hi, tile_scratch);
+    k_filter_scan<<<1, 256, 0, s>>>(tile_scratch, nt, count_out);
+    k_filter_write<<<(unsigned)nt, FLT_THREADS, 0, s>>>(sorted, K, lo, hi, tile_scratch, list);
 }
 
 // Cooperative launch of one whole iteration (everything but the rule kernel).  hsets: two histogram sets of

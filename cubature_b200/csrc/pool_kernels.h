@@ -61,6 +61,9 @@ void pk_sel_compact(const PoolView& pool, long long n, const void* state, const 
 void pk_sum_hist_ranks(const unsigned char* gathered, int R, unsigned long long* cnt, double* sum, cudaStream_t s);
 void pk_shard_gather(const PoolView& src, const PoolView& dst, int dim, int fdim, long long n_local, int R, int rank, const int* perm,
                      cudaStream_t s);
+long long pk_filter_tiles(long long K);
+void pk_filter_range(const int* sorted, long long K, long long lo, long long hi, unsigned long long* tile_scratch, unsigned long long* count_out,
+                     int* list, cudaStream_t s);
 int pk_select_scalar(const PoolView& pool, long long n, const double* totals, long long Kcap, double absTol, double relTol,
                      int norm, double band, const SelScratch& sc, int* list, cudaStream_t s);
 // peer exchange buffer of a sharded pool (one per rank, mapped into every peer; 8-byte words):

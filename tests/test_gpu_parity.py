@@ -322,6 +322,36 @@ def test_sharded_pool_matches_single_gpu(cb, R):
         assert union == key(t1.centers, t1.halfwidths)
 
 
+@pytest.mark.parametrize("R", [2, 3])
+def test_sharded_pool_vector_integrand_matches_single_gpu(cb, R):
+    """Section 8(e) for vector integrands (BASELINE config C4's shape): when the batch has to be cut, the ranks gather
+    errmax / err[f] of the whole partition and run the single-GPU selection on it -- batches, counts and values must be the
+    1-GPU ones for every norm."""
+    inf = float("inf")
+    cases_v = [
+        (cb.Family.CEXP, 3, 8, [0.5, 1.0, 1.5, 2.0], [0] * 3, [inf] * 3, 1e-5, cb.CubatureError.PAIRED, 0),
+        (cb.Family.CEXP, 2, 4, [1.0, 3.0], [0] * 2, [inf] * 2, 1e-7, cb.CubatureError.L2, 0),
+        (cb.Family.CEXP, 3, 6, [0.5, 2.0, 4.0], [0] * 3, [inf] * 3, 1e-9, cb.CubatureError.LINF, 1_500_000),
+        (cb.Family.OSC_VEC, 2, 5, [], [0] * 2, [1] * 2, 1e-8, cb.CubatureError.L1, 0),
+    ]
+    for fam, dim, fdim, p, lo, hi, rel, norm, max_eval in cases_v:
+        ig = cb.Integrand.builtin(fam, dim, fdim, p)
+        args = (lo, hi, rel, NAN, norm, max_eval)
+        r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, trace_batches=4096)
+        assert any(b < 2 * n for b, n in zip(t1.batches[1:], np.cumsum([1] + [x // 2 for x in t1.batches[:-1]])[1:])) or len(t1.batches) > 3
+
+        def fn(comm):
+            return cb.Cubature.integrate_ex(ig, *args, comm=comm, shard_min_regions=16, trace_batches=4096)
+
+        outs = _run_ranks(cb, R, 2000 + 10 * R + dim + fdim, fn)
+        for rr, ss, tt in outs:
+            assert cases.bit_equal(rr, outs[0][0])
+            assert (ss.num_eval, ss.num_regions, ss.iterations, ss.converged) == (s1.num_eval, s1.num_regions, s1.iterations, s1.converged)
+            assert tt.batches == t1.batches
+        assert np.max(np.abs(outs[0][0][0] - r1[0])) <= 1e-12 * np.max(np.abs(r1[0]))
+        assert np.max(np.abs(outs[0][0][1] - r1[1])) <= 1e-12 * np.max(np.abs(r1[1]))
+
+
 def test_strict_all_option_matches_oracle_extension(cb, oracle):
     """cub_options_t.strict_all (section 8f-3): every component must converge; parity with the oracle's extension."""
     inf = float("inf")
@@ -365,3 +395,34 @@ def test_sharded_pool_over_nvlink_peers_matches_single_gpu():
                         "--master-port", "29541", os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout and r.stdout.count("OK") + r.stdout.count("AMBIGUOUS") >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["corner_peak", "product_peak"])
+def test_fast_reciprocal_falls_back_to_ieee_division_out_of_range(cb, oracle, name):
+    """The rational Genz families evaluate 1/x with the branch-free in-range sequence (detmath.h: dm_rcp_flag); a region in
+    which an argument leaves that range (zero, subnormal, overflow, huge) must be re-evaluated with the IEEE division and
+    give the oracle's bits (inf / nan / 0 / subnormals included), next to ordinary regions in the same launch."""
+    dim = 4
+    rng = np.random.default_rng(11)
+    n = 512
+    c = rng.uniform(0.3, 0.7, (n, dim))
+    h = rng.uniform(0.01, 0.2, (n, dim))
+    fam = cases.GENZ[name]
+    if name == "corner_peak":
+        # s = 1 + sum a_i x_i: negative a makes s cross zero inside the boxes (1/0, 1/tiny); huge a overflows s^5
+        variants = [np.array([-0.5, -0.5, -0.5, -0.5, 0, 0, 0, 0.0]), np.array([-2.0, 1.0, -1.0, 0.5, 0, 0, 0, 0.0]),
+                    np.array([1e70, 1e70, 1e70, 1e70, 0, 0, 0, 0.0]), np.array([3e61, 1.0, 1.0, 1.0, 0, 0, 0, 0.0])]
+        c[0] = [0.5, 0.5, 0.5, 0.5]  # 1 - 0.5 * 2 = 0 exactly at the centre for the first variant
+    else:
+        # prod (a_i^-2 + (x_i - u_i)^2): tiny a -> huge a^-2 -> the product overflows (1/inf = 0) or lands in the
+        # range whose reciprocal is subnormal
+        variants = [np.array([1e-80, 1e-80, 1e-80, 1e-80, 0.5, 0.5, 0.5, 0.5]), np.array([1e-77, 1e-77, 1e-77, 1e-77, 0.5, 0.5, 0.5, 0.5]),
+                    np.array([1e-77, 1e-77, 1.0, 1.0, 0.5, 0.5, 0.5, 0.5]), np.array([3e-78, 1e-77, 2.0, 1.0, 0.5, 0.5, 0.5, 0.5])]
+    for p in variants:
+        gv, ge, gs, _ = cb.Integrand.builtin(fam, dim, 1, p).eval_regions(c, h)
+        cv, ce, cs = oracle.eval_regions(fam, dim, 1, p, c, h)
+        for g, o in ((gv, cv), (ge, ce)):  # bit for bit; a NaN must be a NaN (its sign / payload differs between x86 and sm_100)
+            gn, on = np.isnan(g), np.isnan(o)
+            assert np.array_equal(gn, on) and np.array_equal(g[~gn].view(np.uint64), o[~on].view(np.uint64))
+        assert np.array_equal(gs, cs)
