@@ -1180,7 +1180,26 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
         __syncthreads();
     }
     unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;  // smallest errmax bits (highest slot among ties), largest
-    for (int row = 0; row < 2 * fdim; ++row) {
+    const bool warp_rows = fdim > 4;  // many components: one warp per row (no block barrier per row), else one block per row
+    if (warp_rows) {
+        for (int row = (int)w; row < 2 * fdim; row += SEL_WARPS) {
+            const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
+            double s = 0.0;  // fixed order: lane l adds elements l, l + 32, ... of the chunk, then a shuffle tree
+            long long i = lo + lane;
+            for (; i + 96 < hi; i += 128) {
+                const double a0 = src[i], a1 = src[i + 32], a2 = src[i + 64], a3 = src[i + 96];
+                s += a0;
+                s += a1;
+                s += a2;
+                s += a3;
+            }
+            for (; i < hi; i += 32) s += src[i];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) p.partial[(long long)row * G + b] = s;
+        }
+        __syncthreads();
+    }
+    for (int row = 0; row < (warp_rows ? 0 : 2 * fdim); ++row) {
         const double* src = row < fdim ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - fdim) * pool.cap;
         // fixed summation order (thread tid adds elements tid, tid+256, ... in order); the loads of four
         // consecutive steps are issued together
@@ -1302,7 +1321,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) k_iter_coop(IterParams p) {
     double* totals = (double*)(p.ctl + 16);  // CTA 0 publishes; every CTA keeps V, E for fdim == 1 in registers
     double* minvec = totals + 2 * fdim;
     double V = 0.0, E = 0.0;
-    for (int row = 0; row < 2 * fdim; ++row) {
+    if (warp_rows) {  // vector integrands: only CTA 0 needs the totals (it alone takes the decisions below)
+        if (b == 0) {
+            for (int row = (int)w; row < 2 * fdim; row += SEL_WARPS) {
+                double s = 0.0;
+                for (int i = (int)lane; i < G; i += 32) s += __ldcg(&p.partial[(long long)row * G + i]);
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                if (lane == 0) totals[row] = s;
+            }
+        }
+        __syncthreads();
+    }
+    for (int row = 0; row < (warp_rows ? 0 : 2 * fdim); ++row) {
         double s = 0.0;
         for (int i = tid; i < G; i += SEL_THREADS) s += __ldcg(&p.partial[(long long)row * G + i]);
         sh[tid] = s;
