@@ -36,7 +36,31 @@ CASES = [
     ("discontinuous", 3, 1e-3, int(4e7), 64),
     ("c0", 4, 1e-5, int(2e8), 128),
 ]
+# vector integrands (host-driven sharded selection over NCCL all-gathers): family id, dim, fdim, params, xmin, xmax, relTol, norm, maxEval
+INF = float("inf")
+VCASES = [
+    (cb.Family.CEXP, 3, 8, [0.5, 1.0, 1.5, 2.0], [0.0] * 3, [INF] * 3, 1e-5, cb.CubatureError.PAIRED, 0),
+    (cb.Family.OSC_VEC, 2, 5, [], [0.0] * 2, [1.0] * 2, 1e-8, cb.CubatureError.L1, 0),
+]
 bad = 0
+if not os.environ.get("PEER_CASES"):
+    for fam, dim, fdim, p, lo, hi, rel, norm, max_eval in VCASES:
+        ig = cb.Integrand.builtin(fam, dim, fdim, p)
+        tr = [1 if h == INF else 0 for h in hi] if INF in hi else None
+        args = (lo, hi, rel, NAN, norm, max_eval)
+        r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, transform=tr, device=local_rank, trace_batches=4096)
+        dist.barrier()
+        r2, s2, t2 = cb.Cubature.integrate_ex(ig, *args, transform=tr, device=local_rank, comm=comm, shard_min_regions=16, trace_batches=4096)
+        same = (t1.batches == t2.batches and s1.num_eval == s2.num_eval and s1.num_regions == s2.num_regions and s1.converged == s2.converged)
+        import numpy as np
+        rel_v = float(np.max(np.abs(r1[0] - r2[0])) / max(float(np.max(np.abs(r1[0]))), 1e-300))
+        ok = same and rel_v <= 1e-12
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print("vector family %d d=%d fdim=%d norm=%d: %s  regions=%d iters=%d conv=%d  |dv|/v=%.1e" % (
+                int(fam), dim, fdim, int(norm), "OK" if flag.item() == 0 else "MISMATCH", s2.num_regions, s2.iterations, s2.converged, rel_v), flush=True)
+        bad += int(flag.item())
 if os.environ.get("PEER_CASES"):
     CASES = [CASES[int(i)] for i in os.environ["PEER_CASES"].split(",")]
 for name, dim, rel, max_eval, smin in CASES:
