@@ -1310,6 +1310,13 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
     }
     const double t_shard = ms_since(t_begin);
 
+    // One NCCL all-gather (outside the loop) lines the ranks up before the first in-kernel exchange: a rank that is still
+    // compiling its integrand or growing its pool would otherwise be waited for inside a spinning kernel.
+    {
+        int rc0 = cub_comm_allgather(comm, d_u64, 8, d_u64 + 8, S.stream);
+        if (rc0 != CUB_OK) return rc0;
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    }
     PkShard shard;
     shard.R = R;
     shard.rank = rank;

@@ -77,7 +77,7 @@ int pk_select_scalar(const PoolView& pool, long long n, const double* totals, lo
 #define PK_XB_PAY (16 + 2 * 2048 + 48)
 #define PK_XB_WORDS (PK_XB_DATA + 2 * PK_MAX_RANKS * PK_XB_PAY)
 #define PK_XB_BYTES (PK_XB_WORDS * 8)
-#define PK_XCHG_TIMEOUT_NS 8000000000ULL
+#define PK_XCHG_TIMEOUT_NS 20000000000ULL
 // sharded pool: this rank's view of the peer exchange buffers (nullptr / R == 1: single GPU)
 struct PkShard {
     int R, rank;
