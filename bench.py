@@ -16,7 +16,8 @@ the TOTAL over all GPUs at every N (strong scaling; the pool is sharded over the
             region) / its CUDA-event time, against the FP64 FMA peak measured live by a DFMA-chain
             microbenchmark (MEASURED_PEAKS.json has no FP64 entry); the HBM view is reported beside it.
   cpu_baseline = the CPU restatement of the reference (oracle/, kind "port": the Java reference cannot
-            run here, there is no JVM) on a bounded sample of the same workload, one thread like the reference.
+            run here, there is no JVM) on a bounded sample of the same workload: one thread like the reference, and with
+            the integrand batches on all host threads (the reference's vectorized interface); the faster one is reported.
 `--impl reference` times that CPU restatement alone (rank 0 only).
 Each step integrates a fresh pool far larger than the 126 MB L2 (3.4e8 regions x 124 B = 42 GB at E = 1e11),
 so no L2 flush is needed between steps.
@@ -93,14 +94,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port(max_eval):
-    """The oracle (CPU restatement of the reference) on the same integrand with a bounded maxEval."""
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port(max_eval, threads=1):
+    """The oracle (CPU restatement of the reference) on the same integrand with a bounded maxEval.  threads > 1: the
+    integrand batch of every iteration is evaluated by that many threads -- what the reference's README (129-163) invites the
+    user of its vectorized interface to do; point generation, rule sums and the heap stay serial as in the reference."""
     from oracle import oracle as O
     p = workload_params()
+    O.set_threads(threads)
     t0 = time.perf_counter()
     r = O.integrate(3, DIM, 1, p, [0.0] * DIM, [1.0] * DIM, 1e-13, NAN, 0, int(max_eval), want_regions=False)
     dt = time.perf_counter() - t0
+    O.set_threads(1)
     return r.num_eval / P / dt, r.num_eval, dt
+
+
+def cpu_baseline_record(sample):
+    """Both flavours on the bounded sample; the faster one is the reported value."""
+    t_all = cpu_threads()
+    v1, _, dt1 = cpu_port(sample, 1)
+    vt, _, dtt = cpu_port(sample, t_all) if t_all > 1 else (v1, 0, dt1)
+    best, cores = (vt, t_all) if vt > v1 else (v1, 1)
+    return {"value": best, "unit": "regions/s", "cores": cores, "kind": "port",
+            "sample": "same integrand and loop with maxEval=%d; C++ restatement of the Java reference (no JVM in the image). "
+                      "1 thread like the reference: %.4g regions/s (%.1f s); integrand batches on %d threads (the reference's "
+                      "vectorized interface parallelised as its README suggests, everything else serial): %.4g regions/s (%.1f s)"
+                      % (int(sample), v1, dt1, t_all, vt, dtt)}, dt1 + (dtt if t_all > 1 else 0.0)
 
 
 def run_reference(args, rank):
@@ -108,10 +133,11 @@ def run_reference(args, rank):
         return
     sample = int(args.cpu_sample)
     vals, times = [], []
+    rec = None
     for i in range(args.warmup + args.steps):
-        v, ne, dt = cpu_port(sample)
+        rec, dt = cpu_baseline_record(sample)
         if i >= args.warmup:
-            vals.append(v)
+            vals.append(rec["value"])
             times.append(dt)
     value = statistics.mean(vals)
     line = {
@@ -120,9 +146,7 @@ def run_reference(args, rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "genz_corner_peak_d6 [0,1]^6 relTol=1e-13 maxEval=%d (bounded sample of the maxEval=1e11 job)" % sample},
         "fevals_per_s": value * P,
-        "cpu_baseline": {"value": value, "unit": "regions/s", "cores": 1, "kind": "port",
-                         "sample": "same integrand and loop, maxEval=%d per step; C++ restatement of the Java reference "
-                                   "(no JVM in the image), single thread like the reference" % sample},
+        "cpu_baseline": dict(rec, value=value),
         "e2e": {"value": value, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,10 +295,7 @@ def main():
         "per_rank": [{"regions_evaluated": int(p[0]), "rule_ms": p[1], "device_ms": p[2]} for p in per_rank],
     }
     if not args.no_cpu_baseline:
-        v, ne, dt = cpu_port(args.cpu_sample)
-        line["cpu_baseline"] = {"value": v, "unit": "regions/s", "cores": 1, "kind": "port",
-                                "sample": "same integrand and loop with maxEval=%d (%.1f s); C++ restatement of the Java reference "
-                                          "(no JVM in the image), single thread like the reference" % (int(args.cpu_sample), dt)}
+        line["cpu_baseline"], _ = cpu_baseline_record(args.cpu_sample)
     print(json.dumps(line))
     if comm is not None:
         comm.close()

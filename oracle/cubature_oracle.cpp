@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "../cubature_b200/csrc/integrands.h"  // test INPUTS (integrand definitions), shared with the device
@@ -276,6 +277,8 @@ struct Trace {
     std::vector<int64_t> batch;  // nR of every evalError call after the first (Rule.java:135)
 };
 
+static int g_threads = 1;  // threads evaluating one integrand batch (orc_set_threads)
+
 struct Rule {  // Rule.java:6-49
     int dim, fdim, num_points;
     std::vector<std::vector<double>> pts;   // [dim][nR*num_points]
@@ -291,12 +294,35 @@ struct Rule {  // Rule.java:6-49
         pts.assign(dim, std::vector<double>((size_t)(nR * num_points)));
         vals.assign(fdim, std::vector<double>((size_t)(nR * num_points)));
     }
+    // ONE integrand call for all points of the batch (Rule75GenzMalik.java:108, RuleGaussKronrod_1d.java:88).  The
+    // reference is single-threaded; its README (129-163) points out that this batch interface lets the USER evaluate
+    // the points in parallel.  orc_set_threads(T > 1) does exactly that -- the batch is cut into T slices evaluated by T
+    // threads (pointwise integrand: identical bits) -- and nothing else: point generation, rule sums and the heap stay
+    // serial as in the reference.  Used only by bench.py's CPU baseline; the parity tests run with T = 1.
     void call_integrand(int64_t n) {
-        std::vector<const double*> xp(dim);
-        std::vector<double*> fp(fdim);
-        for (int d = 0; d < dim; ++d) xp[d] = pts[d].data();
-        for (int j = 0; j < fdim; ++j) fp[j] = vals[j].data();
-        fn(ctx, dim, n, xp.data(), fdim, fp.data());
+        const int T = g_threads;
+        if (T <= 1 || n < 4096) {
+            std::vector<const double*> xp(dim);
+            std::vector<double*> fp(fdim);
+            for (int d = 0; d < dim; ++d) xp[d] = pts[d].data();
+            for (int j = 0; j < fdim; ++j) fp[j] = vals[j].data();
+            fn(ctx, dim, n, xp.data(), fdim, fp.data());
+            return;
+        }
+        std::vector<std::thread> pool;
+        const int64_t per = (n + T - 1) / T;
+        for (int t = 0; t < T; ++t) {
+            const int64_t lo = per * t, hi = std::min<int64_t>(n, lo + per);
+            if (lo >= hi) break;
+            pool.emplace_back([this, lo, hi] {
+                std::vector<const double*> xp(dim);
+                std::vector<double*> fp(fdim);
+                for (int d = 0; d < dim; ++d) xp[d] = pts[d].data() + lo;
+                for (int j = 0; j < fdim; ++j) fp[j] = vals[j].data() + lo;
+                fn(ctx, dim, hi - lo, xp.data(), fdim, fp.data());
+            });
+        }
+        for (std::thread& th : pool) th.join();
     }
 
     // Rule.java:51-160.  Returns 0, or -1 if both tolerances are NaN.
@@ -802,6 +828,8 @@ static void fill_transform(int dim, const int* transform, const double* xmin, co
 
 // ---- C interface for tests / bench (ctypes) -------------------------------------------------------
 extern "C" {
+
+void orc_set_threads(int t) { orc::g_threads = t < 1 ? 1 : t; }
 
 void* orc_integrate_builtin(int family, int dim, int fdim, const double* params, int nparams, const double* xmin,
                             const double* xmax, const int* transform, double relTol, double absTol, int norm,
