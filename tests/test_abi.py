@@ -106,6 +106,15 @@ def test_no_cpu_fallback(cb):
     ig = cb.Integrand.builtin(cb.Family.GAUSS_ISO, 3, 1, [0.5])
     with pytest.raises(RuntimeError, match="no CUDA device"):
         cb.Cubature.integrate(ig, [-2] * 3, [2] * 3, 1e-4, 0.0)
+    # every other compute entry point fails the same way: rule evaluation, rule benchmark, FP64 probes
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        ig.eval_regions([[0.0] * 3], [[1.0] * 3])
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        cb.bench_rule(ig, [-2] * 3, [2] * 3, 16, 1)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        cb.fp64_peak_tflops()
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        cb.fp64_peak_sustained_tflops(-1, 10.0)
 
 
 def test_convergence_predicate_matches_oracle(cb, oracle):
