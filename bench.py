@@ -292,6 +292,8 @@ def main():
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
                              "frac": rule_regions_per_s * BYTES_REGION / 1e9 / hbm_peak}},
         "clocks": clocks,
+        # rank 0's device time of every timed step (a late host thread on one rank shows up as one long step on all ranks)
+        "rank0_step_ms": [round(float(v), 3) for v in dev_ms],
         "per_rank": [{"regions_evaluated": int(p[0]), "rule_ms": p[1], "device_ms": p[2]} for p in per_rank],
     }
     if not args.no_cpu_baseline:
