@@ -892,7 +892,10 @@ constexpr int SEL_LB = 2048;  // buckets of levels 1..5
 __device__ __forceinline__ int sel_shift(int level) { return level == 0 ? 56 : (level <= 5 ? 56 - 11 * level : 0); }
 // (the last level re-reads bits 7..1, which are already decided, so that it has one bucket per thread like level 0;
 //  only the two buckets that match the prefix can be occupied)
-__device__ __forceinline__ int sel_nbuckets(int level) { return level == 0 ? 256 : (level <= 5 ? SEL_LB : 256); }
+#ifndef SEL_LAST_BUCKETS
+#define SEL_LAST_BUCKETS 256  // (2 reproduces the observation in DESIGN.md section 9, item 5)
+#endif
+__device__ __forceinline__ int sel_nbuckets(int level) { return level == 0 ? 256 : (level <= 5 ? SEL_LB : SEL_LAST_BUCKETS); }
 __device__ __forceinline__ unsigned long long sel_key_of_err(double e) { return ~dbits(e > 0.0 ? e : 0.0); }
 
 struct IterParams {

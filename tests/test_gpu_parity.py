@@ -426,3 +426,34 @@ def test_fast_reciprocal_falls_back_to_ieee_division_out_of_range(cb, oracle, na
             gn, on = np.isnan(g), np.isnan(o)
             assert np.array_equal(gn, on) and np.array_equal(g[~gn].view(np.uint64), o[~on].view(np.uint64))
         assert np.array_equal(gs, cs)
+
+
+@pytest.mark.gpu
+def test_large_tie_group_cut_by_max_eval_tiles_the_domain(cb, oracle):
+    """5e5 regions with exactly equal error estimates (an integrand the rule cannot see: all values 0) and a batch cut by
+    maxEval inside that tie group: many CTAs of the iteration kernel must agree on the threshold key down to its last
+    bit, or the popped list is short / stale.  The values cannot show that (all zero), the partition can: the final
+    boxes must be distinct and tile [0,1]^3 exactly, with the oracle's counts and batches."""
+    dim, name = 3, "discontinuous"
+    p = cases.genz_params(name, dim)
+    ig = cb.Integrand.builtin(cases.GENZ[name], dim, 1, p)
+    args = ([0.0] * dim, [1.0] * dim, 1e-3, NAN, cb.CubatureError.INDIVIDUAL, 40_000_000)
+    o = oracle.integrate(cases.GENZ[name], dim, 1, p, *args[:2], 1e-3, NAN, 0, 40_000_000, want_regions=False)
+    r, st, tr = cb.Cubature.integrate_ex(ig, *args, trace_batches=64, trace_regions=700_000)
+    assert (st.num_eval, st.num_regions) == (o.num_eval, o.num_regions) and tr.batches == o.batches
+    assert tr.n_regions == st.num_regions
+    vol = np.prod(2.0 * tr.halfwidths, axis=1)
+    assert float(np.sum(vol)) == 1.0                                   # powers of two: exact
+    boxes = np.concatenate([tr.centers, tr.halfwidths], axis=1)
+    assert len(np.unique(boxes, axis=0)) == st.num_regions             # no box twice
+    assert np.all(tr.centers - tr.halfwidths >= 0.0) and np.all(tr.centers + tr.halfwidths <= 1.0)
+
+    def fn(comm):
+        return cb.Cubature.integrate_ex(ig, *args, comm=comm, shard_min_regions=64, trace_batches=64, trace_regions=700_000)
+
+    outs = _run_ranks(cb, 2, 4242, fn)
+    allc = np.concatenate([t.centers for _, _, t in outs])
+    allh = np.concatenate([t.halfwidths for _, _, t in outs])
+    assert sum(t.n_regions for _, _, t in outs) == o.num_regions and outs[0][2].batches == o.batches
+    assert float(np.sum(np.prod(2.0 * allh, axis=1))) == 1.0
+    assert len(np.unique(np.concatenate([allc, allh], axis=1), axis=0)) == o.num_regions
