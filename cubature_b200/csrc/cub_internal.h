@@ -34,6 +34,7 @@ struct HostWork {
     double* stage_val;
     double* stage_err;
     long long stage_stride;
+    unsigned long long* acc;  // exact running sums (acc_layout.h) or null
 };
 enum { MODE_PLAIN = 0, MODE_BISECT = 1, MODE_CHILDREN = 2 };
 
@@ -46,6 +47,8 @@ struct RuleKernels {
     cudaKernel_t eval_points = nullptr;
     int staged_max_smem = 0;
     int gm_threads = 128;                 // block size gm_scalar was compiled for
+    int gm_blocks_per_sm = 4;             // resident CTAs per SM (occupancy query): the persistent grid is n_sms times this
+    int gk_blocks_per_sm = 8;
 };
 
 struct cub_integrand {

@@ -144,7 +144,7 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     // branch-free reciprocal fast path of the rational built-in families (detmath.h: dm_rcp_flag; the kernel re-evaluates a
     // region with the IEEE division when an argument leaves the fast path's exact range)
     tu << "#ifndef CUB_FAST_RCP\n#define CUB_FAST_RCP 1\n#endif\n";
-    tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
+    tu << "#include \"acc_layout.h\"\n#include \"detmath.h\"\n#include \"integrands.h\"\n";
     if (integ->family == CUB_FAM_USER) {
         tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";
         tu << "struct CubUserIntegrand {\n"
@@ -260,8 +260,16 @@ int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, Rul
         cudaFuncAttributes fa;
         if (k.gm_scalar && cudaFuncGetAttributes(&fa, (const void*)k.gm_scalar) == cudaSuccess && fa.maxThreadsPerBlock >= 32)
             k.gm_threads = fa.maxThreadsPerBlock;  // = __launch_bounds__(CUB_GM_THREADS, ..) of the compiled kernel
+        int nb = 0;
+        if (k.gm_scalar && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.gm_scalar, k.gm_threads, 0) == cudaSuccess && nb > 0)
+            k.gm_blocks_per_sm = nb;
     }
-    if (integ->dim == 1 && (integ->fdim == 1 || integ->separable)) cudaLibraryGetKernel(&k.gk_separable, k.lib, "cub_gk_separable");
+    if (integ->dim == 1 && (integ->fdim == 1 || integ->separable)) {
+        cudaLibraryGetKernel(&k.gk_separable, k.lib, "cub_gk_separable");
+        int nb = 0;
+        if (k.gk_separable && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.gk_separable, 128, 0) == cudaSuccess && nb > 0)
+            k.gk_blocks_per_sm = nb;
+    }
     cudaLibraryGetKernel(&k.staged, k.lib, "cub_rule_staged");
     cudaLibraryGetKernel(&k.eval_points, k.lib, "cub_eval_points");
     cudaGetLastError();

@@ -108,19 +108,47 @@ struct Region {  // Region.java:3-56
     }
 };
 
+// Variant switch (orc_set_exact_sums; NOT reference behaviour, default off): the heap's running sums and the residual of
+// the batch-pop loop are carried in binary128 (rounding-free for every problem size used here) and handed to
+// Rule.converged as doubles -- values rounded to nearest, errors truncated toward zero, so that `err < tol` on the
+// double is the exact comparison.  This is "the decision the reference would take if its incremental += / -= sums
+// (RegionHeap.java:21-36, Rule.java:122-124) did not drift"; the device-side selection of libcubature_cuda computes
+// exactly that (integer accumulators), and comparing the two variants shows where the reference's own rounding decides.
+static int g_exact_sums = 0;
+static double q_to_double_trunc(__float128 x) {
+    double d = (double)x;
+    if ((__float128)d > x && x >= 0) d = std::nextafter(d, 0.0);
+    if ((__float128)d < x && x < 0) d = std::nextafter(d, 0.0);
+    return d;
+}
+
 // RegionHeap.java:5-37 on top of java.util.PriorityQueue.
 struct RegionHeap {
     int fdim;
     std::vector<ErrorEstimate> ee;
+    std::vector<__float128> qval, qerr;  // exact-sums variant only
     std::vector<Region*> q;  // the PriorityQueue's backing array, q[0..size)
 
-    explicit RegionHeap(int fdim_) : fdim(fdim_), ee(fdim_) {}
+    explicit RegionHeap(int fdim_) : fdim(fdim_), ee(fdim_), qval(fdim_, 0), qerr(fdim_, 0) {}
+    void sync_exact() {  // exact-sums variant: the double sums are roundings of the binary128 ones
+        for (int i = 0; i < fdim; ++i) {
+            ee[i].val = (double)qval[i];
+            ee[i].err = q_to_double_trunc(qerr[i]);
+        }
+    }
     size_t size() const { return q.size(); }
 
     void add(Region* e) {  // RegionHeap.java:30-36 then PriorityQueue.offer/siftUp
         for (int i = 0; i < fdim; ++i) {
             ee[i].val += e->ee[i].val;
             ee[i].err += e->ee[i].err;
+        }
+        if (g_exact_sums) {
+            for (int i = 0; i < fdim; ++i) {
+                qval[i] += e->ee[i].val;
+                qerr[i] += e->ee[i].err;
+            }
+            sync_exact();
         }
         size_t k = q.size();
         q.push_back(nullptr);
@@ -154,6 +182,13 @@ struct RegionHeap {
         for (int i = 0; i < fdim; ++i) {
             ee[i].val -= result->ee[i].val;
             ee[i].err -= result->ee[i].err;
+        }
+        if (g_exact_sums) {
+            for (int i = 0; i < fdim; ++i) {
+                qval[i] -= result->ee[i].val;
+                qerr[i] -= result->ee[i].err;
+            }
+            sync_exact();
         }
         return result;
     }
@@ -353,10 +388,17 @@ struct Rule {  // Rule.java:6-49
                 ee[j].err = regions.ee[j].err;
                 ee[j].val = regions.ee[j].val;
             }
+            std::vector<__float128> qres;
+            if (g_exact_sums) qres = regions.qerr;
             do {
                 if ((size_t)(nR + 2) > R.size()) R.resize((size_t)(nR + 2) * 2, nullptr);
                 R[nR] = regions.poll();
                 for (int j = 0; j < fdim; ++j) ee[j].err -= R[nR]->ee[j].err;
+                if (g_exact_sums)
+                    for (int j = 0; j < fdim; ++j) {
+                        qres[j] -= R[nR]->ee[j].err;
+                        ee[j].err = q_to_double_trunc(qres[j]);
+                    }
                 R[nR + 1] = R[nR]->cut();
                 numEval += (int64_t)num_points * 2;
                 nR += 2;
@@ -830,6 +872,7 @@ static void fill_transform(int dim, const int* transform, const double* xmin, co
 extern "C" {
 
 void orc_set_threads(int t) { orc::g_threads = t < 1 ? 1 : t; }
+void orc_set_exact_sums(int on) { orc::g_exact_sums = on ? 1 : 0; }
 
 void* orc_integrate_builtin(int family, int dim, int fdim, const double* params, int nparams, const double* xmin,
                             const double* xmax, const int* transform, double relTol, double absTol, int norm,

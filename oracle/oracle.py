@@ -50,6 +50,7 @@ def lib():
         L.orc_get_regions.argtypes = [C.c_void_p, dp, dp, ip, dp, dp, dp]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_exact_sums.argtypes = [C.c_int]
         L.orc_eval_regions.restype = C.c_int
         L.orc_eval_regions.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, dp, C.c_longlong, dp, dp, dp, dp, ip]
         for name in ("orc_dm_exp", "orc_dm_sin", "orc_dm_cos", "orc_dm_log"):
@@ -108,6 +109,13 @@ def set_threads(n):
     """Threads evaluating one integrand batch (the reference's vectorized interface parallelised by the user, README.md:
     129-163); 1 = the reference's own single-threaded behaviour.  Everything else stays serial."""
     lib().orc_set_threads(int(n))
+
+
+def set_exact_sums(on):
+    """Variant (NOT reference behaviour): carry the heap's running sums and the batch-pop residual rounding-free
+    (binary128).  Shows where the reference's own accumulated rounding decides a batch size; the device-side selection
+    of libcubature_cuda takes exactly these decisions."""
+    lib().orc_set_exact_sums(1 if on else 0)
 
 
 def integrate(family, dim, fdim, params, xmin, xmax, rel_tol, abs_tol, norm=INDIVIDUAL, max_eval=0, transform=None,
