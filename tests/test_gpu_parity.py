@@ -136,6 +136,26 @@ def test_golden_device(cb, oracle, c):
         assert sum(tr.split_hist(c["dim"])) == sum(c["split_hist"])
 
 
+BASE = json.load(open(os.path.join(GOLD, "baseline_pins.json")))
+
+
+@pytest.mark.parametrize("c", BASE, ids=[c["name"] for c in BASE])
+def test_baseline_settings_device(cb, c):
+    """BASELINE.json's configs at the settings it states (C3: six Genz families, d = 5, relTol 1e-8; C4: d = 4, fdim 32,
+    PAIRED, semi-infinite, relTol 1e-8; C5: 6-D corner peak truncated at maxEval 1e8) against fixtures of the CPU oracle
+    (tests/golden/make_baseline_golden.py; the oracle needs up to a minute per case, so it does not run here): numEval,
+    region count, iterations, EVERY batch size and the split-dimension histogram identical, value / error to 1e-12."""
+    r, st, tr = run_pin(cb, c, cb.Select.DEVICE)
+    val = np.array([float.fromhex(v) for v in c["val_hex"]])
+    err = np.array([float.fromhex(v) for v in c["err_hex"]])
+    assert (st.num_eval, st.num_regions, st.iterations, bool(st.converged)) == (c["numEval"], c["regions"], c["iterations"], c["converged"])
+    assert tr.batches == c["batches"]
+    assert tr.split_hist(c["dim"]) == c["split_hist"]
+    scale = np.max(np.abs(val))
+    assert np.max(np.abs(r[0] - val)) <= 1e-12 * scale       # north_star: within 1e-12 relative
+    assert np.max(np.abs(r[1] - err)) <= 1e-12 * max(np.max(np.abs(err)), scale * 1e-4)
+
+
 def test_final_region_list_is_the_reference_partition(cb, oracle):
     for c in (PINS[0], PINS[1], [p for p in PINS if p["name"] == "genz_gaussian_d3"][0], [p for p in PINS if p["name"] == "cexp_d3_f8_paired_semiinf"][0]):
         rel = NAN if c["relTol"] is None else c["relTol"]
