@@ -25,6 +25,7 @@
 #include "cub_internal.h"
 #include "integrands.h"
 #include "pool_kernels.h"
+#include "iter_exact.h"
 
 // ---- host-side sharding arithmetic of the multi-GPU path (also exported for CPU-only tests) --------
 extern "C" int64_t cubature_cuda_shard_count(int64_t n, int nranks, int rank) {
@@ -312,7 +313,8 @@ struct Workspace {
     SelectBuffers sel;
     DevBuf d_list, d_stage_val, d_stage_err, d_partial, d_small;
     DevBuf g_send, g_recv, g_dense;  // sharded vector select: padded send block, gathered blocks, dense [f + 1][Nglobal]
-    PinnedBuf h_list, h_stage, h_small;
+    DevBuf d_exact;                  // device-resident loop (iter_exact.h): control block, exact sums, histograms
+    PinnedBuf h_list, h_stage, h_small, h_exact;
     long long stage_stride = 0;
 };
 std::mutex g_ws_mu;
@@ -352,7 +354,10 @@ struct Session {
     int dim = 0, fdim = 0, device = 0;
     int64_t P = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> evpool;  // (start, stop) pairs around the rule launches not yet added to rule_ms
+    size_t ev_used = 0;
+    unsigned long long* acc = nullptr;  // exact running sums the rule kernels maintain (device-resident loop), or null
     RuleKernels* kern = nullptr;
     TransformSpec tr;
     std::vector<unsigned char> tr_arg;   // device-side CubTransform bytes
@@ -362,7 +367,6 @@ struct Session {
     double rule_ms = 0.0;
     char* msg = nullptr;
     char msgbuf[256];
-    bool rule_pending = false;
     Workspace* ws = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int64_t local_regions_evaluated = 1;  // regions this rank evaluated (the root box counts for everyone)
@@ -371,8 +375,7 @@ struct Session {
         release_workspace(ws);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (evr0) cudaEventDestroy(evr0);
-        if (evr1) cudaEventDestroy(evr1);
+        for (cudaEvent_t e : evpool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -401,8 +404,6 @@ struct Session {
         CUB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev0), msg);
         CUB_CUDA_CHECK(cudaEventCreate(&ev1), msg);
-        CUB_CUDA_CHECK(cudaEventCreate(&evr0), msg);
-        CUB_CUDA_CHECK(cudaEventCreate(&evr1), msg);
         std::string log;
         int rc = cub_jit_get_kernels(integ, tr.any ? 1 : 0, device, &kern, &log);
         if (rc != CUB_OK) {
@@ -423,7 +424,22 @@ struct Session {
     // bisect kernel + CHILDREN mode.  Rule-kernel time is accumulated with a pair of events.
     int launch_rule(const PoolView& pool, HostWork work) {
         if (work.n_items <= 0) return CUB_OK;
-        flush_rule_timer();
+        if (ev_used + 2 > evpool.size()) {
+            if (evpool.size() >= 512) {
+                flush_rule_timer();
+            } else {
+                cudaEvent_t a = nullptr, b = nullptr;
+                if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+                    cub_set_message(msg, "cudaEventCreate failed");
+                    return CUB_ERR_CUDA;
+                }
+                evpool.push_back(a);
+                evpool.push_back(b);
+            }
+        }
+        cudaEvent_t evr0 = evpool[ev_used], evr1 = evpool[ev_used + 1];
+        ev_used += 2;
+        work.acc = acc;
         const bool one_thread_per_region = (dim >= 2 && fdim == 1) || (dim == 1 && fdim == 1);
         if (work.mode == MODE_BISECT && !one_thread_per_region) {
             pk_bisect(pool, dim, work.list, work.n_items / 2, work.base, stream);
@@ -435,13 +451,15 @@ struct Session {
         cudaEventRecord(evr0, stream);
         cudaError_t e;
         if (dim >= 2 && fdim == 1) {
+            // persistent tiles: at most one resident wave of CTAs, each walks the batch with the grid as its stride
             const int threads = kern->gm_threads;  // the kernel's __launch_bounds__ (CUB_GM_THREADS)
-            const unsigned grid = (unsigned)((work.n_items + threads - 1) / threads);
+            const long long tiles = (work.n_items + threads - 1) / threads;
+            const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm);
             e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(threads), args, 0, stream);
             ++launches;
         } else if (dim == 1 && (fdim == 1 || integ->separable)) {
             const long long threads = work.n_items * fdim;
-            const unsigned grid = (unsigned)((threads + 127) / 128);
+            const unsigned grid = (unsigned)std::min<long long>((threads + 127) / 128, (long long)n_sms * kern->gk_blocks_per_sm);
             e = cudaLaunchKernel((const void*)kern->gk_separable, dim3(grid), dim3(128), args, 0, stream);
             ++launches;
             if (e == cudaSuccess && fdim > 1) {
@@ -468,7 +486,6 @@ struct Session {
             ++launches;
         }
         cudaEventRecord(evr1, stream);
-        rule_pending = true;
         if (e != cudaSuccess) {
             cub_set_message(msg, "rule kernel launch failed: %s", cudaGetErrorString(e));
             return CUB_ERR_CUDA;
@@ -476,12 +493,14 @@ struct Session {
         return CUB_OK;
     }
     void flush_rule_timer() {
-        if (!rule_pending) return;
-        if (cudaEventSynchronize(evr1) == cudaSuccess) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, evr0, evr1) == cudaSuccess) rule_ms += ms;
+        if (!ev_used) return;
+        if (cudaEventSynchronize(evpool[ev_used - 1]) == cudaSuccess) {
+            for (size_t i = 0; i + 1 < ev_used; i += 2) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, evpool[i], evpool[i + 1]) == cudaSuccess) rule_ms += ms;
+            }
         }
-        rule_pending = false;
+        ev_used = 0;
     }
 };
 
@@ -581,6 +600,12 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
 
 int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                            LoopResult* res, const LoopState& st0);
+
+// CUBATURE_LOOP=legacy: the round-1 loop (k_iter_coop on floating-point sums, one host visit per iteration)
+bool legacy_loop() {
+    static const bool v = [] { const char* e = getenv("CUBATURE_LOOP"); return e && strcmp(e, "legacy") == 0; }();
+    return v;
+}
 
 void push_batch(cub_trace_t* tr, int64_t nR) {
     if (!tr) return;
@@ -1717,6 +1742,230 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     return CUB_OK;
 }
 
+// ---- DEVICE mode, scalar integrands: device-resident loop on exact running sums (iter_exact.cu) -------------------------
+// One iteration of Rule.cubature (Rule.java:72-142) = three launches with no host decision in between: k_exact_decide,
+// k_exact_select, the bisect + rule kernel (sized by the control block).  The host enqueues `ahead` iterations, then reads
+// the 256-byte control block once; launches queued behind the end of the loop (or a pause) retire at once.  Pauses:
+// LS_GROW (the pool has to grow: host work), LS_HANDOFF (multi-GPU: time to deal the pool out to the ranks).
+struct ExactBufs {
+    long long* d_ctl = nullptr;
+    long long* h_ctl = nullptr;
+    IterXParams p{};
+    int max_select_blocks = 1;
+    int64_t batches_logged = 0;
+};
+
+int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm) {
+    Workspace& W = *S.ws;
+    const int maxG = ix_select_max_blocks(S.n_sms);
+    const size_t ctl_b = (size_t)(LC_WORDS + LC_LOG_CAP) * 8, acc_b = (size_t)XA_WORDS * 8, hset_b = (size_t)IX_HSET_WORDS * 8,
+                 blk_b = ((size_t)3 * maxG + 8) * 8;
+    CUB_CUDA_CHECK(W.d_exact.ensure(ctl_b + 2 * acc_b + hset_b + 512 + blk_b), S.msg);
+    CUB_CUDA_CHECK(W.h_exact.ensure(ctl_b), S.msg);
+    unsigned char* base = W.d_exact.as<unsigned char>();
+    CUB_CUDA_CHECK(cudaMemsetAsync(base, 0, ctl_b + 2 * acc_b + hset_b + 512 + blk_b, S.stream), S.msg);
+    X.d_ctl = (long long*)base;
+    X.h_ctl = W.h_exact.as<long long>();
+    X.p.ctl = X.d_ctl;
+    X.p.acc = (unsigned long long*)(base + ctl_b);
+    X.p.gbins = (unsigned long long*)(base + ctl_b + acc_b);
+    X.p.hset = (unsigned long long*)(base + ctl_b + 2 * acc_b);
+    X.p.selx = (SelX*)(base + ctl_b + 2 * acc_b + hset_b);
+    X.p.blk = (unsigned long long*)(base + ctl_b + 2 * acc_b + hset_b + 512);
+    X.p.bar = X.p.blk + (size_t)3 * maxG + 4;
+    X.p.absTol = absTol;
+    X.p.relTol = relTol;
+    X.p.norm = norm;
+    X.p.R = 1;
+    X.p.rank = 0;
+    for (int r = 0; r < PK_MAX_RANKS; ++r) X.p.xbuf[r] = nullptr;
+    X.max_select_blocks = maxG;
+    CUB_CUDA_CHECK(cudaMemsetAsync(X.p.acc + XA_M_OFF + XA_M_MINKEY, 0xff, 8, S.stream), S.msg);
+    S.acc = X.p.acc;
+    return CUB_OK;
+}
+
+void exact_bind_pool(Session& S, ExactBufs& X) {
+    Workspace& W = *S.ws;
+    X.p.pool = W.pool.view();
+    X.p.cand_key = W.sel.keysA.as<unsigned long long>();
+    X.p.cand_idx = W.sel.idxB.as<int>();
+    X.p.list = W.sel.idxA.as<int>();
+}
+
+// Runs iterations until the loop ends or pauses for a reason the caller handles (LS_HANDOFF); grows the pool on LS_GROW.
+// On return X.h_ctl holds the final control block.
+int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit) {
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    static const int max_ahead = [] { const char* e = getenv("CUBATURE_AHEAD"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
+    int ahead = std::min(4, max_ahead), visits = 0, grows = 0;
+    long long n_upper = 0;  // upper bound of this rank's region count (doubles at most per iteration)
+    const size_t read_words = trace ? (size_t)(LC_WORDS + LC_LOG_CAP) : (size_t)LC_WORDS;
+    CUB_CUDA_CHECK(cudaMemcpyAsync(X.h_ctl, X.d_ctl, (size_t)LC_WORDS * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    S.d2h_bytes += LC_WORDS * 8;
+    for (;;) {
+        n_upper = X.h_ctl[LC_N];
+        for (int it = 0; it < ahead; ++it) {
+            cudaGetLastError();
+            cudaError_t e = ix_decide(X.p, S.stream);
+            if (e != cudaSuccess) {
+                cub_set_message(S.msg, "decide kernel launch failed: %s", cudaGetErrorString(e));
+                return CUB_ERR_CUDA;
+            }
+            long long G = (n_upper + 4095) / 4096;
+            G = std::max<long long>(1, std::min<long long>(G, X.max_select_blocks));
+            e = ix_select(X.p, (int)G, S.stream);
+            if (e != cudaSuccess) {
+                cub_set_message(S.msg, "select kernel launch failed (%lld CTAs of at most %d): %s", G, X.max_select_blocks, cudaGetErrorString(e));
+                return CUB_ERR_CUDA;
+            }
+            S.launches += 2;
+            HostWork w{};
+            w.list = X.p.list;
+            w.dyn = X.d_ctl;
+            w.n_items = 2 * std::min<long long>(n_upper, pool.cap);  // upper bound: sizes the grid only
+            w.base = 0;
+            w.mode = MODE_BISECT;
+            const int rc = S.launch_rule(pool.view(), w);
+            if (rc != CUB_OK) return rc;
+            n_upper = std::min<long long>(2 * n_upper, pool.cap);
+        }
+        CUB_CUDA_CHECK(cudaMemcpyAsync(X.h_ctl, X.d_ctl, read_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+        S.d2h_bytes += (int64_t)read_words * 8;
+        ++visits;
+        if (trace) {  // batch sizes of the iterations since the last visit (ring log)
+            const int64_t nb = X.h_ctl[LC_NBATCH];
+            for (int64_t i = std::max<int64_t>(X.batches_logged, nb - LC_LOG_CAP); i < nb; ++i) push_batch(trace, X.h_ctl[LC_WORDS + (i % LC_LOG_CAP)]);
+            X.batches_logged = nb;
+        }
+        const long long state = X.h_ctl[LC_STATE];
+        if (state == LS_RUN) {
+            ahead = std::min(2 * ahead, max_ahead);
+            continue;
+        }
+        if (state == LS_GROW) {
+            const long long N = X.h_ctl[LC_N];
+            long long need = 2 * N;
+            if (X.h_ctl[LC_MAXEVAL] > 0) {
+                const long long room = X.h_ctl[LC_MAXEVAL] - X.h_ctl[LC_NUMEVAL];
+                const long long kcap = std::max<long long>(1, (room + 2 * S.P - 1) / (2 * S.P));
+                need = N + std::min(N, kcap);
+            }
+            long long nc = std::max<long long>(pool.cap * 2, need);
+            if (cap_limit > need) nc = std::min(nc, cap_limit);  // never beyond what maxEval can need
+            if (nc > (long long)std::numeric_limits<int>::max()) nc = (long long)std::numeric_limits<int>::max();
+            if (nc < need) {
+                cub_set_message(S.msg, "region pool exceeds 2^31 slots per GPU (%lld regions, %lld needed): shard the pool over more GPUs", N, need);
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+            cudaError_t e = pool.grow(nc, N, S.stream);
+            if (e == cudaSuccess) e = W.sel.ensure_scalar(pool.cap);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
+                return CUB_ERR_POOL_EXHAUSTED;
+            }
+            ++grows;
+            exact_bind_pool(S, X);
+            X.h_ctl[LC_CAP] = pool.cap;
+            X.h_ctl[LC_STATE] = LS_RUN;
+            CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl + LC_CAP, X.h_ctl + LC_CAP, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+            CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl + LC_STATE, X.h_ctl + LC_STATE, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+            S.h2d_bytes += 16;
+            ahead = std::min(ahead, 4);
+            continue;
+        }
+        break;
+    }
+    if (timing)
+        fprintf(stderr, "[cubature] device-resident loop: %lld iterations (%lld cut a batch), %d host visits, %d pool growths, %.2f ms\n",
+                (long long)X.h_ctl[LC_ITER], (long long)X.h_ctl[LC_NSELECT], visits, grows,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    return CUB_OK;
+}
+
+int exact_finish(Session& S, ExactBufs& X, double* out, LoopResult* res, cub_trace_t* trace) {
+    const long long state = X.h_ctl[LC_STATE];
+    if (state == LS_ERROR) {
+        const long long why = X.h_ctl[LC_ERR];
+        if (why == LE_PEER_TIMEOUT)
+            cub_set_message(S.msg, "peer exchange timed out: a rank of the communicator did not take part in the iteration");
+        else if (why == LE_PEER_ABORT)
+            cub_set_message(S.msg, "peer exchange aborted: another rank of the communicator failed");
+        else
+            cub_set_message(S.msg, "internal: the running sums hold %lld regions, the pool %lld", (long long)X.h_ctl[LC_DBG0], (long long)X.h_ctl[LC_NGLOBAL]);
+        return why == LE_INTERNAL ? CUB_ERR_CUDA : CUB_ERR_NCCL;
+    }
+    if (state == LS_GUARD) cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)X.h_ctl[LC_ITER]);
+    double v, e;
+    memcpy(&v, &X.h_ctl[LC_V], 8);
+    memcpy(&e, &X.h_ctl[LC_E], 8);
+    out[0] = v;
+    out[1] = e;
+    S.flush_rule_timer();
+    res->converged = state == LS_CONVERGED ? 1 : 0;
+    res->num_eval = X.h_ctl[LC_NUMEVAL];
+    res->num_regions = X.h_ctl[LC_NGLOBAL];
+    res->iterations = X.h_ctl[LC_ITER];
+    res->ambiguous = X.h_ctl[LC_AMBIG];
+    S.local_regions_evaluated = 1 + X.h_ctl[LC_EVAL_LOCAL];
+    fill_trace_regions(S, S.ws->pool, nullptr, X.h_ctl[LC_N], trace);
+    return CUB_OK;
+}
+
+// One GPU (or the replicated phase of a multi-GPU run: stop_at_regions > 0 pauses the loop for the deal).
+int integrate_device_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, ExactBufs& X, long long stop_at_regions, long long cap_override, bool* handoff) {
+    const int f = S.fdim;  // == 1
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    const size_t extra = 24 + (size_t)8 * f + 1;
+    const long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
+    CUB_CUDA_CHECK(W.sel.ensure_scalar(pool.cap), S.msg);
+    int rc = set_root(S, pool);
+    if (rc != CUB_OK) return rc;
+    rc = exact_setup(S, X, relTol, absTol, norm);
+    if (rc != CUB_OK) return rc;
+    exact_bind_pool(S, X);
+    {
+        HostWork w{};
+        w.n_items = 1;
+        w.base = 0;
+        w.mode = MODE_PLAIN;
+        rc = S.launch_rule(pool.view(), w);  // Rule.java:64-69: the root region, added to the running sums by the kernel
+        if (rc != CUB_OK) return rc;
+    }
+    long long* h = X.h_ctl;
+    memset(h, 0, (size_t)LC_WORDS * 8);
+    h[LC_N] = 1;
+    h[LC_NGLOBAL] = 1;
+    h[LC_NUMEVAL] = P;
+    h[LC_CAP] = pool.cap;
+    h[LC_MAXEVAL] = maxEval;
+    h[LC_P] = P;
+    h[LC_STOP_AT] = stop_at_regions;
+    h[LC_MAXITER] = kMaxIterations;
+    h[LC_SEQ] = 1;
+    CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, h, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+    S.h2d_bytes += LC_WORDS * 8;
+    rc = exact_run(S, X, trace, cap);
+    if (rc != CUB_OK) return rc;
+    if (X.h_ctl[LC_STATE] == LS_HANDOFF) {
+        *handoff = true;
+        return CUB_OK;
+    }
+    if (handoff) *handoff = false;
+    return exact_finish(S, X, out, res, trace);
+}
+
 void init_stats(cub_stats_t* st) {
     if (!st) return;
     const int32_t sz = st->struct_size;
@@ -1948,7 +2197,11 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
         rc = integrate_heap_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
     else if (options && options->comm && options->comm->nranks > 1)
         rc = integrate_device(S, relTol, absTol, norm, maxEval, options, out, &res);
-    else
+    else if (S.fdim == 1 && !legacy_loop()) {
+        ExactBufs X;
+        bool handoff = false;
+        rc = integrate_device_exact(S, relTol, absTol, norm, maxEval, options, out, &res, X, 0, 0, &handoff);
+    } else
         rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, options, out, &res);
     cudaEventRecord(S.ev1, S.stream);
     cudaEventSynchronize(S.ev1);

@@ -45,8 +45,11 @@ CUB_HD xa_u64 xa_mantissa(xa_u64 b) {
 
 struct XaBig {
     xa_u64 l[XA_LIMBS];  // limb j has weight 2^(32 j); values may exceed 2^32 until normalize()
+    int jlo, jhi;        // every limb outside [jlo, jhi] is zero (the loops below only visit this range)
     CUB_HD void clear() {
         for (int j = 0; j < XA_LIMBS; ++j) l[j] = 0ULL;
+        jlo = 0;
+        jhi = XA_LIMBS - 1;
     }
     // += v * 2^pos, v < 2^96, pos + 96 <= 32 * (XA_LIMBS - 1)
     CUB_HD void add_shifted(xa_u128 v, int pos) {
@@ -59,7 +62,7 @@ struct XaBig {
     }
     CUB_HD void normalize() {
         xa_u64 carry = 0;
-        for (int j = 0; j < XA_LIMBS; ++j) {
+        for (int j = jlo; j <= jhi; ++j) {
             const xa_u64 t = l[j] + carry;
             l[j] = t & 0xffffffffULL;
             carry = t >> 32;
@@ -67,22 +70,24 @@ struct XaBig {
     }
     // the functions below need a normalized number
     CUB_HD int top_limb() const {
-        for (int j = XA_LIMBS - 1; j >= 0; --j)
+        for (int j = jhi; j >= jlo; --j)
             if (l[j]) return j;
         return -1;
     }
     CUB_HD bool is_zero() const { return top_limb() < 0; }
     // compare: -1, 0, 1
     CUB_HD int cmp(const XaBig& o) const {
-        for (int j = XA_LIMBS - 1; j >= 0; --j) {
+        const int hi = jhi > o.jhi ? jhi : o.jhi, lo = jlo < o.jlo ? jlo : o.jlo;
+        for (int j = hi; j >= lo; --j) {
             if (l[j] != o.l[j]) return l[j] < o.l[j] ? -1 : 1;
         }
         return 0;
     }
     // this -= o (requires this >= o, both normalized)
     CUB_HD void sub(const XaBig& o) {
+        const int hi = jhi > o.jhi ? jhi : o.jhi, lo = jlo < o.jlo ? jlo : o.jlo;
         long long borrow = 0;
-        for (int j = 0; j < XA_LIMBS; ++j) {
+        for (int j = lo; j <= hi; ++j) {
             long long t = (long long)l[j] - (long long)o.l[j] - borrow;
             borrow = 0;
             if (t < 0) {
@@ -91,6 +96,8 @@ struct XaBig {
             }
             l[j] = (xa_u64)t;
         }
+        jlo = lo;
+        jhi = hi;
     }
     // bits [pos, pos + 64) as an integer, pos >= 0
     CUB_HD xa_u64 window64(int pos) const {
@@ -111,7 +118,7 @@ struct XaBig {
     CUB_HD bool any_below(int pos) const {  // any set bit at a position < pos
         if (pos <= 0) return false;
         const int full = pos >> 5;
-        for (int j = 0; j < full && j < XA_LIMBS; ++j)
+        for (int j = jlo; j < full && j <= jhi; ++j)
             if (l[j]) return true;
         if (full < XA_LIMBS && (pos & 31)) return (l[full] & ((1ULL << (pos & 31)) - 1ULL)) != 0;
         return false;
@@ -145,9 +152,43 @@ struct XaBig {
 };
 
 // ---- 128-bit helpers for the levels below the binade (all mantissas share one exponent there) -------------------
-struct XaS128 {  // unsigned 128-bit as two words (kept POD for shared memory)
-    xa_u64 lo, hi;
-};
-CUB_HD xa_u128 xa_join(xa_u64 lo, xa_u64 hi32sum) { return (xa_u128)lo + ((xa_u128)hi32sum << 32); }
+// bin words -> integer: lo + 2^32 hi with lo UNSIGNED (every contribution adds a low part in [0, 2^32)) and hi SIGNED
+// (acc_device.cuh: a removal is a negative high part)
+CUB_HD xa_i128 xa_join_signed(xa_u64 lo, xa_u64 hi) { return (xa_i128)lo + (xa_i128)(long long)hi * ((xa_i128)1 << 32); }
+CUB_HD double xa_u128_to_double_approx(xa_u128 x) { return (double)(xa_u64)(x >> 64) * 18446744073709551616.0 + (double)(xa_u64)x; }
+CUB_HD int xa_clz64(xa_u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+CUB_HD int xa_top_bit128(xa_u128 x) {  // -1 for zero
+    const xa_u64 hi = (xa_u64)(x >> 64), lo = (xa_u64)x;
+    if (hi) return 127 - xa_clz64(hi);
+    if (lo) return 63 - xa_clz64(lo);
+    return -1;
+}
+// Truncated (toward zero) double of  X = D * 2^pos + L,  0 <= L < 2^pos, for D > 0.  L1 holds bits [pos - 64, pos) of X
+// (zero-extended below bit 0); the unit of X is 2^-1074.  Only the top 53 bits of X matter for truncation, and with D >= 1
+// they lie in D and the top bits of L.
+CUB_HD double xa_trunc_hi(xa_u128 D, xa_u64 L1, int pos) {
+    const int t = xa_top_bit128(D);
+    const int T = pos + t;  // top bit of X
+    if (T <= 52) {          // X < 2^53: the integer is the encoding (subnormals and the first normal binade); pos <= 52
+        const xa_u64 L = pos > 0 ? (L1 >> (64 - pos)) : 0ULL;
+        return xa_from_bits((((xa_u64)D) << pos) | L);
+    }
+    xa_u64 mant;
+    if (t >= 52) {
+        mant = (xa_u64)(D >> (t - 52));
+    } else {
+        const int k = 52 - t;  // 1..52 more bits from L (pos > k here)
+        mant = (((xa_u64)D) << k) | (L1 >> (64 - k));
+    }
+    const int e = T - 51;
+    if (e >= 2047) return xa_from_bits(0x7ff0000000000000ULL);
+    return xa_from_bits(((xa_u64)e << 52) | (mant & 0xfffffffffffffULL));
+}
 
 #endif

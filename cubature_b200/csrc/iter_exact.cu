@@ -1,0 +1,1288 @@
+// iter_exact.cu -- the device-resident refinement loop of scalar integrands (fdim == 1): convergence test, Gladwell batch
+// selection and compaction of Rule.cubature (Rule.java:72-142) on EXACT running sums.
+//
+// The reference keeps Sum(val), Sum(err) of its heap as incremental doubles (RegionHeap.java:21-36) and decides how many
+// regions to pop from the sequential residual `ee.err -= popped.err` (Rule.java:122-124, :129).  Here both sums are integer
+// accumulators (acc_layout.h), maintained by the rule kernels (acc_device.cuh), so every decision is the one the reference's
+// loop takes when its sums carry no rounding error: independent of the order in which threads, CTAs or GPUs contribute, hence
+// identical for any grid size and any number of ranks by construction.  The comparison `residual < tolerance` is exact: the
+// residual is a big integer (exact_acc.h) converted to a double truncated toward zero, for which `double < tol` is the exact
+// test; the value sum is rounded to nearest.  The oracle's exact-sums variant (oracle/cubature_oracle.cpp:
+// orc_set_exact_sums) takes literally these decisions; where they differ from the reference's drifting sums the difference
+// is an artefact of the reference's accumulated rounding (reported as cub_stats_t.ambiguous_decisions).
+//
+//   k_exact_decide (one CTA)   totals from the bins, loop condition and convergence (Rule.java:72-79), evaluation budget,
+//                              the pop-everything shortcut (exact smallest errmax), else the binade in which the batch ends
+//                              (level 0 of the radix select comes for free: the error bins ARE its histogram)
+//   k_exact_select (coop grid) radix select inside that binade on the 52 fraction bits (11+11+11+11+8), integer bucket sums,
+//                              stable compaction of the popped slots; retires at once when there is nothing to cut
+//   rule kernel (NVRTC)        bisects + evaluates the batch, removes the parents from and adds the children to the sums
+// Sharded pools (R > 1): the ranks exchange their bins / histograms through peer-mapped buffers inside these kernels
+// (push over NVLink, flag, spin); integer sums need no fixed rank order.
+#include <cooperative_groups.h>
+
+#include "acc_device.cuh"
+#include "exact_acc.h"
+#include "iter_exact.h"
+
+namespace cg = cooperative_groups;
+
+#define IX_THREADS 256
+#define IX_WARPS (IX_THREADS / 32)
+constexpr int IX_TILE_ITEMS = 8;
+constexpr int IX_TILE = IX_THREADS * IX_TILE_ITEMS;
+
+struct ScalarAccX {
+    double v, e;
+    __host__ __device__ double val(int) const { return v; }
+    __host__ __device__ double err(int) const { return e; }
+};
+__device__ __forceinline__ bool ix_conv(double V, double e, const IterXParams& p) {
+    return cub_converged(1, ScalarAccX{V, e}, p.absTol, p.relTol, p.norm);
+}
+__device__ __forceinline__ unsigned long long ix_bits(double x) { return (unsigned long long)__double_as_longlong(x); }
+__device__ __forceinline__ unsigned long long ix_key_of_err(double e) { return ix_bits(e > 0.0 ? e : 0.0); }  // Rule.java:281-289
+
+// ---- peer exchange ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ix_st_release_sys(unsigned long long* ptr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ix_ld_acquire_sys(const unsigned long long* ptr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ix_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long* ix_pay(unsigned long long* buf, unsigned long long seq, int src_rank) {
+    return buf + PK_XB_DATA + ((size_t)(seq & 1ULL) * PK_MAX_RANKS + (size_t)src_rank) * PK_XB_PAY;
+}
+__device__ __forceinline__ unsigned long long* ix_flag(unsigned long long* buf, unsigned long long seq, int src_rank, int slice) {
+    return buf + PK_XB_FLAGS + ((size_t)(seq & 1ULL) * PK_MAX_RANKS + (size_t)src_rank) * PK_XB_SLICES + (size_t)slice;
+}
+// All IX_THREADS threads of ONE CTA: push payload words [w0, w1) of this rank (src is indexed by payload word) into slot
+// [parity][rank] of every rank's buffer, raise flag `slice`, wait for the same slice of every rank.  Afterwards the words
+// [w0, w1) of all R payloads in the own buffer are valid for this CTA.  Returns 0, or LE_* when a peer timed out / aborted.
+// seq counts the exchanges of the communicator's life; a rank can be at most one exchange ahead of its slowest peer, so two
+// payload slots (parity) suffice.
+__device__ int ix_exchange(const IterXParams& p, unsigned long long seq, int slice, const unsigned long long* src, int w0, int w1) {
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    unsigned long long* own = p.xbuf[p.rank];
+    if (tid == 0) s_fail = 0;
+    for (int r = 0; r < p.R; ++r) {
+        unsigned long long* dst = ix_pay(p.xbuf[r], seq, p.rank);
+        for (int w = w0 + tid; w < w1; w += IX_THREADS) dst[w] = src[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < p.R) {
+        ix_st_release_sys(ix_flag(p.xbuf[tid], seq, p.rank, slice), seq);
+        const unsigned long long* f = ix_flag(own, seq, tid, slice);
+        const unsigned long long t0 = ix_timer_ns();
+        unsigned spins = 0;
+        while (ix_ld_acquire_sys(f) < seq) {
+            if ((++spins & 63u) == 0u) {
+                if (ix_ld_acquire_sys(own + PK_XB_ABORT)) {
+                    s_fail = LE_PEER_ABORT;
+                    break;
+                }
+                if (ix_timer_ns() - t0 > PK_XCHG_TIMEOUT_NS) {
+                    s_fail = LE_PEER_TIMEOUT;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return s_fail;
+}
+
+// ---- big-number helpers of the decide kernel (shared memory, all threads of the CTA) ---------------------------------
+__device__ __forceinline__ void ix_limbs_add(xa_u64* limb, xa_u128 v, int pos) {  // += v * 2^pos, v < 2^96 (atomic)
+    const int j = pos >> 5, s = pos & 31;
+    const xa_u128 lo = v << s;
+    const xa_u64 a = (xa_u64)(lo & 0xffffffffULL), b = (xa_u64)((lo >> 32) & 0xffffffffULL), c = (xa_u64)((lo >> 64) & 0xffffffffULL),
+                 d = (xa_u64)(lo >> 96);
+    if (a) atomicAdd(&limb[j], a);
+    if (b) atomicAdd(&limb[j + 1], b);
+    if (c) atomicAdd(&limb[j + 2], c);
+    if (d) atomicAdd(&limb[j + 3], d);
+}
+
+// Sum of the error bins [0, bound) of the partition as a normalized big number in *out (all threads call; barriers inside).
+// lo / hi: the thread's XA_NBINS / IX_THREADS consecutive bins (mantissa sums), e_min / e_max: non-empty range of all bins.
+__device__ void ix_sum_ebins(XaBig* out, const unsigned long long* lo, const unsigned long long* hi, int bound, int e_min, int e_max) {
+    const int tid = threadIdx.x;
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) out->l[j] = 0ULL;
+    if (tid == 0) {
+        int jl = xa_lsb_pos(e_min < 0 ? 0 : e_min) >> 5, jh = ((xa_lsb_pos(e_max < 0 ? 0 : e_max) + 108) >> 5) + 1;
+        out->jlo = jl;
+        out->jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < XA_NBINS / IX_THREADS; ++q) {
+        const int e = tid * (XA_NBINS / IX_THREADS) + q;
+        if (e < bound && e < 2047) {
+            const xa_i128 v = xa_join_signed(lo[q], hi[q]);
+            if (v > 0) ix_limbs_add(out->l, (xa_u128)v, xa_lsb_pos(e));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) out->normalize();
+    __syncthreads();
+}
+
+struct DecideShared {
+    XaBig A, B;
+    unsigned long long below_c[XA_NBINS];  // regions in bins [0, e)
+    unsigned nz[XA_NBINS / 32];            // non-empty error bins
+    unsigned long long sc_c[IX_THREADS];
+    double sc_d[IX_THREADS];
+    int red_i[IX_THREADS];
+    unsigned long long hdr[PK_MAX_RANKS][16];
+    double r_dbl, r_near;
+    int i0, i1, i2;
+    long long ll0;
+};
+
+__device__ int ix_next_below(const unsigned* nz, int e) {  // largest non-empty bin < e, or -1
+    if (e <= 0) return -1;
+    int w = (e - 1) >> 5;
+    unsigned m = nz[w] & (0xffffffffu >> (31 - ((e - 1) & 31)));
+    for (;;) {
+        if (m) return 32 * w + 31 - __clz(m);
+        if (--w < 0) return -1;
+        m = nz[w];
+    }
+}
+__device__ int ix_next_above(const unsigned* nz, int e) {  // smallest non-empty bin > e, or -1
+    if (e + 1 >= XA_NBINS) return -1;
+    int w = (e + 1) >> 5;
+    unsigned m = nz[w] & (0xffffffffu << ((e + 1) & 31));
+    for (;;) {
+        if (m) return 32 * w + __ffs(m) - 1;
+        if (++w >= XA_NBINS / 32) return -1;
+        m = nz[w];
+    }
+}
+
+__device__ void ix_finish(const IterXParams& p, int state, int err) {
+    p.ctl[LC_STATE] = state;
+    p.ctl[LC_ERR] = err;
+    p.ctl[LC_DYN_N] = 0;
+    p.ctl[LC_SELECT] = 0;
+}
+
+// ---- decide ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
+    __shared__ DecideShared S;
+    const int tid = threadIdx.x;
+    long long* ctl = p.ctl;
+    if (ctl[LC_STATE] != LS_RUN) {  // finished or paused: this launch and the ones queued behind it do nothing
+        if (tid == 0) {
+            ctl[LC_DYN_N] = 0;
+            ctl[LC_SELECT] = 0;
+        }
+        return;
+    }
+    const long long N = ctl[LC_N], Nglobal = ctl[LC_NGLOBAL], numEval = ctl[LC_NUMEVAL], maxEval = ctl[LC_MAXEVAL], P = ctl[LC_P];
+    const bool budget_left = maxEval == 0 || numEval < maxEval;  // Rule.java:72
+    // pops the evaluation budget allows (checked after every pop, Rule.java:133)
+    long long Kcap = Nglobal;
+    if (maxEval > 0 && budget_left) {
+        const long long room = maxEval - numEval, k = (room + 2 * P - 1) / (2 * P);
+        Kcap = k < 1 ? 1 : k;
+        if (Kcap > Nglobal) Kcap = Nglobal;
+    }
+    if (budget_left) {
+        // pauses are taken before any exchange, so that a resumed launch starts the iteration from scratch on every rank
+        if (ctl[LC_STOP_AT] > 0 && Nglobal >= ctl[LC_STOP_AT]) {
+            if (tid == 0) ix_finish(p, LS_HANDOFF, 0);
+            return;
+        }
+        const long long kmax = N < Kcap ? N : Kcap;
+        if (N + kmax > ctl[LC_CAP]) {
+            if (tid == 0) ix_finish(p, LS_GROW, 0);
+            return;
+        }
+    }
+    unsigned long long* acc = p.acc;
+    const unsigned long long* ebins = acc + XA_E_OFF;
+    const unsigned long long* vbins = acc + XA_V_OFF;
+    unsigned long long misc[8];
+    for (int q = 0; q < 8; ++q) misc[q] = acc[XA_M_OFF + q];
+    unsigned long long minkey = acc[XA_M_OFF + XA_M_MINKEY];
+    constexpr int PER = XA_NBINS / IX_THREADS;  // bins per thread
+    if (p.R > 1) {
+        // ---- exchange header + the non-empty windows of the error / value bins; combine into gbins -------------------
+        int elo = XA_NBINS, ehi = -1, vlo = XA_NBINS, vhi = -1;
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid * PER + q;
+            if (ebins[e * 3] | ebins[e * 3 + 1] | ebins[e * 3 + 2]) {
+                elo = e < elo ? e : elo;
+                ehi = e;
+            }
+            if (vbins[e * 2] | vbins[e * 2 + 1]) {
+                vlo = e < vlo ? e : vlo;
+                vhi = e;
+            }
+        }
+        S.red_i[tid] = elo;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
+            __syncthreads();
+        }
+        elo = S.red_i[0];
+        __syncthreads();
+        S.red_i[tid] = ehi;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
+            __syncthreads();
+        }
+        ehi = S.red_i[0];
+        __syncthreads();
+        S.red_i[tid] = vlo;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
+            __syncthreads();
+        }
+        vlo = S.red_i[0];
+        __syncthreads();
+        S.red_i[tid] = vhi;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
+            __syncthreads();
+        }
+        vhi = S.red_i[0];
+        __syncthreads();
+        const int nE = ehi >= elo ? ehi - elo + 1 : 0, nV = vhi >= vlo ? vhi - vlo + 1 : 0;
+        // payload staged in gbins (free until the combine below): header[16] | E window | V window
+        unsigned long long* stage = p.gbins;
+        if (tid < 16) {
+            unsigned long long h = 0ULL;
+            switch (tid) {
+                case 0: h = (unsigned long long)N; break;
+                case 1: h = minkey; break;
+                case 2: h = misc[XA_M_ENAN]; break;
+                case 3: h = misc[XA_M_EINF]; break;
+                case 4: h = misc[XA_M_VNAN]; break;
+                case 5: h = misc[XA_M_VPINF]; break;
+                case 6: h = misc[XA_M_VNINF]; break;
+                case 7: h = misc[XA_M_ESTICKY]; break;
+                case 8: h = misc[XA_M_VSTICKY]; break;
+                case 9: h = (unsigned long long)(nE ? elo : 0); break;
+                case 10: h = (unsigned long long)nE; break;
+                case 11: h = (unsigned long long)(nV ? vlo : 0); break;
+                case 12: h = (unsigned long long)nV; break;
+                default: break;
+            }
+            stage[tid] = h;
+        }
+        for (int w = tid; w < 3 * nE; w += IX_THREADS) stage[16 + w] = ebins[elo * 3 + w];
+        for (int w = tid; w < 2 * nV; w += IX_THREADS) stage[16 + 3 * nE + w] = vbins[vlo * 2 + w];
+        __syncthreads();
+        const unsigned long long seq = (unsigned long long)ctl[LC_SEQ];
+        const int fail = ix_exchange(p, seq, 0, stage, 0, 16 + 3 * nE + 2 * nV);
+        if (tid == 0) ctl[LC_SEQ] = (long long)(seq + 1ULL);
+        if (fail) {
+            if (tid == 0) ix_finish(p, LS_ERROR, fail);
+            return;
+        }
+        unsigned long long* own = p.xbuf[p.rank];
+        if (tid < 16)
+            for (int r = 0; r < p.R; ++r) S.hdr[r][tid] = __ldcg(&ix_pay(own, seq, r)[tid]);
+        __syncthreads();
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid * PER + q;
+            unsigned long long c0 = 0, c1 = 0, c2 = 0, v0 = 0, v1 = 0;
+            for (int r = 0; r < p.R; ++r) {
+                const unsigned long long* pay = ix_pay(own, seq, r);
+                const int lo_e = (int)S.hdr[r][9], n_e = (int)S.hdr[r][10], lo_v = (int)S.hdr[r][11], n_v = (int)S.hdr[r][12];
+                if (e >= lo_e && e < lo_e + n_e) {
+                    const unsigned long long* w = pay + 16 + 3 * (e - lo_e);
+                    c0 += __ldcg(&w[0]);
+                    c1 += __ldcg(&w[1]);
+                    c2 += __ldcg(&w[2]);
+                }
+                if (e >= lo_v && e < lo_v + n_v) {
+                    const unsigned long long* w = pay + 16 + 3 * n_e + 2 * (e - lo_v);
+                    v0 += __ldcg(&w[0]);
+                    v1 += __ldcg(&w[1]);
+                }
+            }
+            p.gbins[XA_E_OFF + e * 3] = c0;
+            p.gbins[XA_E_OFF + e * 3 + 1] = c1;
+            p.gbins[XA_E_OFF + e * 3 + 2] = c2;
+            p.gbins[XA_V_OFF + e * 2] = v0;
+            p.gbins[XA_V_OFF + e * 2 + 1] = v1;
+        }
+        for (int q = 0; q < 8; ++q) misc[q] = 0ULL;
+        minkey = ~0ULL;
+        for (int r = 0; r < p.R; ++r) {
+            misc[XA_M_ENAN] += S.hdr[r][2];
+            misc[XA_M_EINF] += S.hdr[r][3];
+            misc[XA_M_VNAN] += S.hdr[r][4];
+            misc[XA_M_VPINF] += S.hdr[r][5];
+            misc[XA_M_VNINF] += S.hdr[r][6];
+            misc[XA_M_ESTICKY] |= S.hdr[r][7];
+            misc[XA_M_VSTICKY] |= S.hdr[r][8];
+            minkey = S.hdr[r][1] < minkey ? S.hdr[r][1] : minkey;
+        }
+        __syncthreads();
+        ebins = p.gbins + XA_E_OFF;
+        vbins = p.gbins + XA_V_OFF;
+    }
+
+    // ---- counts per bin, non-empty map, approximate bin values ------------------------------------------------------
+    for (int q = tid; q < XA_NBINS / 32; q += IX_THREADS) S.nz[q] = 0u;
+    __syncthreads();
+    unsigned long long cnt[PER], blo[PER], bhi[PER];
+    double apx[PER];
+    unsigned long long csum = 0;
+    double dsum = 0.0;
+    int my_top_e = -1, my_top_v = -1, my_min_e = XA_NBINS, my_min_v = XA_NBINS;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = tid * PER + q;
+        cnt[q] = ebins[e * 3];
+        blo[q] = ebins[e * 3 + 1];
+        bhi[q] = ebins[e * 3 + 2];
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = tid * PER + q;
+        const xa_i128 mv = xa_join_signed(blo[q], bhi[q]);
+        apx[q] = e < 2047 ? scalbn(xa_u128_to_double_approx(mv > 0 ? (xa_u128)mv : (xa_u128)0), xa_lsb_pos(e) - 1074) : 0.0;
+        if (cnt[q]) {
+            atomicOr(&S.nz[e >> 5], 1u << (e & 31));
+            my_top_e = e;
+            my_min_e = e < my_min_e ? e : my_min_e;
+        }
+        if (vbins[e * 2] | vbins[e * 2 + 1]) {
+            my_top_v = e;
+            my_min_v = e < my_min_v ? e : my_min_v;
+        }
+        S.below_c[e] = csum;  // exclusive within the thread; the thread offset is added below
+        csum += cnt[q];
+        dsum += apx[q];
+    }
+    S.sc_c[tid] = csum;
+    S.sc_d[tid] = dsum;
+    S.red_i[tid] = my_top_e;
+    __syncthreads();
+    for (int o = 1; o < IX_THREADS; o <<= 1) {  // inclusive scans over the threads
+        const unsigned long long ta = tid >= o ? S.sc_c[tid - o] : 0ULL;
+        const double tb = tid >= o ? S.sc_d[tid - o] : 0.0;
+        const int tc = tid >= o ? S.red_i[tid - o] : -1;
+        __syncthreads();
+        S.sc_c[tid] += ta;
+        S.sc_d[tid] += tb;
+        S.red_i[tid] = max(S.red_i[tid], tc);
+        __syncthreads();
+    }
+    const unsigned long long c_off = S.sc_c[tid] - csum;
+    const double d_off = S.sc_d[tid] - dsum;
+    const unsigned long long Ntot = S.sc_c[IX_THREADS - 1];
+    const int e_top = S.red_i[IX_THREADS - 1];
+    for (int q = 0; q < PER; ++q) S.below_c[tid * PER + q] += c_off;
+    __syncthreads();
+    S.red_i[tid] = my_top_v;
+    __syncthreads();
+    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
+        __syncthreads();
+    }
+    const int v_top = S.red_i[0];
+    __syncthreads();
+    S.red_i[tid] = my_min_e;
+    __syncthreads();
+    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
+        __syncthreads();
+    }
+    const int e_min = S.red_i[0] >= XA_NBINS ? 0 : S.red_i[0];
+    __syncthreads();
+    S.red_i[tid] = my_min_v;
+    __syncthreads();
+    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
+        __syncthreads();
+    }
+    const int v_min = S.red_i[0] >= XA_NBINS ? 0 : S.red_i[0];
+    __syncthreads();
+
+    // ---- totals: E truncated (exact `<` tests), V rounded to nearest -------------------------------------------------
+    ix_sum_ebins(&S.A, blo, bhi, XA_NBINS, e_min, e_top);
+    const bool e_nonfinite = misc[XA_M_ESTICKY] != 0ULL || misc[XA_M_ENAN] != 0ULL || misc[XA_M_EINF] != 0ULL;
+    if (tid == 0) {
+        S.r_dbl = S.A.to_double(0);
+        S.r_near = S.A.to_double(1);
+    }
+    __syncthreads();
+    double E = S.r_dbl, E_report = S.r_near;  // decisions use the truncated sum, the caller gets the nearest double
+    __syncthreads();
+    if (e_nonfinite) {
+        const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
+        E = ((misc[XA_M_ESTICKY] & 2ULL) || misc[XA_M_ENAN]) ? nan : inf;
+        E_report = E;
+    }
+    // value sum: positive and negative parts separately, then the difference
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) S.A.l[j] = S.B.l[j] = 0ULL;
+    if (tid == 0) {
+        const int jl = xa_lsb_pos(v_min) >> 5, jh = ((xa_lsb_pos(v_top < 0 ? 0 : v_top) + 108) >> 5) + 1;
+        S.A.jlo = S.B.jlo = jl;
+        S.A.jhi = S.B.jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
+    }
+    __syncthreads();
+    for (int q = 0; q < PER; ++q) {
+        const int e = tid * PER + q;
+        if (e < 2047) {
+            const xa_i128 v = xa_join_signed(vbins[e * 2], vbins[e * 2 + 1]);
+            if (v > 0) ix_limbs_add(S.A.l, (xa_u128)v, xa_lsb_pos(e));
+            if (v < 0) ix_limbs_add(S.B.l, (xa_u128)(-v), xa_lsb_pos(e));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        S.A.normalize();
+        S.B.normalize();
+        double V;
+        const int c = S.A.cmp(S.B);
+        if (c == 0) {
+            V = 0.0;
+        } else if (c > 0) {
+            S.A.sub(S.B);
+            V = S.A.to_double(1);
+        } else {
+            S.B.sub(S.A);
+            V = -S.B.to_double(1);
+        }
+        if (misc[XA_M_VSTICKY] | misc[XA_M_VNAN] | misc[XA_M_VPINF] | misc[XA_M_VNINF]) {
+            const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
+            if ((misc[XA_M_VSTICKY] & 2ULL) || misc[XA_M_VNAN] || (misc[XA_M_VPINF] && misc[XA_M_VNINF]))
+                V = nan;
+            else if (misc[XA_M_VPINF])
+                V = inf;
+            else if (misc[XA_M_VNINF])
+                V = -inf;
+        }
+        S.r_dbl = V;
+    }
+    __syncthreads();
+    const double V = S.r_dbl;
+    __syncthreads();
+    const bool count_only = e_nonfinite;
+    const double eps = 2.220446049250313e-16;
+    const double band = 4.0 * eps * sqrt(3.0 * (double)Nglobal);  // rounding band of the reference's drifting sums (diagnostic)
+
+    if (tid == 0) {
+        ctl[LC_V] = (long long)ix_bits(V);
+        ctl[LC_E] = (long long)ix_bits(E_report);
+        // window hints for the rule kernels: children land at or below the current top binades
+        int eb = e_top + 4 - XA_WIN, vb = v_top + 2 - XA_WIN;
+        eb = eb < 0 ? 0 : (eb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : eb);
+        vb = vb < 0 ? 0 : (vb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : vb);
+        acc[XA_M_OFF + XA_M_EBASE] = (unsigned long long)eb;
+        acc[XA_M_OFF + XA_M_VBASE] = (unsigned long long)vb;
+    }
+    if ((long long)Ntot != Nglobal) {  // the sums lost track of the pool: never decide on them
+        if (tid == 0) {
+            ctl[LC_DBG0] = (long long)Ntot;
+            ix_finish(p, LS_ERROR, LE_INTERNAL);
+        }
+        return;
+    }
+    if (!budget_left) {
+        if (tid == 0) ix_finish(p, LS_MAXEVAL, 0);
+        return;
+    }
+    if (ctl[LC_ITER] >= ctl[LC_MAXITER]) {
+        if (tid == 0) ix_finish(p, LS_GUARD, 0);
+        return;
+    }
+    const bool c0 = !count_only && ix_conv(V, E, p);  // Rule.java:73
+    if (tid == 0 && !count_only) {
+        const bool c1 = ix_conv(V, E * (1.0 + band), p), c2 = ix_conv(V, E * (1.0 - band), p);
+        if (c0 != c1 || c0 != c2) ctl[LC_AMBIG] += 1;
+    }
+    if (c0) {
+        if (tid == 0) ix_finish(p, LS_CONVERGED, 0);
+        return;
+    }
+    // ---- the whole pool is popped when the residual left by the smallest region alone does not pass (monotone) -------
+    const double err_min = __longlong_as_double((long long)minkey);
+    bool all = count_only || minkey == ~0ULL || !ix_conv(V, err_min, p);
+    if (tid == 0 && !count_only && minkey != ~0ULL) {
+        const bool a1 = !ix_conv(V, err_min + band * E, p), a2 = !ix_conv(V, err_min - band * E, p);
+        if (a1 != all || a2 != all) ctl[LC_AMBIG] += 1;
+    }
+    if (Nglobal == 1) all = true;
+    all = all && Kcap >= Nglobal;
+    if (all) {
+        if (tid == 0) {
+            ctl[LC_DYN_N] = 2 * N;
+            ctl[LC_DYN_LIST] = 0;
+            ctl[LC_DYN_BASE] = N;
+            ctl[LC_SELECT] = 0;
+            ctl[LC_K] = N;
+            ctl[LC_KGLOBAL] = Nglobal;
+            ctl[LC_N] = 2 * N;
+            ctl[LC_NGLOBAL] = 2 * Nglobal;
+            ctl[LC_NUMEVAL] = numEval + 2 * P * Nglobal;
+            ctl[LC_EVAL_LOCAL] += 2 * N;
+            ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Nglobal;
+            ctl[LC_NBATCH] += 1;
+            ctl[LC_ITER] += 1;
+            acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
+        }
+        return;
+    }
+    // ---- the binade in which the batch ends: the largest b such that popping all bins >= b passes (or uses up the budget)
+    // first with approximate sums, then verified / corrected with the exact ones
+    {
+        int best = -1;
+        double below = d_off;
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid * PER + q;
+            if (cnt[q]) {
+                const unsigned long long Cge = Ntot - S.below_c[e];
+                if (Cge >= (unsigned long long)Kcap || (!count_only && ix_conv(V, below, p))) best = e;
+            }
+            below += apx[q];
+        }
+        S.red_i[tid] = best;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int cand = S.red_i[0];
+            if (cand < 0) cand = ix_next_above(S.nz, -1);  // lowest non-empty bin
+            S.i0 = cand;
+            S.i1 = 0;  // phase: 0 = test cand, 1 = test the bin above, 2 = done
+            S.i2 = -1;
+        }
+        __syncthreads();
+    }
+    for (int guard = 0; guard < 4 * XA_NBINS; ++guard) {
+        const int phase = S.i1;
+        if (phase == 2) break;
+        const int test = phase == 0 ? S.i0 : S.i2;
+        __syncthreads();
+        ix_sum_ebins(&S.A, blo, bhi, test, e_min, e_top);
+        if (tid == 0) {
+            const unsigned long long Cge = Ntot - S.below_c[test];
+            const bool stop = Cge >= (unsigned long long)Kcap || (!count_only && ix_conv(V, S.A.to_double(0), p));
+            if (phase == 0) {
+                if (!stop) {
+                    const int nb = ix_next_below(S.nz, test);
+                    if (nb < 0) {
+                        S.i1 = 2;  // cannot happen (the lowest bin always stops); take it
+                    } else {
+                        S.i0 = nb;
+                    }
+                } else {
+                    const int up = ix_next_above(S.nz, test);
+                    if (up < 0) {
+                        S.i1 = 2;
+                    } else {
+                        S.i2 = up;
+                        S.i1 = 1;
+                    }
+                }
+            } else {
+                if (stop) {  // the bin above stops as well: it becomes the candidate, look further up
+                    S.i0 = test;
+                    const int up = ix_next_above(S.nz, test);
+                    if (up < 0)
+                        S.i1 = 2;
+                    else
+                        S.i2 = up;
+                } else {
+                    S.i1 = 2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int bstar = S.i0;
+    ix_sum_ebins(&S.A, blo, bhi, bstar + 1, e_min, e_top);  // residual before the first pop inside bstar
+    if (tid == 0) {
+        const int pos = xa_lsb_pos(bstar);
+        SelX* sx = p.selx;
+        sx->binade = bstar;
+        sx->pos = pos;
+        sx->count_only = count_only ? 1 : 0;
+        sx->H_lo = S.A.window64(pos);
+        sx->H_hi = S.A.window64(pos + 64);
+        sx->L1 = pos >= 64 ? S.A.window64(pos - 64) : (pos > 0 ? (S.A.window64(0) << (64 - pos)) : 0ULL);
+        // the part below pos as a truncated double (only used when everything above it is popped)
+        for (int j = 0; j < XA_LIMBS; ++j) {
+            const int lo_bit = 32 * j;
+            if (lo_bit >= pos)
+                S.B.l[j] = 0ULL;
+            else if (lo_bit + 32 <= pos)
+                S.B.l[j] = S.A.l[j];
+            else
+                S.B.l[j] = S.A.l[j] & ((1ULL << (pos - lo_bit)) - 1ULL);
+        }
+        S.B.jlo = 0;
+        S.B.jhi = XA_LIMBS - 1;
+        sx->Ldbl = S.B.to_double(0);
+        sx->Cabove = Ntot - S.below_c[bstar] - ebins[bstar * 3];
+        *p.bar = 0ULL;  // grid barrier of the select kernel
+        sx->Kcap = (unsigned long long)Kcap;
+        sx->V = V;
+        sx->E = E;
+        sx->band = band;
+        sx->bin_cnt = ebins[bstar * 3];
+        sx->thr_key = 0ULL;
+        sx->tie_take = 0ULL;
+        sx->K = 0ULL;
+        ctl[LC_SELECT] = 1;
+        ctl[LC_DYN_N] = 0;  // the select kernel sizes the batch
+    }
+}
+
+// ---- select ------------------------------------------------------------------------------------------------------------
+// Radix select inside the threshold binade on the 52 fraction bits, most significant first: two levels of 8 bits that
+// stream the rank's chunk of the pool (256 buckets: four private copies per CTA keep the shared-memory atomics apart, and a
+// CTA adds at most 256 x 3 words to the global histogram), then four levels of 9 bits that only touch the candidates the
+// second scan extracted (the regions that match the 27 bits decided so far, binade included).
+struct PickShared {
+    unsigned long long frac;      // decided fraction bits of the threshold key
+    unsigned long long Pm_lo, Pm_hi;  // mantissa sum of the regions popped inside the binade so far
+    unsigned long long Cc;        // regions popped so far (higher binades included)
+    unsigned long long cb, Sb_lo, Sb_hi;  // chosen bucket: count, mantissa sum
+    unsigned long long tie_take, K, thr_key, ambiguous;
+};
+__device__ __forceinline__ int ix_level_bits(int level) { return level < 2 ? 8 : 9; }
+__device__ __forceinline__ int ix_level_shift(int level) { return level < 2 ? 44 - 8 * level : 27 - 9 * (level - 2); }
+__device__ __forceinline__ int ix_level_nb(int level) { return 1 << ix_level_bits(level); }
+
+__device__ __forceinline__ double ix_residual(const SelX& sx, xa_u128 H, xa_u128 popped) {
+    const xa_u128 D = H - popped;  // >= 0: the popped regions are part of H
+    if (D == 0) return sx.Ldbl;
+    return xa_trunc_hi(D, sx.L1, sx.pos);
+}
+
+// barrier over the first n_ctas CTAs of a cooperative launch (all resident); *bar counts arrivals since the decide kernel
+// cleared it, target = (barriers so far) * n_ctas
+__device__ __forceinline__ void ix_gsync(unsigned long long* bar, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ULL);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Block-wide pick of one level (all threads): buckets in descending order of the mantissa; the first bucket at which the
+// budget runs out or the exact residual passes.  gh: this level's histogram of the partition (global memory:
+// cnt[IX_NB] | low words [IX_NB] | high words [IX_NB]).  Returns 1 when the batch size is final (last level, or the chosen
+// bucket holds one region).
+__device__ int ix_pick(const IterXParams& p, const SelX& sx, PickShared* ps, const unsigned long long* gh, int level,
+                       unsigned long long* shc, unsigned long long* shl, unsigned long long* shh) {
+    const int tid = threadIdx.x;
+    const int NB = ix_level_nb(level), shift = ix_level_shift(level);
+    const int per_t = NB / IX_THREADS;  // 1 or 2
+    const unsigned long long implicit = sx.binade ? (1ULL << 52) : 0ULL;
+    const unsigned long long frac = ps->frac, Cc = ps->Cc;
+    const xa_u128 Pm = ((xa_u128)ps->Pm_hi << 64) | ps->Pm_lo;
+    const xa_u128 H = ((xa_u128)sx.H_hi << 64) | sx.H_lo;
+    unsigned long long c_in[2], cl[2];
+    xa_u128 s_in[2], sl[2];
+    unsigned long long ct = 0;
+    xa_u128 st = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        c_in[j] = 0ULL;
+        s_in[j] = 0;
+        if (j < per_t) {
+            const int jb = NB - 1 - (tid * per_t + j);
+            const unsigned long long c = __ldcg(&gh[jb]);
+            c_in[j] = c;
+            if (c) {
+                const unsigned long long base = implicit | frac | ((unsigned long long)jb << shift);
+                const xa_u128 r = (xa_u128)__ldcg(&gh[IX_NB + jb]) + ((xa_u128)__ldcg(&gh[2 * IX_NB + jb]) << 32);
+                s_in[j] = (xa_u128)c * base + r;
+                ct += c;
+                st += s_in[j];
+            }
+        }
+        cl[j] = ct;
+        sl[j] = st;
+    }
+    __syncthreads();  // everybody has read *ps
+    shc[tid] = ct;
+    shl[tid] = (unsigned long long)st;
+    shh[tid] = (unsigned long long)(st >> 64);
+    __syncthreads();
+    for (int o = 1; o < IX_THREADS; o <<= 1) {  // inclusive scan over the threads
+        unsigned long long ta = 0, tl = 0, th = 0;
+        if (tid >= o) {
+            ta = shc[tid - o];
+            tl = shl[tid - o];
+            th = shh[tid - o];
+        }
+        __syncthreads();
+        if (tid >= o) {
+            shc[tid] += ta;
+            const unsigned long long nl = shl[tid] + tl;
+            shh[tid] += th + (nl < tl ? 1ULL : 0ULL);
+            shl[tid] = nl;
+        }
+        __syncthreads();
+    }
+    const unsigned long long c_off = shc[tid] - ct;
+    const xa_u128 s_off = (((xa_u128)shh[tid] << 64) | shl[tid]) - st;
+    unsigned long long first_stop = ~0ULL, last_nz = 0ULL;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j < per_t && c_in[j]) {
+            const unsigned long long q = (unsigned long long)(tid * per_t + j);
+            last_nz = q + 1ULL;
+            const unsigned long long Cincl = Cc + c_off + cl[j];
+            bool stop = Cincl >= sx.Kcap;
+            if (!stop && !sx.count_only) stop = ix_conv(sx.V, ix_residual(sx, H, Pm + s_off + sl[j]), p);
+            if (stop && first_stop == ~0ULL) first_stop = q;
+        }
+    }
+    __syncthreads();
+    shc[tid] = first_stop;
+    shl[tid] = last_nz;
+    __syncthreads();
+    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            if (shc[tid + o] < shc[tid]) shc[tid] = shc[tid + o];
+            if (shl[tid + o] > shl[tid]) shl[tid] = shl[tid + o];
+        }
+        __syncthreads();
+    }
+    const unsigned long long any_stop = shc[0], nz = shl[0];
+    __syncthreads();
+    if (nz == 0ULL) {  // cannot happen: the binade holds at least one region
+        if (tid == 0) {
+            ps->K = 0ULL;
+            ps->tie_take = 0ULL;
+            ps->thr_key = ~0ULL;
+        }
+        __syncthreads();
+        return 1;
+    }
+    const int chosen = any_stop != ~0ULL ? (int)any_stop : (int)(nz - 1ULL);
+    if (chosen >= tid * per_t && chosen < tid * per_t + per_t) {  // the owner publishes the descent
+        const int j = chosen - tid * per_t;
+        const unsigned long long c_prev = j > 0 ? cl[0] : 0ULL;
+        const xa_u128 s_prev = j > 0 ? sl[0] : (xa_u128)0;
+        const unsigned long long cb = j > 0 ? c_in[1] : c_in[0];
+        const xa_u128 Sb = j > 0 ? s_in[1] : s_in[0];
+        const int jb = NB - 1 - chosen;
+        const xa_u128 Pn = Pm + s_off + s_prev;
+        ps->frac = frac | ((unsigned long long)jb << shift);
+        ps->Cc = Cc + c_off + c_prev;
+        ps->Pm_lo = (unsigned long long)Pn;
+        ps->Pm_hi = (unsigned long long)(Pn >> 64);
+        ps->cb = cb;
+        ps->Sb_lo = (unsigned long long)Sb;
+        ps->Sb_hi = (unsigned long long)(Sb >> 64);
+    }
+    __syncthreads();
+    const unsigned long long cb = ps->cb;
+    int fin = 0;
+    if (level == IX_LEVELS - 1 || cb == 1ULL) {
+        fin = 1;
+        if (tid == 0) {
+            // the bucket is a single key: cb regions with identical errmax (at the last level), or one region whose
+            // mantissa is the bucket's sum
+            const xa_u128 Sb = ((xa_u128)ps->Sb_hi << 64) | ps->Sb_lo;
+            const unsigned long long m = cb == 1ULL ? (unsigned long long)Sb : (implicit | ps->frac);
+            const xa_u128 Pn = ((xa_u128)ps->Pm_hi << 64) | ps->Pm_lo;
+            const unsigned long long cc = ps->Cc;
+            const unsigned long long room = sx.Kcap - cc;  // >= 1
+            const unsigned long long mmax = cb < room ? cb : room;
+            unsigned long long lo = 1, hi = mmax;  // smallest t in [1, mmax] whose residual passes (monotone), else mmax
+            if (!sx.count_only && ix_conv(sx.V, ix_residual(sx, H, Pn + (xa_u128)mmax * m), p)) {
+                while (lo < hi) {
+                    const unsigned long long mid = lo + (hi - lo) / 2;
+                    if (ix_conv(sx.V, ix_residual(sx, H, Pn + (xa_u128)mid * m), p))
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+            } else {
+                lo = mmax;
+            }
+            ps->tie_take = lo;
+            ps->K = cc + lo;
+            ps->thr_key = ((unsigned long long)sx.binade << 52) | (m & 0xfffffffffffffULL);
+            // sensitivity of this decision to the rounding the reference's running sums carry (diagnostic only)
+            unsigned long long amb = 0ULL;
+            if (!sx.count_only) {
+                const double rK = ix_residual(sx, H, Pn + (xa_u128)lo * m), e1 = __longlong_as_double((long long)ps->thr_key), bb = sx.band * sx.E;
+                const bool a0 = ix_conv(sx.V, rK + bb, p) != ix_conv(sx.V, rK - bb, p);
+                const bool a1 = ix_conv(sx.V, rK + e1 + bb, p) != ix_conv(sx.V, rK + e1 - bb, p);
+                amb = (a0 || a1) ? 1ULL : 0ULL;
+            }
+            ps->ambiguous = amb;
+        }
+    }
+    __syncthreads();
+    return fin;
+}
+
+// per-thread run of equal digits -> shared histogram (count, low / high part of the remainder sum)
+__device__ __forceinline__ void ix_hist_flush(unsigned* scnt, unsigned long long* slo, unsigned long long* shi, unsigned cur, unsigned run_c,
+                                              unsigned long long run_lo, unsigned long long run_hi) {
+    if (run_c) {
+        atomicAdd(&scnt[cur], run_c);
+        if (run_lo) atomicAdd(&slo[cur], run_lo);
+        if (run_hi) atomicAdd(&shi[cur], run_hi);
+    }
+}
+
+#define IX_HCOPIES 4  // private histogram copies of the 256-bucket levels (one per pair of warps)
+
+__global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
+    long long* ctl = p.ctl;
+    if (ctl[LC_STATE] != LS_RUN || !ctl[LC_SELECT]) return;  // uniform over the grid
+    const long long n = ctl[LC_N];
+    // CTAs that take part: one per 4096 regions (the grid is sized for the largest pool the host could not rule out)
+    long long G_ll = (n + 4095) / 4096;
+    if (G_ll > (long long)gridDim.x) G_ll = (long long)gridDim.x;
+    if (G_ll < 1) G_ll = 1;
+    const int G = (int)G_ll, b = blockIdx.x, tid = threadIdx.x;
+    if (b >= G) return;
+    __shared__ unsigned scnt[IX_HCOPIES * 256];
+    __shared__ unsigned long long slo[IX_HCOPIES * 256], shi[IX_HCOPIES * 256];
+    __shared__ unsigned long long shc[IX_THREADS], shl[IX_THREADS], shh[IX_THREADS];
+    __shared__ PickShared ps;
+    __shared__ SelX sx;
+    const unsigned lane = tid & 31u;
+    const bool sharded = p.R > 1;
+    unsigned long long xseq = (unsigned long long)ctl[LC_SEQ];
+    unsigned long long* const bar = p.bar;
+    unsigned long long nsync = 0;
+    if (tid == 0) {
+        sx = *p.selx;
+        ps.frac = 0ULL;
+        ps.Pm_lo = ps.Pm_hi = 0ULL;
+        ps.Cc = p.selx->Cabove;
+        ps.cb = ps.Sb_lo = ps.Sb_hi = 0ULL;
+        ps.tie_take = ps.K = ps.thr_key = ps.ambiguous = 0ULL;
+    }
+    __syncthreads();
+    const double* err = p.pool.err;
+    const long long per = (n + G - 1) / G;
+    const long long lo = per * b;
+    long long hi = lo + per;
+    if (hi > n) hi = n;
+    if (lo > hi) hi = lo;
+    const unsigned long long top_mask = 0xfffULL << 52;  // sign + exponent
+    const unsigned long long top_prefix = (unsigned long long)sx.binade << 52;
+    unsigned long long* const cand_count = p.hset + (size_t)IX_LEVELS * 3 * IX_NB;
+    bool have_cand = false;
+    unsigned long long above_def = 0;  // (thread-local) regions of this chunk that are certainly popped
+    long long M = 0;
+    int failed = 0, levels_run = 0;
+    for (int level = 0; level < IX_LEVELS; ++level) {
+        const int shift = ix_level_shift(level), NB = ix_level_nb(level);
+        const int copies = level <= 1 ? IX_HCOPIES : 1;
+        for (int q = tid; q < copies * NB; q += IX_THREADS) {
+            scnt[q] = 0u;
+            slo[q] = 0ULL;
+            shi[q] = 0ULL;
+        }
+        __syncthreads();
+        // keys decided so far: sign, exponent and the fraction bits above this level's digit
+        const unsigned long long mask = top_mask | (0xfffffffffffffULL & ~((1ULL << (shift + ix_level_bits(level))) - 1ULL));
+        const unsigned long long prefix = top_prefix | ps.frac;
+        const unsigned long long rmask = (1ULL << shift) - 1ULL;
+        unsigned cur = 0, run_c = 0;
+        unsigned long long run_lo = 0, run_hi = 0;
+        ++levels_run;
+        if (level <= 1) {
+            // full scan of the chunk; the second scan also extracts the candidates and counts the certain pops
+            unsigned* const myc = scnt + (tid >> 6) * 256;
+            unsigned long long* const mylo = slo + (tid >> 6) * 256;
+            unsigned long long* const myhi = shi + (tid >> 6) * 256;
+            for (long long w0 = lo + (long long)(tid - (int)lane); w0 < hi; w0 += 4 * IX_THREADS) {
+                const long long i0 = w0 + lane;
+                double a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = i0 + u * IX_THREADS < hi ? err[i0 + u * IX_THREADS] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = i0 + u * IX_THREADS;
+                    const bool in = i < hi;
+                    const unsigned long long k = ix_key_of_err(a[u]);
+                    const bool match = in && (k & mask) == prefix;
+                    if (level == 1) {
+                        above_def += (in && (k & mask) > prefix) ? 1ULL : 0ULL;
+                        const unsigned bal = __ballot_sync(0xffffffffu, match);  // warp-aggregated append
+                        if (bal) {
+                            unsigned long long base = 0;
+                            if (lane == (unsigned)(__ffs(bal) - 1)) base = atomicAdd(cand_count, (unsigned long long)__popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                            if (match) {
+                                const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+                                p.cand_key[pos] = k;
+                                p.cand_idx[pos] = (int)i;
+                            }
+                        }
+                    }
+                    if (match) {
+                        const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                        if (d != cur) {
+                            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
+                            cur = d;
+                            run_c = 0;
+                            run_lo = run_hi = 0;
+                        }
+                        const unsigned long long r = k & rmask;
+                        ++run_c;
+                        run_lo += r & 0xffffffffULL;
+                        run_hi += r >> 32;
+                    }
+                }
+            }
+            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
+            if (level == 1) have_cand = true;
+        } else {
+            for (long long q = (long long)b * IX_THREADS + tid; q < M; q += (long long)G * IX_THREADS) {
+                const unsigned long long k = p.cand_key[q];
+                if ((k & mask) == prefix) {
+                    const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                    if (d != cur) {
+                        ix_hist_flush(scnt, slo, shi, cur, run_c, run_lo, run_hi);
+                        cur = d;
+                        run_c = 0;
+                        run_lo = run_hi = 0;
+                    }
+                    const unsigned long long r = k & rmask;
+                    ++run_c;
+                    run_lo += r & 0xffffffffULL;
+                    run_hi += r >> 32;
+                }
+            }
+            ix_hist_flush(scnt, slo, shi, cur, run_c, run_lo, run_hi);
+        }
+        __syncthreads();
+        unsigned long long* gh = p.hset + (size_t)level * 3 * IX_NB;
+        for (int q = tid; q < NB; q += IX_THREADS) {
+            unsigned c = 0;
+            unsigned long long a = 0, h = 0;
+            for (int cp = 0; cp < copies; ++cp) {
+                c += scnt[cp * 256 + q];
+                a += slo[cp * 256 + q];
+                h += shi[cp * 256 + q];
+            }
+            if (c) {  // remainder sum = a + 2^32 h; the global low word grows by less than 2^32 per CTA
+                atomicAdd(&gh[q], (unsigned long long)c);
+                if (a & 0xffffffffULL) atomicAdd(&gh[IX_NB + q], a & 0xffffffffULL);
+                const unsigned long long h2 = h + (a >> 32);
+                if (h2) atomicAdd(&gh[2 * IX_NB + q], h2);
+            }
+        }
+        if (level == 1) {  // certain pops of this chunk -> per-CTA counters of the compaction
+            shc[tid] = above_def;
+            __syncthreads();
+            for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+                if (tid < o) shc[tid] += shc[tid + o];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                p.blk[b] = shc[0];
+                p.blk[G + b] = 0ULL;
+            }
+            __syncthreads();
+        }
+        ix_gsync(bar, ++nsync * (unsigned long long)G);
+        if (sharded) {  // this level's histogram of the whole partition: sum of the R local ones, sliced over the first CTAs
+            const int words = 3 * IX_NB;
+            const int nsl = G < PK_XB_SLICES ? G : PK_XB_SLICES;
+            const int chunk = (words + nsl - 1) / nsl;
+            if (b < nsl) {
+                const int w0 = b * chunk, w1 = min(words, w0 + chunk);
+                const int f = ix_exchange(p, xseq, b, gh, w0, w1);
+                if (f) atomicExch((unsigned long long*)&ctl[LC_DBG1], (unsigned long long)f);
+                unsigned long long* own = p.xbuf[p.rank];
+                for (int w = w0 + tid; w < w1; w += IX_THREADS) {
+                    unsigned long long s = 0;
+                    for (int r = 0; r < p.R; ++r) s += __ldcg(&ix_pay(own, xseq, r)[w]);
+                    gh[w] = s;
+                }
+            }
+            ++xseq;
+            ix_gsync(bar, ++nsync * (unsigned long long)G);
+            if (__ldcg((const unsigned long long*)&ctl[LC_DBG1])) {
+                failed = (int)ctl[LC_DBG1];
+                break;
+            }
+        }
+        if (level == 1) M = (long long)__ldcg(cand_count);
+        const int fin = ix_pick(p, sx, &ps, gh, level, shc, shl, shh);
+        if (fin) break;
+    }
+    if (failed) {
+        if (b == 0 && tid == 0) {
+            ix_finish(p, LS_ERROR, failed);
+            ctl[LC_SEQ] = (long long)xseq;
+        }
+        return;
+    }
+    // ---- stable compaction of the popped slots (every CTA holds the same selection state: integer arithmetic on the
+    // same global histograms) -----------------------------------------------------------------------------------------
+    const unsigned long long thr = ps.thr_key, tie_take = ps.tie_take;
+    if (have_cand) {
+        // per-CTA counts: certain pops (second scan) + the candidates above / at the threshold key
+        for (long long q = (long long)b * IX_THREADS + tid; q < M; q += (long long)G * IX_THREADS) {
+            const unsigned long long k = p.cand_key[q];
+            if (k >= thr) {
+                const long long owner = (long long)p.cand_idx[q] / per;
+                atomicAdd(&p.blk[(k > thr ? 0 : 1) * (long long)G + owner], 1ULL);
+            }
+        }
+    } else {
+        unsigned long long my_gt = 0, my_eq = 0;
+        for (long long i = lo + tid; i < hi; i += IX_THREADS) {
+            const unsigned long long k = ix_key_of_err(err[i]);
+            my_gt += k > thr;
+            my_eq += k == thr;
+        }
+        shc[tid] = my_gt;
+        shl[tid] = my_eq;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                shc[tid] += shc[tid + o];
+                shl[tid] += shl[tid + o];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            p.blk[b] = shc[0];
+            p.blk[G + b] = shl[0];
+        }
+    }
+    ix_gsync(bar, ++nsync * (unsigned long long)G);
+    // the histograms are not read any more: clear the levels that were used (and the candidate counter) for the next launch
+    for (long long q = (long long)b * IX_THREADS + tid; q < (long long)levels_run * 3 * IX_NB; q += (long long)G * IX_THREADS) p.hset[q] = 0ULL;
+    if (b == 0 && tid < 8) cand_count[tid] = 0ULL;
+    unsigned long long tie_take_local = tie_take, K_local = ps.K;
+    if (sharded) {
+        // regions equal to the threshold key are taken in (rank, slot) order: every rank publishes how many of its regions are
+        // above / at the threshold and takes its share of the tie budget
+        if (b == 0) {
+            unsigned long long a = 0, c = 0;
+            for (int i = tid; i < G; i += IX_THREADS) {
+                a += __ldcg(&p.blk[i]);
+                c += __ldcg(&p.blk[G + i]);
+            }
+            shc[tid] = a;
+            shl[tid] = c;
+            __syncthreads();
+            for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+                if (tid < o) {
+                    shc[tid] += shc[tid + o];
+                    shl[tid] += shl[tid + o];
+                }
+                __syncthreads();
+            }
+            if (tid < 16) shh[tid] = tid == 0 ? shc[0] : (tid == 1 ? shl[0] : 0ULL);
+            __syncthreads();
+            const int f = ix_exchange(p, xseq, 0, shh, 0, 16);
+            if (tid == 0) {
+                unsigned long long eq_before = 0ULL, my_gt = 0ULL, my_eq = 0ULL;
+                for (int r = 0; r < p.R; ++r) {
+                    const unsigned long long* pay = ix_pay(p.xbuf[p.rank], xseq, r);
+                    if (r < p.rank) eq_before += __ldcg(&pay[1]);
+                    if (r == p.rank) {
+                        my_gt = __ldcg(&pay[0]);
+                        my_eq = __ldcg(&pay[1]);
+                    }
+                }
+                unsigned long long share = tie_take > eq_before ? tie_take - eq_before : 0ULL;
+                if (share > my_eq) share = my_eq;
+                p.blk[2 * G] = share;
+                p.blk[2 * G + 1] = my_gt + share;
+                p.blk[2 * G + 2] = (unsigned long long)f;
+            }
+            __threadfence();
+        }
+        ++xseq;
+        ix_gsync(bar, ++nsync * (unsigned long long)G);
+        if (__ldcg(&p.blk[2 * G + 2])) {
+            if (b == 0 && tid == 0) {
+                ix_finish(p, LS_ERROR, (int)p.blk[2 * G + 2]);
+                ctl[LC_SEQ] = (long long)xseq;
+            }
+            return;
+        }
+        tie_take_local = __ldcg(&p.blk[2 * G]);
+        K_local = __ldcg(&p.blk[2 * G + 1]);
+    }
+    {
+        unsigned long long a = 0, c = 0;
+        for (int i = tid; i < b; i += IX_THREADS) {
+            a += __ldcg(&p.blk[i]);
+            c += __ldcg(&p.blk[G + i]);
+        }
+        shc[tid] = a;
+        shl[tid] = c;
+        __syncthreads();
+        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                shc[tid] += shc[tid + o];
+                shl[tid] += shl[tid + o];
+            }
+            __syncthreads();
+        }
+    }
+    unsigned long long gt_base = shc[0], eq_base = shl[0];
+    __syncthreads();
+    unsigned* const sl = scnt;
+    unsigned* const se = scnt + IX_THREADS;
+    for (long long t_lo = lo; t_lo < hi; t_lo += IX_TILE) {
+        const long long i_lo = t_lo + (long long)tid * IX_TILE_ITEMS;  // consecutive slots per thread
+        unsigned fl = 0, fe = 0, gt = 0, eq = 0;
+#pragma unroll
+        for (int u = 0; u < IX_TILE_ITEMS; ++u) {
+            const long long i = i_lo + u;
+            if (i < hi) {
+                const unsigned long long k = ix_key_of_err(err[i]);
+                if (k > thr) {
+                    fl |= 1u << u;
+                    ++gt;
+                } else if (k == thr) {
+                    fe |= 1u << u;
+                    ++eq;
+                }
+            }
+        }
+        sl[tid] = gt;
+        se[tid] = eq;
+        __syncthreads();
+        for (int o = 1; o < IX_THREADS; o <<= 1) {
+            const unsigned ta = tid >= o ? sl[tid - o] : 0u, tb = tid >= o ? se[tid - o] : 0u;
+            __syncthreads();
+            sl[tid] += ta;
+            se[tid] += tb;
+            __syncthreads();
+        }
+        unsigned long long gt_before = gt_base + (sl[tid] - gt);
+        unsigned long long eq_before = eq_base + (se[tid] - eq);
+        const unsigned tile_gt = sl[IX_THREADS - 1], tile_eq = se[IX_THREADS - 1];
+#pragma unroll
+        for (int u = 0; u < IX_TILE_ITEMS; ++u) {
+            const bool is_gt = (fl >> u) & 1u, is_eq = (fe >> u) & 1u;
+            if (is_gt || (is_eq && eq_before < tie_take_local)) {
+                const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
+                p.list[pos] = (int)(i_lo + u);
+            }
+            gt_before += is_gt;
+            eq_before += is_eq;
+        }
+        gt_base += tile_gt;
+        eq_base += tile_eq;
+        __syncthreads();
+    }
+    if (b == 0 && tid == 0) {
+        const long long Kl = (long long)K_local, Kg = (long long)ps.K, Nglobal = ctl[LC_NGLOBAL];
+        p.selx->thr_key = ps.thr_key;
+        p.selx->tie_take = ps.tie_take;
+        p.selx->K = ps.K;
+        ctl[LC_DYN_N] = 2 * Kl;
+        ctl[LC_DYN_LIST] = 1;
+        ctl[LC_DYN_BASE] = n;
+        ctl[LC_K] = Kl;
+        ctl[LC_KGLOBAL] = Kg;
+        ctl[LC_N] = n + Kl;
+        ctl[LC_NGLOBAL] = Nglobal + Kg;
+        ctl[LC_NUMEVAL] += 2 * ctl[LC_P] * Kg;
+        ctl[LC_EVAL_LOCAL] += 2 * Kl;
+        ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Kg;
+        ctl[LC_NBATCH] += 1;
+        ctl[LC_ITER] += 1;
+        ctl[LC_NSELECT] += 1;
+        ctl[LC_AMBIG] += (long long)ps.ambiguous;
+        ctl[LC_SEQ] = (long long)xseq;
+        ctl[LC_SELECT] = 0;
+        if (Kg >= Nglobal) p.acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
+    }
+}
+
+// ---- rebuild the sums from the pool ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IX_THREADS) k_acc_rebuild(PoolView pool, long long n, unsigned long long* acc) {
+    __shared__ CubAccWin win;
+    cub_acc_begin(acc, &win);
+    unsigned long long my_min = ~0ULL;
+    for (long long base = (long long)blockIdx.x * IX_THREADS; base < n; base += (long long)gridDim.x * IX_THREADS) {
+        const long long i = base + threadIdx.x;
+        const bool active = i < n;
+        const double v = active ? pool.val[i] : 0.0, e = active ? pool.err[i] : 0.0;
+        cub_acc_warp(acc, &win, active, v, e, 1);
+        if (active) {
+            const unsigned long long kb = cub_errmax_bits(e);
+            my_min = kb < my_min ? kb : my_min;
+        }
+    }
+    cub_acc_end(acc, &win, my_min);
+}
+
+__global__ void k_abort_peers(int R, IterXParams p) {
+    if (threadIdx.x < R && p.xbuf[threadIdx.x]) {
+        p.xbuf[threadIdx.x][PK_XB_ABORT] = 1ULL;
+        __threadfence_system();
+    }
+}
+
+// ---- host launchers ----------------------------------------------------------------------------------------------------
+cudaError_t ix_decide(const IterXParams& p, cudaStream_t s) {
+    k_exact_decide<<<1, IX_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+static int g_select_blocks_per_sm = -1, g_select_max_blocks = 1;
+int ix_select_max_blocks(int n_sms) {
+    if (g_select_blocks_per_sm < 0) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_exact_select, IX_THREADS, 0);
+        g_select_blocks_per_sm = nb > 0 ? (nb > 4 ? 4 : nb) : 1;
+    }
+    g_select_max_blocks = n_sms * g_select_blocks_per_sm;
+    return g_select_max_blocks;
+}
+cudaError_t ix_select(const IterXParams& p, int n_blocks, cudaStream_t s) {
+    IterXParams q = p;
+    void* args[1] = {&q};
+    return cudaLaunchCooperativeKernel((const void*)k_exact_select, dim3((unsigned)n_blocks), dim3(IX_THREADS), args, 0, s);
+}
+void ix_rebuild(const PoolView& pool, long long n, unsigned long long* acc, int n_sms, cudaStream_t s) {
+    cudaMemsetAsync(acc, 0, (size_t)XA_WORDS * 8, s);
+    cudaMemsetAsync(acc + XA_M_OFF + XA_M_MINKEY, 0xff, 8, s);
+    long long g = (n + IX_THREADS - 1) / IX_THREADS;
+    if (g > (long long)n_sms * 8) g = (long long)n_sms * 8;
+    if (g < 1) g = 1;
+    k_acc_rebuild<<<(unsigned)g, IX_THREADS, 0, s>>>(pool, n, acc);
+}
+void ix_abort_peers(int R, void* const* xbuf, cudaStream_t s) {
+    IterXParams p{};
+    for (int r = 0; r < R && r < PK_MAX_RANKS; ++r) p.xbuf[r] = (unsigned long long*)xbuf[r];
+    k_abort_peers<<<1, 32, 0, s>>>(R, p);
+}

@@ -1,0 +1,96 @@
+// iter_exact.h -- the device-resident refinement loop for scalar integrands (iter_exact.cu): loop-control block, selection
+// state and host launchers.  One iteration of Rule.cubature (Rule.java:72-142) is three launches that need no host
+// decision in between -- decide (1 CTA), select (cooperative grid; retires at once when the batch is the whole pool),
+// bisect + rule (persistent grid, sized by the control block) -- so the host enqueues several iterations per visit.
+#ifndef CUB_ITER_EXACT_H
+#define CUB_ITER_EXACT_H
+
+#include <cuda_runtime.h>
+
+#include "acc_layout.h"
+#include "pool_kernels.h"
+
+// ---- loop-control block: 8-byte words in device memory ---------------------------------------------------------------
+enum {
+    LC_DYN_N = 0,     // rule kernel: number of work items (CubWork::dyn[0]); 0 = nothing to do
+    LC_DYN_LIST = 1,  //   1: parents come from the popped list, 0: identity (the whole pool is popped)
+    LC_DYN_BASE = 2,  //   first slot of the right children
+    LC_N = 3,         // regions in this rank's pool
+    LC_NGLOBAL = 4,   // regions of the partition
+    LC_NUMEVAL = 5,   // Rule.java:54,69,127
+    LC_ITER = 6,      // iterations done
+    LC_STATE = 7,     // LS_*
+    LC_ERR = 8,       // detail of LS_ERROR
+    LC_CAP = 9,       // pool capacity (host)
+    LC_MAXEVAL = 10,  // host
+    LC_P = 11,        // points per region (host)
+    LC_SELECT = 12,   // 1: the select kernel of this iteration has work
+    LC_AMBIG = 13,    // decisions within the rounding band of the reference's drifting sums (diagnostic)
+    LC_SEQ = 14,      // sequence number of the next peer exchange (sharded pool)
+    LC_K = 15,        // regions popped by this rank / by the partition in the last iteration
+    LC_KGLOBAL = 16,
+    LC_NBATCH = 17,   // entries written to the batch log
+    LC_STOP_AT = 18,  // pause (LS_HANDOFF) when the partition holds this many regions (0: never)
+    LC_V = 19,        // totals (double bits) at the last decision
+    LC_E = 20,
+    LC_MAXITER = 21,  // iteration guard (host)
+    LC_NSELECT = 22,  // iterations that had to cut a batch
+    LC_EVAL_LOCAL = 23,  // regions evaluated by this rank
+    LC_DBG0 = 24,
+    LC_DBG1 = 25,
+    LC_WORDS = 32,
+};
+#define LC_LOG_CAP 1024  // batch-size log [LC_WORDS .. LC_WORDS + LC_LOG_CAP): 2 K of iteration i at i % LC_LOG_CAP
+enum { LS_RUN = 0, LS_CONVERGED = 1, LS_MAXEVAL = 2, LS_GROW = 3, LS_ERROR = 4, LS_GUARD = 5, LS_HANDOFF = 6 };
+enum { LE_NONE = 0, LE_PEER_TIMEOUT = 1, LE_PEER_ABORT = 2, LE_INTERNAL = 3 };
+
+// selection state handed from the decide kernel to the select kernel (device memory)
+struct SelX {
+    int binade;         // binary exponent (biased) of the threshold region
+    int pos;            // bit position of that binade's mantissa lsb (unit 2^-1074)
+    int count_only;     // the error sum is not finite: batches are cut by the evaluation budget alone
+    int pad;
+    unsigned long long H_lo, H_hi;  // residual before the first pop of this binade, >> pos
+    unsigned long long L1;          // its 64 bits below pos
+    double Ldbl;                    // its part below pos as a (truncated) double
+    unsigned long long Cabove;      // regions in higher binades: all popped
+    unsigned long long Kcap;        // pops the evaluation budget allows (Rule.java:133)
+    double V, E, band;
+    unsigned long long bin_cnt;     // regions of the partition in this binade
+    // results of the select kernel
+    unsigned long long thr_key, tie_take, K;
+};
+
+// histogram set of the select kernel: [IX_LEVELS][3][IX_NB] words (count, low / high part of the mantissa remainders) + misc[8]
+// levels: 8 + 8 bits (streamed), then 4 x 9 bits (candidates only) of the 52 fraction bits
+#define IX_LEVELS 6
+#define IX_NB 512
+#define IX_HSET_WORDS (IX_LEVELS * 3 * IX_NB + 8)
+
+struct IterXParams {
+    PoolView pool;
+    unsigned long long* acc;   // [XA_WORDS] exact running sums of this rank's pool (acc_layout.h)
+    long long* ctl;            // [LC_WORDS + LC_LOG_CAP]
+    SelX* selx;
+    unsigned long long* hset;  // [IX_HSET_WORDS], zero between launches
+    unsigned long long* blk;   // [3 * maxG + 8] per-CTA counters of the compaction
+    unsigned long long* bar;   // arrival counter of the select kernel's grid barrier (cleared by the decide kernel)
+    unsigned long long* gbins; // [XA_WORDS] combined bins of the partition (sharded pool)
+    unsigned long long* cand_key;  // [cap]
+    int* cand_idx;                 // [cap]
+    int* list;                     // [cap] popped slots
+    double absTol, relTol;
+    int norm;
+    int R, rank;
+    unsigned long long* xbuf[PK_MAX_RANKS];
+};
+
+cudaError_t ix_decide(const IterXParams& p, cudaStream_t s);
+cudaError_t ix_select(const IterXParams& p, int n_blocks, cudaStream_t s);
+int ix_select_max_blocks(int n_sms);
+// acc := exact sums of the first n regions of the pool (after dealing a pool out to the ranks; consistency checks)
+void ix_rebuild(const PoolView& pool, long long n, unsigned long long* acc, int n_sms, cudaStream_t s);
+// raises the abort word in every rank's exchange buffer: peers spinning in an exchange fail at once
+void ix_abort_peers(int R, void* const* xbuf, cudaStream_t s);
+
+#endif

@@ -74,7 +74,8 @@ int pk_select_scalar(const PoolView& pool, long long n, const double* totals, lo
 #define PK_XB_FLAGS 0
 #define PK_XB_SLICES 8
 #define PK_XB_DATA 512
-#define PK_XB_PAY (16 + 2 * 2048 + 48)
+#define PK_XB_ABORT 300  // != 0: a rank gave up (iter_exact.cu: ix_abort_peers); spinning exchanges fail at once
+#define PK_XB_PAY (5 * 2048 + 64)  // header[16] + the largest payload: all error / value bins of a rank (iter_exact.cu)
 #define PK_XB_WORDS (PK_XB_DATA + 2 * PK_MAX_RANKS * PK_XB_PAY)
 #define PK_XB_BYTES (PK_XB_WORDS * 8)
 #define PK_XCHG_TIMEOUT_NS 20000000000ULL

@@ -26,7 +26,7 @@
 #ifndef CUBATURE_RULE_KERNELS_CUH
 #define CUBATURE_RULE_KERNELS_CUH
 
-#include "acc_layout.h"
+#include "acc_device.cuh"
 #include "detmath.h"
 #include "integrands.h"
 
@@ -114,94 +114,14 @@ __device__ __forceinline__ long long cub_item_slot(const CubWork& w, long long i
     return (i & 1) ? w.base + pi : (w.list ? (long long)w.list[pi] : pi);
 }
 
-// ---- exact running sums (acc_layout.h) -----------------------------------------------------------------------------
-// A CTA pre-aggregates in a shared-memory window of XA_WIN binades (integer atomics: order-independent) and flushes the
-// window once at the end; values outside the window go to global memory directly.  sign = +1 adds a region, -1 removes it.
-struct CubAccWin {
-    unsigned long long e[XA_WIN * 3];
-    unsigned long long v[XA_WIN * 2];
-    int e_base, v_base;
-};
-__device__ __forceinline__ void cub_acc_word(unsigned long long* g, unsigned long long* sm, int idx, int base, int stride, int field,
-                                             unsigned long long x) {
-    const int w = idx - base;
-    if (w >= 0 && w < XA_WIN)
-        atomicAdd(&sm[w * stride + field], x);
-    else
-        atomicAdd(&g[(long long)idx * stride + field], x);
-}
-__device__ __forceinline__ void cub_acc_region(unsigned long long* acc, CubAccWin* win, double val, double err, long long sign) {
-    const unsigned long long s = (unsigned long long)sign;  // two's complement: multiplying by s negates when sign = -1
-    unsigned long long* misc = acc + XA_M_OFF;
-    {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(err);
-        const int e = (int)((b >> 52) & 2047ULL);
-        const unsigned long long fr = b & 0xfffffffffffffULL;
-        int bin = e;
-        unsigned long long m = e ? (fr | (1ULL << 52)) : fr;
-        if (e == 2047) {  // non-finite: ordered like errmax (NaN -> 0, Rule.java:281-289), summed through the counters
-            m = 0ULL;
-            if (fr) bin = 0;
-            atomicAdd(&misc[fr ? XA_M_ENAN : XA_M_EINF], s);
-            if (sign > 0) misc[XA_M_ESTICKY] = 1ULL;
-        } else if (b >> 63) {  // cannot happen (err is an absolute value); ordered as errmax = 0
-            bin = 0;
-            m = 0ULL;
-        }
-        unsigned long long* g = acc + XA_E_OFF;
-        cub_acc_word(g, win->e, bin, win->e_base, 3, 0, s);
-        if (m) {
-            cub_acc_word(g, win->e, bin, win->e_base, 3, 1, (m & 0xffffffffULL) * s);
-            cub_acc_word(g, win->e, bin, win->e_base, 3, 2, (m >> 32) * s);
-        }
-    }
-    {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(val);
-        const int e = (int)((b >> 52) & 2047ULL);
-        const unsigned long long fr = b & 0xfffffffffffffULL;
-        if (e == 2047) {
-            atomicAdd(&misc[fr ? XA_M_VNAN : ((b >> 63) ? XA_M_VNINF : XA_M_VPINF)], s);
-            if (sign > 0) misc[XA_M_VSTICKY] = 1ULL;
-        } else {
-            const unsigned long long m = e ? (fr | (1ULL << 52)) : fr;
-            if (m) {
-                const unsigned long long sv = (b >> 63) ? (0ULL - s) : s;
-                unsigned long long* g = acc + XA_V_OFF;
-                cub_acc_word(g, win->v, e, win->v_base, 2, 0, (m & 0xffffffffULL) * sv);
-                cub_acc_word(g, win->v, e, win->v_base, 2, 1, (m >> 32) * sv);
-            }
-        }
-    }
-    atomicAdd(&misc[XA_M_COUNT], s);
-}
-// every thread of the CTA calls these (barriers inside)
-__device__ __forceinline__ void cub_acc_begin(const unsigned long long* acc, CubAccWin* win) {
-    for (int q = threadIdx.x; q < XA_WIN * 3; q += blockDim.x) win->e[q] = 0ULL;
-    for (int q = threadIdx.x; q < XA_WIN * 2; q += blockDim.x) win->v[q] = 0ULL;
-    if (threadIdx.x == 0) {  // window hints of the iteration kernel (0 before the first iteration)
-        win->e_base = (int)acc[XA_M_OFF + 8];
-        win->v_base = (int)acc[XA_M_OFF + 9];
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void cub_acc_end(unsigned long long* acc, CubAccWin* win) {
-    __syncthreads();
-    for (int q = threadIdx.x; q < XA_WIN * 3; q += blockDim.x) {
-        const unsigned long long x = win->e[q];
-        if (x) atomicAdd(&acc[XA_E_OFF + (long long)win->e_base * 3 + q], x);
-    }
-    for (int q = threadIdx.x; q < XA_WIN * 2; q += blockDim.x) {
-        const unsigned long long x = win->v[q];
-        if (x) atomicAdd(&acc[XA_V_OFF + (long long)win->v_base * 2 + q], x);
-    }
-}
-
 // Loads the geometry of work item `i` (bisecting the parent when asked to) and returns its slot.
 // All loads of a warp happen before any of its stores (__syncwarp) because in BISECT mode the two
 // children of one parent sit in adjacent lanes and the left child overwrites what the right reads.
 __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, const CubWork& w, long long i, bool active,
                                                    double (&c)[CUB_DIM], double (&h)[CUB_DIM], CubAccWin* win = nullptr) {
     long long slot = 0;
+    double pval = 0.0, perr = 0.0;
+    bool premove = false;
     if (active) {
         slot = cub_item_slot(w, i);
         if (w.mode != CUB_MODE_BISECT) {
@@ -230,11 +150,18 @@ __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, cons
 #if CUB_FDIM == 1
             // the popped parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28); its slot still holds
             // its val / err until the left child overwrites them at the end of this thread
-            if (win && !right) cub_acc_region(w.acc, win, pool.val[parent], pool.err[parent], -1);
+            if (win && !right) {
+                pval = pool.val[parent];
+                perr = pool.err[parent];
+                premove = true;
+            }
 #endif
         }
     }
     if (w.mode == CUB_MODE_BISECT) {
+#if CUB_FDIM == 1
+        if (win) cub_acc_warp(w.acc, win, premove, pval, perr, -1);  // all lanes of the warp
+#endif
         __syncwarp();
         if (active) {
 #pragma unroll
@@ -447,6 +374,7 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
     const long long n = work.n_items;
     __shared__ CubAccWin win_storage;
     CubAccWin* const win = work.acc ? &win_storage : nullptr;
+    unsigned long long my_min = ~0ULL;
     if (win) cub_acc_begin(work.acc, win);
     for (long long tile = blockIdx.x; tile * CUB_GM_THREADS < n; tile += gridDim.x) {
         const long long i = tile * CUB_GM_THREADS + threadIdx.x;
@@ -455,32 +383,38 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
 #pragma unroll
         for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
         const long long slot = cub_load_item(pool, work, i, active, c, h, win);
-        if (!active) continue;
+        double result = 0.0, err = 0.0;
+        if (active) {
+            const CUB_INTEGRAND fn(prm.v, 1);
+            int split;
+            cub_gm_region(fn, tr, c, h, result, err, split);
+            if (cub_fast_failed(fn, 0)) {  // an argument left the fast path's exact range: redo with IEEE division
+                const CubRegionResult r = cub_gm_region_exact<CUB_INTEGRAND>(pool, slot, prm, tr, 0);
+                result = r.result;
+                err = r.err;
+                split = r.split;
+            }
+            double emax = 0.0;  // Rule.java:281-289
+            if (err > emax) emax = err;
 
-        const CUB_INTEGRAND fn(prm.v, 1);
-        double result, err;
-        int split;
-        cub_gm_region(fn, tr, c, h, result, err, split);
-        if (cub_fast_failed(fn, 0)) {  // an argument left the fast path's exact range: redo with IEEE division
-            const CubRegionResult r = cub_gm_region_exact<CUB_INTEGRAND>(pool, slot, prm, tr, 0);
-            result = r.result;
-            err = r.err;
-            split = r.split;
+            pool.val[slot] = result;
+            pool.err[slot] = err;
+            pool.errmax[slot] = emax;
+            pool.splitdim[slot] = split;
+            if (work.stage_val) {
+                work.stage_val[i] = result;
+                work.stage_err[i] = err;
+            }
         }
-        double emax = 0.0;  // Rule.java:281-289
-        if (err > emax) emax = err;
-
-        pool.val[slot] = result;
-        pool.err[slot] = err;
-        pool.errmax[slot] = emax;
-        pool.splitdim[slot] = split;
-        if (work.stage_val) {
-            work.stage_val[i] = result;
-            work.stage_err[i] = err;
+        if (win) {  // RegionHeap.add, RegionHeap.java:30-36 (all lanes of the warp take part)
+            cub_acc_warp(work.acc, win, active, result, err, 1);
+            if (active) {
+                const unsigned long long kb = cub_errmax_bits(err);
+                my_min = kb < my_min ? kb : my_min;
+            }
         }
-        if (win) cub_acc_region(work.acc, win, result, err, 1);  // RegionHeap.add, RegionHeap.java:30-36
     }
-    if (win) cub_acc_end(work.acc, win);
+    if (win) cub_acc_end(work.acc, win, my_min);
 }
 #endif  // CUB_FDIM == 1
 #endif  // CUB_DIM >= 2
@@ -569,6 +503,7 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
     const long long n = work.n_items;
     __shared__ CubAccWin win_storage;
     CubAccWin* win = nullptr;
+    unsigned long long my_min = ~0ULL;
 #if CUB_FDIM == 1
     if (work.acc) win = &win_storage;
     if (win) cub_acc_begin(work.acc, win);
@@ -580,50 +515,58 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
         const int j = active ? (int)(t / n) : 0;
         double cc[1] = {0.0}, hh[1] = {0.0};
         const long long slot = cub_load_item(pool, work, i, active, cc, hh, win);
-        if (!active) continue;
-        const double c = cc[0], h = hh[0];
-
-        const CubExactIntegrand fn(prm.v, CUB_FDIM);
-        double q[15];
+        double val = 0.0, err = 0.0;
+        if (active) {
+            const double c = cc[0], h = hh[0];
+            const CubExactIntegrand fn(prm.v, CUB_FDIM);
+            double q[15];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
-            double tt[1] = {cub_gk15_node(k, c, h)};
+            for (int k = 0; k < 15; ++k) {
+                double tt[1] = {cub_gk15_node(k, c, h)};
 #if CUB_HAS_TRANSFORM
-            double xx[1];
-            const double jac = 1.0 * cub_transform_coord(tr.code[0], tr.shift[0], tt[0], &xx[0]);
+                double xx[1];
+                const double jac = 1.0 * cub_transform_coord(tr.code[0], tr.shift[0], tt[0], &xx[0]);
 #if CUB_FDIM == 1
-            fn.eval(xx, &q[k]);
+                fn.eval(xx, &q[k]);
 #else
-            q[k] = fn.eval1(xx, j);
+                q[k] = fn.eval1(xx, j);
 #endif
-            q[k] = q[k] * jac;
+                q[k] = q[k] * jac;
 #else
 #if CUB_FDIM == 1
-            fn.eval(tt, &q[k]);
+                fn.eval(tt, &q[k]);
 #else
-            q[k] = fn.eval1(tt, j);
+                q[k] = fn.eval1(tt, j);
 #endif
 #endif
+            }
+            cub_gk15_sums(q, h, &val, &err);
+            pool.val[(long long)j * pool.cap + slot] = val;
+            pool.err[(long long)j * pool.cap + slot] = err;
+#if CUB_FDIM == 1
+            double emax = 0.0;
+            if (err > emax) emax = err;
+            pool.errmax[slot] = emax;
+            pool.splitdim[slot] = 0;
+#endif
+            // fdim > 1: errmax / splitdim are produced by cub_errmax_rows (pool_kernels.cu) after this launch
+            if (work.stage_val) {
+                work.stage_val[(long long)j * work.stage_stride + i] = val;
+                work.stage_err[(long long)j * work.stage_stride + i] = err;
+            }
         }
-        double val, err;
-        cub_gk15_sums(q, h, &val, &err);
-        pool.val[(long long)j * pool.cap + slot] = val;
-        pool.err[(long long)j * pool.cap + slot] = err;
 #if CUB_FDIM == 1
-        double emax = 0.0;
-        if (err > emax) emax = err;
-        pool.errmax[slot] = emax;
-        pool.splitdim[slot] = 0;
-        if (win) cub_acc_region(work.acc, win, val, err, 1);
-#endif
-        // fdim > 1: errmax / splitdim are produced by cub_errmax_rows (pool_kernels.cu) after this launch
-        if (work.stage_val) {
-            work.stage_val[(long long)j * work.stage_stride + i] = val;
-            work.stage_err[(long long)j * work.stage_stride + i] = err;
+        if (win) {
+            cub_acc_warp(work.acc, win, active, val, err, 1);
+            if (active) {
+                const unsigned long long kb = cub_errmax_bits(err);
+                my_min = kb < my_min ? kb : my_min;
+            }
         }
+#endif
     }
 #if CUB_FDIM == 1
-    if (win) cub_acc_end(work.acc, win);
+    if (win) cub_acc_end(work.acc, win, my_min);
 #endif
 }
 #endif  // CUB_FDIM == 1 || CUB_SEPARABLE
