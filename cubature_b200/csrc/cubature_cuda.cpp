@@ -1883,6 +1883,12 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
         break;
     }
     if (timing)
+        fprintf(stderr, "[cubature] decide kernel phases (last select iteration, us): setup %.1f counts %.1f totals %.1f conv %.1f approx %.1f verify %.1f final %.1f\n",
+                (X.h_ctl[LC_STAMP + 1] - X.h_ctl[LC_STAMP]) * 1e-3, (X.h_ctl[LC_STAMP + 2] - X.h_ctl[LC_STAMP + 1]) * 1e-3,
+                (X.h_ctl[LC_STAMP + 3] - X.h_ctl[LC_STAMP + 2]) * 1e-3, (X.h_ctl[LC_STAMP + 4] - X.h_ctl[LC_STAMP + 3]) * 1e-3,
+                (X.h_ctl[LC_STAMP + 5] - X.h_ctl[LC_STAMP + 4]) * 1e-3, (X.h_ctl[LC_STAMP + 6] - X.h_ctl[LC_STAMP + 5]) * 1e-3,
+                (X.h_ctl[LC_STAMP + 7] - X.h_ctl[LC_STAMP + 6]) * 1e-3);
+    if (timing)
         fprintf(stderr, "[cubature] device-resident loop: %lld iterations (%lld cut a batch), %d host visits, %d pool growths, %.2f ms\n",
                 (long long)X.h_ctl[LC_ITER], (long long)X.h_ctl[LC_NSELECT], visits, grows,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());

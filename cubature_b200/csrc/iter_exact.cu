@@ -102,53 +102,21 @@ __device__ int ix_exchange(const IterXParams& p, unsigned long long seq, int sli
     return s_fail;
 }
 
-// ---- big-number helpers of the decide kernel (shared memory, all threads of the CTA) ---------------------------------
-__device__ __forceinline__ void ix_limbs_add(xa_u64* limb, xa_u128 v, int pos) {  // += v * 2^pos, v < 2^96 (atomic)
-    const int j = pos >> 5, s = pos & 31;
-    const xa_u128 lo = v << s;
-    const xa_u64 a = (xa_u64)(lo & 0xffffffffULL), b = (xa_u64)((lo >> 32) & 0xffffffffULL), c = (xa_u64)((lo >> 64) & 0xffffffffULL),
-                 d = (xa_u64)(lo >> 96);
-    if (a) atomicAdd(&limb[j], a);
-    if (b) atomicAdd(&limb[j + 1], b);
-    if (c) atomicAdd(&limb[j + 2], c);
-    if (d) atomicAdd(&limb[j + 3], d);
-}
-
-// Sum of the error bins [0, bound) of the partition as a normalized big number in *out (all threads call; barriers inside).
-// lo / hi: the thread's XA_NBINS / IX_THREADS consecutive bins (mantissa sums), e_min / e_max: non-empty range of all bins.
-__device__ void ix_sum_ebins(XaBig* out, const unsigned long long* lo, const unsigned long long* hi, int bound, int e_min, int e_max) {
-    const int tid = threadIdx.x;
-    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) out->l[j] = 0ULL;
-    if (tid == 0) {
-        int jl = xa_lsb_pos(e_min < 0 ? 0 : e_min) >> 5, jh = ((xa_lsb_pos(e_max < 0 ? 0 : e_max) + 108) >> 5) + 1;
-        out->jlo = jl;
-        out->jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < XA_NBINS / IX_THREADS; ++q) {
-        const int e = tid * (XA_NBINS / IX_THREADS) + q;
-        if (e < bound && e < 2047) {
-            const xa_i128 v = xa_join_signed(lo[q], hi[q]);
-            if (v > 0) ix_limbs_add(out->l, (xa_u128)v, xa_lsb_pos(e));
-        }
-    }
-    __syncthreads();
-    if (tid == 0) out->normalize();
-    __syncthreads();
-}
+// ---- decide ------------------------------------------------------------------------------------------------------------
+// The sums are built and walked by single threads (big-integer arithmetic on a handful of limbs); the other threads only
+// fetch the bins and pre-add their eight consecutive binades into one 128-bit partial each.
+#define IX_PER (XA_NBINS / IX_THREADS)  // bins per thread
+#define IX_TOPW 256                      // bins below the top non-empty one staged in shared memory for the walk
 
 struct DecideShared {
-    XaBig A, B;
-    unsigned long long below_c[XA_NBINS];  // regions in bins [0, e)
-    unsigned nz[XA_NBINS / 32];            // non-empty error bins
-    unsigned long long sc_c[IX_THREADS];
-    double sc_d[IX_THREADS];
-    int red_i[IX_THREADS];
+    XaBig E, Vp, Vn;
+    unsigned long long part[3][IX_THREADS][2];  // per-thread partial sums (E, V > 0, V < 0) at bit position xa_lsb_pos(8 tid)
+    unsigned part_mask[3][IX_WARPS];            // threads with a non-zero partial
+    unsigned long long wcnt[IX_TOPW], wlo[IX_TOPW], whi[IX_TOPW];  // error bins [e_top - IX_TOPW + 1, e_top]
+    unsigned nz[XA_NBINS / 32];                 // non-empty error bins
+    unsigned long long red_c[IX_WARPS];
+    int red_a[IX_WARPS], red_b[IX_WARPS], red_c2[IX_WARPS], red_d[IX_WARPS];
     unsigned long long hdr[PK_MAX_RANKS][16];
-    double r_dbl, r_near;
-    int i0, i1, i2;
-    long long ll0;
 };
 
 __device__ int ix_next_below(const unsigned* nz, int e) {  // largest non-empty bin < e, or -1
@@ -161,15 +129,28 @@ __device__ int ix_next_below(const unsigned* nz, int e) {  // largest non-empty 
         m = nz[w];
     }
 }
-__device__ int ix_next_above(const unsigned* nz, int e) {  // smallest non-empty bin > e, or -1
-    if (e + 1 >= XA_NBINS) return -1;
-    int w = (e + 1) >> 5;
-    unsigned m = nz[w] & (0xffffffffu << ((e + 1) & 31));
-    for (;;) {
-        if (m) return 32 * w + __ffs(m) - 1;
-        if (++w >= XA_NBINS / 32) return -1;
-        m = nz[w];
+
+// a -= v * 2^pos for a normalized a >= v * 2^pos, v < 2^96
+__device__ void ix_big_sub(XaBig* a, xa_u128 v, int pos) {
+    const int j = pos >> 5, sh = pos & 31;
+    const xa_u128 lo = v << sh;
+    long long borrow = 0;
+    for (int q = 0; q < 4 || borrow; ++q) {
+        if (j + q >= XA_LIMBS) break;
+        const long long piece = q < 4 ? (long long)(xa_u64)((lo >> (32 * q)) & 0xffffffffULL) : 0LL;
+        long long t = (long long)a->l[j + q] - piece - borrow;
+        borrow = 0;
+        if (t < 0) {
+            t += (1LL << 32);
+            borrow = 1;
+        }
+        a->l[j + q] = (xa_u64)t;
     }
+}
+// a += v * 2^pos, v < 2^128 (not normalized afterwards)
+__device__ __forceinline__ void ix_big_add128(XaBig* a, xa_u64 v_lo, xa_u64 v_hi, int pos) {
+    if (v_lo) a->add_shifted((xa_u128)v_lo, pos);
+    if (v_hi) a->add_shifted((xa_u128)v_hi, pos + 64);
 }
 
 __device__ void ix_finish(const IterXParams& p, int state, int err) {
@@ -179,10 +160,20 @@ __device__ void ix_finish(const IterXParams& p, int state, int err) {
     p.ctl[LC_SELECT] = 0;
 }
 
-// ---- decide ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ix_block_max(int v, int* red) {  // all threads; result for everybody
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = red[0];
+#pragma unroll
+    for (int q = 1; q < IX_WARPS; ++q) r = max(r, red[q]);
+    return r;
+}
+
 __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
     __shared__ DecideShared S;
     const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
     long long* ctl = p.ctl;
     if (ctl[LC_STATE] != LS_RUN) {  // finished or paused: this launch and the ones queued behind it do nothing
         if (tid == 0) {
@@ -191,6 +182,7 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         }
         return;
     }
+    if (tid == 0) ctl[LC_STAMP] = (long long)ix_timer_ns();
     const long long N = ctl[LC_N], Nglobal = ctl[LC_NGLOBAL], numEval = ctl[LC_NUMEVAL], maxEval = ctl[LC_MAXEVAL], P = ctl[LC_P];
     const bool budget_left = maxEval == 0 || numEval < maxEval;  // Rule.java:72
     // pops the evaluation budget allows (checked after every pop, Rule.java:133)
@@ -216,57 +208,41 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
     const unsigned long long* ebins = acc + XA_E_OFF;
     const unsigned long long* vbins = acc + XA_V_OFF;
     unsigned long long misc[8];
+#pragma unroll
     for (int q = 0; q < 8; ++q) misc[q] = acc[XA_M_OFF + q];
     unsigned long long minkey = acc[XA_M_OFF + XA_M_MINKEY];
-    constexpr int PER = XA_NBINS / IX_THREADS;  // bins per thread
+    // the thread's bins
+    unsigned long long cnt[IX_PER], blo[IX_PER], bhi[IX_PER], vlo[IX_PER], vhi[IX_PER];
+#pragma unroll
+    for (int q = 0; q < IX_PER; ++q) {
+        const int e = tid * IX_PER + q;
+        cnt[q] = ebins[e * 3];
+        blo[q] = ebins[e * 3 + 1];
+        bhi[q] = ebins[e * 3 + 2];
+        vlo[q] = vbins[e * 2];
+        vhi[q] = vbins[e * 2 + 1];
+    }
     if (p.R > 1) {
-        // ---- exchange header + the non-empty windows of the error / value bins; combine into gbins -------------------
-        int elo = XA_NBINS, ehi = -1, vlo = XA_NBINS, vhi = -1;
-        for (int q = 0; q < PER; ++q) {
-            const int e = tid * PER + q;
-            if (ebins[e * 3] | ebins[e * 3 + 1] | ebins[e * 3 + 2]) {
+        // ---- exchange header + the non-empty windows of the error / value bins; combine ------------------------------
+        int elo = XA_NBINS, ehi = -1, wlo_ = XA_NBINS, whi_ = -1;
+#pragma unroll
+        for (int q = 0; q < IX_PER; ++q) {
+            const int e = tid * IX_PER + q;
+            if (cnt[q] | blo[q] | bhi[q]) {
                 elo = e < elo ? e : elo;
                 ehi = e;
             }
-            if (vbins[e * 2] | vbins[e * 2 + 1]) {
-                vlo = e < vlo ? e : vlo;
-                vhi = e;
+            if (vlo[q] | vhi[q]) {
+                wlo_ = e < wlo_ ? e : wlo_;
+                whi_ = e;
             }
         }
-        S.red_i[tid] = elo;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
-            __syncthreads();
-        }
-        elo = S.red_i[0];
-        __syncthreads();
-        S.red_i[tid] = ehi;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
-            __syncthreads();
-        }
-        ehi = S.red_i[0];
-        __syncthreads();
-        S.red_i[tid] = vlo;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
-            __syncthreads();
-        }
-        vlo = S.red_i[0];
-        __syncthreads();
-        S.red_i[tid] = vhi;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
-            __syncthreads();
-        }
-        vhi = S.red_i[0];
-        __syncthreads();
-        const int nE = ehi >= elo ? ehi - elo + 1 : 0, nV = vhi >= vlo ? vhi - vlo + 1 : 0;
-        // payload staged in gbins (free until the combine below): header[16] | E window | V window
+        ehi = ix_block_max(ehi, S.red_a);
+        elo = -ix_block_max(-elo, S.red_b);
+        whi_ = ix_block_max(whi_, S.red_c2);
+        wlo_ = -ix_block_max(-wlo_, S.red_d);
+        const int nE = ehi >= elo ? ehi - elo + 1 : 0, nV = whi_ >= wlo_ ? whi_ - wlo_ + 1 : 0;
+        // payload staged in gbins: header[16] | E window | V window
         unsigned long long* stage = p.gbins;
         if (tid < 16) {
             unsigned long long h = 0ULL;
@@ -282,14 +258,25 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
                 case 8: h = misc[XA_M_VSTICKY]; break;
                 case 9: h = (unsigned long long)(nE ? elo : 0); break;
                 case 10: h = (unsigned long long)nE; break;
-                case 11: h = (unsigned long long)(nV ? vlo : 0); break;
+                case 11: h = (unsigned long long)(nV ? wlo_ : 0); break;
                 case 12: h = (unsigned long long)nV; break;
                 default: break;
             }
             stage[tid] = h;
         }
-        for (int w = tid; w < 3 * nE; w += IX_THREADS) stage[16 + w] = ebins[elo * 3 + w];
-        for (int w = tid; w < 2 * nV; w += IX_THREADS) stage[16 + 3 * nE + w] = vbins[vlo * 2 + w];
+#pragma unroll
+        for (int q = 0; q < IX_PER; ++q) {
+            const int e = tid * IX_PER + q;
+            if (nE && e >= elo && e <= ehi) {
+                stage[16 + 3 * (e - elo)] = cnt[q];
+                stage[16 + 3 * (e - elo) + 1] = blo[q];
+                stage[16 + 3 * (e - elo) + 2] = bhi[q];
+            }
+            if (nV && e >= wlo_ && e <= whi_) {
+                stage[16 + 3 * nE + 2 * (e - wlo_)] = vlo[q];
+                stage[16 + 3 * nE + 2 * (e - wlo_) + 1] = vhi[q];
+            }
+        }
         __syncthreads();
         const unsigned long long seq = (unsigned long long)ctl[LC_SEQ];
         const int fail = ix_exchange(p, seq, 0, stage, 0, 16 + 3 * nE + 2 * nV);
@@ -302,8 +289,9 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         if (tid < 16)
             for (int r = 0; r < p.R; ++r) S.hdr[r][tid] = __ldcg(&ix_pay(own, seq, r)[tid]);
         __syncthreads();
-        for (int q = 0; q < PER; ++q) {
-            const int e = tid * PER + q;
+#pragma unroll
+        for (int q = 0; q < IX_PER; ++q) {
+            const int e = tid * IX_PER + q;
             unsigned long long c0 = 0, c1 = 0, c2 = 0, v0 = 0, v1 = 0;
             for (int r = 0; r < p.R; ++r) {
                 const unsigned long long* pay = ix_pay(own, seq, r);
@@ -320,11 +308,14 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
                     v1 += __ldcg(&w[1]);
                 }
             }
-            p.gbins[XA_E_OFF + e * 3] = c0;
+            cnt[q] = c0;
+            blo[q] = c1;
+            bhi[q] = c2;
+            vlo[q] = v0;
+            vhi[q] = v1;
+            p.gbins[XA_E_OFF + e * 3] = c0;  // (the walk below reads bins outside its shared window from here)
             p.gbins[XA_E_OFF + e * 3 + 1] = c1;
             p.gbins[XA_E_OFF + e * 3 + 2] = c2;
-            p.gbins[XA_V_OFF + e * 2] = v0;
-            p.gbins[XA_V_OFF + e * 2 + 1] = v1;
         }
         for (int q = 0; q < 8; ++q) misc[q] = 0ULL;
         minkey = ~0ULL;
@@ -340,135 +331,120 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         }
         __syncthreads();
         ebins = p.gbins + XA_E_OFF;
-        vbins = p.gbins + XA_V_OFF;
     }
+    if (tid == 0) ctl[LC_STAMP + 1] = (long long)ix_timer_ns();
 
-    // ---- counts per bin, non-empty map, approximate bin values ------------------------------------------------------
+    // ---- per-thread partial sums, non-empty map, extremes ------------------------------------------------------------
     for (int q = tid; q < XA_NBINS / 32; q += IX_THREADS) S.nz[q] = 0u;
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) S.E.l[j] = S.Vp.l[j] = S.Vn.l[j] = 0ULL;
     __syncthreads();
-    unsigned long long cnt[PER], blo[PER], bhi[PER];
-    double apx[PER];
+    const int pb = xa_lsb_pos(tid * IX_PER);
+    xa_u128 pe = 0, pvp = 0, pvn = 0;
     unsigned long long csum = 0;
-    double dsum = 0.0;
     int my_top_e = -1, my_top_v = -1, my_min_e = XA_NBINS, my_min_v = XA_NBINS;
+    unsigned my_nz = 0;
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int e = tid * PER + q;
-        cnt[q] = ebins[e * 3];
-        blo[q] = ebins[e * 3 + 1];
-        bhi[q] = ebins[e * 3 + 2];
-    }
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int e = tid * PER + q;
-        const xa_i128 mv = xa_join_signed(blo[q], bhi[q]);
-        apx[q] = e < 2047 ? scalbn(xa_u128_to_double_approx(mv > 0 ? (xa_u128)mv : (xa_u128)0), xa_lsb_pos(e) - 1074) : 0.0;
+    for (int q = 0; q < IX_PER; ++q) {
+        const int e = tid * IX_PER + q;
+        const int shq = xa_lsb_pos(e) - pb;
         if (cnt[q]) {
-            atomicOr(&S.nz[e >> 5], 1u << (e & 31));
+            my_nz |= 1u << q;
             my_top_e = e;
             my_min_e = e < my_min_e ? e : my_min_e;
+            csum += cnt[q];
         }
-        if (vbins[e * 2] | vbins[e * 2 + 1]) {
-            my_top_v = e;
-            my_min_v = e < my_min_v ? e : my_min_v;
+        if (e < 2047) {
+            const xa_i128 mv = xa_join_signed(blo[q], bhi[q]);
+            if (mv > 0) pe += (xa_u128)mv << shq;
+            const xa_i128 vv = xa_join_signed(vlo[q], vhi[q]);
+            if (vv > 0) pvp += (xa_u128)vv << shq;
+            if (vv < 0) pvn += (xa_u128)(-vv) << shq;
+            if (vv != 0) {
+                my_top_v = e;
+                my_min_v = e < my_min_v ? e : my_min_v;
+            }
         }
-        S.below_c[e] = csum;  // exclusive within the thread; the thread offset is added below
-        csum += cnt[q];
-        dsum += apx[q];
     }
-    S.sc_c[tid] = csum;
-    S.sc_d[tid] = dsum;
-    S.red_i[tid] = my_top_e;
-    __syncthreads();
-    for (int o = 1; o < IX_THREADS; o <<= 1) {  // inclusive scans over the threads
-        const unsigned long long ta = tid >= o ? S.sc_c[tid - o] : 0ULL;
-        const double tb = tid >= o ? S.sc_d[tid - o] : 0.0;
-        const int tc = tid >= o ? S.red_i[tid - o] : -1;
-        __syncthreads();
-        S.sc_c[tid] += ta;
-        S.sc_d[tid] += tb;
-        S.red_i[tid] = max(S.red_i[tid], tc);
-        __syncthreads();
+    if (my_nz) atomicOr(&S.nz[(tid * IX_PER) >> 5], my_nz << ((tid * IX_PER) & 31));
+    S.part[0][tid][0] = (unsigned long long)pe;
+    S.part[0][tid][1] = (unsigned long long)(pe >> 64);
+    S.part[1][tid][0] = (unsigned long long)pvp;
+    S.part[1][tid][1] = (unsigned long long)(pvp >> 64);
+    S.part[2][tid][0] = (unsigned long long)pvn;
+    S.part[2][tid][1] = (unsigned long long)(pvn >> 64);
+    {
+        const unsigned b0 = __ballot_sync(0xffffffffu, pe != 0), b1 = __ballot_sync(0xffffffffu, pvp != 0), b2 = __ballot_sync(0xffffffffu, pvn != 0);
+        if (lane == 0) {
+            S.part_mask[0][warp] = b0;
+            S.part_mask[1][warp] = b1;
+            S.part_mask[2][warp] = b2;
+        }
+        unsigned long long cw = csum;
+        for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
+        if (lane == 0) S.red_c[warp] = cw;
     }
-    const unsigned long long c_off = S.sc_c[tid] - csum;
-    const double d_off = S.sc_d[tid] - dsum;
-    const unsigned long long Ntot = S.sc_c[IX_THREADS - 1];
-    const int e_top = S.red_i[IX_THREADS - 1];
-    for (int q = 0; q < PER; ++q) S.below_c[tid * PER + q] += c_off;
-    __syncthreads();
-    S.red_i[tid] = my_top_v;
-    __syncthreads();
-    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
-        __syncthreads();
+    const int e_top = ix_block_max(my_top_e, S.red_a);
+    const int e_min_n = ix_block_max(-my_min_e, S.red_b);
+    const int v_top = ix_block_max(my_top_v, S.red_c2);
+    const int v_min_n = ix_block_max(-my_min_v, S.red_d);
+    const int e_min = -e_min_n >= XA_NBINS ? 0 : -e_min_n, v_min = -v_min_n >= XA_NBINS ? 0 : -v_min_n;
+    unsigned long long Ntot = 0;
+#pragma unroll
+    for (int q = 0; q < IX_WARPS; ++q) Ntot += S.red_c[q];
+    // stage the bins near the top for the walk
+#pragma unroll
+    for (int q = 0; q < IX_PER; ++q) {
+        const int e = tid * IX_PER + q, w = e - (e_top - IX_TOPW + 1);
+        if (e <= e_top && w >= 0 && w < IX_TOPW) {
+            S.wcnt[w] = cnt[q];
+            S.wlo[w] = blo[q];
+            S.whi[w] = bhi[q];
+        }
     }
-    const int v_top = S.red_i[0];
     __syncthreads();
-    S.red_i[tid] = my_min_e;
-    __syncthreads();
-    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
-        __syncthreads();
+    if (tid == 0) ctl[LC_STAMP + 2] = (long long)ix_timer_ns();
+    // ---- three lanes build the three sums: error, positive values, negative values -----------------------------------
+    if (tid < 3) {
+        XaBig* A = tid == 0 ? &S.E : (tid == 1 ? &S.Vp : &S.Vn);
+        const int lo_e = tid == 0 ? e_min : v_min, hi_e = tid == 0 ? e_top : v_top;
+        const int jl = xa_lsb_pos((lo_e < 0 ? 0 : lo_e) & ~(IX_PER - 1)) >> 5, jh = ((xa_lsb_pos(hi_e < 0 ? 0 : hi_e) + 120) >> 5) + 1;
+        A->jlo = jl;
+        A->jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
+        for (int w = 0; w < IX_WARPS; ++w) {
+            unsigned m = S.part_mask[tid][w];
+            while (m) {
+                const int t = 32 * w + __ffs(m) - 1;
+                m &= m - 1;
+                ix_big_add128(A, S.part[tid][t][0], S.part[tid][t][1], xa_lsb_pos(t * IX_PER));
+            }
+        }
+        A->normalize();
     }
-    const int e_min = S.red_i[0] >= XA_NBINS ? 0 : S.red_i[0];
     __syncthreads();
-    S.red_i[tid] = my_min_v;
-    __syncthreads();
-    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) S.red_i[tid] = min(S.red_i[tid], S.red_i[tid + o]);
-        __syncthreads();
-    }
-    const int v_min = S.red_i[0] >= XA_NBINS ? 0 : S.red_i[0];
-    __syncthreads();
+    if (tid != 0) return;  // the rest is one thread's work
 
+    ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
     // ---- totals: E truncated (exact `<` tests), V rounded to nearest -------------------------------------------------
-    ix_sum_ebins(&S.A, blo, bhi, XA_NBINS, e_min, e_top);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
     const bool e_nonfinite = misc[XA_M_ESTICKY] != 0ULL || misc[XA_M_ENAN] != 0ULL || misc[XA_M_EINF] != 0ULL;
-    if (tid == 0) {
-        S.r_dbl = S.A.to_double(0);
-        S.r_near = S.A.to_double(1);
-    }
-    __syncthreads();
-    double E = S.r_dbl, E_report = S.r_near;  // decisions use the truncated sum, the caller gets the nearest double
-    __syncthreads();
+    double E = S.E.to_double(0), E_report = S.E.to_double(1);  // decisions use the truncated sum, the caller gets the nearest double
     if (e_nonfinite) {
-        const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
         E = ((misc[XA_M_ESTICKY] & 2ULL) || misc[XA_M_ENAN]) ? nan : inf;
         E_report = E;
     }
-    // value sum: positive and negative parts separately, then the difference
-    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) S.A.l[j] = S.B.l[j] = 0ULL;
-    if (tid == 0) {
-        const int jl = xa_lsb_pos(v_min) >> 5, jh = ((xa_lsb_pos(v_top < 0 ? 0 : v_top) + 108) >> 5) + 1;
-        S.A.jlo = S.B.jlo = jl;
-        S.A.jhi = S.B.jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
-    }
-    __syncthreads();
-    for (int q = 0; q < PER; ++q) {
-        const int e = tid * PER + q;
-        if (e < 2047) {
-            const xa_i128 v = xa_join_signed(vbins[e * 2], vbins[e * 2 + 1]);
-            if (v > 0) ix_limbs_add(S.A.l, (xa_u128)v, xa_lsb_pos(e));
-            if (v < 0) ix_limbs_add(S.B.l, (xa_u128)(-v), xa_lsb_pos(e));
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        S.A.normalize();
-        S.B.normalize();
-        double V;
-        const int c = S.A.cmp(S.B);
+    double V;
+    {
+        const int c = S.Vp.cmp(S.Vn);
         if (c == 0) {
             V = 0.0;
         } else if (c > 0) {
-            S.A.sub(S.B);
-            V = S.A.to_double(1);
+            S.Vp.sub(S.Vn);
+            V = S.Vp.to_double(1);
         } else {
-            S.B.sub(S.A);
-            V = -S.B.to_double(1);
+            S.Vn.sub(S.Vp);
+            V = -S.Vn.to_double(1);
         }
         if (misc[XA_M_VSTICKY] | misc[XA_M_VNAN] | misc[XA_M_VPINF] | misc[XA_M_VNINF]) {
-            const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
             if ((misc[XA_M_VSTICKY] & 2ULL) || misc[XA_M_VNAN] || (misc[XA_M_VPINF] && misc[XA_M_VNINF]))
                 V = nan;
             else if (misc[XA_M_VPINF])
@@ -476,19 +452,13 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
             else if (misc[XA_M_VNINF])
                 V = -inf;
         }
-        S.r_dbl = V;
     }
-    __syncthreads();
-    const double V = S.r_dbl;
-    __syncthreads();
     const bool count_only = e_nonfinite;
     const double eps = 2.220446049250313e-16;
     const double band = 4.0 * eps * sqrt(3.0 * (double)Nglobal);  // rounding band of the reference's drifting sums (diagnostic)
-
-    if (tid == 0) {
-        ctl[LC_V] = (long long)ix_bits(V);
-        ctl[LC_E] = (long long)ix_bits(E_report);
-        // window hints for the rule kernels: children land at or below the current top binades
+    ctl[LC_V] = (long long)ix_bits(V);
+    ctl[LC_E] = (long long)ix_bits(E_report);
+    {   // window hints for the rule kernels: children land at or below the current top binades
         int eb = e_top + 4 - XA_WIN, vb = v_top + 2 - XA_WIN;
         eb = eb < 0 ? 0 : (eb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : eb);
         vb = vb < 0 ? 0 : (vb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : vb);
@@ -496,162 +466,118 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         acc[XA_M_OFF + XA_M_VBASE] = (unsigned long long)vb;
     }
     if ((long long)Ntot != Nglobal) {  // the sums lost track of the pool: never decide on them
-        if (tid == 0) {
-            ctl[LC_DBG0] = (long long)Ntot;
-            ix_finish(p, LS_ERROR, LE_INTERNAL);
-        }
+        ctl[LC_DBG0] = (long long)Ntot;
+        ix_finish(p, LS_ERROR, LE_INTERNAL);
         return;
     }
     if (!budget_left) {
-        if (tid == 0) ix_finish(p, LS_MAXEVAL, 0);
+        ix_finish(p, LS_MAXEVAL, 0);
         return;
     }
     if (ctl[LC_ITER] >= ctl[LC_MAXITER]) {
-        if (tid == 0) ix_finish(p, LS_GUARD, 0);
+        ix_finish(p, LS_GUARD, 0);
         return;
     }
     const bool c0 = !count_only && ix_conv(V, E, p);  // Rule.java:73
-    if (tid == 0 && !count_only) {
+    if (!count_only) {
         const bool c1 = ix_conv(V, E * (1.0 + band), p), c2 = ix_conv(V, E * (1.0 - band), p);
         if (c0 != c1 || c0 != c2) ctl[LC_AMBIG] += 1;
     }
     if (c0) {
-        if (tid == 0) ix_finish(p, LS_CONVERGED, 0);
+        ix_finish(p, LS_CONVERGED, 0);
         return;
     }
     // ---- the whole pool is popped when the residual left by the smallest region alone does not pass (monotone) -------
     const double err_min = __longlong_as_double((long long)minkey);
     bool all = count_only || minkey == ~0ULL || !ix_conv(V, err_min, p);
-    if (tid == 0 && !count_only && minkey != ~0ULL) {
+    if (!count_only && minkey != ~0ULL) {
         const bool a1 = !ix_conv(V, err_min + band * E, p), a2 = !ix_conv(V, err_min - band * E, p);
         if (a1 != all || a2 != all) ctl[LC_AMBIG] += 1;
     }
     if (Nglobal == 1) all = true;
     all = all && Kcap >= Nglobal;
     if (all) {
-        if (tid == 0) {
-            ctl[LC_DYN_N] = 2 * N;
-            ctl[LC_DYN_LIST] = 0;
-            ctl[LC_DYN_BASE] = N;
-            ctl[LC_SELECT] = 0;
-            ctl[LC_K] = N;
-            ctl[LC_KGLOBAL] = Nglobal;
-            ctl[LC_N] = 2 * N;
-            ctl[LC_NGLOBAL] = 2 * Nglobal;
-            ctl[LC_NUMEVAL] = numEval + 2 * P * Nglobal;
-            ctl[LC_EVAL_LOCAL] += 2 * N;
-            ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Nglobal;
-            ctl[LC_NBATCH] += 1;
-            ctl[LC_ITER] += 1;
-            acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
-        }
+        ctl[LC_DYN_N] = 2 * N;
+        ctl[LC_DYN_LIST] = 0;
+        ctl[LC_DYN_BASE] = N;
+        ctl[LC_SELECT] = 0;
+        ctl[LC_K] = N;
+        ctl[LC_KGLOBAL] = Nglobal;
+        ctl[LC_N] = 2 * N;
+        ctl[LC_NGLOBAL] = 2 * Nglobal;
+        ctl[LC_NUMEVAL] = numEval + 2 * P * Nglobal;
+        ctl[LC_EVAL_LOCAL] += 2 * N;
+        ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Nglobal;
+        ctl[LC_NBATCH] += 1;
+        ctl[LC_ITER] += 1;
+        acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
         return;
     }
-    // ---- the binade in which the batch ends: the largest b such that popping all bins >= b passes (or uses up the budget)
-    // first with approximate sums, then verified / corrected with the exact ones
+    ctl[LC_STAMP + 4] = (long long)ix_timer_ns();
+    // ---- walk down from the top binade, popping whole bins, until the evaluation budget is used up or the exact residual
+    // passes (Rule.java:109-133 at bin granularity): the batch ends inside that binade ---------------------------------
+    int bstar = e_top;
+    unsigned long long Cabove = 0;
+    for (int e = e_top; e >= 0; e = ix_next_below(S.nz, e)) {
+        const int w = e - (e_top - IX_TOPW + 1);
+        const unsigned long long c = w >= 0 ? S.wcnt[w] : ebins[e * 3];
+        const xa_i128 mv = w >= 0 ? xa_join_signed(S.wlo[w], S.whi[w]) : xa_join_signed(ebins[e * 3 + 1], ebins[e * 3 + 2]);
+        bstar = e;
+        if (Cabove + c >= (unsigned long long)Kcap) break;
+        if (ix_next_below(S.nz, e) < 0) break;  // the lowest bin: popping everything was ruled out above, so the batch ends here
+        if (!count_only) {
+            // residual after popping this bin as well; put the bin back when that passes
+            const bool has = mv > 0 && e < 2047;
+            if (has) ix_big_sub(&S.E, (xa_u128)mv, xa_lsb_pos(e));
+            if (ix_conv(V, S.E.to_double(0), p)) {
+                if (has) {
+                    S.E.add_shifted((xa_u128)mv, xa_lsb_pos(e));
+                    S.E.normalize();
+                }
+                break;
+            }
+        }
+        Cabove += c;
+    }
+    ctl[LC_STAMP + 5] = (long long)ix_timer_ns();
+    // S.E is the residual before the first pop inside bstar
     {
-        int best = -1;
-        double below = d_off;
-        for (int q = 0; q < PER; ++q) {
-            const int e = tid * PER + q;
-            if (cnt[q]) {
-                const unsigned long long Cge = Ntot - S.below_c[e];
-                if (Cge >= (unsigned long long)Kcap || (!count_only && ix_conv(V, below, p))) best = e;
-            }
-            below += apx[q];
-        }
-        S.red_i[tid] = best;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) S.red_i[tid] = max(S.red_i[tid], S.red_i[tid + o]);
-            __syncthreads();
-        }
-        if (tid == 0) {
-            int cand = S.red_i[0];
-            if (cand < 0) cand = ix_next_above(S.nz, -1);  // lowest non-empty bin
-            S.i0 = cand;
-            S.i1 = 0;  // phase: 0 = test cand, 1 = test the bin above, 2 = done
-            S.i2 = -1;
-        }
-        __syncthreads();
-    }
-    for (int guard = 0; guard < 4 * XA_NBINS; ++guard) {
-        const int phase = S.i1;
-        if (phase == 2) break;
-        const int test = phase == 0 ? S.i0 : S.i2;
-        __syncthreads();
-        ix_sum_ebins(&S.A, blo, bhi, test, e_min, e_top);
-        if (tid == 0) {
-            const unsigned long long Cge = Ntot - S.below_c[test];
-            const bool stop = Cge >= (unsigned long long)Kcap || (!count_only && ix_conv(V, S.A.to_double(0), p));
-            if (phase == 0) {
-                if (!stop) {
-                    const int nb = ix_next_below(S.nz, test);
-                    if (nb < 0) {
-                        S.i1 = 2;  // cannot happen (the lowest bin always stops); take it
-                    } else {
-                        S.i0 = nb;
-                    }
-                } else {
-                    const int up = ix_next_above(S.nz, test);
-                    if (up < 0) {
-                        S.i1 = 2;
-                    } else {
-                        S.i2 = up;
-                        S.i1 = 1;
-                    }
-                }
-            } else {
-                if (stop) {  // the bin above stops as well: it becomes the candidate, look further up
-                    S.i0 = test;
-                    const int up = ix_next_above(S.nz, test);
-                    if (up < 0)
-                        S.i1 = 2;
-                    else
-                        S.i2 = up;
-                } else {
-                    S.i1 = 2;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    const int bstar = S.i0;
-    ix_sum_ebins(&S.A, blo, bhi, bstar + 1, e_min, e_top);  // residual before the first pop inside bstar
-    if (tid == 0) {
         const int pos = xa_lsb_pos(bstar);
+        const int w = bstar - (e_top - IX_TOPW + 1);
         SelX* sx = p.selx;
         sx->binade = bstar;
         sx->pos = pos;
         sx->count_only = count_only ? 1 : 0;
-        sx->H_lo = S.A.window64(pos);
-        sx->H_hi = S.A.window64(pos + 64);
-        sx->L1 = pos >= 64 ? S.A.window64(pos - 64) : (pos > 0 ? (S.A.window64(0) << (64 - pos)) : 0ULL);
+        sx->H_lo = S.E.window64(pos);
+        sx->H_hi = S.E.window64(pos + 64);
+        sx->L1 = pos >= 64 ? S.E.window64(pos - 64) : (pos > 0 ? (S.E.window64(0) << (64 - pos)) : 0ULL);
         // the part below pos as a truncated double (only used when everything above it is popped)
+        S.Vn.jlo = S.E.jlo;
+        S.Vn.jhi = S.E.jhi;
         for (int j = 0; j < XA_LIMBS; ++j) {
             const int lo_bit = 32 * j;
-            if (lo_bit >= pos)
-                S.B.l[j] = 0ULL;
+            if (lo_bit >= pos || j < S.E.jlo || j > S.E.jhi)
+                S.Vn.l[j] = 0ULL;
             else if (lo_bit + 32 <= pos)
-                S.B.l[j] = S.A.l[j];
+                S.Vn.l[j] = S.E.l[j];
             else
-                S.B.l[j] = S.A.l[j] & ((1ULL << (pos - lo_bit)) - 1ULL);
+                S.Vn.l[j] = S.E.l[j] & ((1ULL << (pos - lo_bit)) - 1ULL);
         }
-        S.B.jlo = 0;
-        S.B.jhi = XA_LIMBS - 1;
-        sx->Ldbl = S.B.to_double(0);
-        sx->Cabove = Ntot - S.below_c[bstar] - ebins[bstar * 3];
-        *p.bar = 0ULL;  // grid barrier of the select kernel
+        sx->Ldbl = S.Vn.to_double(0);
+        sx->Cabove = Cabove;
         sx->Kcap = (unsigned long long)Kcap;
         sx->V = V;
         sx->E = E;
         sx->band = band;
-        sx->bin_cnt = ebins[bstar * 3];
+        sx->bin_cnt = w >= 0 ? S.wcnt[w] : ebins[bstar * 3];
         sx->thr_key = 0ULL;
         sx->tie_take = 0ULL;
         sx->K = 0ULL;
+        *p.bar = 0ULL;  // grid barrier of the select kernel
         ctl[LC_SELECT] = 1;
         ctl[LC_DYN_N] = 0;  // the select kernel sizes the batch
+        ctl[LC_STAMP + 6] = (long long)ix_timer_ns();
+        ctl[LC_STAMP + 7] = ctl[LC_STAMP + 6];
     }
 }
 

@@ -38,7 +38,8 @@ enum {
     LC_EVAL_LOCAL = 23,  // regions evaluated by this rank
     LC_DBG0 = 24,
     LC_DBG1 = 25,
-    LC_WORDS = 32,
+    LC_STAMP = 32,  // [8] time stamps of the decide kernel's phases (CUBATURE_TIMING)
+    LC_WORDS = 48,
 };
 #define LC_LOG_CAP 1024  // batch-size log [LC_WORDS .. LC_WORDS + LC_LOG_CAP): 2 K of iteration i at i % LC_LOG_CAP
 enum { LS_RUN = 0, LS_CONVERGED = 1, LS_MAXEVAL = 2, LS_GROW = 3, LS_ERROR = 4, LS_GUARD = 5, LS_HANDOFF = 6 };
