@@ -82,6 +82,7 @@ struct cub_comm {
     // into all peers with CUDA IPC; the sharded iteration kernel publishes and gathers through these
     // directly (pool_kernels.cu: k_iter_coop with R > 1), so the refinement loop itself makes no NCCL call.
     bool peer_ok = false;
+    bool poisoned = false;  // a call failed inside a peer exchange: the ranks no longer agree on seq; later calls fail fast
     unsigned long long seq = 1;  // sequence number of the next exchange (every launch reports how many it ran)
     void* xbuf[CUB_MAX_RANKS] = {nullptr};  // xbuf[rank] = own buffer, others = IPC mappings
 };

@@ -1236,51 +1236,14 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     return CUB_OK;
 }
 
-// ---- DEVICE mode, sharded pool, scalar integrand, NVLink peer exchange ---------------------------------------
-// After the replicated phase every rank ranks the (identical) pool by errmax, keeps every R-th region and then
-// runs the same device-driven loop as a single GPU: per iteration ONE cooperative kernel (k_iter_coop with R > 1:
-// shard totals and histograms, exchanged with the other ranks through peer-mapped buffers inside the kernel,
-// identical decisions on every rank, compaction of this rank's share of the batch) and the fused bisect + rule
-// kernel on the rank's own regions, then one 200-byte read-back.  No NCCL call and no host-side exchange in the loop.
-int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
-                           LoopResult* res, const LoopState& st0) {
-    const int f = S.fdim;  // == 1
-    const int64_t P = S.P;
-    cub_trace_t* trace = opt ? opt->trace : nullptr;
-    cub_comm* comm = opt->comm;
-    const int R = comm->nranks, rank = comm->rank;
+// Deals a replicated pool of N regions out to the R ranks: the regions are ranked by errmax (stable radix sort, identical on
+// every rank) and rank r keeps ranks r, r + R, ... of that order -- every rank owns the same share of the regions that will
+// be refined most.  Gathered into the free upper part of the pool, then moved down.  d_u64 / h_u64: 16 bytes of scratch.
+int deal_pool_ranked(Session& S, long long& N, int R, int rank, unsigned long long* d_u64, unsigned long long* h_u64) {
+    const int f = S.fdim;
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     SelectBuffers& sel = W.sel;
-    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
-    const bool debug_peer = getenv("CUBATURE_DEBUG_PEER") != nullptr;
-    auto t_begin = std::chrono::steady_clock::now();
-    auto ms_since = [](std::chrono::steady_clock::time_point t) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
-    };
-
-    long long N = st0.N;
-    long long Nglobal = st0.N;
-    int64_t numEval = st0.numEval;
-    double ops = st0.ops;
-    const double eps = 2.220446049250313e-16;
-
-    const int G = 1184;
-    const size_t ctl_words = PK_CTL_WORDS + (size_t)4 * f;
-    CUB_CUDA_CHECK(W.d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * (5 * G + 8)), S.msg);
-    CUB_CUDA_CHECK(W.d_small.ensure(ctl_words * 8 + 256 + 128), S.msg);
-    CUB_CUDA_CHECK(W.h_small.ensure(ctl_words * 8 + 256), S.msg);
-    double* d_part = W.d_partial.as<double>();
-    unsigned long long* d_blk = (unsigned long long*)(d_part + (size_t)2 * f * G);
-    long long* d_ctl = W.d_small.as<long long>();
-    unsigned long long* d_u64 = (unsigned long long*)(d_ctl + ctl_words) + 8;
-    unsigned long long* d_gblock = (unsigned long long*)((unsigned char*)W.d_small.p + ctl_words * 8 + 256);
-    long long* h_ctl = W.h_small.as<long long>();
-    const double* h_totals = (const double*)(h_ctl + PK_CTL_WORDS);
-    unsigned long long* h_u64 = (unsigned long long*)(h_ctl + ctl_words) + 8;
-
-    // ---- deal the replicated pool out: rank the regions by errmax (stable radix sort, identical on every rank), rank r
-    // keeps ranks r, r + R, ... of that order.  Gathered into the free upper part of the pool, then moved down.
     const long long n_local = cubature_cuda_shard_count(N, R, rank);
     {
         if (N + n_local > pool.cap) {
@@ -1332,6 +1295,56 @@ int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, i
             CUB_CUDA_CHECK(rows(pool.splitdim, 1, 4), S.msg);
         }
         N = n_local;
+    }
+    return CUB_OK;
+}
+
+// ---- DEVICE mode, sharded pool, scalar integrand, NVLink peer exchange ---------------------------------------
+// After the replicated phase every rank ranks the (identical) pool by errmax, keeps every R-th region and then
+// runs the same device-driven loop as a single GPU: per iteration ONE cooperative kernel (k_iter_coop with R > 1:
+// shard totals and histograms, exchanged with the other ranks through peer-mapped buffers inside the kernel,
+// identical decisions on every rank, compaction of this rank's share of the batch) and the fused bisect + rule
+// kernel on the rank's own regions, then one 200-byte read-back.  No NCCL call and no host-side exchange in the loop.
+int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, const LoopState& st0) {
+    const int f = S.fdim;  // == 1
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    cub_comm* comm = opt->comm;
+    const int R = comm->nranks, rank = comm->rank;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    SelectBuffers& sel = W.sel;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    const bool debug_peer = getenv("CUBATURE_DEBUG_PEER") != nullptr;
+    auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+
+    long long N = st0.N;
+    long long Nglobal = st0.N;
+    int64_t numEval = st0.numEval;
+    double ops = st0.ops;
+    const double eps = 2.220446049250313e-16;
+
+    const int G = 1184;
+    const size_t ctl_words = PK_CTL_WORDS + (size_t)4 * f;
+    CUB_CUDA_CHECK(W.d_partial.ensure((size_t)8 * 2 * f * G + (size_t)8 * (5 * G + 8)), S.msg);
+    CUB_CUDA_CHECK(W.d_small.ensure(ctl_words * 8 + 256 + 128), S.msg);
+    CUB_CUDA_CHECK(W.h_small.ensure(ctl_words * 8 + 256), S.msg);
+    double* d_part = W.d_partial.as<double>();
+    unsigned long long* d_blk = (unsigned long long*)(d_part + (size_t)2 * f * G);
+    long long* d_ctl = W.d_small.as<long long>();
+    unsigned long long* d_u64 = (unsigned long long*)(d_ctl + ctl_words) + 8;
+    unsigned long long* d_gblock = (unsigned long long*)((unsigned char*)W.d_small.p + ctl_words * 8 + 256);
+    long long* h_ctl = W.h_small.as<long long>();
+    const double* h_totals = (const double*)(h_ctl + PK_CTL_WORDS);
+    unsigned long long* h_u64 = (unsigned long long*)(h_ctl + ctl_words) + 8;
+
+    {
+        const int rc_deal = deal_pool_ranked(S, N, R, rank, d_u64, h_u64);
+        if (rc_deal != CUB_OK) return rc_deal;
     }
     const double t_shard = ms_since(t_begin);
 
@@ -1972,6 +1985,87 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     return exact_finish(S, X, out, res, trace);
 }
 
+// Multi-GPU (section 8e), scalar integrands, NVLink peers: replicated phase on every rank, ranked deal, then the same
+// device-resident loop on the rank's shard; the decide / select kernels exchange bins and histograms with the other ranks
+// through peer-mapped buffers (iter_exact.cu), no NCCL call and no host decision inside the loop.
+int integrate_sharded_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                            LoopResult* res) {
+    const int f = S.fdim;  // == 1
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    cub_comm* comm = opt->comm;
+    const int R = comm->nranks, rank = comm->rank;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    if (comm->poisoned) {
+        cub_set_message(S.msg, "communicator unusable: an earlier call on it failed inside a peer exchange; create a new one");
+        return CUB_ERR_NCCL;
+    }
+    const size_t extra = 24 + (size_t)8 * f + 1;
+    long long cap = auto_capacity(S.dim, f, P, maxEval, opt->pool_capacity, extra);
+    const long long shard_min = opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
+    if (!(opt->pool_capacity > 0) && maxEval > 0) {
+        // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
+        const long long total = maxEval / (2 * P) + 8;
+        cap = std::min(cap, std::max<long long>(total / R + total / (4 * R) + 1024, 4 * shard_min));
+    }
+    ExactBufs X;
+    bool handoff = false;
+    int rc = integrate_device_exact(S, relTol, absTol, norm, maxEval, opt, out, res, X, shard_min, cap, &handoff);
+    if (rc != CUB_OK || !handoff) return rc;  // finished before sharding: every rank holds the complete result
+    const auto t_begin = std::chrono::steady_clock::now();
+    long long N = X.h_ctl[LC_N];
+    CUB_CUDA_CHECK(W.d_small.ensure(256), S.msg);
+    CUB_CUDA_CHECK(W.h_small.ensure(256), S.msg);
+    unsigned long long* d_u64 = W.d_small.as<unsigned long long>();
+    unsigned long long* h_u64 = W.h_small.as<unsigned long long>();
+    rc = deal_pool_ranked(S, N, R, rank, d_u64, h_u64);
+    if (rc == CUB_OK && W.sel.ensure_scalar(pool.cap) != cudaSuccess) {
+        cudaGetLastError();
+        cub_set_message(S.msg, "out of device memory for the selection buffers");
+        rc = CUB_ERR_POOL_EXHAUSTED;
+    }
+    if (rc == CUB_OK) {
+        exact_bind_pool(S, X);
+        ix_rebuild(pool.view(), N, X.p.acc, S.n_sms, S.stream);  // running sums of this rank's shard
+        S.launches += 1;
+        // one NCCL all-gather (outside the loop) lines the ranks up before the first in-kernel exchange
+        rc = cub_comm_allgather(comm, d_u64, 8, d_u64 + 8, S.stream);
+        if (rc == CUB_OK && cudaStreamSynchronize(S.stream) != cudaSuccess) rc = CUB_ERR_CUDA;
+    }
+    if (rc == CUB_OK) {
+        X.p.R = R;
+        X.p.rank = rank;
+        for (int r = 0; r < PK_MAX_RANKS; ++r) X.p.xbuf[r] = r < R ? (unsigned long long*)comm->xbuf[r] : nullptr;
+        X.h_ctl[LC_N] = N;
+        X.h_ctl[LC_CAP] = pool.cap;
+        X.h_ctl[LC_STOP_AT] = 0;
+        X.h_ctl[LC_STATE] = LS_RUN;
+        X.h_ctl[LC_SEQ] = (long long)comm->seq;
+        X.h_ctl[LC_DBG1] = 0;
+        if (cudaMemcpyAsync(X.d_ctl, X.h_ctl, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream) != cudaSuccess) rc = CUB_ERR_CUDA;
+        S.h2d_bytes += LC_WORDS * 8;
+    }
+    const double t_deal = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (rc == CUB_OK) rc = exact_run(S, X, trace, cap);
+    if (rc == CUB_OK && X.h_ctl[LC_STATE] == LS_ERROR) {
+        comm->poisoned = true;  // the ranks no longer agree on the exchange sequence
+        return exact_finish(S, X, out, res, trace);
+    }
+    if (rc != CUB_OK) {
+        // this rank gives up: release the peers that wait for it inside an exchange
+        comm->poisoned = true;
+        ix_abort_peers(R, comm->xbuf, S.stream);
+        cudaStreamSynchronize(S.stream);
+        return rc;
+    }
+    comm->seq = (unsigned long long)X.h_ctl[LC_SEQ];
+    if (getenv("CUBATURE_TIMING"))
+        fprintf(stderr, "[cubature rank %d] sharded: deal %.2f ms, %lld local of %lld regions\n", rank, t_deal, (long long)X.h_ctl[LC_N],
+                (long long)X.h_ctl[LC_NGLOBAL]);
+    return exact_finish(S, X, out, res, trace);
+}
+
 void init_stats(cub_stats_t* st) {
     if (!st) return;
     const int32_t sz = st->struct_size;
@@ -2201,8 +2295,13 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
     cudaEventRecord(S.ev0, S.stream);
     if (select == CUB_SELECT_HEAP_EXACT)
         rc = integrate_heap_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
-    else if (options && options->comm && options->comm->nranks > 1)
-        rc = integrate_device(S, relTol, absTol, norm, maxEval, options, out, &res);
+    else if (options && options->comm && options->comm->nranks > 1) {
+        const char* env = getenv("CUBATURE_PEER_LOOP");
+        if (S.fdim == 1 && options->comm->peer_ok && !legacy_loop() && !(env && env[0] == '0'))
+            rc = integrate_sharded_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
+        else
+            rc = integrate_device(S, relTol, absTol, norm, maxEval, options, out, &res);
+    }
     else if (S.fdim == 1 && !legacy_loop()) {
         ExactBufs X;
         bool handoff = false;

@@ -940,13 +940,12 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             __syncthreads();
         }
         ix_gsync(bar, ++nsync * (unsigned long long)G);
-        if (sharded) {  // this level's histogram of the whole partition: sum of the R local ones, sliced over the first CTAs
+        if (sharded) {  // this level's histogram of the whole partition: sum of the R local ones
+            // (one CTA: the ranks' grids differ in size, and 1 536 words per peer are not worth slicing)
             const int words = 3 * IX_NB;
-            const int nsl = G < PK_XB_SLICES ? G : PK_XB_SLICES;
-            const int chunk = (words + nsl - 1) / nsl;
-            if (b < nsl) {
-                const int w0 = b * chunk, w1 = min(words, w0 + chunk);
-                const int f = ix_exchange(p, xseq, b, gh, w0, w1);
+            if (b == 0) {
+                const int w0 = 0, w1 = words;
+                const int f = ix_exchange(p, xseq, 0, gh, w0, w1);
                 if (f) atomicExch((unsigned long long*)&ctl[LC_DBG1], (unsigned long long)f);
                 unsigned long long* own = p.xbuf[p.rank];
                 for (int w = w0 + tid; w < w1; w += IX_THREADS) {
