@@ -454,7 +454,9 @@ struct Session {
             // persistent tiles: at most one resident wave of CTAs, each walks the batch with the grid as its stride
             const int threads = kern->gm_threads;  // the kernel's __launch_bounds__ (CUB_GM_THREADS)
             const long long tiles = (work.n_items + threads - 1) / threads;
-            const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm);
+            // CUBATURE_RULE_WAVES: CTAs per resident slot (default 1 = one wave; 0 = one CTA per tile, as many waves as it takes)
+            static const int waves = [] { const char* e = getenv("CUBATURE_RULE_WAVES"); return e ? atoi(e) : 1; }();
+            const unsigned grid = (unsigned)(waves > 0 ? std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm * waves) : tiles);
             e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(threads), args, 0, stream);
             ++launches;
         } else if (dim == 1 && (fdim == 1 || integ->separable)) {
@@ -2458,6 +2460,17 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
             for (int64_t i = 0; i < n_regions; ++i) row[(size_t)i] = d == 0 ? 0.5 * (hi - lo) / (double)n_regions : 0.5 * (hi - lo);
             CUB_CUDA_CHECK(cudaMemcpy(pool.halfw.as<double>() + (size_t)d * pool.cap, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
         }
+    }
+    DevBuf acc_buf;
+    if (getenv("CUBATURE_BENCH_ACC") && f == 1) {  // also maintain the exact running sums, as the device-resident loop does
+        CUB_CUDA_CHECK(acc_buf.ensure((size_t)XA_WORDS * 8), S.msg);
+        CUB_CUDA_CHECK(cudaMemset(acc_buf.p, 0, (size_t)XA_WORDS * 8), S.msg);
+        CUB_CUDA_CHECK(cudaMemset(acc_buf.as<unsigned long long>() + XA_M_OFF + XA_M_MINKEY, 0xff, 8), S.msg);
+        const char* eb = getenv("CUBATURE_BENCH_ACC_EBASE");
+        const char* vb = getenv("CUBATURE_BENCH_ACC_VBASE");
+        unsigned long long hint[2] = {(unsigned long long)(eb ? atoi(eb) : 0), (unsigned long long)(vb ? atoi(vb) : 0)};
+        CUB_CUDA_CHECK(cudaMemcpy(acc_buf.as<unsigned long long>() + XA_M_OFF + XA_M_EBASE, hint, 16, cudaMemcpyHostToDevice), S.msg);
+        S.acc = acc_buf.as<unsigned long long>();
     }
     HostWork w{};
     w.n_items = n_regions;

@@ -15,8 +15,6 @@ typedef unsigned long long xa_u64;
 typedef unsigned __int128 xa_u128;
 typedef __int128 xa_i128;
 
-#define XA_LIMBS 72
-
 CUB_HD xa_u64 xa_bits(double x) {
 #if defined(__CUDA_ARCH__)
     return (xa_u64)__double_as_longlong(x);
@@ -150,6 +148,16 @@ struct XaBig {
         add_shifted((xa_u128)xa_mantissa(b), xa_lsb_pos((int)((b >> 52) & 2047ULL)));
     }
 };
+
+// a += v * 2^pos for a signed v (|v| < 2^63): positive parts go to *pos_part, negative ones to *neg_part
+CUB_HD void xa_add_signed(XaBig* pos_part, XaBig* neg_part, long long v, int pos) {
+    if (v > 0) pos_part->add_shifted((xa_u128)(xa_u64)v, pos);
+    if (v < 0) neg_part->add_shifted((xa_u128)(xa_u64)(-v), pos);
+}
+// the XA_HALVES delta cells of a window that starts at bit `base` (acc_layout.h): cell j has weight 2^(base + 32 j)
+CUB_HD void xa_fold_cells(XaBig* pos_part, XaBig* neg_part, const long long* cell, int base) {
+    for (int j = 0; j < XA_HALVES; ++j) xa_add_signed(pos_part, neg_part, cell[j], base + 32 * j);
+}
 
 // ---- 128-bit helpers for the levels below the binade (all mantissas share one exponent there) -------------------
 // bin words -> integer: lo + 2^32 hi with lo UNSIGNED (every contribution adds a low part in [0, 2^32)) and hi SIGNED

@@ -103,33 +103,18 @@ __device__ int ix_exchange(const IterXParams& p, unsigned long long seq, int sli
 }
 
 // ---- decide ------------------------------------------------------------------------------------------------------------
-// The sums are built and walked by single threads (big-integer arithmetic on a handful of limbs); the other threads only
-// fetch the bins and pre-add their eight consecutive binades into one 128-bit partial each.
-#define IX_PER (XA_NBINS / IX_THREADS)  // bins per thread
-#define IX_TOPW 256                      // bins below the top non-empty one staged in shared memory for the walk
-
+// Folds the deltas the rule kernels left (acc_layout.h) into the totals, takes the loop decisions of Rule.java:72-79 and
+// the pop-everything shortcut; when a batch has to be cut it hands the totals to the select kernel.  One CTA; the
+// arbitrary-precision arithmetic (a handful of limbs) is one thread's work.
 struct DecideShared {
-    XaBig E, Vp, Vn;
-    unsigned long long part[3][IX_THREADS][2];  // per-thread partial sums (E, V > 0, V < 0) at bit position xa_lsb_pos(8 tid)
-    unsigned part_mask[3][IX_WARPS];            // threads with a non-zero partial
-    unsigned long long wcnt[IX_TOPW], wlo[IX_TOPW], whi[IX_TOPW];  // error bins [e_top - IX_TOPW + 1, e_top]
-    unsigned nz[XA_NBINS / 32];                 // non-empty error bins
-    unsigned long long red_c[IX_WARPS];
-    int red_a[IX_WARPS], red_b[IX_WARPS], red_c2[IX_WARPS], red_d[IX_WARPS];
+    XaBig E, V, P, Q;
+    long long dcell[XA_CELLS];
+    long long far_e[XA_LIMBS], far_v[XA_LIMBS];
     unsigned long long hdr[PK_MAX_RANKS][16];
+    int fail;
 };
 
-__device__ int ix_next_below(const unsigned* nz, int e) {  // largest non-empty bin < e, or -1
-    if (e <= 0) return -1;
-    int w = (e - 1) >> 5;
-    unsigned m = nz[w] & (0xffffffffu >> (31 - ((e - 1) & 31)));
-    for (;;) {
-        if (m) return 32 * w + 31 - __clz(m);
-        if (--w < 0) return -1;
-        m = nz[w];
-    }
-}
-
+__device__ __forceinline__ void ix_big_add_signed(XaBig* pos_part, XaBig* neg_part, long long v, int pos) { xa_add_signed(pos_part, neg_part, v, pos); }
 // a -= v * 2^pos for a normalized a >= v * 2^pos, v < 2^96
 __device__ void ix_big_sub(XaBig* a, xa_u128 v, int pos) {
     const int j = pos >> 5, sh = pos & 31;
@@ -147,10 +132,16 @@ __device__ void ix_big_sub(XaBig* a, xa_u128 v, int pos) {
         a->l[j + q] = (xa_u64)t;
     }
 }
-// a += v * 2^pos, v < 2^128 (not normalized afterwards)
-__device__ __forceinline__ void ix_big_add128(XaBig* a, xa_u64 v_lo, xa_u64 v_hi, int pos) {
-    if (v_lo) a->add_shifted((xa_u128)v_lo, pos);
-    if (v_hi) a->add_shifted((xa_u128)v_hi, pos + 64);
+__device__ void ix_big_full_range(XaBig* a) {
+    a->jlo = 0;
+    a->jhi = XA_LIMBS - 1;
+}
+__device__ void ix_big_tighten(XaBig* a) {  // normalized number: shrink [jlo, jhi] to the non-zero limbs
+    int lo = 0, hi = XA_LIMBS - 1;
+    while (hi > 0 && a->l[hi] == 0ULL) --hi;
+    while (lo < hi && a->l[lo] == 0ULL) ++lo;
+    a->jlo = lo;
+    a->jhi = hi + 2 < XA_LIMBS ? hi + 2 : XA_LIMBS - 1;  // head room for carries of later additions
 }
 
 __device__ void ix_finish(const IterXParams& p, int state, int err) {
@@ -160,20 +151,14 @@ __device__ void ix_finish(const IterXParams& p, int state, int err) {
     p.ctl[LC_SELECT] = 0;
 }
 
-__device__ __forceinline__ int ix_block_max(int v, int* red) {  // all threads; result for everybody
-    v = __reduce_max_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int r = red[0];
-#pragma unroll
-    for (int q = 1; q < IX_WARPS; ++q) r = max(r, red[q]);
-    return r;
-}
+// layout of the totals the decide kernel publishes for the select kernel (p.gbins): E limbs [XA_LIMBS] | jlo | jhi
+#define IX_PUB_JLO XA_LIMBS
+#define IX_PUB_JHI (XA_LIMBS + 1)
+#define IX_PUB_TOPE (XA_LIMBS + 2)
 
 __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
     __shared__ DecideShared S;
     const int tid = threadIdx.x;
-    const unsigned lane = tid & 31u, warp = tid >> 5;
     long long* ctl = p.ctl;
     if (ctl[LC_STATE] != LS_RUN) {  // finished or paused: this launch and the ones queued behind it do nothing
         if (tid == 0) {
@@ -205,81 +190,132 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         }
     }
     unsigned long long* acc = p.acc;
-    const unsigned long long* ebins = acc + XA_E_OFF;
-    const unsigned long long* vbins = acc + XA_V_OFF;
-    unsigned long long misc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) misc[q] = acc[XA_M_OFF + q];
-    unsigned long long minkey = acc[XA_M_OFF + XA_M_MINKEY];
-    // the thread's bins
-    unsigned long long cnt[IX_PER], blo[IX_PER], bhi[IX_PER], vlo[IX_PER], vhi[IX_PER];
-#pragma unroll
-    for (int q = 0; q < IX_PER; ++q) {
-        const int e = tid * IX_PER + q;
-        cnt[q] = ebins[e * 3];
-        blo[q] = ebins[e * 3 + 1];
-        bhi[q] = ebins[e * 3 + 2];
-        vlo[q] = vbins[e * 2];
-        vhi[q] = vbins[e * 2 + 1];
+    unsigned long long* tot = acc + XA_TOT_OFF;
+    // ---- collect the deltas (and clear them for the next launch) -----------------------------------------------------
+    if (tid < XA_CELLS) {
+        long long s = 0;
+        for (int r = 0; r < XA_REPL; ++r) {
+            unsigned long long* c = acc + XA_D_OFF + (size_t)r * XA_CELLS + tid;
+            s += (long long)*c;
+            *c = 0ULL;
+        }
+        S.dcell[tid] = s;
     }
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
+        S.far_e[j] = (long long)acc[XA_FAR_E_OFF + j];
+        S.far_v[j] = (long long)acc[XA_FAR_V_OFF + j];
+        acc[XA_FAR_E_OFF + j] = 0ULL;
+        acc[XA_FAR_V_OFF + j] = 0ULL;
+        S.E.l[j] = tot[XA_TOT_E + j];
+        S.V.l[j] = tot[XA_TOT_V + j];
+        S.P.l[j] = 0ULL;
+        S.Q.l[j] = 0ULL;
+    }
+    bool far_mine = false;
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) far_mine = far_mine || S.far_e[j] != 0 || S.far_v[j] != 0;
+    const bool far_any = __syncthreads_or(far_mine ? 1 : 0) != 0;
+    unsigned long long misc[8];
+    unsigned long long minkey = 0, my_count = 0, topkey = 0;
+    int v_neg = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) misc[q] = acc[XA_M_OFF + q];
+        minkey = acc[XA_M_OFF + XA_M_MINKEY];
+        topkey = acc[XA_M_OFF + XA_M_TOPKEY];
+        const int ebase = (int)acc[XA_M_OFF + XA_M_EBASE], vbase = (int)acc[XA_M_OFF + XA_M_VBASE];
+        v_neg = (int)tot[XA_TOT_MISC + 0];
+        my_count = tot[XA_TOT_MISC + 1] + (unsigned long long)S.dcell[XA_C_COUNT];
+        // limbs that can be touched: the stored totals, the delta window (256 bits + 64-bit cells), carries
+        int e_lo = (int)tot[XA_TOT_MISC + 2], e_hi = (int)tot[XA_TOT_MISC + 3], v_lo = (int)tot[XA_TOT_MISC + 4], v_hi = (int)tot[XA_TOT_MISC + 5];
+        e_lo = min(e_lo, ebase >> 5);
+        e_hi = max(e_hi, ((ebase + 32 * XA_HALVES + 64) >> 5) + 2);
+        v_lo = min(v_lo, vbase >> 5);
+        v_hi = max(v_hi, ((vbase + 32 * XA_HALVES + 64) >> 5) + 2);
+        if (far_any) {
+            e_lo = v_lo = 0;
+            e_hi = v_hi = XA_LIMBS - 1;
+        }
+        e_hi = min(e_hi, XA_LIMBS - 1);
+        v_hi = min(v_hi, XA_LIMBS - 1);
+        // error sum: E += (positive part of the delta) - (negative part)
+        S.P.jlo = S.Q.jlo = S.E.jlo = e_lo;
+        S.P.jhi = S.Q.jhi = S.E.jhi = e_hi;
+        xa_fold_cells(&S.P, &S.Q, &S.dcell[XA_C_E], ebase);
+        if (far_any)
+            for (int j = 0; j < XA_LIMBS - 3; ++j) ix_big_add_signed(&S.P, &S.Q, S.far_e[j], 32 * j);
+        for (int j = e_lo; j <= e_hi; ++j) S.E.l[j] += S.P.l[j];
+        S.E.normalize();
+        S.Q.normalize();
+        S.E.sub(S.Q);  // the regions removed were added before: never negative
+        ix_big_tighten(&S.E);
+        // value sum, sign and magnitude: A = (V if V >= 0) + positive part, B = (|V| if V < 0) + negative part, V = A - B
+        for (int j = e_lo; j <= e_hi; ++j) S.P.l[j] = S.Q.l[j] = 0ULL;
+        S.P.jlo = S.Q.jlo = v_lo;
+        S.P.jhi = S.Q.jhi = v_hi;
+        xa_fold_cells(&S.P, &S.Q, &S.dcell[XA_C_V], vbase);
+        if (far_any)
+            for (int j = 0; j < XA_LIMBS - 3; ++j) ix_big_add_signed(&S.P, &S.Q, S.far_v[j], 32 * j);
+        XaBig* same = v_neg ? &S.Q : &S.P;
+        for (int j = v_lo; j <= v_hi; ++j) same->l[j] += S.V.l[j];
+        S.P.normalize();
+        S.Q.normalize();
+        const int c = S.P.cmp(S.Q);
+        if (c >= 0) {
+            S.P.sub(S.Q);
+            for (int j = v_lo; j <= v_hi; ++j) S.V.l[j] = S.P.l[j];
+            v_neg = 0;
+        } else {
+            S.Q.sub(S.P);
+            for (int j = v_lo; j <= v_hi; ++j) S.V.l[j] = S.Q.l[j];
+            v_neg = 1;
+        }
+        ix_big_full_range(&S.V);
+        ix_big_tighten(&S.V);
+        // store this rank's totals
+        tot[XA_TOT_MISC + 0] = (unsigned long long)v_neg;
+        tot[XA_TOT_MISC + 1] = my_count;
+        tot[XA_TOT_MISC + 2] = (unsigned long long)S.E.jlo;
+        tot[XA_TOT_MISC + 3] = (unsigned long long)S.E.jhi;
+        tot[XA_TOT_MISC + 4] = (unsigned long long)S.V.jlo;
+        tot[XA_TOT_MISC + 5] = (unsigned long long)S.V.jhi;
+        // window hints for the next rule launch from the largest values of the last one
+        const unsigned long long ek = acc[XA_M_OFF + XA_M_EMAXKEY], vk = acc[XA_M_OFF + XA_M_VMAXKEY];
+        if (ek) {
+            const int b = xa_lsb_pos((int)(ek >> 52)) + 8 - XA_WIN_MAX_SHIFT;
+            acc[XA_M_OFF + XA_M_EBASE] = (unsigned long long)(b < 0 ? 0 : b);
+            acc[XA_M_OFF + XA_M_EMAXKEY] = 0ULL;
+        }
+        if (vk) {
+            const int b = xa_lsb_pos((int)(vk >> 52)) + 8 - XA_WIN_MAX_SHIFT;
+            acc[XA_M_OFF + XA_M_VBASE] = (unsigned long long)(b < 0 ? 0 : b);
+            acc[XA_M_OFF + XA_M_VMAXKEY] = 0ULL;
+        }
+        ctl[LC_STAMP + 1] = (long long)ix_timer_ns();
+    }
+    __syncthreads();
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
+        tot[XA_TOT_E + j] = S.E.l[j];
+        tot[XA_TOT_V + j] = S.V.l[j];
+    }
+    unsigned long long Ntot = my_count;
     if (p.R > 1) {
-        // ---- exchange header + the non-empty windows of the error / value bins; combine ------------------------------
-        int elo = XA_NBINS, ehi = -1, wlo_ = XA_NBINS, whi_ = -1;
-#pragma unroll
-        for (int q = 0; q < IX_PER; ++q) {
-            const int e = tid * IX_PER + q;
-            if (cnt[q] | blo[q] | bhi[q]) {
-                elo = e < elo ? e : elo;
-                ehi = e;
-            }
-            if (vlo[q] | vhi[q]) {
-                wlo_ = e < wlo_ ? e : wlo_;
-                whi_ = e;
-            }
+        // ---- exchange the ranks' totals: header[16] | E limbs | V limbs; every rank adds them up -------------------
+        unsigned long long* stage = p.gbins + 256;
+        if (tid == 0) {
+            stage[0] = my_count;
+            stage[1] = minkey;
+            for (int q = 0; q < 7; ++q) stage[2 + q] = misc[q];
+            stage[9] = (unsigned long long)v_neg;
+            stage[10] = topkey;
+            for (int q = 11; q < 16; ++q) stage[q] = 0ULL;
         }
-        ehi = ix_block_max(ehi, S.red_a);
-        elo = -ix_block_max(-elo, S.red_b);
-        whi_ = ix_block_max(whi_, S.red_c2);
-        wlo_ = -ix_block_max(-wlo_, S.red_d);
-        const int nE = ehi >= elo ? ehi - elo + 1 : 0, nV = whi_ >= wlo_ ? whi_ - wlo_ + 1 : 0;
-        // payload staged in gbins: header[16] | E window | V window
-        unsigned long long* stage = p.gbins;
-        if (tid < 16) {
-            unsigned long long h = 0ULL;
-            switch (tid) {
-                case 0: h = (unsigned long long)N; break;
-                case 1: h = minkey; break;
-                case 2: h = misc[XA_M_ENAN]; break;
-                case 3: h = misc[XA_M_EINF]; break;
-                case 4: h = misc[XA_M_VNAN]; break;
-                case 5: h = misc[XA_M_VPINF]; break;
-                case 6: h = misc[XA_M_VNINF]; break;
-                case 7: h = misc[XA_M_ESTICKY]; break;
-                case 8: h = misc[XA_M_VSTICKY]; break;
-                case 9: h = (unsigned long long)(nE ? elo : 0); break;
-                case 10: h = (unsigned long long)nE; break;
-                case 11: h = (unsigned long long)(nV ? wlo_ : 0); break;
-                case 12: h = (unsigned long long)nV; break;
-                default: break;
-            }
-            stage[tid] = h;
-        }
-#pragma unroll
-        for (int q = 0; q < IX_PER; ++q) {
-            const int e = tid * IX_PER + q;
-            if (nE && e >= elo && e <= ehi) {
-                stage[16 + 3 * (e - elo)] = cnt[q];
-                stage[16 + 3 * (e - elo) + 1] = blo[q];
-                stage[16 + 3 * (e - elo) + 2] = bhi[q];
-            }
-            if (nV && e >= wlo_ && e <= whi_) {
-                stage[16 + 3 * nE + 2 * (e - wlo_)] = vlo[q];
-                stage[16 + 3 * nE + 2 * (e - wlo_) + 1] = vhi[q];
-            }
+        for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
+            stage[16 + j] = S.E.l[j];
+            stage[16 + XA_LIMBS + j] = S.V.l[j];
         }
         __syncthreads();
         const unsigned long long seq = (unsigned long long)ctl[LC_SEQ];
-        const int fail = ix_exchange(p, seq, 0, stage, 0, 16 + 3 * nE + 2 * nV);
+        const int fail = ix_exchange(p, seq, 0, stage, 0, 16 + 2 * XA_LIMBS);
         if (tid == 0) ctl[LC_SEQ] = (long long)(seq + 1ULL);
         if (fail) {
             if (tid == 0) ix_finish(p, LS_ERROR, fail);
@@ -288,142 +324,64 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         unsigned long long* own = p.xbuf[p.rank];
         if (tid < 16)
             for (int r = 0; r < p.R; ++r) S.hdr[r][tid] = __ldcg(&ix_pay(own, seq, r)[tid]);
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < IX_PER; ++q) {
-            const int e = tid * IX_PER + q;
-            unsigned long long c0 = 0, c1 = 0, c2 = 0, v0 = 0, v1 = 0;
+        // limb-wise sums over the ranks (not normalized): E, and V split by sign
+        for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
+            unsigned long long e = 0, vp = 0, vn = 0;
             for (int r = 0; r < p.R; ++r) {
                 const unsigned long long* pay = ix_pay(own, seq, r);
-                const int lo_e = (int)S.hdr[r][9], n_e = (int)S.hdr[r][10], lo_v = (int)S.hdr[r][11], n_v = (int)S.hdr[r][12];
-                if (e >= lo_e && e < lo_e + n_e) {
-                    const unsigned long long* w = pay + 16 + 3 * (e - lo_e);
-                    c0 += __ldcg(&w[0]);
-                    c1 += __ldcg(&w[1]);
-                    c2 += __ldcg(&w[2]);
-                }
-                if (e >= lo_v && e < lo_v + n_v) {
-                    const unsigned long long* w = pay + 16 + 3 * n_e + 2 * (e - lo_v);
-                    v0 += __ldcg(&w[0]);
-                    v1 += __ldcg(&w[1]);
-                }
+                e += __ldcg(&pay[16 + j]);
+                const unsigned long long v = __ldcg(&pay[16 + XA_LIMBS + j]);
+                if (__ldcg(&pay[9]))
+                    vn += v;
+                else
+                    vp += v;
             }
-            cnt[q] = c0;
-            blo[q] = c1;
-            bhi[q] = c2;
-            vlo[q] = v0;
-            vhi[q] = v1;
-            p.gbins[XA_E_OFF + e * 3] = c0;  // (the walk below reads bins outside its shared window from here)
-            p.gbins[XA_E_OFF + e * 3 + 1] = c1;
-            p.gbins[XA_E_OFF + e * 3 + 2] = c2;
-        }
-        for (int q = 0; q < 8; ++q) misc[q] = 0ULL;
-        minkey = ~0ULL;
-        for (int r = 0; r < p.R; ++r) {
-            misc[XA_M_ENAN] += S.hdr[r][2];
-            misc[XA_M_EINF] += S.hdr[r][3];
-            misc[XA_M_VNAN] += S.hdr[r][4];
-            misc[XA_M_VPINF] += S.hdr[r][5];
-            misc[XA_M_VNINF] += S.hdr[r][6];
-            misc[XA_M_ESTICKY] |= S.hdr[r][7];
-            misc[XA_M_VSTICKY] |= S.hdr[r][8];
-            minkey = S.hdr[r][1] < minkey ? S.hdr[r][1] : minkey;
+            S.E.l[j] = e;
+            S.P.l[j] = vp;
+            S.Q.l[j] = vn;
         }
         __syncthreads();
-        ebins = p.gbins + XA_E_OFF;
-    }
-    if (tid == 0) ctl[LC_STAMP + 1] = (long long)ix_timer_ns();
-
-    // ---- per-thread partial sums, non-empty map, extremes ------------------------------------------------------------
-    for (int q = tid; q < XA_NBINS / 32; q += IX_THREADS) S.nz[q] = 0u;
-    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) S.E.l[j] = S.Vp.l[j] = S.Vn.l[j] = 0ULL;
-    __syncthreads();
-    const int pb = xa_lsb_pos(tid * IX_PER);
-    xa_u128 pe = 0, pvp = 0, pvn = 0;
-    unsigned long long csum = 0;
-    int my_top_e = -1, my_top_v = -1, my_min_e = XA_NBINS, my_min_v = XA_NBINS;
-    unsigned my_nz = 0;
-#pragma unroll
-    for (int q = 0; q < IX_PER; ++q) {
-        const int e = tid * IX_PER + q;
-        const int shq = xa_lsb_pos(e) - pb;
-        if (cnt[q]) {
-            my_nz |= 1u << q;
-            my_top_e = e;
-            my_min_e = e < my_min_e ? e : my_min_e;
-            csum += cnt[q];
-        }
-        if (e < 2047) {
-            const xa_i128 mv = xa_join_signed(blo[q], bhi[q]);
-            if (mv > 0) pe += (xa_u128)mv << shq;
-            const xa_i128 vv = xa_join_signed(vlo[q], vhi[q]);
-            if (vv > 0) pvp += (xa_u128)vv << shq;
-            if (vv < 0) pvn += (xa_u128)(-vv) << shq;
-            if (vv != 0) {
-                my_top_v = e;
-                my_min_v = e < my_min_v ? e : my_min_v;
+        if (tid == 0) {
+            for (int q = 0; q < 8; ++q) misc[q] = 0ULL;
+            minkey = ~0ULL;
+            Ntot = 0;
+            for (int r = 0; r < p.R; ++r) {
+                Ntot += S.hdr[r][0];
+                minkey = S.hdr[r][1] < minkey ? S.hdr[r][1] : minkey;
+                topkey = S.hdr[r][10] > topkey ? S.hdr[r][10] : topkey;
+                for (int q = 0; q < 5; ++q) misc[q] += S.hdr[r][2 + q];
+                misc[XA_M_ESTICKY] |= S.hdr[r][2 + XA_M_ESTICKY];
+                misc[XA_M_VSTICKY] |= S.hdr[r][2 + XA_M_VSTICKY];
             }
-        }
-    }
-    if (my_nz) atomicOr(&S.nz[(tid * IX_PER) >> 5], my_nz << ((tid * IX_PER) & 31));
-    S.part[0][tid][0] = (unsigned long long)pe;
-    S.part[0][tid][1] = (unsigned long long)(pe >> 64);
-    S.part[1][tid][0] = (unsigned long long)pvp;
-    S.part[1][tid][1] = (unsigned long long)(pvp >> 64);
-    S.part[2][tid][0] = (unsigned long long)pvn;
-    S.part[2][tid][1] = (unsigned long long)(pvn >> 64);
-    {
-        const unsigned b0 = __ballot_sync(0xffffffffu, pe != 0), b1 = __ballot_sync(0xffffffffu, pvp != 0), b2 = __ballot_sync(0xffffffffu, pvn != 0);
-        if (lane == 0) {
-            S.part_mask[0][warp] = b0;
-            S.part_mask[1][warp] = b1;
-            S.part_mask[2][warp] = b2;
-        }
-        unsigned long long cw = csum;
-        for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
-        if (lane == 0) S.red_c[warp] = cw;
-    }
-    const int e_top = ix_block_max(my_top_e, S.red_a);
-    const int e_min_n = ix_block_max(-my_min_e, S.red_b);
-    const int v_top = ix_block_max(my_top_v, S.red_c2);
-    const int v_min_n = ix_block_max(-my_min_v, S.red_d);
-    const int e_min = -e_min_n >= XA_NBINS ? 0 : -e_min_n, v_min = -v_min_n >= XA_NBINS ? 0 : -v_min_n;
-    unsigned long long Ntot = 0;
-#pragma unroll
-    for (int q = 0; q < IX_WARPS; ++q) Ntot += S.red_c[q];
-    // stage the bins near the top for the walk
-#pragma unroll
-    for (int q = 0; q < IX_PER; ++q) {
-        const int e = tid * IX_PER + q, w = e - (e_top - IX_TOPW + 1);
-        if (e <= e_top && w >= 0 && w < IX_TOPW) {
-            S.wcnt[w] = cnt[q];
-            S.wlo[w] = blo[q];
-            S.whi[w] = bhi[q];
-        }
-    }
-    __syncthreads();
-    if (tid == 0) ctl[LC_STAMP + 2] = (long long)ix_timer_ns();
-    // ---- three lanes build the three sums: error, positive values, negative values -----------------------------------
-    if (tid < 3) {
-        XaBig* A = tid == 0 ? &S.E : (tid == 1 ? &S.Vp : &S.Vn);
-        const int lo_e = tid == 0 ? e_min : v_min, hi_e = tid == 0 ? e_top : v_top;
-        const int jl = xa_lsb_pos((lo_e < 0 ? 0 : lo_e) & ~(IX_PER - 1)) >> 5, jh = ((xa_lsb_pos(hi_e < 0 ? 0 : hi_e) + 120) >> 5) + 1;
-        A->jlo = jl;
-        A->jhi = jh > XA_LIMBS - 1 ? XA_LIMBS - 1 : jh;
-        for (int w = 0; w < IX_WARPS; ++w) {
-            unsigned m = S.part_mask[tid][w];
-            while (m) {
-                const int t = 32 * w + __ffs(m) - 1;
-                m &= m - 1;
-                ix_big_add128(A, S.part[tid][t][0], S.part[tid][t][1], xa_lsb_pos(t * IX_PER));
+            ix_big_full_range(&S.E);
+            S.E.normalize();
+            ix_big_tighten(&S.E);
+            ix_big_full_range(&S.P);
+            ix_big_full_range(&S.Q);
+            S.P.normalize();
+            S.Q.normalize();
+            if (S.P.cmp(S.Q) >= 0) {
+                S.P.sub(S.Q);
+                for (int j = 0; j < XA_LIMBS; ++j) S.V.l[j] = S.P.l[j];
+                v_neg = 0;
+            } else {
+                S.Q.sub(S.P);
+                for (int j = 0; j < XA_LIMBS; ++j) S.V.l[j] = S.Q.l[j];
+                v_neg = 1;
             }
+            ix_big_full_range(&S.V);
+            ix_big_tighten(&S.V);
         }
-        A->normalize();
+        __syncthreads();
     }
-    __syncthreads();
+    // the partition's error sum for the select kernel
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) p.gbins[j] = S.E.l[j];
     if (tid != 0) return;  // the rest is one thread's work
+    p.gbins[IX_PUB_JLO] = (unsigned long long)S.E.jlo;
+    p.gbins[IX_PUB_JHI] = (unsigned long long)S.E.jhi;
+    p.gbins[IX_PUB_TOPE] = topkey >> 52;  // no region of the partition has a larger binary exponent of errmax
 
-    ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
+    ctl[LC_STAMP + 2] = (long long)ix_timer_ns();
     // ---- totals: E truncated (exact `<` tests), V rounded to nearest -------------------------------------------------
     const double inf = __longlong_as_double(0x7ff0000000000000LL), nan = __longlong_as_double(0x7ff8000000000000LL);
     const bool e_nonfinite = misc[XA_M_ESTICKY] != 0ULL || misc[XA_M_ENAN] != 0ULL || misc[XA_M_EINF] != 0ULL;
@@ -432,39 +390,21 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         E = ((misc[XA_M_ESTICKY] & 2ULL) || misc[XA_M_ENAN]) ? nan : inf;
         E_report = E;
     }
-    double V;
-    {
-        const int c = S.Vp.cmp(S.Vn);
-        if (c == 0) {
-            V = 0.0;
-        } else if (c > 0) {
-            S.Vp.sub(S.Vn);
-            V = S.Vp.to_double(1);
-        } else {
-            S.Vn.sub(S.Vp);
-            V = -S.Vn.to_double(1);
-        }
-        if (misc[XA_M_VSTICKY] | misc[XA_M_VNAN] | misc[XA_M_VPINF] | misc[XA_M_VNINF]) {
-            if ((misc[XA_M_VSTICKY] & 2ULL) || misc[XA_M_VNAN] || (misc[XA_M_VPINF] && misc[XA_M_VNINF]))
-                V = nan;
-            else if (misc[XA_M_VPINF])
-                V = inf;
-            else if (misc[XA_M_VNINF])
-                V = -inf;
-        }
+    double V = S.V.to_double(1);
+    if (v_neg) V = -V;
+    if (misc[XA_M_VSTICKY] | misc[XA_M_VNAN] | misc[XA_M_VPINF] | misc[XA_M_VNINF]) {
+        if ((misc[XA_M_VSTICKY] & 2ULL) || misc[XA_M_VNAN] || (misc[XA_M_VPINF] && misc[XA_M_VNINF]))
+            V = nan;
+        else if (misc[XA_M_VPINF])
+            V = inf;
+        else if (misc[XA_M_VNINF])
+            V = -inf;
     }
     const bool count_only = e_nonfinite;
     const double eps = 2.220446049250313e-16;
     const double band = 4.0 * eps * sqrt(3.0 * (double)Nglobal);  // rounding band of the reference's drifting sums (diagnostic)
     ctl[LC_V] = (long long)ix_bits(V);
     ctl[LC_E] = (long long)ix_bits(E_report);
-    {   // window hints for the rule kernels: children land at or below the current top binades
-        int eb = e_top + 4 - XA_WIN, vb = v_top + 2 - XA_WIN;
-        eb = eb < 0 ? 0 : (eb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : eb);
-        vb = vb < 0 ? 0 : (vb > XA_NBINS - XA_WIN ? XA_NBINS - XA_WIN : vb);
-        acc[XA_M_OFF + XA_M_EBASE] = (unsigned long long)eb;
-        acc[XA_M_OFF + XA_M_VBASE] = (unsigned long long)vb;
-    }
     if ((long long)Ntot != Nglobal) {  // the sums lost track of the pool: never decide on them
         ctl[LC_DBG0] = (long long)Ntot;
         ix_finish(p, LS_ERROR, LE_INTERNAL);
@@ -511,74 +451,23 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         ctl[LC_NBATCH] += 1;
         ctl[LC_ITER] += 1;
         acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
+        ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
         return;
     }
-    ctl[LC_STAMP + 4] = (long long)ix_timer_ns();
-    // ---- walk down from the top binade, popping whole bins, until the evaluation budget is used up or the exact residual
-    // passes (Rule.java:109-133 at bin granularity): the batch ends inside that binade ---------------------------------
-    int bstar = e_top;
-    unsigned long long Cabove = 0;
-    for (int e = e_top; e >= 0; e = ix_next_below(S.nz, e)) {
-        const int w = e - (e_top - IX_TOPW + 1);
-        const unsigned long long c = w >= 0 ? S.wcnt[w] : ebins[e * 3];
-        const xa_i128 mv = w >= 0 ? xa_join_signed(S.wlo[w], S.whi[w]) : xa_join_signed(ebins[e * 3 + 1], ebins[e * 3 + 2]);
-        bstar = e;
-        if (Cabove + c >= (unsigned long long)Kcap) break;
-        if (ix_next_below(S.nz, e) < 0) break;  // the lowest bin: popping everything was ruled out above, so the batch ends here
-        if (!count_only) {
-            // residual after popping this bin as well; put the bin back when that passes
-            const bool has = mv > 0 && e < 2047;
-            if (has) ix_big_sub(&S.E, (xa_u128)mv, xa_lsb_pos(e));
-            if (ix_conv(V, S.E.to_double(0), p)) {
-                if (has) {
-                    S.E.add_shifted((xa_u128)mv, xa_lsb_pos(e));
-                    S.E.normalize();
-                }
-                break;
-            }
-        }
-        Cabove += c;
-    }
-    ctl[LC_STAMP + 5] = (long long)ix_timer_ns();
-    // S.E is the residual before the first pop inside bstar
-    {
-        const int pos = xa_lsb_pos(bstar);
-        const int w = bstar - (e_top - IX_TOPW + 1);
-        SelX* sx = p.selx;
-        sx->binade = bstar;
-        sx->pos = pos;
-        sx->count_only = count_only ? 1 : 0;
-        sx->H_lo = S.E.window64(pos);
-        sx->H_hi = S.E.window64(pos + 64);
-        sx->L1 = pos >= 64 ? S.E.window64(pos - 64) : (pos > 0 ? (S.E.window64(0) << (64 - pos)) : 0ULL);
-        // the part below pos as a truncated double (only used when everything above it is popped)
-        S.Vn.jlo = S.E.jlo;
-        S.Vn.jhi = S.E.jhi;
-        for (int j = 0; j < XA_LIMBS; ++j) {
-            const int lo_bit = 32 * j;
-            if (lo_bit >= pos || j < S.E.jlo || j > S.E.jhi)
-                S.Vn.l[j] = 0ULL;
-            else if (lo_bit + 32 <= pos)
-                S.Vn.l[j] = S.E.l[j];
-            else
-                S.Vn.l[j] = S.E.l[j] & ((1ULL << (pos - lo_bit)) - 1ULL);
-        }
-        sx->Ldbl = S.Vn.to_double(0);
-        sx->Cabove = Cabove;
-        sx->Kcap = (unsigned long long)Kcap;
-        sx->V = V;
-        sx->E = E;
-        sx->band = band;
-        sx->bin_cnt = w >= 0 ? S.wcnt[w] : ebins[bstar * 3];
-        sx->thr_key = 0ULL;
-        sx->tie_take = 0ULL;
-        sx->K = 0ULL;
-        *p.bar = 0ULL;  // grid barrier of the select kernel
-        ctl[LC_SELECT] = 1;
-        ctl[LC_DYN_N] = 0;  // the select kernel sizes the batch
-        ctl[LC_STAMP + 6] = (long long)ix_timer_ns();
-        ctl[LC_STAMP + 7] = ctl[LC_STAMP + 6];
-    }
+    // ---- a batch has to be cut: the select kernel finds the threshold ------------------------------------------------
+    SelX* sx = p.selx;
+    sx->count_only = count_only ? 1 : 0;
+    sx->Kcap = (unsigned long long)Kcap;
+    sx->V = V;
+    sx->E = E;
+    sx->band = band;
+    sx->thr_key = 0ULL;
+    sx->tie_take = 0ULL;
+    sx->K = 0ULL;
+    *p.bar = 0ULL;  // grid barrier of the select kernel
+    ctl[LC_SELECT] = 1;
+    ctl[LC_DYN_N] = 0;  // the select kernel sizes the batch
+    ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
 }
 
 // ---- select ------------------------------------------------------------------------------------------------------------
@@ -809,7 +698,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         sx = *p.selx;
         ps.frac = 0ULL;
         ps.Pm_lo = ps.Pm_hi = 0ULL;
-        ps.Cc = p.selx->Cabove;
+        ps.Cc = 0ULL;
         ps.cb = ps.Sb_lo = ps.Sb_hi = 0ULL;
         ps.tie_take = ps.K = ps.thr_key = ps.ambiguous = 0ULL;
     }
@@ -820,13 +709,172 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     long long hi = lo + per;
     if (hi > n) hi = n;
     if (lo > hi) hi = lo;
+    unsigned long long* const cand_count = p.hset + (size_t)(IX_LEVELS + 1) * 3 * IX_NB;
+    int failed = 0, levels_run = 0;
+    // ---- binary exponents: histogram (count, mantissa sum) of windows of IX_NB binades from the top, then every CTA walks
+    // down the bins, popping whole binades, until the evaluation budget is used up or the exact residual passes
+    // (Rule.java:109-133 at binade granularity): the batch ends inside that binade ------------------------------------
+    __shared__ XaBig sE;
+    __shared__ unsigned long long s_walk[4];  // found, binade, regions popped above it
+    for (int j = tid; j < XA_LIMBS; j += IX_THREADS) sE.l[j] = __ldcg(&p.gbins[j]);
+    if (tid == 0) {
+        sE.jlo = (int)__ldcg(&p.gbins[IX_PUB_JLO]);
+        sE.jhi = (int)__ldcg(&p.gbins[IX_PUB_JHI]);
+        s_walk[0] = 0ULL;
+        s_walk[1] = 0ULL;
+        s_walk[2] = 0ULL;
+    }
+    __syncthreads();
+    const int e_hi_all = (int)__ldcg(&p.gbins[IX_PUB_TOPE]);
+    const unsigned long long Nglobal_now = (unsigned long long)ctl[LC_NGLOBAL];
+    for (int wdx = 0; !failed; ++wdx) {
+        const int e_top_w = e_hi_all - IX_NB * wdx;
+        if (e_top_w < 0) break;  // (cannot happen: the walk stops at the last non-empty bin)
+        for (int q = tid; q < 2 * IX_NB; q += IX_THREADS) {
+            scnt[q] = 0u;
+            slo[q] = 0ULL;
+            shi[q] = 0ULL;
+        }
+        __syncthreads();
+        {
+            unsigned* const myc = scnt + (tid >> 7) * IX_NB;
+            unsigned long long* const mylo = slo + (tid >> 7) * IX_NB;
+            unsigned long long* const myhi = shi + (tid >> 7) * IX_NB;
+            unsigned cur = 0, run_c = 0;
+            unsigned long long run_lo = 0, run_hi = 0;
+            for (long long i0 = lo + tid; i0 < hi; i0 += 4 * IX_THREADS) {
+                double a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = i0 + u * IX_THREADS < hi ? err[i0 + u * IX_THREADS] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + u * IX_THREADS < hi) {
+                        const unsigned long long k = ix_key_of_err(a[u]);
+                        const int e = (int)(k >> 52), d = e_top_w - e;
+                        if (d >= 0 && d < IX_NB) {
+                            if ((unsigned)d != cur) {
+                                ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
+                                cur = (unsigned)d;
+                                run_c = 0;
+                                run_lo = run_hi = 0;
+                            }
+                            const unsigned long long m = (e ? (1ULL << 52) : 0ULL) | (k & 0xfffffffffffffULL);
+                            ++run_c;
+                            run_lo += m & 0xffffffffULL;
+                            run_hi += m >> 32;
+                        }
+                    }
+                }
+            }
+            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
+        }
+        __syncthreads();
+        unsigned long long* gh0 = p.hset;
+        for (int q = tid; q < IX_NB; q += IX_THREADS) {
+            const unsigned c = scnt[q] + scnt[IX_NB + q];
+            if (c) {
+                const unsigned long long a = slo[q] + slo[IX_NB + q], h = shi[q] + shi[IX_NB + q];
+                atomicAdd(&gh0[q], (unsigned long long)c);
+                if (a & 0xffffffffULL) atomicAdd(&gh0[IX_NB + q], a & 0xffffffffULL);
+                const unsigned long long h2 = h + (a >> 32);
+                if (h2) atomicAdd(&gh0[2 * IX_NB + q], h2);
+            }
+        }
+        levels_run = 1;
+        ix_gsync(bar, ++nsync * (unsigned long long)G);
+        if (sharded) {
+            if (b == 0) {
+                const int f = ix_exchange(p, xseq, 0, gh0, 0, 3 * IX_NB);
+                if (f) atomicExch((unsigned long long*)&ctl[LC_DBG1], (unsigned long long)f);
+                unsigned long long* own = p.xbuf[p.rank];
+                for (int w = tid; w < 3 * IX_NB; w += IX_THREADS) {
+                    unsigned long long sacc = 0;
+                    for (int r = 0; r < p.R; ++r) sacc += __ldcg(&ix_pay(own, xseq, r)[w]);
+                    gh0[w] = sacc;
+                }
+            }
+            ++xseq;
+            ix_gsync(bar, ++nsync * (unsigned long long)G);
+            if (__ldcg((const unsigned long long*)&ctl[LC_DBG1])) {
+                failed = (int)ctl[LC_DBG1];
+                break;
+            }
+        }
+        // the window's bins of the partition -> shared memory (the private histograms are dead): slo[0..NB) counts,
+        // slo[NB..2NB) low words, shi[0..NB) high words
+        for (int q = tid; q < IX_NB; q += IX_THREADS) {
+            slo[q] = __ldcg(&gh0[q]);
+            slo[IX_NB + q] = __ldcg(&gh0[IX_NB + q]);
+            shi[q] = __ldcg(&gh0[2 * IX_NB + q]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long Cabove = s_walk[2];
+            for (int d = 0; d < IX_NB; ++d) {
+                const unsigned long long c = slo[d];
+                if (!c) continue;
+                const int e = e_top_w - d;
+                const xa_u128 mv = (xa_u128)slo[IX_NB + d] + ((xa_u128)shi[d] << 32);
+                bool stop = Cabove + c >= sx.Kcap || Cabove + c >= Nglobal_now;  // the budget ends here / the lowest bin
+                if (!stop && !sx.count_only) {
+                    // residual after popping this bin as well; put the bin back when that passes
+                    const bool has = mv > 0 && e < 2047;
+                    if (has) ix_big_sub(&sE, mv, xa_lsb_pos(e));
+                    if (ix_conv(sx.V, sE.to_double(0), p)) {
+                        if (has) {
+                            sE.add_shifted(mv, xa_lsb_pos(e));
+                            sE.normalize();
+                        }
+                        stop = true;
+                    }
+                }
+                if (stop) {
+                    s_walk[0] = 1ULL;
+                    s_walk[1] = (unsigned long long)e;
+                    break;
+                }
+                Cabove += c;
+            }
+            s_walk[2] = Cabove;
+            if (s_walk[0]) {  // sE is the residual before the first pop inside the binade
+                const int bstar = (int)s_walk[1], pos = xa_lsb_pos(bstar);
+                sx.binade = bstar;
+                sx.pos = pos;
+                sx.H_lo = sE.window64(pos);
+                sx.H_hi = sE.window64(pos + 64);
+                sx.L1 = pos >= 64 ? sE.window64(pos - 64) : (pos > 0 ? (sE.window64(0) << (64 - pos)) : 0ULL);
+                // the part below pos as a truncated double (only used when everything above it is popped)
+                for (int j = sE.jlo; j <= sE.jhi; ++j) {
+                    const int lo_bit = 32 * j;
+                    if (lo_bit >= pos)
+                        sE.l[j] = 0ULL;
+                    else if (lo_bit + 32 > pos)
+                        sE.l[j] &= (1ULL << (pos - lo_bit)) - 1ULL;
+                }
+                sx.Ldbl = sE.to_double(0);
+                sx.Cabove = Cabove;
+                ps.Cc = Cabove;
+            }
+        }
+        __syncthreads();
+        if (s_walk[0]) break;
+        // the batch reaches below this window (more than IX_NB binades under the top): clear the histogram and go on
+        ix_gsync(bar, ++nsync * (unsigned long long)G);
+        for (long long q = (long long)b * IX_THREADS + tid; q < 3 * IX_NB; q += (long long)G * IX_THREADS) p.hset[q] = 0ULL;
+        ix_gsync(bar, ++nsync * (unsigned long long)G);
+    }
+    if (failed) {
+        if (b == 0 && tid == 0) {
+            ix_finish(p, LS_ERROR, failed);
+            ctl[LC_SEQ] = (long long)xseq;
+        }
+        return;
+    }
     const unsigned long long top_mask = 0xfffULL << 52;  // sign + exponent
     const unsigned long long top_prefix = (unsigned long long)sx.binade << 52;
-    unsigned long long* const cand_count = p.hset + (size_t)IX_LEVELS * 3 * IX_NB;
     bool have_cand = false;
     unsigned long long above_def = 0;  // (thread-local) regions of this chunk that are certainly popped
     long long M = 0;
-    int failed = 0, levels_run = 0;
     for (int level = 0; level < IX_LEVELS; ++level) {
         const int shift = ix_level_shift(level), NB = ix_level_nb(level);
         const int copies = level <= 1 ? IX_HCOPIES : 1;
@@ -842,7 +890,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         const unsigned long long rmask = (1ULL << shift) - 1ULL;
         unsigned cur = 0, run_c = 0;
         unsigned long long run_lo = 0, run_hi = 0;
-        ++levels_run;
+        levels_run = level + 2;
         if (level <= 1) {
             // full scan of the chunk; the second scan also extracts the candidates and counts the certain pops
             unsigned* const myc = scnt + (tid >> 6) * 256;
@@ -910,7 +958,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             ix_hist_flush(scnt, slo, shi, cur, run_c, run_lo, run_hi);
         }
         __syncthreads();
-        unsigned long long* gh = p.hset + (size_t)level * 3 * IX_NB;
+        unsigned long long* gh = p.hset + (size_t)(level + 1) * 3 * IX_NB;
         for (int q = tid; q < NB; q += IX_THREADS) {
             unsigned c = 0;
             unsigned long long a = 0, h = 0;
@@ -1155,20 +1203,11 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
 
 // ---- rebuild the sums from the pool ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(IX_THREADS) k_acc_rebuild(PoolView pool, long long n, unsigned long long* acc) {
-    __shared__ CubAccWin win;
+    __shared__ CubAccWin<IX_THREADS> win;
     cub_acc_begin(acc, &win);
-    unsigned long long my_min = ~0ULL;
-    for (long long base = (long long)blockIdx.x * IX_THREADS; base < n; base += (long long)gridDim.x * IX_THREADS) {
-        const long long i = base + threadIdx.x;
-        const bool active = i < n;
-        const double v = active ? pool.val[i] : 0.0, e = active ? pool.err[i] : 0.0;
-        cub_acc_warp(acc, &win, active, v, e, 1);
-        if (active) {
-            const unsigned long long kb = cub_errmax_bits(e);
-            my_min = kb < my_min ? kb : my_min;
-        }
-    }
-    cub_acc_end(acc, &win, my_min);
+    for (long long i = (long long)blockIdx.x * IX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * IX_THREADS)
+        cub_acc_thread(&win, acc, 0, 0.0, 0.0, pool.val[i], pool.err[i]);
+    cub_acc_end(acc, &win);
 }
 
 __global__ void k_abort_peers(int R, IterXParams p) {
@@ -1199,8 +1238,12 @@ cudaError_t ix_select(const IterXParams& p, int n_blocks, cudaStream_t s) {
     return cudaLaunchCooperativeKernel((const void*)k_exact_select, dim3((unsigned)n_blocks), dim3(IX_THREADS), args, 0, s);
 }
 void ix_rebuild(const PoolView& pool, long long n, unsigned long long* acc, int n_sms, cudaStream_t s) {
-    cudaMemsetAsync(acc, 0, (size_t)XA_WORDS * 8, s);
+    // everything but the window hints, the sticky flags and the upper bound of the largest errmax starts from zero
+    cudaMemsetAsync(acc + XA_D_OFF, 0, (size_t)XA_REPL * XA_CELLS * 8, s);
+    cudaMemsetAsync(acc + XA_M_OFF, 0, 5 * 8, s);
     cudaMemsetAsync(acc + XA_M_OFF + XA_M_MINKEY, 0xff, 8, s);
+    cudaMemsetAsync(acc + XA_M_OFF + XA_M_EMAXKEY, 0, 2 * 8, s);
+    cudaMemsetAsync(acc + XA_FAR_E_OFF, 0, (size_t)(XA_WORDS - XA_FAR_E_OFF) * 8, s);
     long long g = (n + IX_THREADS - 1) / IX_THREADS;
     if (g > (long long)n_sms * 8) g = (long long)n_sms * 8;
     if (g < 1) g = 1;

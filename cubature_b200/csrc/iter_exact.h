@@ -66,7 +66,7 @@ struct SelX {
 // levels: 8 + 8 bits (streamed), then 4 x 9 bits (candidates only) of the 52 fraction bits
 #define IX_LEVELS 6
 #define IX_NB 512
-#define IX_HSET_WORDS (IX_LEVELS * 3 * IX_NB + 8)
+#define IX_HSET_WORDS ((IX_LEVELS + 1) * 3 * IX_NB + 8)  // slot 0: binary exponents, slots 1..IX_LEVELS: fraction digits
 
 struct IterXParams {
     PoolView pool;

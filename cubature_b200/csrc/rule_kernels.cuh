@@ -117,11 +117,11 @@ __device__ __forceinline__ long long cub_item_slot(const CubWork& w, long long i
 // Loads the geometry of work item `i` (bisecting the parent when asked to) and returns its slot.
 // All loads of a warp happen before any of its stores (__syncwarp) because in BISECT mode the two
 // children of one parent sit in adjacent lanes and the left child overwrites what the right reads.
+// *parent_out (when given): slot of the parent this thread replaces (left child of a bisection), else -1.
 __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, const CubWork& w, long long i, bool active,
-                                                   double (&c)[CUB_DIM], double (&h)[CUB_DIM], CubAccWin* win = nullptr) {
+                                                   double (&c)[CUB_DIM], double (&h)[CUB_DIM], long long* parent_out = nullptr) {
     long long slot = 0;
-    double pval = 0.0, perr = 0.0;
-    bool premove = false;
+    if (parent_out) *parent_out = -1;
     if (active) {
         slot = cub_item_slot(w, i);
         if (w.mode != CUB_MODE_BISECT) {
@@ -147,21 +147,16 @@ __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, cons
                     c[d] = right ? c[d] + h[d] : c[d] - h[d];   // Region.java:35-36
                 }
             }
-#if CUB_FDIM == 1
-            // the popped parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28); its slot still holds
-            // its val / err until the left child overwrites them at the end of this thread
-            if (win && !right) {
-                pval = pool.val[parent];
-                perr = pool.err[parent];
-                premove = true;
+            if (parent_out && !right) {
+                *parent_out = parent;
+                if (w.acc) {  // the caller reads the parent's val / err after the rule: have them in L1 by then
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.val + parent));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.err + parent));
+                }
             }
-#endif
         }
     }
     if (w.mode == CUB_MODE_BISECT) {
-#if CUB_FDIM == 1
-        if (win) cub_acc_warp(w.acc, win, premove, pval, perr, -1);  // all lanes of the warp
-#endif
         __syncwarp();
         if (active) {
 #pragma unroll
@@ -372,9 +367,8 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
     // so a launch needs no host knowledge of the batch size (device-sized launches: CubWork::dyn).
     const CubWork work = cub_resolve(work_in);
     const long long n = work.n_items;
-    __shared__ CubAccWin win_storage;
-    CubAccWin* const win = work.acc ? &win_storage : nullptr;
-    unsigned long long my_min = ~0ULL;
+    __shared__ CubAccWin<CUB_GM_THREADS> win_storage;
+    CubAccWin<CUB_GM_THREADS>* const win = work.acc ? &win_storage : nullptr;
     if (win) cub_acc_begin(work.acc, win);
     for (long long tile = blockIdx.x; tile * CUB_GM_THREADS < n; tile += gridDim.x) {
         const long long i = tile * CUB_GM_THREADS + threadIdx.x;
@@ -382,11 +376,12 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
         double c[CUB_DIM], h[CUB_DIM];
 #pragma unroll
         for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
-        const long long slot = cub_load_item(pool, work, i, active, c, h, win);
+        long long parent = -1;
+        const long long slot = cub_load_item(pool, work, i, active, c, h, &parent);
         double result = 0.0, err = 0.0;
+        int split = 0;
         if (active) {
             const CUB_INTEGRAND fn(prm.v, 1);
-            int split;
             cub_gm_region(fn, tr, c, h, result, err, split);
             if (cub_fast_failed(fn, 0)) {  // an argument left the fast path's exact range: redo with IEEE division
                 const CubRegionResult r = cub_gm_region_exact<CUB_INTEGRAND>(pool, slot, prm, tr, 0);
@@ -394,9 +389,20 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
                 err = r.err;
                 split = r.split;
             }
+        }
+        if (win && active) {
+            // running sums: the child enters (RegionHeap.add, RegionHeap.java:30-36), the parent a left child replaces leaves
+            // (poll, :21-28) -- its slot holds its val / err until the stores below
+            double pval = 0.0, perr = 0.0;
+            if (parent >= 0) {
+                pval = pool.val[parent];
+                perr = pool.err[parent];
+            }
+            cub_acc_thread(win, work.acc, parent >= 0 ? 1 : 0, pval, perr, result, err);
+        }
+        if (active) {
             double emax = 0.0;  // Rule.java:281-289
             if (err > emax) emax = err;
-
             pool.val[slot] = result;
             pool.err[slot] = err;
             pool.errmax[slot] = emax;
@@ -406,15 +412,8 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
                 work.stage_err[i] = err;
             }
         }
-        if (win) {  // RegionHeap.add, RegionHeap.java:30-36 (all lanes of the warp take part)
-            cub_acc_warp(work.acc, win, active, result, err, 1);
-            if (active) {
-                const unsigned long long kb = cub_errmax_bits(err);
-                my_min = kb < my_min ? kb : my_min;
-            }
-        }
     }
-    if (win) cub_acc_end(work.acc, win, my_min);
+    if (win) cub_acc_end(work.acc, win);
 }
 #endif  // CUB_FDIM == 1
 #endif  // CUB_DIM >= 2
@@ -501,10 +500,9 @@ extern "C" __global__ void __launch_bounds__(128)
 cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
     const CubWork work = cub_resolve(work_in);
     const long long n = work.n_items;
-    __shared__ CubAccWin win_storage;
-    CubAccWin* win = nullptr;
-    unsigned long long my_min = ~0ULL;
 #if CUB_FDIM == 1
+    __shared__ CubAccWin<128> win_storage;
+    CubAccWin<128>* win = nullptr;
     if (work.acc) win = &win_storage;
     if (win) cub_acc_begin(work.acc, win);
 #endif
@@ -514,7 +512,8 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
         const long long i = active ? t % n : 0;
         const int j = active ? (int)(t / n) : 0;
         double cc[1] = {0.0}, hh[1] = {0.0};
-        const long long slot = cub_load_item(pool, work, i, active, cc, hh, win);
+        long long parent = -1;
+        const long long slot = cub_load_item(pool, work, i, active, cc, hh, &parent);
         double val = 0.0, err = 0.0;
         if (active) {
             const double c = cc[0], h = hh[0];
@@ -541,6 +540,18 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
 #endif
             }
             cub_gk15_sums(q, h, &val, &err);
+        }
+#if CUB_FDIM == 1
+        if (win && active) {  // running sums, see cub_gm_scalar
+            double pval = 0.0, perr = 0.0;
+            if (parent >= 0) {
+                pval = pool.val[parent];
+                perr = pool.err[parent];
+            }
+            cub_acc_thread(win, work.acc, parent >= 0 ? 1 : 0, pval, perr, val, err);
+        }
+#endif
+        if (active) {
             pool.val[(long long)j * pool.cap + slot] = val;
             pool.err[(long long)j * pool.cap + slot] = err;
 #if CUB_FDIM == 1
@@ -555,18 +566,9 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
                 work.stage_err[(long long)j * work.stage_stride + i] = err;
             }
         }
-#if CUB_FDIM == 1
-        if (win) {
-            cub_acc_warp(work.acc, win, active, val, err, 1);
-            if (active) {
-                const unsigned long long kb = cub_errmax_bits(err);
-                my_min = kb < my_min ? kb : my_min;
-            }
-        }
-#endif
     }
 #if CUB_FDIM == 1
-    if (win) cub_acc_end(work.acc, win, my_min);
+    if (win) cub_acc_end(work.acc, win);
 #endif
 }
 #endif  // CUB_FDIM == 1 || CUB_SEPARABLE

@@ -27,6 +27,8 @@ def xa():
     L.xa_diff.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int]
     L.xa_residual.restype = ctypes.c_double
     L.xa_residual.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+    L.xa_window_sum.restype = ctypes.c_double
+    L.xa_window_sum.argtypes = [dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     return L
 
 
@@ -134,3 +136,33 @@ def test_residual_inside_a_binade(xa):
         exact = sum(Fraction(float(v)) for v in x) - sum(Fraction(float(v)) for v in top[:k])
         got = xa.xa_residual(_dp(np.ascontiguousarray(x)), len(x), binade, popped.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), k)
         assert got == to_double(exact, 0), (binade, k, n_top, n_low, got.hex(), to_double(exact, 0).hex())
+
+
+def test_thread_windows_and_cells(xa):
+    """The rule kernels' accumulation (acc_window.h): signed values spread over T per-thread 256-bit windows at some base,
+    outliers through the far cells, windows summed as 32-bit cells and folded like the decide kernel does -- equal to the
+    exact signed sum for every base, including windows that are wrong for the data."""
+    rng = np.random.default_rng(9)
+    for trial in range(300):
+        n = int(rng.integers(1, 400))
+        T = int(rng.choice([1, 32, 128]))
+        e0 = int(rng.integers(-1000, 900))
+        spread = int(rng.choice([4, 40, 150, 400]))
+        x = np.ldexp(rng.uniform(0.5, 1.0, n), e0 + rng.integers(-spread, 1, n))
+        x *= rng.choice([-1.0, 1.0], n)
+        if trial % 5 == 0:
+            x[rng.integers(0, n)] = 0.0
+        if trial % 7 == 0:
+            x[: n // 2] = np.ldexp(rng.uniform(0.0, 1.0, n // 2), -1074 + rng.integers(0, 60, n // 2))  # subnormals
+        sgn = rng.choice([-1, 1], n).astype(np.int32)
+        # window base: where the iteration kernel would put it (top of the data 8 bits below the window top), or off
+        top = int(np.max(np.frexp(np.abs(x[x != 0]))[1])) + 1022 - 1 if np.any(x != 0) else 0  # biased exponent - 1 = lsb pos
+        base = max(0, top + 8 - 159)
+        if trial % 3 == 1:
+            base = int(rng.integers(0, 1900))
+        exact = sum(Fraction(float(v)) * int(s) for v, s in zip(x, sgn))
+        n_far = ctypes.c_int(0)
+        for nearest in (0, 1):
+            got = xa.xa_window_sum(_dp(x), sgn.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n, T, base, nearest, ctypes.byref(n_far))
+            want = to_double(abs(exact), nearest) * (-1.0 if exact < 0 else 1.0)
+            assert got == want, (trial, n, T, base, nearest, got.hex(), want.hex(), n_far.value)

@@ -1,6 +1,8 @@
 // Test harness for cubature_b200/csrc/exact_acc.h (compiled by tests/test_exact_acc.py with g++): exposes the big-integer
 // arithmetic of the exact running sums through a C ABI so that Python integers can check it.
 #include "../cubature_b200/csrc/exact_acc.h"
+#include "../cubature_b200/csrc/acc_window.h"
+#include <vector>
 
 extern "C" {
 // sum of n non-negative finite doubles -> double, truncated (nearest = 0) or rounded to nearest even (1)
@@ -50,5 +52,48 @@ double xa_residual(const double* x, int n, int binade, const unsigned long long*
     const xa_u128 D = H - P;
     if (D == 0) return Ldbl;
     return xa_trunc_hi(D, L1, pos);
+}
+// The rule kernels' path (acc_device.cuh): value i, with sign sgn[i], is added by "thread" i % T to its 256-bit window at
+// `base` (or to the far cells when it does not fit); the windows are summed as 32-bit cells and folded into the totals the
+// way k_exact_decide does.  Returns the signed sum as a double; *n_far = values that took the far path.
+double xa_window_sum(const double* x, const int* sgn, int n, int T, int base, int nearest, int* n_far) {
+    std::vector<xaw_u64> w((size_t)T * XA_WLIMBS, 0ULL);
+    long long far[XA_LIMBS] = {0};
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+        const xa_u64 b = xa_bits(x[i]);
+        bool neg = sgn[i] < 0;
+        if (b >> 63) neg = !neg;
+        const xa_u64 m = xa_mantissa(b);
+        if (!m) continue;
+        const int pos = xa_lsb_pos((int)((b >> 52) & 2047ULL));
+        xaw_u64(&a)[XA_WLIMBS] = *reinterpret_cast<xaw_u64(*)[XA_WLIMBS]>(&w[(size_t)(i % T) * XA_WLIMBS]);
+        if (!xaw_addend(a, m, pos, base, neg)) {
+            int j;
+            long long c[3];
+            xaw_far_cells(m, pos, neg, &j, c);
+            far[j] += c[0];
+            far[j + 1] += c[1];
+            far[j + 2] += c[2];
+            ++nf;
+        }
+    }
+    if (n_far) *n_far = nf;
+    long long cell[XA_HALVES] = {0};
+    for (int t = 0; t < T; ++t)
+        for (int h = 0; h < XA_HALVES; ++h) cell[h] += xaw_cell(w[(size_t)t * XA_WLIMBS + (h >> 1)], h);
+    XaBig P, Q;
+    P.clear();
+    Q.clear();
+    xa_fold_cells(&P, &Q, cell, base);
+    for (int j = 0; j < XA_LIMBS - 3; ++j) xa_add_signed(&P, &Q, far[j], 32 * j);
+    P.normalize();
+    Q.normalize();
+    if (P.cmp(Q) >= 0) {
+        P.sub(Q);
+        return P.to_double(nearest);
+    }
+    Q.sub(P);
+    return -Q.to_double(nearest);
 }
 }
