@@ -1,14 +1,15 @@
 // acc_device.cuh -- device-side maintenance of the exact running sums of a region pool (layout: acc_layout.h, arithmetic:
-// acc_window.h).  Included by the NVRTC-compiled rule kernels (rule_kernels.cuh) and by the nvcc-compiled iteration
-// kernels (iter_exact.cu).
+// acc_window.h).  Used by the iteration kernels (iter_exact.cu): the decide kernel streams over the regions the last rule
+// launch wrote (RegionHeap.add, RegionHeap.java:30-36) and over the (val, err) pairs of the regions the last selection popped
+// (RegionHeap.poll, :21-28).  The rule kernels themselves do not take part: their loop body fills the instruction cache and
+// they run at four warps per scheduler, where every additional instruction costs its full latency (measured: +14 % run
+// time for 400 integer instructions per region, profiles/r02_acc_cost.md); a streaming pass over 16 bytes per region costs
+// 2 - 3 %.
 //
 // Every thread owns one 256-bit window accumulator per sum in shared memory (limb-major: consecutive threads touch
-// consecutive 8-byte words).  Per region it builds its net contribution -- its child in, and for a left child the parent out
-// (RegionHeap.add / poll, RegionHeap.java:21-36) -- in registers and adds it to its window with one carry chain: no atomics,
-// no shuffles, about a hundred integer instructions next to the few thousand FP64 instructions of the rule.  When the CTA
-// retires the windows are summed as 32-bit cells and added to one replica of the delta cells in global memory.  No
-// floating-point addition is involved anywhere, so the result does not depend on how the regions are spread over lanes,
-// warps, CTAs or GPUs.
+// consecutive 8-byte words) and adds a value with one two-limb carry chain: no atomics, no shuffles.  When the CTA is done
+// the windows are summed as 32-bit cells and added to one replica of the delta cells in global memory.  No floating-point
+// addition is involved anywhere, so the result does not depend on how the regions are spread over lanes, warps, CTAs or GPUs.
 #ifndef CUB_ACC_DEVICE_CUH
 #define CUB_ACC_DEVICE_CUH
 
@@ -78,46 +79,70 @@ __device__ __noinline__ void cub_acc_cold(CubAccWin<T>* win, unsigned long long*
     if (c[2]) atomicAdd(&far[j + 2], (unsigned long long)c[2]);
     win->far_used = 1;
 }
-// a += sgn * x, kind 0: x is an error estimate (an absolute value; a negative one counts as errmax = 0, Rule.java:281-289),
-// kind 1: a (signed) integral estimate.
-template <int T>
-__device__ __forceinline__ void cub_acc_term(CubAccWin<T>* win, unsigned long long* acc, int kind, xaw_u64 (&a)[XA_WLIMBS], double x, int sgn) {
+// sum KIND += sgn * x.  KIND 0: x is an error estimate (an absolute value; a negative one counts as errmax = 0,
+// Rule.java:281-289), KIND 1: a (signed) integral estimate.  The hot path is straight-line: decode, shift, two-limb add.
+template <int T, int KIND>
+__device__ __forceinline__ void cub_acc_term(CubAccWin<T>* win, unsigned long long* acc, unsigned long long* w, int base, double x, int sgn) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    const int e = (int)((b >> 52) & 2047ULL);
-    const unsigned long long fr = b & 0xfffffffffffffULL;
-    bool neg = sgn < 0;
-    if (b >> 63) {
-        if (kind == 0 && e != 2047) return;
-        neg = !neg;
+    const unsigned hi32 = (unsigned)(b >> 32);
+    const int e = (int)((hi32 >> 20) & 2047u);
+    const unsigned long long m = (b & 0xfffffffffffffULL) | (e ? (1ULL << 52) : 0ULL);
+    const bool minus = (hi32 >> 31) != 0u;
+    const int sh = (e > 0 ? e - 1 : 0) - base;
+    if ((unsigned)sh > (unsigned)XA_WIN_MAX_SHIFT || e == 2047 || (KIND == 0 && minus)) {  // rare
+        if ((m != 0ULL || e == 2047) && !(KIND == 0 && minus && e != 2047)) cub_acc_cold(win, acc, KIND, b, sgn);
+        return;
     }
-    const unsigned long long m = e ? (fr | (1ULL << 52)) : fr;
-    if (m == 0ULL) return;
-    if (e == 2047 || !xaw_addend(a, m, e > 0 ? e - 1 : 0, kind ? win->v_base : win->e_base, neg)) cub_acc_cold(win, acc, kind, b, sgn);
+    const int q = sh >> 6, r = sh & 63;
+    const unsigned long long alo = m << r, ahi = (m >> 1) >> (63 - r);
+    unsigned long long* p = w + q * T;
+    unsigned long long lo = p[0], hi = p[T];
+    const bool neg = KIND == 0 ? sgn < 0 : ((sgn < 0) != minus);
+    unsigned long long c = xaw_addsub2(lo, hi, alo, ahi, neg);
+    p[0] = lo;
+    p[T] = hi;
+    if (c) {  // a carry / borrow beyond the two limbs: rare (the running sum changes sign, or a limb fills up)
+        for (int k = q + 2; c && k < XA_WLIMBS; ++k) {
+            const unsigned long long v = w[k * T];
+            w[k * T] = neg ? v - 1ULL : v + 1ULL;
+            c = (neg ? v == 0ULL : v == ~0ULL) ? 1ULL : 0ULL;
+        }
+    }
 }
 
-// One region enters the sums (val, err); when has_parent, the parent it replaces (pval, perr) leaves them.  Called by the
-// threads that hold a region (no warp-level cooperation).  Out of line: the rule's register allocation is not disturbed.
+// One region enters (sgn = +1) or leaves (-1) the sums.  Called by the threads that hold a region (no warp-level
+// cooperation).  keys: the caller's running {smallest errmax, largest errmax, largest |val|} bits of the regions added.
+struct CubAccKeys {
+    unsigned long long mn, ex, vx;
+    int cnt;
+};
+__device__ __forceinline__ void cub_acc_keys_init(CubAccKeys& k) {
+    k.mn = ~0ULL;
+    k.ex = 0ULL;
+    k.vx = 0ULL;
+    k.cnt = 0;
+}
 template <int T>
-__device__ __noinline__ void cub_acc_thread(CubAccWin<T>* win, unsigned long long* acc, int has_parent, double pval, double perr, double val,
-                                            double err) {
+__device__ __forceinline__ void cub_acc_region(CubAccWin<T>* win, unsigned long long* acc, CubAccKeys& k, double val, double err, int sgn) {
     const int t = threadIdx.x;
-#pragma unroll
-    for (int kind = 0; kind < 2; ++kind) {
-        xaw_u64 a[XA_WLIMBS] = {0ULL, 0ULL, 0ULL, 0ULL};
-        cub_acc_term(win, acc, kind, a, kind ? val : err, 1);
-        if (has_parent) cub_acc_term(win, acc, kind, a, kind ? pval : perr, -1);
-        xaw_u64 s[XA_WLIMBS];
-#pragma unroll
-        for (int k = 0; k < XA_WLIMBS; ++k) s[k] = win->w[kind][k][t];
-        xaw_add4(s, a, 0ULL);
-#pragma unroll
-        for (int k = 0; k < XA_WLIMBS; ++k) win->w[kind][k][t] = s[k];
+    cub_acc_term<T, 0>(win, acc, &win->w[0][0][t], win->e_base, err, sgn);
+    cub_acc_term<T, 1>(win, acc, &win->w[1][0][t], win->v_base, val, sgn);
+    k.cnt += sgn;
+    if (sgn > 0) {
+        const unsigned long long kb = cub_errmax_bits(err), vb = cub_abs_bits(val);
+        k.mn = kb < k.mn ? kb : k.mn;
+        k.ex = kb > k.ex ? kb : k.ex;
+        k.vx = vb > k.vx ? vb : k.vx;
     }
-    const unsigned long long kb = cub_errmax_bits(err), vb = cub_abs_bits(val);
-    if (kb < win->key[0][t]) win->key[0][t] = kb;
-    if (kb > win->key[1][t]) win->key[1][t] = kb;
-    if (vb > win->key[2][t]) win->key[2][t] = vb;
-    if (!has_parent) win->cnt[t] += 1;
+}
+// before cub_acc_end: the thread's keys go to shared memory
+template <int T>
+__device__ __forceinline__ void cub_acc_keys_store(CubAccWin<T>* win, const CubAccKeys& k) {
+    const int t = threadIdx.x;
+    win->key[0][t] = k.mn;
+    win->key[1][t] = k.ex;
+    win->key[2][t] = k.vx;
+    win->cnt[t] = k.cnt;
 }
 
 template <int T>

@@ -14,47 +14,61 @@
 
 typedef unsigned long long xaw_u64;
 
-// a += b + cin over four 64-bit limbs (wraps at 2^256); cin is 0 or 1
-XAW_FN void xaw_add4(xaw_u64 (&a)[XA_WLIMBS], const xaw_u64 (&b)[XA_WLIMBS], xaw_u64 cin) {
+// (lo, hi) +/-= (alo, ahi) with the carry / borrow out of the pair
+XAW_FN xaw_u64 xaw_addsub2(xaw_u64& lo, xaw_u64& hi, xaw_u64 alo, xaw_u64 ahi, bool neg) {
+    xaw_u64 c;
 #if defined(__CUDA_ARCH__)
-    // one carry chain: `cin + (2^64 - 1)` raises the carry flag exactly when cin == 1
-    asm("{\n\t"
-        ".reg .u64 t;\n\t"
-        "add.cc.u64 t, %8, 0xffffffffffffffff;\n\t"
-        "addc.cc.u64 %0, %0, %4;\n\t"
-        "addc.cc.u64 %1, %1, %5;\n\t"
-        "addc.cc.u64 %2, %2, %6;\n\t"
-        "addc.u64 %3, %3, %7;\n\t"
-        "}"
-        : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3])
-        : "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3]), "l"(cin));
+    if (!neg)
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, 0, 0;" : "+l"(lo), "+l"(hi), "=l"(c) : "l"(alo), "l"(ahi));
+    else
+        asm("sub.cc.u64 %0, %0, %3;\n\tsubc.cc.u64 %1, %1, %4;\n\tsubc.u64 %2, 0, 0;" : "+l"(lo), "+l"(hi), "=l"(c) : "l"(alo), "l"(ahi));
+    return c & 1ULL;  // subc leaves 0 - borrow
 #else
-    xaw_u64 c = cin;
-    for (int k = 0; k < XA_WLIMBS; ++k) {
-        const xaw_u64 t = a[k] + b[k];
-        const xaw_u64 c1 = t < b[k] ? 1ULL : 0ULL;
-        const xaw_u64 u = t + c;
-        const xaw_u64 c2 = u < c ? 1ULL : 0ULL;
-        a[k] = u;
+    if (!neg) {
+        const xaw_u64 t = lo + alo, c0 = t < alo ? 1ULL : 0ULL;
+        const xaw_u64 u = hi + ahi, c1 = u < ahi ? 1ULL : 0ULL;
+        const xaw_u64 v = u + c0, c2 = v < c0 ? 1ULL : 0ULL;
+        lo = t;
+        hi = v;
         c = c1 | c2;
+    } else {
+        const xaw_u64 b0 = lo < alo ? 1ULL : 0ULL;
+        const xaw_u64 t = lo - alo;
+        const xaw_u64 b1 = hi < ahi ? 1ULL : 0ULL;
+        const xaw_u64 u = hi - ahi;
+        const xaw_u64 b2 = u < b0 ? 1ULL : 0ULL;
+        lo = t;
+        hi = u - b0;
+        c = b1 | b2;
     }
+    return c;
 #endif
 }
 
-// a += (neg ? -1 : 1) * m * 2^(pos - base) for a 53-bit mantissa m.  Returns false (a untouched) when the value does not
-// fit the window: its lsb lies below `base` or more than XA_WIN_MAX_SHIFT bits above it.
-XAW_FN bool xaw_addend(xaw_u64 (&a)[XA_WLIMBS], xaw_u64 m, int pos, int base, bool neg) {
+// window (limb k at w[k * stride], 256-bit two's complement) += (neg ? -1 : 1) * m * 2^(pos - base) for a 53-bit mantissa m.
+// Returns false (window untouched) when the value does not fit: its lsb lies below `base` or more than XA_WIN_MAX_SHIFT bits
+// above it.  Only the two limbs the shifted mantissa covers are touched; a carry / borrow beyond them is rare (a sign change
+// of the running sum, or a limb filling up) and walks up limb by limb.
+XAW_FN bool xaw_accumulate(xaw_u64* w, int stride, xaw_u64 m, int pos, int base, bool neg) {
     const int sh = pos - base;
     if ((unsigned)sh > (unsigned)XA_WIN_MAX_SHIFT) return false;
-    const int q = sh >> 6, r = sh & 63;                  // q <= 2
-    const xaw_u64 lo = m << r, hi = (m >> 1) >> (63 - r);  // (m * 2^r) as two limbs; no shift by 64
-    const xaw_u64 mask = neg ? ~0ULL : 0ULL;             // -x = ~x + 1
-    xaw_u64 b[XA_WLIMBS];
-    b[0] = (q == 0 ? lo : 0ULL) ^ mask;
-    b[1] = (q == 0 ? hi : (q == 1 ? lo : 0ULL)) ^ mask;
-    b[2] = (q == 1 ? hi : (q == 2 ? lo : 0ULL)) ^ mask;
-    b[3] = (q == 2 ? hi : 0ULL) ^ mask;
-    xaw_add4(a, b, neg ? 1ULL : 0ULL);
+    const int q = sh >> 6, r = sh & 63;                    // q <= 2
+    const xaw_u64 alo = m << r, ahi = (m >> 1) >> (63 - r);  // m * 2^r as two limbs (no shift by 64)
+    xaw_u64* p = w + q * stride;
+    xaw_u64 lo = p[0], hi = p[stride];
+    xaw_u64 c = xaw_addsub2(lo, hi, alo, ahi, neg);
+    p[0] = lo;
+    p[stride] = hi;
+    for (int k = q + 2; c && k < XA_WLIMBS; ++k) {
+        const xaw_u64 x = w[k * stride];
+        if (!neg) {
+            w[k * stride] = x + 1ULL;
+            c = x == ~0ULL ? 1ULL : 0ULL;
+        } else {
+            w[k * stride] = x - 1ULL;
+            c = x == 0ULL ? 1ULL : 0ULL;
+        }
+    }
     return true;
 }
 

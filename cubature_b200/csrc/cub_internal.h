@@ -34,7 +34,6 @@ struct HostWork {
     double* stage_val;
     double* stage_err;
     long long stage_stride;
-    unsigned long long* acc;  // exact running sums (acc_layout.h) or null
 };
 enum { MODE_PLAIN = 0, MODE_BISECT = 1, MODE_CHILDREN = 2 };
 

@@ -267,6 +267,7 @@ struct SelectBuffers {
         cudaError_t e;
         if ((e = idxA.ensure((size_t)4 * n)) != cudaSuccess) return e;
         if ((e = keysA.ensure((size_t)8 * n)) != cudaSuccess) return e;  // candidate keys / slots of the cooperative select
+        if ((e = keysB.ensure((size_t)8 * n)) != cudaSuccess) return e;  // val of the popped regions (iter_exact.h: stash_val)
         if ((e = idxB.ensure((size_t)4 * n)) != cudaSuccess) return e;
         if ((e = small.ensure(512 + PK_COOP_HIST_BYTES)) != cudaSuccess) return e;
         if ((e = hist.ensure((size_t)16 * pk_sel_tiles(n) + 64)) != cudaSuccess) return e;
@@ -357,7 +358,6 @@ struct Session {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> evpool;  // (start, stop) pairs around the rule launches not yet added to rule_ms
     size_t ev_used = 0;
-    unsigned long long* acc = nullptr;  // exact running sums the rule kernels maintain (device-resident loop), or null
     RuleKernels* kern = nullptr;
     TransformSpec tr;
     std::vector<unsigned char> tr_arg;   // device-side CubTransform bytes
@@ -439,7 +439,6 @@ struct Session {
         }
         cudaEvent_t evr0 = evpool[ev_used], evr1 = evpool[ev_used + 1];
         ev_used += 2;
-        work.acc = acc;
         const bool one_thread_per_region = (dim >= 2 && fdim == 1) || (dim == 1 && fdim == 1);
         if (work.mode == MODE_BISECT && !one_thread_per_region) {
             pk_bisect(pool, dim, work.list, work.n_items / 2, work.base, stream);
@@ -451,11 +450,13 @@ struct Session {
         cudaEventRecord(evr0, stream);
         cudaError_t e;
         if (dim >= 2 && fdim == 1) {
-            // persistent tiles: at most one resident wave of CTAs, each walks the batch with the grid as its stride
+            // persistent tiles: a bounded number of CTAs, each walks the batch with the grid as its stride (the device-resident
+            // loop sizes launches by an upper bound of the batch).  16 CTAs per resident slot: with a single wave the four CTAs
+            // of an SM run their load / compute / store phases in step and the kernel is 10 % slower (6.5e9 vs 7.2e9 regions/s,
+            // profiles/r02_acc_cost.md); CUBATURE_RULE_WAVES overrides (0 = one CTA per tile).
             const int threads = kern->gm_threads;  // the kernel's __launch_bounds__ (CUB_GM_THREADS)
             const long long tiles = (work.n_items + threads - 1) / threads;
-            // CUBATURE_RULE_WAVES: CTAs per resident slot (default 1 = one wave; 0 = one CTA per tile, as many waves as it takes)
-            static const int waves = [] { const char* e = getenv("CUBATURE_RULE_WAVES"); return e ? atoi(e) : 1; }();
+            static const int waves = [] { const char* e = getenv("CUBATURE_RULE_WAVES"); return e ? atoi(e) : 16; }();
             const unsigned grid = (unsigned)(waves > 0 ? std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm * waves) : tiles);
             e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(threads), args, 0, stream);
             ++launches;
@@ -1764,9 +1765,10 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
 // LS_GROW (the pool has to grow: host work), LS_HANDOFF (multi-GPU: time to deal the pool out to the ranks).
 struct ExactBufs {
     long long* d_ctl = nullptr;
-    long long* h_ctl = nullptr;
+    long long* h_ctl = nullptr;            // pinned: the control block as the host last wrote / finally read it
+    long long* h_snap[2] = {nullptr, nullptr};  // pinned: snapshots taken behind the batches in flight
     IterXParams p{};
-    int max_select_blocks = 1;
+    int max_select_blocks = 1, max_decide_blocks = 1;
     int64_t batches_logged = 0;
 };
 
@@ -1776,11 +1778,13 @@ int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm
     const size_t ctl_b = (size_t)(LC_WORDS + LC_LOG_CAP) * 8, acc_b = (size_t)XA_WORDS * 8, hset_b = (size_t)IX_HSET_WORDS * 8,
                  blk_b = ((size_t)3 * maxG + 8) * 8;
     CUB_CUDA_CHECK(W.d_exact.ensure(ctl_b + 2 * acc_b + hset_b + 512 + blk_b), S.msg);
-    CUB_CUDA_CHECK(W.h_exact.ensure(ctl_b), S.msg);
+    CUB_CUDA_CHECK(W.h_exact.ensure(3 * ctl_b), S.msg);
     unsigned char* base = W.d_exact.as<unsigned char>();
     CUB_CUDA_CHECK(cudaMemsetAsync(base, 0, ctl_b + 2 * acc_b + hset_b + 512 + blk_b, S.stream), S.msg);
     X.d_ctl = (long long*)base;
     X.h_ctl = W.h_exact.as<long long>();
+    X.h_snap[0] = X.h_ctl + (LC_WORDS + LC_LOG_CAP);
+    X.h_snap[1] = X.h_ctl + 2 * (LC_WORDS + LC_LOG_CAP);
     X.p.ctl = X.d_ctl;
     X.p.acc = (unsigned long long*)(base + ctl_b);
     X.p.gbins = (unsigned long long*)(base + ctl_b + acc_b);
@@ -1795,8 +1799,8 @@ int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm
     X.p.rank = 0;
     for (int r = 0; r < PK_MAX_RANKS; ++r) X.p.xbuf[r] = nullptr;
     X.max_select_blocks = maxG;
+    X.max_decide_blocks = ix_decide_max_blocks(S.n_sms);
     CUB_CUDA_CHECK(cudaMemsetAsync(X.p.acc + XA_M_OFF + XA_M_MINKEY, 0xff, 8, S.stream), S.msg);
-    S.acc = X.p.acc;
     return CUB_OK;
 }
 
@@ -1806,27 +1810,48 @@ void exact_bind_pool(Session& S, ExactBufs& X) {
     X.p.cand_key = W.sel.keysA.as<unsigned long long>();
     X.p.cand_idx = W.sel.idxB.as<int>();
     X.p.list = W.sel.idxA.as<int>();
+    X.p.stash_val = W.sel.keysB.as<double>();
+    X.p.stash_err = W.sel.keysA.as<double>();
 }
 
 // Runs iterations until the loop ends or pauses for a reason the caller handles (LS_HANDOFF); grows the pool on LS_GROW.
-// On return X.h_ctl holds the final control block.
+// On entry X.h_ctl holds the control block the host has just written to the device; on return the final one.
+// The host never makes the device wait: while it looks at the control block as it was after batch i, batch i + 1 is already
+// queued (two snapshot buffers, one event each).  A host thread that is descheduled for milliseconds -- seen on shared boxes
+// as 10 - 40 ms added to single steps of a 118 ms job when every visit was a stream synchronisation -- then costs nothing;
+// the price is at most two batches of launches that find the loop finished and retire at once.
 int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit) {
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     const bool timing = getenv("CUBATURE_TIMING") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
-    static const int max_ahead = [] { const char* e = getenv("CUBATURE_AHEAD"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
-    int ahead = std::min(4, max_ahead), visits = 0, grows = 0;
+    static const int batch = [] { const char* e = getenv("CUBATURE_AHEAD"); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, 40) : 8; }();
+    int visits = 0, grows = 0;
     long long n_upper = 0;  // upper bound of this rank's region count (doubles at most per iteration)
     const size_t read_words = trace ? (size_t)(LC_WORDS + LC_LOG_CAP) : (size_t)LC_WORDS;
-    CUB_CUDA_CHECK(cudaMemcpyAsync(X.h_ctl, X.d_ctl, (size_t)LC_WORDS * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
-    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
-    S.d2h_bytes += LC_WORDS * 8;
-    for (;;) {
-        n_upper = X.h_ctl[LC_N];
-        for (int it = 0; it < ahead; ++it) {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) CUB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming), S.msg);
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() {
+            for (int i = 0; i < 2; ++i)
+                if (e[i]) cudaEventDestroy(e[i]);
+        }
+    } guard{ev};
+    auto log_batches = [&](const long long* ctl) {  // batch sizes since the last look (ring log)
+        if (!trace) return;
+        const int64_t nb = ctl[LC_NBATCH];
+        for (int64_t i = std::max<int64_t>(X.batches_logged, nb - LC_LOG_CAP); i < nb; ++i) push_batch(trace, ctl[LC_WORDS + (i % LC_LOG_CAP)]);
+        X.batches_logged = nb;
+    };
+    auto enqueue_batch = [&](int slot) -> int {
+        for (int it = 0; it < batch; ++it) {
             cudaGetLastError();
-            cudaError_t e = ix_decide(X.p, S.stream);
+            // the decide kernel first folds what the previous iteration changed: at most 2 n_upper children (written by the
+            // rule launch before it; n_upper already counts them) and half as many popped parents, 8 per thread
+            long long Gd = (3 * n_upper / 2 + 8 * 256 - 1) / (8 * 256);
+            Gd = std::max<long long>(1, std::min<long long>(Gd, X.max_decide_blocks));
+            cudaError_t e = ix_decide(X.p, (int)Gd, S.n_sms, S.stream);
             if (e != cudaSuccess) {
                 cub_set_message(S.msg, "decide kernel launch failed: %s", cudaGetErrorString(e));
                 return CUB_ERR_CUDA;
@@ -1849,20 +1874,36 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
             if (rc != CUB_OK) return rc;
             n_upper = std::min<long long>(2 * n_upper, pool.cap);
         }
+        CUB_CUDA_CHECK(cudaMemcpyAsync(X.h_snap[slot], X.d_ctl, read_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+        CUB_CUDA_CHECK(cudaEventRecord(ev[slot], S.stream), S.msg);
+        S.d2h_bytes += (int64_t)read_words * 8;
+        return CUB_OK;
+    };
+    for (;;) {
+        n_upper = X.h_ctl[LC_N];
+        int cur = 0;
+        int rc = enqueue_batch(0);
+        if (rc != CUB_OK) return rc;
+        for (;;) {
+            rc = enqueue_batch(cur ^ 1);
+            if (rc != CUB_OK) return rc;
+            CUB_CUDA_CHECK(cudaEventSynchronize(ev[cur]), S.msg);
+            ++visits;
+            const long long* snap = X.h_snap[cur];
+            log_batches(snap);
+            if (snap[LC_STATE] != LS_RUN) break;
+            // regions after batch `cur`; the batch queued behind it can at most double them per iteration
+            long long nb = snap[LC_N];
+            for (int it = 0; it < batch && nb < pool.cap; ++it) nb *= 2;
+            n_upper = std::min<long long>(nb, pool.cap);
+            cur ^= 1;
+        }
+        // the loop has stopped on the device: what is queued behind retires at once; the final control block
         CUB_CUDA_CHECK(cudaMemcpyAsync(X.h_ctl, X.d_ctl, read_words * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
         CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
         S.d2h_bytes += (int64_t)read_words * 8;
-        ++visits;
-        if (trace) {  // batch sizes of the iterations since the last visit (ring log)
-            const int64_t nb = X.h_ctl[LC_NBATCH];
-            for (int64_t i = std::max<int64_t>(X.batches_logged, nb - LC_LOG_CAP); i < nb; ++i) push_batch(trace, X.h_ctl[LC_WORDS + (i % LC_LOG_CAP)]);
-            X.batches_logged = nb;
-        }
+        log_batches(X.h_ctl);
         const long long state = X.h_ctl[LC_STATE];
-        if (state == LS_RUN) {
-            ahead = std::min(2 * ahead, max_ahead);
-            continue;
-        }
         if (state == LS_GROW) {
             const long long N = X.h_ctl[LC_N];
             long long need = 2 * N;
@@ -1892,17 +1933,14 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
             CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl + LC_CAP, X.h_ctl + LC_CAP, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
             CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl + LC_STATE, X.h_ctl + LC_STATE, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
             S.h2d_bytes += 16;
-            ahead = std::min(ahead, 4);
             continue;
         }
         break;
     }
     if (timing)
-        fprintf(stderr, "[cubature] decide kernel phases (last select iteration, us): setup %.1f counts %.1f totals %.1f conv %.1f approx %.1f verify %.1f final %.1f\n",
-                (X.h_ctl[LC_STAMP + 1] - X.h_ctl[LC_STAMP]) * 1e-3, (X.h_ctl[LC_STAMP + 2] - X.h_ctl[LC_STAMP + 1]) * 1e-3,
-                (X.h_ctl[LC_STAMP + 3] - X.h_ctl[LC_STAMP + 2]) * 1e-3, (X.h_ctl[LC_STAMP + 4] - X.h_ctl[LC_STAMP + 3]) * 1e-3,
-                (X.h_ctl[LC_STAMP + 5] - X.h_ctl[LC_STAMP + 4]) * 1e-3, (X.h_ctl[LC_STAMP + 6] - X.h_ctl[LC_STAMP + 5]) * 1e-3,
-                (X.h_ctl[LC_STAMP + 7] - X.h_ctl[LC_STAMP + 6]) * 1e-3);
+        fprintf(stderr, "[cubature] decide kernel of the last iteration (us): streaming + arrival %.1f, fold %.1f, exchange %.1f, decision %.1f\n",
+                (X.h_ctl[LC_STAMP] - X.h_ctl[LC_STAMP + 4]) * 1e-3, (X.h_ctl[LC_STAMP + 1] - X.h_ctl[LC_STAMP]) * 1e-3,
+                (X.h_ctl[LC_STAMP + 2] - X.h_ctl[LC_STAMP + 1]) * 1e-3, (X.h_ctl[LC_STAMP + 3] - X.h_ctl[LC_STAMP + 2]) * 1e-3);
     if (timing)
         fprintf(stderr, "[cubature] device-resident loop: %lld iterations (%lld cut a batch), %d host visits, %d pool growths, %.2f ms\n",
                 (long long)X.h_ctl[LC_ITER], (long long)X.h_ctl[LC_NSELECT], visits, grows,
@@ -1947,25 +1985,33 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     cub_trace_t* trace = opt ? opt->trace : nullptr;
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
+    const bool timing = getenv("CUBATURE_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     const size_t extra = 24 + (size_t)8 * f + 1;
     const long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    const double t_cap = since();
     CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
     CUB_CUDA_CHECK(W.sel.ensure_scalar(pool.cap), S.msg);
+    const double t_alloc = since();
     int rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
+    const double t_root = since();
     rc = exact_setup(S, X, relTol, absTol, norm);
     if (rc != CUB_OK) return rc;
     exact_bind_pool(S, X);
+    if (timing) fprintf(stderr, "[cubature] start-up (host ms): capacity %.3f, buffers %.3f, root box %.3f, loop state %.3f\n", t_cap, t_alloc - t_cap, t_root - t_alloc, since() - t_root);
     {
         HostWork w{};
         w.n_items = 1;
         w.base = 0;
         w.mode = MODE_PLAIN;
-        rc = S.launch_rule(pool.view(), w);  // Rule.java:64-69: the root region, added to the running sums by the kernel
+        rc = S.launch_rule(pool.view(), w);  // Rule.java:64-69: the root region
         if (rc != CUB_OK) return rc;
     }
     long long* h = X.h_ctl;
     memset(h, 0, (size_t)LC_WORDS * 8);
+    h[LC_DYN_N] = 1;  // the first decide kernel adds the root region (item 0 of an identity batch = slot 0) to the sums
     h[LC_N] = 1;
     h[LC_NGLOBAL] = 1;
     h[LC_NUMEVAL] = P;
@@ -1977,6 +2023,7 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     h[LC_SEQ] = 1;
     CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, h, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
     S.h2d_bytes += LC_WORDS * 8;
+    const double t_run0 = since();
     rc = exact_run(S, X, trace, cap);
     if (rc != CUB_OK) return rc;
     if (X.h_ctl[LC_STATE] == LS_HANDOFF) {
@@ -1984,7 +2031,10 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
         return CUB_OK;
     }
     if (handoff) *handoff = false;
-    return exact_finish(S, X, out, res, trace);
+    const double t_run1 = since();
+    rc = exact_finish(S, X, out, res, trace);
+    if (timing) fprintf(stderr, "[cubature] root launch + control block %.3f ms, loop %.3f ms, finish %.3f ms (host clock)\n", t_run0 - t_root, t_run1 - t_run0, since() - t_run1);
+    return rc;
 }
 
 // Multi-GPU (section 8e), scalar integrands, NVLink peers: replicated phase on every rank, ranked deal, then the same
@@ -2040,6 +2090,8 @@ int integrate_sharded_exact(Session& S, double relTol, double absTol, int norm, 
         X.p.rank = rank;
         for (int r = 0; r < PK_MAX_RANKS; ++r) X.p.xbuf[r] = r < R ? (unsigned long long*)comm->xbuf[r] : nullptr;
         X.h_ctl[LC_N] = N;
+        X.h_ctl[LC_DYN_N] = 0;  // the sums were rebuilt from the shard: nothing pending
+        X.h_ctl[LC_SUB_K] = 0;
         X.h_ctl[LC_CAP] = pool.cap;
         X.h_ctl[LC_STOP_AT] = 0;
         X.h_ctl[LC_STATE] = LS_RUN;
@@ -2290,9 +2342,12 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
         options->trace->n_batches = 0;
         options->trace->n_regions = 0;
     }
+    const auto t_call = std::chrono::steady_clock::now();
+    auto call_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
     Session S;
     rc = S.open(integrand, dim, options ? options->device : -1, tr, stats);
     if (rc != CUB_OK) return rc;
+    const double t_open = call_ms();
     LoopResult res;
     cudaEventRecord(S.ev0, S.stream);
     if (select == CUB_SELECT_HEAP_EXACT)
@@ -2310,8 +2365,15 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
         rc = integrate_device_exact(S, relTol, absTol, norm, maxEval, options, out, &res, X, 0, 0, &handoff);
     } else
         rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, options, out, &res);
+    const double t_body = call_ms();
     cudaEventRecord(S.ev1, S.stream);
     cudaEventSynchronize(S.ev1);
+    if (getenv("CUBATURE_TIMING")) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, S.ev0, S.ev1);
+        fprintf(stderr, "[cubature] call (host ms): session %.3f, body %.3f, closing event %.3f; device events %.3f ms\n", t_open, t_body - t_open,
+                call_ms() - t_body, ms);
+    }
     if (stats) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) stats->device_ms = ms;
@@ -2460,17 +2522,6 @@ int cubature_cuda_bench_rule(cub_integrand_t* integrand, int dim, const double* 
             for (int64_t i = 0; i < n_regions; ++i) row[(size_t)i] = d == 0 ? 0.5 * (hi - lo) / (double)n_regions : 0.5 * (hi - lo);
             CUB_CUDA_CHECK(cudaMemcpy(pool.halfw.as<double>() + (size_t)d * pool.cap, row.data(), (size_t)8 * n_regions, cudaMemcpyHostToDevice), S.msg);
         }
-    }
-    DevBuf acc_buf;
-    if (getenv("CUBATURE_BENCH_ACC") && f == 1) {  // also maintain the exact running sums, as the device-resident loop does
-        CUB_CUDA_CHECK(acc_buf.ensure((size_t)XA_WORDS * 8), S.msg);
-        CUB_CUDA_CHECK(cudaMemset(acc_buf.p, 0, (size_t)XA_WORDS * 8), S.msg);
-        CUB_CUDA_CHECK(cudaMemset(acc_buf.as<unsigned long long>() + XA_M_OFF + XA_M_MINKEY, 0xff, 8), S.msg);
-        const char* eb = getenv("CUBATURE_BENCH_ACC_EBASE");
-        const char* vb = getenv("CUBATURE_BENCH_ACC_VBASE");
-        unsigned long long hint[2] = {(unsigned long long)(eb ? atoi(eb) : 0), (unsigned long long)(vb ? atoi(vb) : 0)};
-        CUB_CUDA_CHECK(cudaMemcpy(acc_buf.as<unsigned long long>() + XA_M_OFF + XA_M_EBASE, hint, 16, cudaMemcpyHostToDevice), S.msg);
-        S.acc = acc_buf.as<unsigned long long>();
     }
     HostWork w{};
     w.n_items = n_regions;

@@ -3,7 +3,7 @@
 //
 // The reference keeps Sum(val), Sum(err) of its heap as incremental doubles (RegionHeap.java:21-36) and decides how many
 // regions to pop from the sequential residual `ee.err -= popped.err` (Rule.java:122-124, :129).  Here both sums are integer
-// accumulators (acc_layout.h), maintained by the rule kernels (acc_device.cuh), so every decision is the one the reference's
+// accumulators (acc_layout.h), maintained by the decide kernel (acc_device.cuh), so every decision is the one the reference's
 // loop takes when its sums carry no rounding error: independent of the order in which threads, CTAs or GPUs contribute, hence
 // identical for any grid size and any number of ranks by construction.  The comparison `residual < tolerance` is exact: the
 // residual is a big integer (exact_acc.h) converted to a double truncated toward zero, for which `double < tol` is the exact
@@ -11,12 +11,14 @@
 // orc_set_exact_sums) takes literally these decisions; where they differ from the reference's drifting sums the difference
 // is an artefact of the reference's accumulated rounding (reported as cub_stats_t.ambiguous_decisions).
 //
-//   k_exact_decide (one CTA)   totals from the bins, loop condition and convergence (Rule.java:72-79), evaluation budget,
-//                              the pop-everything shortcut (exact smallest errmax), else the binade in which the batch ends
-//                              (level 0 of the radix select comes for free: the error bins ARE its histogram)
-//   k_exact_select (coop grid) radix select inside that binade on the 52 fraction bits (11+11+11+11+8), integer bucket sums,
-//                              stable compaction of the popped slots; retires at once when there is nothing to cut
-//   rule kernel (NVRTC)        bisects + evaluates the batch, removes the parents from and adds the children to the sums
+//   k_exact_decide (grid)      phase 1, all CTAs: stream over the children the last rule launch wrote and over the (val, err)
+//                              pairs of the parents the last selection popped, and add / subtract them (acc_device.cuh);
+//                              phase 2, the CTA that finishes last: totals, loop condition and convergence (Rule.java:72-79),
+//                              evaluation budget, the pop-everything shortcut (exact smallest errmax)
+//   k_exact_select (coop grid) walk down the binades, radix select inside the threshold binade on the 52 fraction bits
+//                              (8+8+4x9), integer bucket sums, stable compaction of the popped slots (and a copy of their
+//                              val / err for the next decide); retires at once when there is nothing to cut
+//   rule kernel (NVRTC)        bisects + evaluates the batch; knows nothing about the sums
 // Sharded pools (R > 1): the ranks exchange their bins / histograms through peer-mapped buffers inside these kernels
 // (push over NVLink, flag, spin); integer sums need no fixed rank order.
 #include <cooperative_groups.h>
@@ -145,6 +147,7 @@ __device__ void ix_big_tighten(XaBig* a) {  // normalized number: shrink [jlo, j
 }
 
 __device__ void ix_finish(const IterXParams& p, int state, int err) {
+    p.ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
     p.ctl[LC_STATE] = state;
     p.ctl[LC_ERR] = err;
     p.ctl[LC_DYN_N] = 0;
@@ -156,18 +159,88 @@ __device__ void ix_finish(const IterXParams& p, int state, int err) {
 #define IX_PUB_JHI (XA_LIMBS + 1)
 #define IX_PUB_TOPE (XA_LIMBS + 2)
 
-__global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
+// Two builds of the same code: <4> for large pools (phase 1 wants occupancy; phase 2's single thread spills, which does not
+// matter next to a millisecond of streaming) and <1> for small ones (no spills: phase 2 is the latency of the iteration).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXParams p) {
     __shared__ DecideShared S;
+    __shared__ CubAccWin<IX_THREADS> win;
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     long long* ctl = p.ctl;
     if (ctl[LC_STATE] != LS_RUN) {  // finished or paused: this launch and the ones queued behind it do nothing
-        if (tid == 0) {
+        if (blockIdx.x == 0 && tid == 0) {
             ctl[LC_DYN_N] = 0;
             ctl[LC_SELECT] = 0;
         }
         return;
     }
-    if (tid == 0) ctl[LC_STAMP] = (long long)ix_timer_ns();
+    if (blockIdx.x == 0 && tid == 0) ctl[LC_STAMP + 4] = (long long)ix_timer_ns();
+    // ---- phase 1 (every CTA): what happened to the pool since the last decision ---------------------------------------
+    // the children of the last batch enter the sums (item j of the rule launch: slot arithmetic of CUB_MODE_BISECT), the
+    // popped parents leave them (their val / err were copied by the select kernel before the left children overwrote them)
+    {
+        const long long n_add = ctl[LC_DYN_N], use_list = ctl[LC_DYN_LIST], base = ctl[LC_DYN_BASE], n_sub = ctl[LC_SUB_K];
+        const long long n_pairs = n_add >> 1;  // (left, right) children of one parent; an odd item is the root region
+        const long long first = (long long)blockIdx.x * IX_THREADS, stride = (long long)gridDim.x * IX_THREADS;
+        if (first < n_pairs + (n_add & 1) || first < n_sub) {
+            cub_acc_begin(p.acc, &win);
+            CubAccKeys keys;
+            cub_acc_keys_init(keys);
+            const double* __restrict__ val = p.pool.val;
+            const double* __restrict__ err = p.pool.err;
+            const double* __restrict__ rval = val + base;
+            const double* __restrict__ rerr = err + base;
+            for (long long i0 = first + tid; i0 < n_pairs; i0 += 2 * stride) {
+                const long long i1 = i0 + stride;
+                const bool two = i1 < n_pairs;
+                const long long l0 = use_list ? (long long)p.list[i0] : i0, l1 = two ? (use_list ? (long long)p.list[i1] : i1) : l0;
+                const double v0 = val[l0], e0 = err[l0], v1 = rval[i0], e1 = rerr[i0];
+                double v2 = 0.0, e2 = 0.0, v3 = 0.0, e3 = 0.0;
+                if (two) {
+                    v2 = val[l1];
+                    e2 = err[l1];
+                    v3 = rval[i1];
+                    e3 = rerr[i1];
+                }
+                cub_acc_region(&win, p.acc, keys, v0, e0, 1);
+                cub_acc_region(&win, p.acc, keys, v1, e1, 1);
+                if (two) {
+                    cub_acc_region(&win, p.acc, keys, v2, e2, 1);
+                    cub_acc_region(&win, p.acc, keys, v3, e3, 1);
+                }
+            }
+            if ((n_add & 1) && first + tid == n_pairs) {
+                const long long l0 = use_list ? (long long)p.list[n_pairs] : n_pairs;
+                cub_acc_region(&win, p.acc, keys, val[l0], err[l0], 1);
+            }
+            for (long long i0 = first + tid; i0 < n_sub; i0 += 2 * stride) {
+                const long long i1 = i0 + stride;
+                const bool two = i1 < n_sub;
+                const double v0 = p.stash_val[i0], e0 = p.stash_err[i0];
+                const double v1 = two ? p.stash_val[i1] : 0.0, e1 = two ? p.stash_err[i1] : 0.0;
+                cub_acc_region(&win, p.acc, keys, v0, e0, -1);
+                if (two) cub_acc_region(&win, p.acc, keys, v1, e1, -1);
+            }
+            cub_acc_keys_store(&win, keys);
+            cub_acc_end(p.acc, &win);
+        }
+    }
+    // ---- the CTA that arrives last goes on (the others are done) ----------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&p.bar[1], 1ULL);
+        s_last = prev + 1ULL == (unsigned long long)gridDim.x ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        p.bar[1] = 0ULL;
+        ctl[LC_SUB_K] = 0;
+        ctl[LC_STAMP] = (long long)ix_timer_ns();
+    }
     const long long N = ctl[LC_N], Nglobal = ctl[LC_NGLOBAL], numEval = ctl[LC_NUMEVAL], maxEval = ctl[LC_MAXEVAL], P = ctl[LC_P];
     const bool budget_left = maxEval == 0 || numEval < maxEval;  // Rule.java:72
     // pops the evaluation budget allows (checked after every pop, Rule.java:133)
@@ -177,18 +250,6 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         Kcap = k < 1 ? 1 : k;
         if (Kcap > Nglobal) Kcap = Nglobal;
     }
-    if (budget_left) {
-        // pauses are taken before any exchange, so that a resumed launch starts the iteration from scratch on every rank
-        if (ctl[LC_STOP_AT] > 0 && Nglobal >= ctl[LC_STOP_AT]) {
-            if (tid == 0) ix_finish(p, LS_HANDOFF, 0);
-            return;
-        }
-        const long long kmax = N < Kcap ? N : Kcap;
-        if (N + kmax > ctl[LC_CAP]) {
-            if (tid == 0) ix_finish(p, LS_GROW, 0);
-            return;
-        }
-    }
     unsigned long long* acc = p.acc;
     unsigned long long* tot = acc + XA_TOT_OFF;
     // ---- collect the deltas (and clear them for the next launch) -----------------------------------------------------
@@ -196,14 +257,14 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         long long s = 0;
         for (int r = 0; r < XA_REPL; ++r) {
             unsigned long long* c = acc + XA_D_OFF + (size_t)r * XA_CELLS + tid;
-            s += (long long)*c;
+            s += (long long)__ldcg(c);  // written by the other CTAs' atomics: read at L2
             *c = 0ULL;
         }
         S.dcell[tid] = s;
     }
     for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
-        S.far_e[j] = (long long)acc[XA_FAR_E_OFF + j];
-        S.far_v[j] = (long long)acc[XA_FAR_V_OFF + j];
+        S.far_e[j] = (long long)__ldcg(&acc[XA_FAR_E_OFF + j]);
+        S.far_v[j] = (long long)__ldcg(&acc[XA_FAR_V_OFF + j]);
         acc[XA_FAR_E_OFF + j] = 0ULL;
         acc[XA_FAR_V_OFF + j] = 0ULL;
         S.E.l[j] = tot[XA_TOT_E + j];
@@ -214,15 +275,15 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
     bool far_mine = false;
     for (int j = tid; j < XA_LIMBS; j += IX_THREADS) far_mine = far_mine || S.far_e[j] != 0 || S.far_v[j] != 0;
     const bool far_any = __syncthreads_or(far_mine ? 1 : 0) != 0;
-    unsigned long long misc[8];
+    unsigned long long misc[8], my_misc[8];
     unsigned long long minkey = 0, my_count = 0, topkey = 0;
     int v_neg = 0;
     if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) misc[q] = acc[XA_M_OFF + q];
-        minkey = acc[XA_M_OFF + XA_M_MINKEY];
-        topkey = acc[XA_M_OFF + XA_M_TOPKEY];
-        const int ebase = (int)acc[XA_M_OFF + XA_M_EBASE], vbase = (int)acc[XA_M_OFF + XA_M_VBASE];
+        for (int q = 0; q < 8; ++q) misc[q] = my_misc[q] = __ldcg(&acc[XA_M_OFF + q]);
+        minkey = __ldcg(&acc[XA_M_OFF + XA_M_MINKEY]);
+        topkey = __ldcg(&acc[XA_M_OFF + XA_M_TOPKEY]);
+        const int ebase = (int)__ldcg(&acc[XA_M_OFF + XA_M_EBASE]), vbase = (int)__ldcg(&acc[XA_M_OFF + XA_M_VBASE]);
         v_neg = (int)tot[XA_TOT_MISC + 0];
         my_count = tot[XA_TOT_MISC + 1] + (unsigned long long)S.dcell[XA_C_COUNT];
         // limbs that can be touched: the stored totals, the delta window (256 bits + 64-bit cells), carries
@@ -279,7 +340,7 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         tot[XA_TOT_MISC + 4] = (unsigned long long)S.V.jlo;
         tot[XA_TOT_MISC + 5] = (unsigned long long)S.V.jhi;
         // window hints for the next rule launch from the largest values of the last one
-        const unsigned long long ek = acc[XA_M_OFF + XA_M_EMAXKEY], vk = acc[XA_M_OFF + XA_M_VMAXKEY];
+        const unsigned long long ek = __ldcg(&acc[XA_M_OFF + XA_M_EMAXKEY]), vk = __ldcg(&acc[XA_M_OFF + XA_M_VMAXKEY]);
         if (ek) {
             const int b = xa_lsb_pos((int)(ek >> 52)) + 8 - XA_WIN_MAX_SHIFT;
             acc[XA_M_OFF + XA_M_EBASE] = (unsigned long long)(b < 0 ? 0 : b);
@@ -296,6 +357,20 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
     for (int j = tid; j < XA_LIMBS; j += IX_THREADS) {
         tot[XA_TOT_E + j] = S.E.l[j];
         tot[XA_TOT_V + j] = S.V.l[j];
+    }
+    __syncthreads();  // (thread 0 may reset the totals below)
+    if (budget_left) {
+        // pauses are taken before any exchange, so that a resumed launch starts the iteration from scratch on every rank (the
+        // sums are up to date: a resumed launch finds nothing left to fold)
+        if (ctl[LC_STOP_AT] > 0 && Nglobal >= ctl[LC_STOP_AT]) {
+            if (tid == 0) ix_finish(p, LS_HANDOFF, 0);
+            return;
+        }
+        const long long kmax = N < Kcap ? N : Kcap;
+        if (N + kmax > ctl[LC_CAP]) {
+            if (tid == 0) ix_finish(p, LS_GROW, 0);
+            return;
+        }
     }
     unsigned long long Ntot = my_count;
     if (p.R > 1) {
@@ -450,7 +525,17 @@ __global__ void __launch_bounds__(IX_THREADS, 1) k_exact_decide(IterXParams p) {
         ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Nglobal;
         ctl[LC_NBATCH] += 1;
         ctl[LC_ITER] += 1;
-        acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;  // every region leaves the pool
+        // every region leaves the pool (one RegionHeap.poll per region): this rank's sums restart from zero; a non-finite
+        // value that leaves turns the reference's running sum into NaN for good (Inf - Inf)
+        acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;
+        for (int j = 0; j < 2 * XA_LIMBS; ++j) tot[j] = 0ULL;
+        tot[XA_TOT_MISC + 0] = 0ULL;
+        tot[XA_TOT_MISC + 1] = 0ULL;
+        tot[XA_TOT_MISC + 2] = tot[XA_TOT_MISC + 4] = (unsigned long long)(XA_LIMBS - 1);
+        tot[XA_TOT_MISC + 3] = tot[XA_TOT_MISC + 5] = 0ULL;
+        if (my_misc[XA_M_ENAN] | my_misc[XA_M_EINF]) acc[XA_M_OFF + XA_M_ESTICKY] = my_misc[XA_M_ESTICKY] | 2ULL;
+        if (my_misc[XA_M_VNAN] | my_misc[XA_M_VPINF] | my_misc[XA_M_VNINF]) acc[XA_M_OFF + XA_M_VSTICKY] = my_misc[XA_M_VSTICKY] | 2ULL;
+        for (int q = 0; q < 5; ++q) acc[XA_M_OFF + q] = 0ULL;
         ctl[LC_STAMP + 3] = (long long)ix_timer_ns();
         return;
     }
@@ -1168,6 +1253,10 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             if (is_gt || (is_eq && eq_before < tie_take_local)) {
                 const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
                 p.list[pos] = (int)(i_lo + u);
+                // the parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28): the next decide kernel subtracts
+                // this copy, the slot itself is about to be overwritten by the left child
+                p.stash_val[pos] = p.pool.val[i_lo + u];
+                p.stash_err[pos] = err[i_lo + u];
             }
             gt_before += is_gt;
             eq_before += is_eq;
@@ -1185,6 +1274,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         ctl[LC_DYN_LIST] = 1;
         ctl[LC_DYN_BASE] = n;
         ctl[LC_K] = Kl;
+        ctl[LC_SUB_K] = Kl;
         ctl[LC_KGLOBAL] = Kg;
         ctl[LC_N] = n + Kl;
         ctl[LC_NGLOBAL] = Nglobal + Kg;
@@ -1205,8 +1295,11 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
 __global__ void __launch_bounds__(IX_THREADS) k_acc_rebuild(PoolView pool, long long n, unsigned long long* acc) {
     __shared__ CubAccWin<IX_THREADS> win;
     cub_acc_begin(acc, &win);
+    CubAccKeys keys;
+    cub_acc_keys_init(keys);
     for (long long i = (long long)blockIdx.x * IX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * IX_THREADS)
-        cub_acc_thread(&win, acc, 0, 0.0, 0.0, pool.val[i], pool.err[i]);
+        cub_acc_region(&win, acc, keys, pool.val[i], pool.err[i], 1);
+    cub_acc_keys_store(&win, keys);
     cub_acc_end(acc, &win);
 }
 
@@ -1218,8 +1311,21 @@ __global__ void k_abort_peers(int R, IterXParams p) {
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------------------
-cudaError_t ix_decide(const IterXParams& p, cudaStream_t s) {
-    k_exact_decide<<<1, IX_THREADS, 0, s>>>(p);
+static int g_decide_blocks_per_sm = -1;
+int ix_decide_max_blocks(int n_sms) {
+    if (g_decide_blocks_per_sm < 0) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_exact_decide<4>, IX_THREADS, 0);
+        g_decide_blocks_per_sm = nb > 0 ? (nb > 4 ? 4 : nb) : 1;
+    }
+    return n_sms * g_decide_blocks_per_sm;
+}
+cudaError_t ix_decide(const IterXParams& p, int n_blocks, int n_sms, cudaStream_t s) {
+    if (n_blocks < 1) n_blocks = 1;
+    if (n_blocks <= n_sms)
+        k_exact_decide<1><<<(unsigned)n_blocks, IX_THREADS, 0, s>>>(p);
+    else
+        k_exact_decide<4><<<(unsigned)n_blocks, IX_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 static int g_select_blocks_per_sm = -1, g_select_max_blocks = 1;

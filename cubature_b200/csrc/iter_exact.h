@@ -1,7 +1,8 @@
 // iter_exact.h -- the device-resident refinement loop for scalar integrands (iter_exact.cu): loop-control block, selection
 // state and host launchers.  One iteration of Rule.cubature (Rule.java:72-142) is three launches that need no host
-// decision in between -- decide (1 CTA), select (cooperative grid; retires at once when the batch is the whole pool),
-// bisect + rule (persistent grid, sized by the control block) -- so the host enqueues several iterations per visit.
+// decision in between -- decide (streams over what the last iteration changed, then one CTA decides), select (cooperative
+// grid; retires at once when the batch is the whole pool), bisect + rule (persistent grid, sized by the control block) --
+// so the host enqueues several iterations per visit.
 #ifndef CUB_ITER_EXACT_H
 #define CUB_ITER_EXACT_H
 
@@ -12,7 +13,8 @@
 
 // ---- loop-control block: 8-byte words in device memory ---------------------------------------------------------------
 enum {
-    LC_DYN_N = 0,     // rule kernel: number of work items (CubWork::dyn[0]); 0 = nothing to do
+    LC_DYN_N = 0,     // rule kernel: number of work items (CubWork::dyn[0]); 0 = nothing to do.  The next decide kernel adds
+                      //   exactly these items to the running sums (the host seeds 1: the root region)
     LC_DYN_LIST = 1,  //   1: parents come from the popped list, 0: identity (the whole pool is popped)
     LC_DYN_BASE = 2,  //   first slot of the right children
     LC_N = 3,         // regions in this rank's pool
@@ -38,6 +40,7 @@ enum {
     LC_EVAL_LOCAL = 23,  // regions evaluated by this rank
     LC_DBG0 = 24,
     LC_DBG1 = 25,
+    LC_SUB_K = 26,  // popped parents whose (val, err) copies the next decide kernel has to subtract from the sums
     LC_STAMP = 32,  // [8] time stamps of the decide kernel's phases (CUBATURE_TIMING)
     LC_WORDS = 48,
 };
@@ -75,18 +78,22 @@ struct IterXParams {
     SelX* selx;
     unsigned long long* hset;  // [IX_HSET_WORDS], zero between launches
     unsigned long long* blk;   // [3 * maxG + 8] per-CTA counters of the compaction
-    unsigned long long* bar;   // arrival counter of the select kernel's grid barrier (cleared by the decide kernel)
+    unsigned long long* bar;   // [0] arrival counter of the select kernel's grid barrier (cleared by the decide kernel),
+                               // [1] arrival counter of the decide kernel's CTAs
     unsigned long long* gbins; // [XA_WORDS] combined bins of the partition (sharded pool)
     unsigned long long* cand_key;  // [cap]
     int* cand_idx;                 // [cap]
     int* list;                     // [cap] popped slots
+    double* stash_val;             // [cap] val / err of the popped regions in list order (stash_err shares cand_key's storage:
+    double* stash_err;             //   the candidates are dead when the compaction writes it)
     double absTol, relTol;
     int norm;
     int R, rank;
     unsigned long long* xbuf[PK_MAX_RANKS];
 };
 
-cudaError_t ix_decide(const IterXParams& p, cudaStream_t s);
+cudaError_t ix_decide(const IterXParams& p, int n_blocks, int n_sms, cudaStream_t s);
+int ix_decide_max_blocks(int n_sms);
 cudaError_t ix_select(const IterXParams& p, int n_blocks, cudaStream_t s);
 int ix_select_max_blocks(int n_sms);
 // acc := exact sums of the first n regions of the pool (after dealing a pool out to the ranks; consistency checks)

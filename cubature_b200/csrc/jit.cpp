@@ -144,7 +144,7 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     // branch-free reciprocal fast path of the rational built-in families (detmath.h: dm_rcp_flag; the kernel re-evaluates a
     // region with the IEEE division when an argument leaves the fast path's exact range)
     tu << "#ifndef CUB_FAST_RCP\n#define CUB_FAST_RCP 1\n#endif\n";
-    tu << "#include \"acc_layout.h\"\n#include \"acc_device.cuh\"\n#include \"detmath.h\"\n#include \"integrands.h\"\n";
+    tu << "#include \"detmath.h\"\n#include \"integrands.h\"\n";
     if (integ->family == CUB_FAM_USER) {
         tu << "#line 1 \"user_integrand.cu\"\n" << integ->user_src << "\n";
         tu << "struct CubUserIntegrand {\n"

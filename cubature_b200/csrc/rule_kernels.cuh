@@ -26,7 +26,6 @@
 #ifndef CUBATURE_RULE_KERNELS_CUH
 #define CUBATURE_RULE_KERNELS_CUH
 
-#include "acc_device.cuh"
 #include "detmath.h"
 #include "integrands.h"
 
@@ -70,9 +69,6 @@ struct CubWork {
     double* stage_val;  // [CUB_FDIM][stage_stride]
     double* stage_err;  // [CUB_FDIM][stage_stride]
     long long stage_stride;
-    // optional exact running sums of the pool (acc_layout.h; scalar integrands): every evaluated region is added, and in
-    // BISECT mode the parent it replaces is removed first (RegionHeap.java:21-36 without the drift)
-    unsigned long long* acc;
 };
 
 struct CubParams {
@@ -117,11 +113,9 @@ __device__ __forceinline__ long long cub_item_slot(const CubWork& w, long long i
 // Loads the geometry of work item `i` (bisecting the parent when asked to) and returns its slot.
 // All loads of a warp happen before any of its stores (__syncwarp) because in BISECT mode the two
 // children of one parent sit in adjacent lanes and the left child overwrites what the right reads.
-// *parent_out (when given): slot of the parent this thread replaces (left child of a bisection), else -1.
 __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, const CubWork& w, long long i, bool active,
-                                                   double (&c)[CUB_DIM], double (&h)[CUB_DIM], long long* parent_out = nullptr) {
+                                                   double (&c)[CUB_DIM], double (&h)[CUB_DIM]) {
     long long slot = 0;
-    if (parent_out) *parent_out = -1;
     if (active) {
         slot = cub_item_slot(w, i);
         if (w.mode != CUB_MODE_BISECT) {
@@ -145,13 +139,6 @@ __device__ __forceinline__ long long cub_load_item(const CubPoolView& pool, cons
                 if (d == s) {
                     h[d] = h[d] * 0.5;                          // Region.java:32
                     c[d] = right ? c[d] + h[d] : c[d] - h[d];   // Region.java:35-36
-                }
-            }
-            if (parent_out && !right) {
-                *parent_out = parent;
-                if (w.acc) {  // the caller reads the parent's val / err after the rule: have them in L1 by then
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.val + parent));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.err + parent));
                 }
             }
         }
@@ -367,17 +354,13 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
     // so a launch needs no host knowledge of the batch size (device-sized launches: CubWork::dyn).
     const CubWork work = cub_resolve(work_in);
     const long long n = work.n_items;
-    __shared__ CubAccWin<CUB_GM_THREADS> win_storage;
-    CubAccWin<CUB_GM_THREADS>* const win = work.acc ? &win_storage : nullptr;
-    if (win) cub_acc_begin(work.acc, win);
     for (long long tile = blockIdx.x; tile * CUB_GM_THREADS < n; tile += gridDim.x) {
         const long long i = tile * CUB_GM_THREADS + threadIdx.x;
         const bool active = i < n;
         double c[CUB_DIM], h[CUB_DIM];
 #pragma unroll
         for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
-        long long parent = -1;
-        const long long slot = cub_load_item(pool, work, i, active, c, h, &parent);
+        const long long slot = cub_load_item(pool, work, i, active, c, h);
         double result = 0.0, err = 0.0;
         int split = 0;
         if (active) {
@@ -389,16 +372,6 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
                 err = r.err;
                 split = r.split;
             }
-        }
-        if (win && active) {
-            // running sums: the child enters (RegionHeap.add, RegionHeap.java:30-36), the parent a left child replaces leaves
-            // (poll, :21-28) -- its slot holds its val / err until the stores below
-            double pval = 0.0, perr = 0.0;
-            if (parent >= 0) {
-                pval = pool.val[parent];
-                perr = pool.err[parent];
-            }
-            cub_acc_thread(win, work.acc, parent >= 0 ? 1 : 0, pval, perr, result, err);
         }
         if (active) {
             double emax = 0.0;  // Rule.java:281-289
@@ -413,7 +386,6 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
             }
         }
     }
-    if (win) cub_acc_end(work.acc, win);
 }
 #endif  // CUB_FDIM == 1
 #endif  // CUB_DIM >= 2
@@ -500,20 +472,13 @@ extern "C" __global__ void __launch_bounds__(128)
 cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
     const CubWork work = cub_resolve(work_in);
     const long long n = work.n_items;
-#if CUB_FDIM == 1
-    __shared__ CubAccWin<128> win_storage;
-    CubAccWin<128>* win = nullptr;
-    if (work.acc) win = &win_storage;
-    if (win) cub_acc_begin(work.acc, win);
-#endif
     for (long long tile = blockIdx.x; tile * 128 < n * CUB_FDIM; tile += gridDim.x) {  // persistent, see cub_gm_scalar
         const long long t = tile * 128 + threadIdx.x;
         const bool active = t < n * CUB_FDIM;
         const long long i = active ? t % n : 0;
         const int j = active ? (int)(t / n) : 0;
         double cc[1] = {0.0}, hh[1] = {0.0};
-        long long parent = -1;
-        const long long slot = cub_load_item(pool, work, i, active, cc, hh, &parent);
+        const long long slot = cub_load_item(pool, work, i, active, cc, hh);
         double val = 0.0, err = 0.0;
         if (active) {
             const double c = cc[0], h = hh[0];
@@ -541,16 +506,6 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
             }
             cub_gk15_sums(q, h, &val, &err);
         }
-#if CUB_FDIM == 1
-        if (win && active) {  // running sums, see cub_gm_scalar
-            double pval = 0.0, perr = 0.0;
-            if (parent >= 0) {
-                pval = pool.val[parent];
-                perr = pool.err[parent];
-            }
-            cub_acc_thread(win, work.acc, parent >= 0 ? 1 : 0, pval, perr, val, err);
-        }
-#endif
         if (active) {
             pool.val[(long long)j * pool.cap + slot] = val;
             pool.err[(long long)j * pool.cap + slot] = err;
@@ -567,9 +522,6 @@ cub_gk_separable(CubPoolView pool, CubWork work_in, const __grid_constant__ CubP
             }
         }
     }
-#if CUB_FDIM == 1
-    if (win) cub_acc_end(work.acc, win);
-#endif
 }
 #endif  // CUB_FDIM == 1 || CUB_SEPARABLE
 #endif  // CUB_DIM == 1

@@ -67,8 +67,7 @@ double xa_window_sum(const double* x, const int* sgn, int n, int T, int base, in
         const xa_u64 m = xa_mantissa(b);
         if (!m) continue;
         const int pos = xa_lsb_pos((int)((b >> 52) & 2047ULL));
-        xaw_u64(&a)[XA_WLIMBS] = *reinterpret_cast<xaw_u64(*)[XA_WLIMBS]>(&w[(size_t)(i % T) * XA_WLIMBS]);
-        if (!xaw_addend(a, m, pos, base, neg)) {
+        if (!xaw_accumulate(&w[(size_t)(i % T)], T, m, pos, base, neg)) {  // limb-major, like the shared-memory layout
             int j;
             long long c[3];
             xaw_far_cells(m, pos, neg, &j, c);
@@ -81,7 +80,7 @@ double xa_window_sum(const double* x, const int* sgn, int n, int T, int base, in
     if (n_far) *n_far = nf;
     long long cell[XA_HALVES] = {0};
     for (int t = 0; t < T; ++t)
-        for (int h = 0; h < XA_HALVES; ++h) cell[h] += xaw_cell(w[(size_t)t * XA_WLIMBS + (h >> 1)], h);
+        for (int h = 0; h < XA_HALVES; ++h) cell[h] += xaw_cell(w[(size_t)(h >> 1) * T + t], h);
     XaBig P, Q;
     P.clear();
     Q.clear();
