@@ -196,6 +196,70 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def time_to_tol_block(cb, cases, dist, local_rank, comm, world):
+    """BASELINE's second headline: wall time to relTol 1e-8 for the six Genz families at dim 5 (config C3), at this number of
+    GPUs (a pool is only sharded once it is large enough, so small problems run replicated).  Outside the timed region of the
+    regions/s metric.  Per family: second call (the first one compiles the rule kernel), device time = max over ranks."""
+    import torch
+    out = {}
+    dim = 5
+    for name, fam in cases.GENZ.items():
+        p = cases.genz_params(name, dim)
+        ig = cb.Integrand.builtin(fam, dim, 1, p)
+        args = ([0.0] * dim, [1.0] * dim, 1e-8, NAN, cb.CubatureError.INDIVIDUAL, 0)
+        cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm)
+        best = None
+        for _ in range(3):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r, st, _ = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm)
+            wall = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([st.device_ms, wall, st.rule_ms], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev, wall, rule = [float(v) for v in t.cpu()]
+            if best is None or wall < best["wall_ms"]:
+                best = {"wall_ms": round(wall, 3), "device_ms": round(dev, 3), "rule_kernel_ms": round(rule, 3), "converged": bool(st.converged),
+                        "regions": int(st.num_regions), "num_eval": int(st.num_eval), "iterations": int(st.iterations),
+                        "val": float(r[0][0]), "err": float(r[1][0]), "ambiguous_decisions": int(st.ambiguous_decisions)}
+        out[name] = best
+    return out
+
+
+def parity_block(cb, cases, dist, local_rank, comm, world, rank):
+    """Every bench record doubles as a parity witness (outside the timed region).
+    N > 1: the bench integrand with maxEval 3e9 on the sharded pool against the same call on this rank's GPU alone -- scalar
+    integrands run on exact integer sums, so batches, numEval, value and error must be bit-identical.
+    Every N: the device loop against the host-heap mode (the literal replay of the reference's loop with the JDK heap and its
+    drifting sums) on a 5-D Gaussian -- same batches and counts, value to 1e-12."""
+    import torch
+    out = {}
+    p = cases.genz_params("gaussian", 5)
+    ig = cb.Integrand.builtin(cases.GENZ["gaussian"], 5, 1, p)
+    args = ([0.0] * 5, [1.0] * 5, 1e-6, NAN, cb.CubatureError.INDIVIDUAL, 0)
+    r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, trace_batches=4096)
+    r2, s2, t2 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, trace_batches=4096, select=cb.Select.HEAP_EXACT)
+    out["device_vs_host_heap"] = {"case": "genz_gaussian d=5 relTol=1e-6", "batches_equal": t1.batches == t2.batches,
+                                  "numEval_equal": s1.num_eval == s2.num_eval, "regions_equal": s1.num_regions == s2.num_regions,
+                                  "rel_diff": abs(r1[0][0] - r2[0][0]) / abs(r2[0][0]), "ambiguous_decisions": int(s1.ambiguous_decisions)}
+    if world > 1:
+        ig = cb.Integrand.builtin(cb.Family.GENZ_CORNER_PEAK, DIM, 1, workload_params())
+        args = ([0.0] * DIM, [1.0] * DIM, 1e-13, NAN, cb.CubatureError.INDIVIDUAL, int(3e9))
+        r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, trace_batches=4096)
+        dist.barrier()
+        r2, s2, t2 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm, trace_batches=4096)
+        ok = [t1.batches == t2.batches, s1.num_eval == s2.num_eval, r1[0][0] == r2[0][0] and r1[1][0] == r2[1][0]]
+        flags = torch.tensor([0 if v else 1 for v in ok], device="cuda")
+        dist.all_reduce(flags)
+        flags = [int(v) == 0 for v in flags.cpu()]
+        out["sharded_vs_one_gpu"] = {"case": "bench integrand, maxEval=3e9, %d ranks vs 1" % world, "batches_equal": flags[0], "numEval_equal": flags[1],
+                                     "bit_identical": flags[2], "rel_diff": abs(r1[0][0] - r2[0][0]) / abs(r1[0][0]),
+                                     "ambiguous_decisions": int(s2.ambiguous_decisions)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +269,8 @@ def main():
     ap.add_argument("--max-eval", type=float, default=1e11, help="TOTAL maxEval of one step (all GPUs)")
     ap.add_argument("--cpu-sample", type=float, default=1.5e8, help="maxEval of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-time-to-tol", action="store_true", help="skip the time-to-relTol-1e-8 block (six Genz families, dim 5)")
+    ap.add_argument("--no-parity-check", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 1)
@@ -277,6 +343,10 @@ def main():
         h2d += st.h2d_bytes
         d2h += st.d2h_bytes
     clocks = sampler.stop() if rank == 0 else None
+    ambiguous_last = st.ambiguous_decisions
+    import cases
+    ttt = None if args.no_time_to_tol else time_to_tol_block(cb, cases, dist, local_rank, comm, world)
+    parity = None if args.no_parity_check else parity_block(cb, cases, dist, local_rank, comm, world, rank)
 
     t_dev = torch.tensor([sum(dev_ms), sum(wall_s) * 1e3, sum(rule_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -310,14 +380,21 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # nominal FP64 FMA peak: 64 FMA lanes per SM per clock at the maximum SM clock
+    n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp64_nominal = n_sms * 64 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
     line = {
         "metric": "genz_malik_regions_per_s", "value": value, "unit": "regions/s", "n_gpus": world, "steps": steps,
         "warmup": args.warmup, "ms_per_step": tot_dev_ms / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "genz_corner_peak_d6 [0,1]^6 relTol=1e-13 maxEval=%d total (BASELINE config C5), select=device" % max_eval,
                    "regions_per_step": regions, "points_per_region": P, "l2": "pool per step >> 126 MB L2, no flush needed",
-                   "parallelism": ("pool sharded over %d GPUs, one cooperative kernel per iteration with the exchange over NVLink peer memory "
-                                   "(no NCCL call in the loop)" % world) if world > 1 else "1 GPU"},
+                   "parallelism": ("pool sharded over %d GPUs; the decide / select kernels of every iteration exchange sums and histograms over "
+                                   "NVLink peer memory (no NCCL call and no host decision in the loop)" % world) if world > 1 else "1 GPU",
+                   "loop": "device-resident: decide / select / rule enqueued ahead in batches of 8 iterations, host reads a 384-byte control block "
+                           "behind each batch while the next is queued",
+                   "cpu_arm": "cpu_baseline and --impl reference time the CPU restatement of the reference on a bounded sample of this job "
+                              "(maxEval=%d instead of %d): a stated baseline, not the target" % (int(args.cpu_sample), max_eval)},
         "fevals_per_s": value * P,
         "result": {"val": float(result[0][0]), "err": float(result[1][0])},
         "e2e": {"value": e2e, "unit": "regions/s", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
@@ -330,6 +407,9 @@ def main():
                      "traffic": TRAFFIC_REGION * regions / max(1, rule_launches_per_step),
                      "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak), best 10 ms launch; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_sustained": fp64_sustained,
+                     "peak_nominal": fp64_nominal, "frac_of_nominal": achieved_tflops / fp64_nominal if fp64_nominal else None,
+                     "traffic_source": "constant: 185 B per evaluated region x regions per average launch, from the ncu --set full capture "
+                                       "profiles/r01b_ncu_gm_scalar_raw.csv (dram read + write of one bisecting launch); not measured in this run",
                      "flops_per_region": F_REGION, "rule_kernel_ms_per_step": tot_rule_ms / steps,
                      "rule_regions_per_s_per_gpu": rule_regions_per_s,
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
@@ -338,7 +418,13 @@ def main():
         # rank 0's device time of every timed step (a late host thread on one rank shows up as one long step on all ranks)
         "rank0_step_ms": [round(float(v), 3) for v in dev_ms],
         "per_rank": [{"regions_evaluated": int(p[0]), "rule_ms": p[1], "device_ms": p[2]} for p in per_rank],
+        "ambiguous_decisions_per_step": int(ambiguous_last),
     }
+    if ttt is not None:
+        line["time_to_tol_ms"] = {"config": "BASELINE config C3: six Genz families, dim 5, relTol 1e-8, INDIVIDUAL, no maxEval; best wall of 3 calls after "
+                                            "a compile call; device_ms = max over ranks", "n_gpus": world, "families": ttt}
+    if parity is not None:
+        line["parity_check"] = parity
     if not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_baseline_record(args.cpu_sample)
     print(json.dumps(line))

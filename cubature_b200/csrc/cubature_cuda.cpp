@@ -1941,6 +1941,17 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
         fprintf(stderr, "[cubature] decide kernel of the last iteration (us): streaming + arrival %.1f, fold %.1f, exchange %.1f, decision %.1f\n",
                 (X.h_ctl[LC_STAMP] - X.h_ctl[LC_STAMP + 4]) * 1e-3, (X.h_ctl[LC_STAMP + 1] - X.h_ctl[LC_STAMP]) * 1e-3,
                 (X.h_ctl[LC_STAMP + 2] - X.h_ctl[LC_STAMP + 1]) * 1e-3, (X.h_ctl[LC_STAMP + 3] - X.h_ctl[LC_STAMP + 2]) * 1e-3);
+    if (timing) {
+        const long long* t = X.h_ctl + LC_STAMP + 5;
+        fprintf(stderr, "[cubature] select kernel of the last cut (us, CTA 0): binade histogram %.1f, walk %.1f, levels", (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3);
+        long long prev = t[2];
+        for (int l = 0; l < 6; ++l)
+            if (t[3 + l] > prev) {
+                fprintf(stderr, " %.1f", (t[3 + l] - prev) * 1e-3);
+                prev = t[3 + l];
+            }
+        fprintf(stderr, ", counts %.1f, compaction %.1f\n", (t[9] - prev) * 1e-3, (t[10] - t[9]) * 1e-3);
+    }
     if (timing)
         fprintf(stderr, "[cubature] device-resident loop: %lld iterations (%lld cut a batch), %d host visits, %d pool growths, %.2f ms\n",
                 (long long)X.h_ctl[LC_ITER], (long long)X.h_ctl[LC_NSELECT], visits, grows,

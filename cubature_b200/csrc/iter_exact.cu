@@ -747,21 +747,69 @@ __device__ int ix_pick(const IterXParams& p, const SelX& sx, PickShared* ps, con
     return fin;
 }
 
-// per-thread run of equal digits -> shared histogram (count, low / high part of the remainder sum)
-__device__ __forceinline__ void ix_hist_flush(unsigned* scnt, unsigned long long* slo, unsigned long long* shi, unsigned cur, unsigned run_c,
-                                              unsigned long long run_lo, unsigned long long run_hi) {
+// ---- shared-memory histograms of the select kernel ------------------------------------------------------------------
+// hist[5][1024] 32-bit cells: plane 0 counts, planes 1..4 the 16-bit digits of the summed values (mantissas / remainders,
+// < 2^53 each), bucket q of private copy cp at [plane * 1024 + cp * NB + q] (bucket-major for the binade histogram).  32-bit cells because shared memory has native
+// 32-bit atomic adds only (64-bit ones are compare-and-swap loops: the binade histogram of 2e5 regions took 56 us with
+// them).  A cell takes fewer than 2^16 additions of less than 2^16 each between two flushes (IX_ROUND elements per CTA).
+#define IX_HPLANE 1024
+#define IX_BW 64  // binary exponents per window of the binade walk
+#define IX_ROUND 65536
+// a thread's run of `run_c` equal digits with value sum `run` (< 2^63) -> histogram copy `h`
+__device__ __forceinline__ void ix_hist_flush(unsigned* h, unsigned cur, unsigned run_c, unsigned long long run) {
     if (run_c) {
-        atomicAdd(&scnt[cur], run_c);
-        if (run_lo) atomicAdd(&slo[cur], run_lo);
-        if (run_hi) atomicAdd(&shi[cur], run_hi);
+        atomicAdd(&h[cur], run_c);
+        const unsigned p0 = (unsigned)(run & 0xffffULL), p1 = (unsigned)((run >> 16) & 0xffffULL), p2 = (unsigned)((run >> 32) & 0xffffULL),
+                       p3 = (unsigned)(run >> 48);
+        if (p0) atomicAdd(&h[IX_HPLANE + cur], p0);
+        if (p1) atomicAdd(&h[2 * IX_HPLANE + cur], p1);
+        if (p2) atomicAdd(&h[3 * IX_HPLANE + cur], p2);
+        if (p3) atomicAdd(&h[4 * IX_HPLANE + cur], p3);
     }
+}
+__device__ __forceinline__ void ix_hist_clear(unsigned* hist) {
+    for (int q = threadIdx.x; q < 5 * IX_HPLANE; q += IX_THREADS) hist[q] = 0u;
+    __syncthreads();
+}
+// all threads: adds the CTA's histogram (NB buckets, `copies` private copies; bucket q of copy cp at cp * cs + q * qs) to the
+// global one (count | low 32 bits | rest of the value sums, IX_NB words each) and clears it
+__device__ void ix_hist_to_global(unsigned* hist, int NB, int copies, int cs, int qs, unsigned long long* gh) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < NB; q += IX_THREADS) {
+        unsigned c = 0;
+        unsigned long long pc[4] = {0ULL, 0ULL, 0ULL, 0ULL};
+        for (int cp = 0; cp < copies; ++cp) {
+            const int at = cp * cs + q * qs;
+            c += hist[at];
+            hist[at] = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                pc[k] += hist[(1 + k) * IX_HPLANE + at];
+                hist[(1 + k) * IX_HPLANE + at] = 0u;
+            }
+        }
+        if (c) {
+            const xa_u128 v = (xa_u128)pc[0] + ((xa_u128)pc[1] << 16) + ((xa_u128)pc[2] << 32) + ((xa_u128)pc[3] << 48);
+            atomicAdd(&gh[q], (unsigned long long)c);
+            const unsigned long long lo = (unsigned long long)(v & 0xffffffffULL), hi = (unsigned long long)(v >> 32);
+            if (lo) atomicAdd(&gh[IX_NB + q], lo);
+            if (hi) atomicAdd(&gh[2 * IX_NB + q], hi);
+        }
+    }
+    __syncthreads();
 }
 
 #define IX_HCOPIES 4  // private histogram copies of the 256-bucket levels (one per pair of warps)
 
+#define IX_SEL_STAMP(k)                                                                 \
+    do {                                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.ctl[LC_STAMP + 5 + (k)] = (long long)ix_timer_ns(); \
+    } while (0)
+
 __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     long long* ctl = p.ctl;
     if (ctl[LC_STATE] != LS_RUN || !ctl[LC_SELECT]) return;  // uniform over the grid
+    IX_SEL_STAMP(0);
     const long long n = ctl[LC_N];
     // CTAs that take part: one per 4096 regions (the grid is sized for the largest pool the host could not rule out)
     long long G_ll = (n + 4095) / 4096;
@@ -769,8 +817,8 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     if (G_ll < 1) G_ll = 1;
     const int G = (int)G_ll, b = blockIdx.x, tid = threadIdx.x;
     if (b >= G) return;
-    __shared__ unsigned scnt[IX_HCOPIES * 256];
-    __shared__ unsigned long long slo[IX_HCOPIES * 256], shi[IX_HCOPIES * 256];
+    __shared__ __align__(16) unsigned hist[5 * IX_HPLANE];
+    unsigned long long* const stage = (unsigned long long*)hist;  // 3 x IX_NB words: the partition's bins of a window (hist is dead then)
     __shared__ unsigned long long shc[IX_THREADS], shl[IX_THREADS], shh[IX_THREADS];
     __shared__ PickShared ps;
     __shared__ SelX sx;
@@ -796,7 +844,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     if (lo > hi) hi = lo;
     unsigned long long* const cand_count = p.hset + (size_t)(IX_LEVELS + 1) * 3 * IX_NB;
     int failed = 0, levels_run = 0;
-    // ---- binary exponents: histogram (count, mantissa sum) of windows of IX_NB binades from the top, then every CTA walks
+    // ---- binary exponents: histogram (count, mantissa sum) of windows of IX_BW binades from the top, then every CTA walks
     // down the bins, popping whole binades, until the evaluation budget is used up or the exact residual passes
     // (Rule.java:109-133 at binade granularity): the batch ends inside that binade ------------------------------------
     __shared__ XaBig sE;
@@ -813,60 +861,35 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     const int e_hi_all = (int)__ldcg(&p.gbins[IX_PUB_TOPE]);
     const unsigned long long Nglobal_now = (unsigned long long)ctl[LC_NGLOBAL];
     for (int wdx = 0; !failed; ++wdx) {
-        const int e_top_w = e_hi_all - IX_NB * wdx;
+        const int e_top_w = e_hi_all - IX_BW * wdx;
         if (e_top_w < 0) break;  // (cannot happen: the walk stops at the last non-empty bin)
-        for (int q = tid; q < 2 * IX_NB; q += IX_THREADS) {
-            scnt[q] = 0u;
-            slo[q] = 0ULL;
-            shi[q] = 0ULL;
-        }
-        __syncthreads();
+        ix_hist_clear(hist);
+        unsigned long long* gh0 = p.hset;
         {
-            unsigned* const myc = scnt + (tid >> 7) * IX_NB;
-            unsigned long long* const mylo = slo + (tid >> 7) * IX_NB;
-            unsigned long long* const myhi = shi + (tid >> 7) * IX_NB;
-            unsigned cur = 0, run_c = 0;
-            unsigned long long run_lo = 0, run_hi = 0;
-            for (long long i0 = lo + tid; i0 < hi; i0 += 4 * IX_THREADS) {
-                double a[4];
+            // binary exponents cluster on a few values: a histogram shared by the lanes of a warp would serialise on them.  Every
+            // lane pair (l, l + 16) owns a private copy; the 16 copies of a bucket sit in consecutive banks
+            unsigned* const my = hist + (lane & 15u);
+            for (long long r0 = lo; r0 < hi; r0 += IX_ROUND) {
+                const long long r1 = r0 + IX_ROUND < hi ? r0 + IX_ROUND : hi;
+                for (long long i0 = r0 + tid; i0 < r1; i0 += 8 * IX_THREADS) {
+                    double a[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = i0 + u * IX_THREADS < hi ? err[i0 + u * IX_THREADS] : 0.0;
+                    for (int u = 0; u < 8; ++u) a[u] = i0 + u * IX_THREADS < r1 ? err[i0 + u * IX_THREADS] : -1.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (i0 + u * IX_THREADS < hi) {
-                        const unsigned long long k = ix_key_of_err(a[u]);
-                        const int e = (int)(k >> 52), d = e_top_w - e;
-                        if (d >= 0 && d < IX_NB) {
-                            if ((unsigned)d != cur) {
-                                ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
-                                cur = (unsigned)d;
-                                run_c = 0;
-                                run_lo = run_hi = 0;
-                            }
-                            const unsigned long long m = (e ? (1ULL << 52) : 0ULL) | (k & 0xfffffffffffffULL);
-                            ++run_c;
-                            run_lo += m & 0xffffffffULL;
-                            run_hi += m >> 32;
+                    for (int u = 0; u < 8; ++u) {
+                        if (i0 + u * IX_THREADS < r1) {
+                            const unsigned long long k = ix_key_of_err(a[u]);
+                            const int e = (int)(k >> 52), d = e_top_w - e;
+                            if (d >= 0 && d < IX_BW) ix_hist_flush(my, (unsigned)d * 16u, 1u, (e ? (1ULL << 52) : 0ULL) | (k & 0xfffffffffffffULL));
                         }
                     }
                 }
-            }
-            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
-        }
-        __syncthreads();
-        unsigned long long* gh0 = p.hset;
-        for (int q = tid; q < IX_NB; q += IX_THREADS) {
-            const unsigned c = scnt[q] + scnt[IX_NB + q];
-            if (c) {
-                const unsigned long long a = slo[q] + slo[IX_NB + q], h = shi[q] + shi[IX_NB + q];
-                atomicAdd(&gh0[q], (unsigned long long)c);
-                if (a & 0xffffffffULL) atomicAdd(&gh0[IX_NB + q], a & 0xffffffffULL);
-                const unsigned long long h2 = h + (a >> 32);
-                if (h2) atomicAdd(&gh0[2 * IX_NB + q], h2);
+                ix_hist_to_global(hist, IX_BW, 16, 1, 16, gh0);
             }
         }
         levels_run = 1;
         ix_gsync(bar, ++nsync * (unsigned long long)G);
+        IX_SEL_STAMP(1);
         if (sharded) {
             if (b == 0) {
                 const int f = ix_exchange(p, xseq, 0, gh0, 0, 3 * IX_NB);
@@ -885,21 +908,16 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
                 break;
             }
         }
-        // the window's bins of the partition -> shared memory (the private histograms are dead): slo[0..NB) counts,
-        // slo[NB..2NB) low words, shi[0..NB) high words
-        for (int q = tid; q < IX_NB; q += IX_THREADS) {
-            slo[q] = __ldcg(&gh0[q]);
-            slo[IX_NB + q] = __ldcg(&gh0[IX_NB + q]);
-            shi[q] = __ldcg(&gh0[2 * IX_NB + q]);
-        }
+        // the window's bins of the partition -> shared memory (the private histograms are dead): counts, low words, high words
+        for (int q = tid; q < 3 * IX_NB; q += IX_THREADS) stage[q] = __ldcg(&gh0[q]);
         __syncthreads();
         if (tid == 0) {
             unsigned long long Cabove = s_walk[2];
-            for (int d = 0; d < IX_NB; ++d) {
-                const unsigned long long c = slo[d];
+            for (int d = 0; d < IX_BW; ++d) {
+                const unsigned long long c = stage[d];
                 if (!c) continue;
                 const int e = e_top_w - d;
-                const xa_u128 mv = (xa_u128)slo[IX_NB + d] + ((xa_u128)shi[d] << 32);
+                const xa_u128 mv = (xa_u128)stage[IX_NB + d] + ((xa_u128)stage[2 * IX_NB + d] << 32);
                 bool stop = Cabove + c >= sx.Kcap || Cabove + c >= Nglobal_now;  // the budget ends here / the lowest bin
                 if (!stop && !sx.count_only) {
                     // residual after popping this bin as well; put the bin back when that passes
@@ -942,8 +960,9 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             }
         }
         __syncthreads();
+        IX_SEL_STAMP(2);
         if (s_walk[0]) break;
-        // the batch reaches below this window (more than IX_NB binades under the top): clear the histogram and go on
+        // the batch reaches below this window (more than IX_BW binades under the top): clear the histogram and go on
         ix_gsync(bar, ++nsync * (unsigned long long)G);
         for (long long q = (long long)b * IX_THREADS + tid; q < 3 * IX_NB; q += (long long)G * IX_THREADS) p.hset[q] = 0ULL;
         ix_gsync(bar, ++nsync * (unsigned long long)G);
@@ -963,100 +982,84 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     for (int level = 0; level < IX_LEVELS; ++level) {
         const int shift = ix_level_shift(level), NB = ix_level_nb(level);
         const int copies = level <= 1 ? IX_HCOPIES : 1;
-        for (int q = tid; q < copies * NB; q += IX_THREADS) {
-            scnt[q] = 0u;
-            slo[q] = 0ULL;
-            shi[q] = 0ULL;
-        }
-        __syncthreads();
+        ix_hist_clear(hist);
         // keys decided so far: sign, exponent and the fraction bits above this level's digit
         const unsigned long long mask = top_mask | (0xfffffffffffffULL & ~((1ULL << (shift + ix_level_bits(level))) - 1ULL));
         const unsigned long long prefix = top_prefix | ps.frac;
         const unsigned long long rmask = (1ULL << shift) - 1ULL;
-        unsigned cur = 0, run_c = 0;
-        unsigned long long run_lo = 0, run_hi = 0;
+        unsigned long long* gh = p.hset + (size_t)(level + 1) * 3 * IX_NB;
         levels_run = level + 2;
         if (level <= 1) {
             // full scan of the chunk; the second scan also extracts the candidates and counts the certain pops
-            unsigned* const myc = scnt + (tid >> 6) * 256;
-            unsigned long long* const mylo = slo + (tid >> 6) * 256;
-            unsigned long long* const myhi = shi + (tid >> 6) * 256;
-            for (long long w0 = lo + (long long)(tid - (int)lane); w0 < hi; w0 += 4 * IX_THREADS) {
-                const long long i0 = w0 + lane;
-                double a[4];
+            unsigned* const my = hist + (tid >> 6) * 256;
+            for (long long r0 = lo; r0 < hi; r0 += IX_ROUND) {
+                const long long r1 = r0 + IX_ROUND < hi ? r0 + IX_ROUND : hi;
+                unsigned cur = 0, run_c = 0;
+                unsigned long long run = 0;
+                for (long long w0 = r0 + (long long)(tid - (int)lane); w0 < r1; w0 += 4 * IX_THREADS) {
+                    const long long i0 = w0 + lane;
+                    double a[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = i0 + u * IX_THREADS < hi ? err[i0 + u * IX_THREADS] : 0.0;
+                    for (int u = 0; u < 4; ++u) a[u] = i0 + u * IX_THREADS < r1 ? err[i0 + u * IX_THREADS] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long i = i0 + u * IX_THREADS;
-                    const bool in = i < hi;
-                    const unsigned long long k = ix_key_of_err(a[u]);
-                    const bool match = in && (k & mask) == prefix;
-                    if (level == 1) {
-                        above_def += (in && (k & mask) > prefix) ? 1ULL : 0ULL;
-                        const unsigned bal = __ballot_sync(0xffffffffu, match);  // warp-aggregated append
-                        if (bal) {
-                            unsigned long long base = 0;
-                            if (lane == (unsigned)(__ffs(bal) - 1)) base = atomicAdd(cand_count, (unsigned long long)__popc(bal));
-                            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-                            if (match) {
-                                const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
-                                p.cand_key[pos] = k;
-                                p.cand_idx[pos] = (int)i;
+                    for (int u = 0; u < 4; ++u) {
+                        const long long i = i0 + u * IX_THREADS;
+                        const bool in = i < r1;
+                        const unsigned long long k = ix_key_of_err(a[u]);
+                        const bool match = in && (k & mask) == prefix;
+                        if (level == 1) {
+                            above_def += (in && (k & mask) > prefix) ? 1ULL : 0ULL;
+                            const unsigned bal = __ballot_sync(0xffffffffu, match);  // warp-aggregated append
+                            if (bal) {
+                                unsigned long long base = 0;
+                                if (lane == (unsigned)(__ffs(bal) - 1)) base = atomicAdd(cand_count, (unsigned long long)__popc(bal));
+                                base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                                if (match) {
+                                    const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+                                    p.cand_key[pos] = k;
+                                    p.cand_idx[pos] = (int)i;
+                                }
                             }
                         }
-                    }
-                    if (match) {
-                        const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
-                        if (d != cur) {
-                            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
-                            cur = d;
-                            run_c = 0;
-                            run_lo = run_hi = 0;
+                        if (match) {
+                            const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                            if (d != cur) {
+                                ix_hist_flush(my, cur, run_c, run);
+                                cur = d;
+                                run_c = 0;
+                                run = 0;
+                            }
+                            ++run_c;
+                            run += k & rmask;
                         }
-                        const unsigned long long r = k & rmask;
-                        ++run_c;
-                        run_lo += r & 0xffffffffULL;
-                        run_hi += r >> 32;
                     }
                 }
+                ix_hist_flush(my, cur, run_c, run);
+                ix_hist_to_global(hist, NB, copies, NB, 1, gh);
             }
-            ix_hist_flush(myc, mylo, myhi, cur, run_c, run_lo, run_hi);
             if (level == 1) have_cand = true;
         } else {
-            for (long long q = (long long)b * IX_THREADS + tid; q < M; q += (long long)G * IX_THREADS) {
-                const unsigned long long k = p.cand_key[q];
-                if ((k & mask) == prefix) {
-                    const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
-                    if (d != cur) {
-                        ix_hist_flush(scnt, slo, shi, cur, run_c, run_lo, run_hi);
-                        cur = d;
-                        run_c = 0;
-                        run_lo = run_hi = 0;
+            const long long cstride = (long long)G * IX_THREADS;
+            for (long long r0 = 0; r0 < M; r0 += cstride * (IX_ROUND / IX_THREADS)) {  // a CTA takes IX_ROUND candidates per round
+                const long long r1 = r0 + cstride * (IX_ROUND / IX_THREADS) < M ? r0 + cstride * (IX_ROUND / IX_THREADS) : M;
+                unsigned cur = 0, run_c = 0;
+                unsigned long long run = 0;
+                for (long long q = r0 + (long long)b * IX_THREADS + tid; q < r1; q += cstride) {
+                    const unsigned long long k = p.cand_key[q];
+                    if ((k & mask) == prefix) {
+                        const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
+                        if (d != cur) {
+                            ix_hist_flush(hist, cur, run_c, run);
+                            cur = d;
+                            run_c = 0;
+                            run = 0;
+                        }
+                        ++run_c;
+                        run += k & rmask;
                     }
-                    const unsigned long long r = k & rmask;
-                    ++run_c;
-                    run_lo += r & 0xffffffffULL;
-                    run_hi += r >> 32;
                 }
-            }
-            ix_hist_flush(scnt, slo, shi, cur, run_c, run_lo, run_hi);
-        }
-        __syncthreads();
-        unsigned long long* gh = p.hset + (size_t)(level + 1) * 3 * IX_NB;
-        for (int q = tid; q < NB; q += IX_THREADS) {
-            unsigned c = 0;
-            unsigned long long a = 0, h = 0;
-            for (int cp = 0; cp < copies; ++cp) {
-                c += scnt[cp * 256 + q];
-                a += slo[cp * 256 + q];
-                h += shi[cp * 256 + q];
-            }
-            if (c) {  // remainder sum = a + 2^32 h; the global low word grows by less than 2^32 per CTA
-                atomicAdd(&gh[q], (unsigned long long)c);
-                if (a & 0xffffffffULL) atomicAdd(&gh[IX_NB + q], a & 0xffffffffULL);
-                const unsigned long long h2 = h + (a >> 32);
-                if (h2) atomicAdd(&gh[2 * IX_NB + q], h2);
+                ix_hist_flush(hist, cur, run_c, run);
+                ix_hist_to_global(hist, NB, copies, NB, 1, gh);
             }
         }
         if (level == 1) {  // certain pops of this chunk -> per-CTA counters of the compaction
@@ -1096,6 +1099,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         }
         if (level == 1) M = (long long)__ldcg(cand_count);
         const int fin = ix_pick(p, sx, &ps, gh, level, shc, shl, shh);
+        if (level < 6) IX_SEL_STAMP(3 + level);
         if (fin) break;
     }
     if (failed) {
@@ -1140,6 +1144,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         }
     }
     ix_gsync(bar, ++nsync * (unsigned long long)G);
+    IX_SEL_STAMP(9);
     // the histograms are not read any more: clear the levels that were used (and the candidate counter) for the next launch
     for (long long q = (long long)b * IX_THREADS + tid; q < (long long)levels_run * 3 * IX_NB; q += (long long)G * IX_THREADS) p.hset[q] = 0ULL;
     if (b == 0 && tid < 8) cand_count[tid] = 0ULL;
@@ -1215,56 +1220,69 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     }
     unsigned long long gt_base = shc[0], eq_base = shl[0];
     __syncthreads();
-    unsigned* const sl = scnt;
-    unsigned* const se = scnt + IX_THREADS;
+    // tiles of IX_TILE consecutive slots, element (u, thread) at t_lo + u * IX_THREADS + thread (coalesced); the rank of an
+    // element among the popped ones follows from warp ballots and one scan over the tile's 64 (u, warp) counts
+    unsigned* const sgt = hist;
+    unsigned* const seq = hist + 80;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int warp = tid >> 5;
     for (long long t_lo = lo; t_lo < hi; t_lo += IX_TILE) {
-        const long long i_lo = t_lo + (long long)tid * IX_TILE_ITEMS;  // consecutive slots per thread
-        unsigned fl = 0, fe = 0, gt = 0, eq = 0;
+        unsigned bg[IX_TILE_ITEMS], be[IX_TILE_ITEMS];
 #pragma unroll
         for (int u = 0; u < IX_TILE_ITEMS; ++u) {
-            const long long i = i_lo + u;
-            if (i < hi) {
-                const unsigned long long k = ix_key_of_err(err[i]);
-                if (k > thr) {
-                    fl |= 1u << u;
-                    ++gt;
-                } else if (k == thr) {
-                    fe |= 1u << u;
-                    ++eq;
+            const long long i = t_lo + (long long)u * IX_THREADS + tid;
+            const unsigned long long k = i < hi ? ix_key_of_err(err[i]) : 0ULL;
+            bg[u] = __ballot_sync(0xffffffffu, i < hi && k > thr);
+            be[u] = __ballot_sync(0xffffffffu, i < hi && k == thr);
+            if (lane == 0) {
+                sgt[u * IX_WARPS + warp] = (unsigned)__popc(bg[u]);
+                seq[u * IX_WARPS + warp] = (unsigned)__popc(be[u]);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 64 counts (two per lane), totals behind them
+            const unsigned g0 = sgt[2 * lane], g1 = sgt[2 * lane + 1], q0 = seq[2 * lane], q1 = seq[2 * lane + 1];
+            unsigned gs = g0 + g1, qs = q0 + q1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned tg = __shfl_up_sync(0xffffffffu, gs, o), tq = __shfl_up_sync(0xffffffffu, qs, o);
+                if ((int)lane >= o) {
+                    gs += tg;
+                    qs += tq;
+                }
+            }
+            sgt[2 * lane] = gs - g0 - g1;
+            sgt[2 * lane + 1] = gs - g1;
+            seq[2 * lane] = qs - q0 - q1;
+            seq[2 * lane + 1] = qs - q1;
+            if (lane == 31) {
+                sgt[64] = gs;
+                seq[64] = qs;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < IX_TILE_ITEMS; ++u) {
+            const bool is_gt = (bg[u] >> lane) & 1u, is_eq = (be[u] >> lane) & 1u;
+            if (is_gt || is_eq) {
+                const unsigned long long gt_before = gt_base + sgt[u * IX_WARPS + warp] + (unsigned)__popc(bg[u] & lt_mask);
+                const unsigned long long eq_before = eq_base + seq[u * IX_WARPS + warp] + (unsigned)__popc(be[u] & lt_mask);
+                if (is_gt || eq_before < tie_take_local) {
+                    const long long i = t_lo + (long long)u * IX_THREADS + tid;
+                    const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
+                    p.list[pos] = (int)i;
+                    // the parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28): the next decide kernel subtracts
+                    // this copy, the slot itself is about to be overwritten by the left child
+                    p.stash_val[pos] = p.pool.val[i];
+                    p.stash_err[pos] = err[i];
                 }
             }
         }
-        sl[tid] = gt;
-        se[tid] = eq;
-        __syncthreads();
-        for (int o = 1; o < IX_THREADS; o <<= 1) {
-            const unsigned ta = tid >= o ? sl[tid - o] : 0u, tb = tid >= o ? se[tid - o] : 0u;
-            __syncthreads();
-            sl[tid] += ta;
-            se[tid] += tb;
-            __syncthreads();
-        }
-        unsigned long long gt_before = gt_base + (sl[tid] - gt);
-        unsigned long long eq_before = eq_base + (se[tid] - eq);
-        const unsigned tile_gt = sl[IX_THREADS - 1], tile_eq = se[IX_THREADS - 1];
-#pragma unroll
-        for (int u = 0; u < IX_TILE_ITEMS; ++u) {
-            const bool is_gt = (fl >> u) & 1u, is_eq = (fe >> u) & 1u;
-            if (is_gt || (is_eq && eq_before < tie_take_local)) {
-                const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
-                p.list[pos] = (int)(i_lo + u);
-                // the parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28): the next decide kernel subtracts
-                // this copy, the slot itself is about to be overwritten by the left child
-                p.stash_val[pos] = p.pool.val[i_lo + u];
-                p.stash_err[pos] = err[i_lo + u];
-            }
-            gt_before += is_gt;
-            eq_before += is_eq;
-        }
-        gt_base += tile_gt;
-        eq_base += tile_eq;
+        gt_base += sgt[64];
+        eq_base += seq[64];
         __syncthreads();
     }
+    IX_SEL_STAMP(10);
     if (b == 0 && tid == 0) {
         const long long Kl = (long long)K_local, Kg = (long long)ps.K, Nglobal = ctl[LC_NGLOBAL];
         p.selx->thr_key = ps.thr_key;

@@ -41,7 +41,7 @@ enum {
     LC_DBG0 = 24,
     LC_DBG1 = 25,
     LC_SUB_K = 26,  // popped parents whose (val, err) copies the next decide kernel has to subtract from the sums
-    LC_STAMP = 32,  // [8] time stamps of the decide kernel's phases (CUBATURE_TIMING)
+    LC_STAMP = 32,  // [16] time stamps (CUBATURE_TIMING): [0..4] decide kernel, [5..15] select kernel (CTA 0)
     LC_WORDS = 48,
 };
 #define LC_LOG_CAP 1024  // batch-size log [LC_WORDS .. LC_WORDS + LC_LOG_CAP): 2 K of iteration i at i % LC_LOG_CAP
