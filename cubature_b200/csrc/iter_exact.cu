@@ -138,9 +138,9 @@ __device__ void ix_big_full_range(XaBig* a) {
     a->jlo = 0;
     a->jhi = XA_LIMBS - 1;
 }
-__device__ void ix_big_tighten(XaBig* a) {  // normalized number: shrink [jlo, jhi] to the non-zero limbs
-    int lo = 0, hi = XA_LIMBS - 1;
-    while (hi > 0 && a->l[hi] == 0ULL) --hi;
+__device__ void ix_big_tighten(XaBig* a) {  // normalized number, zero outside [jlo, jhi]: shrink the range to the non-zero limbs
+    int lo = a->jlo, hi = a->jhi;
+    while (hi > lo && a->l[hi] == 0ULL) --hi;
     while (lo < hi && a->l[lo] == 0ULL) ++lo;
     a->jlo = lo;
     a->jhi = hi + 2 < XA_LIMBS ? hi + 2 : XA_LIMBS - 1;  // head room for carries of later additions
@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
             for (int j = v_lo; j <= v_hi; ++j) S.V.l[j] = S.Q.l[j];
             v_neg = 1;
         }
-        ix_big_full_range(&S.V);
+        S.V.jlo = v_lo;
+        S.V.jhi = v_hi;
         ix_big_tighten(&S.V);
         // store this rank's totals
         tot[XA_TOT_MISC + 0] = (unsigned long long)v_neg;
@@ -630,52 +631,63 @@ __device__ int ix_pick(const IterXParams& p, const SelX& sx, PickShared* ps, con
         sl[j] = st;
     }
     __syncthreads();  // everybody has read *ps
-    shc[tid] = ct;
-    shl[tid] = (unsigned long long)st;
-    shh[tid] = (unsigned long long)(st >> 64);
-    __syncthreads();
-    for (int o = 1; o < IX_THREADS; o <<= 1) {  // inclusive scan over the threads
-        unsigned long long ta = 0, tl = 0, th = 0;
-        if (tid >= o) {
-            ta = shc[tid - o];
-            tl = shl[tid - o];
-            th = shh[tid - o];
+    // inclusive scan over the threads: shuffles inside a warp, the warps' totals through shared memory
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    unsigned long long sc = ct, sl_ = (unsigned long long)st, sh_ = (unsigned long long)(st >> 64);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ta = __shfl_up_sync(0xffffffffu, sc, o), tl = __shfl_up_sync(0xffffffffu, sl_, o), th = __shfl_up_sync(0xffffffffu, sh_, o);
+        if ((int)lane >= o) {
+            sc += ta;
+            const unsigned long long nl = sl_ + tl;
+            sh_ += th + (nl < tl ? 1ULL : 0ULL);
+            sl_ = nl;
         }
-        __syncthreads();
-        if (tid >= o) {
-            shc[tid] += ta;
-            const unsigned long long nl = shl[tid] + tl;
-            shh[tid] += th + (nl < tl ? 1ULL : 0ULL);
-            shl[tid] = nl;
-        }
-        __syncthreads();
     }
-    const unsigned long long c_off = shc[tid] - ct;
-    const xa_u128 s_off = (((xa_u128)shh[tid] << 64) | shl[tid]) - st;
-    unsigned long long first_stop = ~0ULL, last_nz = 0ULL;
+    if (lane == 31u) {
+        shc[warp] = sc;
+        shl[warp] = sl_;
+        shh[warp] = sh_;
+    }
+    __syncthreads();
+    for (unsigned w = 0; w < warp; ++w) {
+        sc += shc[w];
+        const unsigned long long tl = shl[w], nl = sl_ + tl;
+        sh_ += shh[w] + (nl < tl ? 1ULL : 0ULL);
+        sl_ = nl;
+    }
+    const unsigned long long c_off = sc - ct;
+    const xa_u128 s_off = (((xa_u128)sh_ << 64) | sl_) - st;
+    unsigned first_stop = ~0u, last_nz = 0u;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         if (j < per_t && c_in[j]) {
-            const unsigned long long q = (unsigned long long)(tid * per_t + j);
-            last_nz = q + 1ULL;
+            const unsigned q = (unsigned)(tid * per_t + j);
+            last_nz = q + 1u;
             const unsigned long long Cincl = Cc + c_off + cl[j];
             bool stop = Cincl >= sx.Kcap;
             if (!stop && !sx.count_only) stop = ix_conv(sx.V, ix_residual(sx, H, Pm + s_off + sl[j]), p);
-            if (stop && first_stop == ~0ULL) first_stop = q;
+            if (stop && first_stop == ~0u) first_stop = q;
         }
     }
-    __syncthreads();
-    shc[tid] = first_stop;
-    shl[tid] = last_nz;
-    __syncthreads();
-    for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) {
-            if (shc[tid + o] < shc[tid]) shc[tid] = shc[tid + o];
-            if (shl[tid + o] > shl[tid]) shl[tid] = shl[tid + o];
-        }
-        __syncthreads();
+    first_stop = __reduce_min_sync(0xffffffffu, first_stop);
+    last_nz = __reduce_max_sync(0xffffffffu, last_nz);
+    __syncthreads();  // the warps' scan totals have been read
+    if (lane == 0u) {
+        shc[warp] = first_stop;
+        shl[warp] = last_nz;
     }
-    const unsigned long long any_stop = shc[0], nz = shl[0];
+    __syncthreads();
+    unsigned long long any_stop = ~0ULL, nz = 0ULL;
+    {
+        unsigned fs = ~0u, ln = 0u;
+        for (int w = 0; w < IX_WARPS; ++w) {
+            fs = (unsigned)shc[w] < fs ? (unsigned)shc[w] : fs;
+            ln = (unsigned)shl[w] > ln ? (unsigned)shl[w] : ln;
+        }
+        any_stop = fs == ~0u ? ~0ULL : (unsigned long long)fs;
+        nz = ln;
+    }
     __syncthreads();
     if (nz == 0ULL) {  // cannot happen: the binade holds at least one region
         if (tid == 0) {
@@ -800,6 +812,27 @@ __device__ void ix_hist_to_global(unsigned* hist, int NB, int copies, int cs, in
 }
 
 #define IX_HCOPIES 4  // private histogram copies of the 256-bucket levels (one per pair of warps)
+
+// block-wide sums of two counters (all threads; the sums come back to every thread): shuffles, then the warps' totals
+__device__ __forceinline__ void ix_block_sum2(unsigned long long& a, unsigned long long& c, unsigned long long* sha, unsigned long long* shb) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();  // earlier readers of sha / shb are done
+    if ((threadIdx.x & 31u) == 0u) {
+        sha[threadIdx.x >> 5] = a;
+        shb[threadIdx.x >> 5] = c;
+    }
+    __syncthreads();
+    a = 0ULL;
+    c = 0ULL;
+    for (int w = 0; w < IX_WARPS; ++w) {
+        a += sha[w];
+        c += shb[w];
+    }
+}
 
 #define IX_SEL_STAMP(k)                                                                 \
     do {                                                                                \
@@ -1063,17 +1096,12 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             }
         }
         if (level == 1) {  // certain pops of this chunk -> per-CTA counters of the compaction
-            shc[tid] = above_def;
-            __syncthreads();
-            for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-                if (tid < o) shc[tid] += shc[tid + o];
-                __syncthreads();
-            }
+            unsigned long long sa = above_def, sb = 0ULL;
+            ix_block_sum2(sa, sb, shc, shl);
             if (tid == 0) {
-                p.blk[b] = shc[0];
+                p.blk[b] = sa;
                 p.blk[G + b] = 0ULL;
             }
-            __syncthreads();
         }
         ix_gsync(bar, ++nsync * (unsigned long long)G);
         if (sharded) {  // this level's histogram of the whole partition: sum of the R local ones
@@ -1128,19 +1156,10 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             my_gt += k > thr;
             my_eq += k == thr;
         }
-        shc[tid] = my_gt;
-        shl[tid] = my_eq;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                shc[tid] += shc[tid + o];
-                shl[tid] += shl[tid + o];
-            }
-            __syncthreads();
-        }
+        ix_block_sum2(my_gt, my_eq, shc, shl);
         if (tid == 0) {
-            p.blk[b] = shc[0];
-            p.blk[G + b] = shl[0];
+            p.blk[b] = my_gt;
+            p.blk[G + b] = my_eq;
         }
     }
     ix_gsync(bar, ++nsync * (unsigned long long)G);
@@ -1158,17 +1177,8 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
                 a += __ldcg(&p.blk[i]);
                 c += __ldcg(&p.blk[G + i]);
             }
-            shc[tid] = a;
-            shl[tid] = c;
-            __syncthreads();
-            for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-                if (tid < o) {
-                    shc[tid] += shc[tid + o];
-                    shl[tid] += shl[tid + o];
-                }
-                __syncthreads();
-            }
-            if (tid < 16) shh[tid] = tid == 0 ? shc[0] : (tid == 1 ? shl[0] : 0ULL);
+            ix_block_sum2(a, c, shc, shl);
+            if (tid < 16) shh[tid] = tid == 0 ? a : (tid == 1 ? c : 0ULL);
             __syncthreads();
             const int f = ix_exchange(p, xseq, 0, shh, 0, 16);
             if (tid == 0) {
@@ -1201,24 +1211,17 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         tie_take_local = __ldcg(&p.blk[2 * G]);
         K_local = __ldcg(&p.blk[2 * G + 1]);
     }
+    unsigned long long gt_base = 0, eq_base = 0;
     {
         unsigned long long a = 0, c = 0;
         for (int i = tid; i < b; i += IX_THREADS) {
             a += __ldcg(&p.blk[i]);
             c += __ldcg(&p.blk[G + i]);
         }
-        shc[tid] = a;
-        shl[tid] = c;
-        __syncthreads();
-        for (int o = IX_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                shc[tid] += shc[tid + o];
-                shl[tid] += shl[tid + o];
-            }
-            __syncthreads();
-        }
+        ix_block_sum2(a, c, shc, shl);
+        gt_base = a;
+        eq_base = c;
     }
-    unsigned long long gt_base = shc[0], eq_base = shl[0];
     __syncthreads();
     // tiles of IX_TILE consecutive slots, element (u, thread) at t_lo + u * IX_THREADS + thread (coalesced); the rank of an
     // element among the popped ones follows from warp ballots and one scan over the tile's 64 (u, warp) counts
