@@ -2331,7 +2331,9 @@ int64_t cubature_cuda_integrand_cubin(cub_integrand_t* integrand, int has_transf
     return (int64_t)c.size();
 }
 
-int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax, const int* transform,
+}  // extern "C"
+namespace {
+int integrate_impl(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax, const int* transform,
                             double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* options, double* out,
                             cub_stats_t* stats) {
     const auto t0 = std::chrono::steady_clock::now();
@@ -2406,10 +2408,58 @@ int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* x
     return rc;
 }
 
+// struct_size versioning of the two ABI structs: the library works on full-size private copies.  Of the caller's options
+// only the first struct_size bytes are read (fields beyond them keep their defaults); of the statistics only the first
+// struct_size bytes are written back.
+struct StatsBridge {
+    cub_stats_t local;
+    cub_stats_t* user;
+    int32_t user_size;
+    bool ok;
+    explicit StatsBridge(cub_stats_t* u) : user(u), user_size(u ? u->struct_size : 0), ok(true) {
+        memset(&local, 0, sizeof local);
+        local.struct_size = (int32_t)sizeof local;
+        if (u && user_size < (int32_t)(2 * sizeof(int32_t))) ok = false;  // cannot even hold struct_size and the converged flag
+    }
+    cub_stats_t* get() { return user && ok ? &local : nullptr; }
+    ~StatsBridge() {
+        if (!user || !ok) return;
+        const size_t n = std::min<size_t>((size_t)user_size, sizeof local);
+        memcpy(user, &local, n);
+        user->struct_size = user_size;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int cubature_cuda_integrate(cub_integrand_t* integrand, int dim, const double* xmin, const double* xmax, const int* transform, double relTol,
+                            double absTol, int norm, int64_t maxEval, const cub_options_t* options, double* out, cub_stats_t* stats) {
+    StatsBridge sb(stats);
+    if (!sb.ok) return CUB_ERR_BAD_ARGS;
+    cub_options_t opt;
+    memset(&opt, 0, sizeof opt);
+    opt.struct_size = (int32_t)sizeof opt;
+    opt.select = CUB_SELECT_DEVICE;
+    opt.device = -1;
+    if (options) {
+        const int32_t sz = options->struct_size;
+        if (sz < (int32_t)(2 * sizeof(int32_t))) {
+            if (sb.get()) cub_set_message(sb.get()->message, "cub_options_t.struct_size = %d: set it to sizeof(cub_options_t)", (int)sz);
+            return CUB_ERR_BAD_ARGS;
+        }
+        memcpy(&opt, options, std::min<size_t>((size_t)sz, sizeof opt));
+        opt.struct_size = (int32_t)sizeof opt;
+    }
+    return integrate_impl(integrand, dim, xmin, xmax, transform, relTol, absTol, norm, maxEval, options ? &opt : nullptr, out, sb.get());
+}
+
 int cubature_cuda_eval_regions(cub_integrand_t* integrand, int dim, const int* transform, const double* shift, int64_t nR,
                                const double* centers, const double* halfwidths, double* val, double* err, int32_t* split_dim,
-                               cub_stats_t* stats) {
-    init_stats(stats);
+                               cub_stats_t* stats_user) {
+    StatsBridge sb(stats_user);
+    if (!sb.ok) return CUB_ERR_BAD_ARGS;
+    cub_stats_t* stats = sb.get();
     if (!integrand || !centers || !halfwidths || !val || !err || !split_dim || nR < 0) return CUB_ERR_BAD_ARGS;
     if (dim != integrand->dim) return CUB_ERR_BAD_DIM;
     if (nR == 0) return CUB_OK;

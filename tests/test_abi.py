@@ -163,3 +163,92 @@ def test_rule_points_follow_the_reference_order(cb):
     gk = cb.rule_points([0.5], [0.5])
     assert gk.shape == (15, 1) and gk[0, 0] == 0.5 and gk[1, 0] < 0.5 < gk[2, 0]
     assert abs(gk[7, 0] - (0.5 - 0.5 * 0.991455371120812639)) < 1e-16
+
+
+def test_struct_size_versioning(cb):
+    """cub_options_t / cub_stats_t are versioned by struct_size: the library reads / writes only the bytes the caller
+    declares (no GPU needed: the checks come before the device is opened)."""
+    import ctypes as C
+    L = cb._ffi.lib()
+    ig = cb.Integrand.builtin(cb.Family.GAUSS_ISO, 3, 1, [0.5])
+    xmin = (C.c_double * 3)(-2, -2, -2)
+    xmax = (C.c_double * 3)(2, 2, 2)
+    out = (C.c_double * 2)()
+    dp = cb._ffi.c_double_p
+
+    def call(opt, st):
+        return L.cubature_cuda_integrate(ig._h, 3, C.cast(xmin, dp), C.cast(xmax, dp), None, 1e-4, 0.0, 0, 0,
+                                         None if opt is None else C.byref(opt), C.cast(out, dp), None if st is None else C.byref(st))
+
+    # a caller built against an older, shorter cub_stats_t: bytes beyond its struct_size stay untouched
+    class Guarded(C.Structure):
+        _fields_ = [("st", cb._ffi.CubStats), ("canary", C.c_uint8 * 64)]
+    g = Guarded()
+    C.memset(C.byref(g), 0xAB, C.sizeof(g))
+    small = 24
+    g.st.struct_size = small
+    rc = call(None, g.st)
+    raw = bytes(C.string_at(C.byref(g), C.sizeof(g)))
+    assert raw[small:] == b"\xab" * (C.sizeof(g) - small), "bytes beyond struct_size were written"
+    assert g.st.struct_size == small
+    assert rc in (0, -5)  # CUB_OK on a GPU box, CUB_ERR_NO_DEVICE here
+    # struct_size missing / nonsensical: rejected before anything is read or written
+    bad = cb._ffi.CubStats()
+    bad.struct_size = 0
+    assert call(None, bad) == -1  # CUB_ERR_BAD_ARGS
+    opt = cb._ffi.CubOptions()
+    opt.struct_size = 0
+    st = cb._ffi.CubStats()
+    st.struct_size = C.sizeof(cb._ffi.CubStats)
+    assert call(opt, st) == -1
+    assert b"struct_size" in bytes(st.message)
+    # a shorter options struct: fields beyond it take their defaults (select = DEVICE), the call goes through
+    opt.struct_size = 8
+    opt.select = 0
+    opt.device = 12345  # beyond the declared size: must not be read
+    rc = call(opt, st)
+    assert rc in (0, -5), (rc, bytes(st.message))
+
+
+def test_java_shim_descriptors_match_header():
+    """The Panama FFM shim (java/.../Native.java, shipped as source: there is no JVM in the image) against
+    include/cubature_cuda.h: every downcall handle names an exported function, and its FunctionDescriptor has the C
+    prototype's arity and argument classes (pointer / 32-bit int / 64-bit int / double)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "cubature_cuda.h")).read()
+    java = open(os.path.join(root, "java", "de", "labathome", "cubature", "Native.java")).read()
+    header_nc = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(cubature_cuda_\w+)\s*\(([^;{]*?)\)\s*;", header_nc):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        protos[name] = (ret, [] if args in ("", "void") else [a.strip() for a in args.split(",")])
+
+    def c_class(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ADDRESS"
+        base = re.sub(r"\b(const|unsigned|signed)\b", "", decl)
+        base = re.sub(r"\b[a-z_]\w*$", "", base.strip()).strip() or decl  # drop the parameter name
+        if re.search(r"\bdouble\b", decl):
+            return "JAVA_DOUBLE"
+        if re.search(r"\b(int64_t|size_t|long long|uint64_t)\b", decl):
+            return "JAVA_LONG"
+        if re.search(r"\b(int|int32_t|uint32_t)\b", decl):
+            return "JAVA_INT"
+        raise AssertionError("unclassified C type: %r" % decl)
+
+    handles = re.findall(r'h\("(cubature_cuda_\w+)",\s*FunctionDescriptor\.(ofVoid|of)\(([^;]*?)\)\);', java, flags=re.S)
+    assert len(handles) >= 5
+    for name, kind, layouts in handles:
+        assert name in protos, "%s is not declared in include/cubature_cuda.h" % name
+        ret, args = protos[name]
+        lay = [t.strip() for t in layouts.replace("\n", " ").split(",") if t.strip()]
+        if kind == "of":
+            assert lay[0] == c_class(ret + " x" if "*" not in ret else ret), (name, "return", lay[0], ret)
+            lay = lay[1:]
+        else:
+            assert ret == "void", (name, ret)
+        assert len(lay) == len(args), (name, lay, args)
+        for j, (l, a) in enumerate(zip(lay, args)):
+            assert l == c_class(a), (name, j, l, a)
