@@ -97,8 +97,36 @@ void mkdirs(const std::string& path) {
     std::string cur;
     for (size_t i = 0; i < path.size(); ++i) {
         cur.push_back(path[i]);
-        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0755);
+        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0700);
     }
+}
+// a cache directory other users can write to is not used (a cubin found there would be loaded into this process)
+bool cache_dir_trusted(const std::string& dir) {
+    struct stat sb;
+    if (stat(dir.c_str(), &sb) != 0) return false;
+    if (!S_ISDIR(sb.st_mode)) return false;
+    if (sb.st_uid != geteuid()) return false;
+    return (sb.st_mode & (S_IWGRP | S_IWOTH)) == 0;
+}
+// cache file: header | cubin.  A file is used only when every header field matches what this process would have written.
+struct CacheHeader {
+    char magic[8];            // "CUBJIT01"
+    uint64_t key;             // hash of translation unit + embedded headers + options
+    uint64_t key2;            // second, independent hash of the same material
+    int32_t nvrtc_major, nvrtc_minor;
+    uint64_t cubin_bytes;
+    uint64_t cubin_hash;      // FNV-1a of the cubin
+};
+uint64_t fnv1a_bytes(const char* p, size_t n, uint64_t h = 1469598103934665603ULL) {
+    for (size_t i = 0; i < n; ++i) {
+        h ^= (unsigned char)p[i];
+        h *= 1099511628211ULL;
+    }
+    return h;
+}
+uint64_t djb2(const std::string& s, uint64_t h = 5381ULL) {
+    for (unsigned char c : s) h = h * 33ULL + c;
+    return h;
 }
 
 const char* family_type(int family) {
@@ -175,24 +203,44 @@ int cub_jit_compile(cub_integrand* integ, int has_transform, std::string* log) {
         std::string tok;
         while (is >> tok) opts.push_back(tok);
     }
-    // cache key: translation unit + embedded headers + options
-    uint64_t h = fnv1a(tu);
-    for (int i = 0; i < kNumEmbedded; ++i) h = fnv1a(kEmbeddedSources[i], h);
-    for (const std::string& o : opts) h = fnv1a(o, h);
+    // cache key: translation unit + embedded headers + options (two independent hashes; the NVRTC version is checked too)
+    uint64_t h = fnv1a(tu), h2 = djb2(tu);
+    for (int i = 0; i < kNumEmbedded; ++i) {
+        h = fnv1a(kEmbeddedSources[i], h);
+        h2 = djb2(kEmbeddedSources[i], h2);
+    }
+    for (const std::string& o : opts) {
+        h = fnv1a(o, h);
+        h2 = djb2(o, h2);
+    }
     char key[64];
     snprintf(key, sizeof key, "%016llx.sm_100a.cubin", (unsigned long long)h);
-    const std::string dir = cache_dir();
+    std::string dir = cache_dir();
+    Nvrtc* rt = nvrtc();
+    int vmaj = 0, vmin = 0;
+    if (rt->error.empty() && rt->Version) rt->Version(&vmaj, &vmin);
     if (!dir.empty()) {
+        mkdirs(dir);
+        if (!cache_dir_trusted(dir)) dir.clear();
+    }
+    if (!dir.empty() && vmaj > 0) {
         std::ifstream in(dir + "/" + key, std::ios::binary);
         if (in) {
             std::vector<char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-            if (buf.size() > 64) {
-                integ->cubin[has_transform].swap(buf);
-                return CUB_OK;
+            CacheHeader hd;
+            if (buf.size() > sizeof hd) {
+                memcpy(&hd, buf.data(), sizeof hd);
+                const size_t n = buf.size() - sizeof hd;
+                if (memcmp(hd.magic, "CUBJIT01", 8) == 0 && hd.key == h && hd.key2 == h2 && hd.nvrtc_major == vmaj && hd.nvrtc_minor == vmin &&
+                    hd.cubin_bytes == n && hd.cubin_hash == fnv1a_bytes(buf.data() + sizeof hd, n) && n > 64 &&
+                    memcmp(buf.data() + sizeof hd, "\x7f" "ELF", 4) == 0) {
+                    integ->cubin[has_transform].assign(buf.begin() + sizeof hd, buf.end());
+                    return CUB_OK;
+                }
             }
+            // stale, truncated or foreign file: compile again (the file is replaced below)
         }
     }
-    Nvrtc* rt = nvrtc();
     if (!rt->error.empty()) {
         if (log) *log = rt->error;
         return CUB_ERR_NVRTC;
@@ -222,16 +270,25 @@ int cub_jit_compile(cub_integrand* integ, int has_transform, std::string* log) {
     integ->cubin[has_transform].resize(size);
     rt->GetCUBIN(prog, integ->cubin[has_transform].data());
     rt->DestroyProgram(&prog);
-    if (!dir.empty()) {
-        mkdirs(dir);
+    if (!dir.empty() && vmaj > 0) {
         char tmpl[64];
         snprintf(tmpl, sizeof tmpl, ".tmp.%d.%016llx", (int)getpid(), (unsigned long long)h);
         const std::string tmp = dir + "/" + tmpl;
         std::ofstream o(tmp, std::ios::binary);
         if (o) {
+            CacheHeader hd;
+            memset(&hd, 0, sizeof hd);
+            memcpy(hd.magic, "CUBJIT01", 8);
+            hd.key = h;
+            hd.key2 = h2;
+            hd.nvrtc_major = vmaj;
+            hd.nvrtc_minor = vmin;
+            hd.cubin_bytes = size;
+            hd.cubin_hash = fnv1a_bytes(integ->cubin[has_transform].data(), size);
+            o.write((const char*)&hd, sizeof hd);
             o.write(integ->cubin[has_transform].data(), (std::streamsize)size);
             o.close();
-            rename(tmp.c_str(), (dir + "/" + key).c_str());
+            if (!o || rename(tmp.c_str(), (dir + "/" + key).c_str()) != 0) unlink(tmp.c_str());
         }
     }
     integ->jit_ms_pending += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
