@@ -13,6 +13,7 @@
 //
 // Nothing in this file (or anywhere in cubature_b200/) touches oracle/: there is no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 
 #include "converge.h"
 #include "cub_internal.h"
@@ -59,12 +61,44 @@ struct VecAcc {  // accessor over dense val[f], err[f] for cub_converged
     CUB_HD double err(int j) const { return e[j]; }
 };
 
+// cudaMemGetInfo is a driver-wide query: 0.1 ms on an idle process, but 8 - 30 ms per call once the process holds tens of
+// GB or another thread polls NVML (measured inside the bench: 30 ms of a 112 ms step, profiles/r02/summary.md).  The
+// free-memory figure only bounds the pool capacity, so it is cached per device and refreshed after this library's own
+// allocations / frees (a stale figure costs at most a failed cudaMalloc, which is reported as CUB_ERR_POOL_EXHAUSTED).
+struct MemInfoCache {
+    std::atomic<unsigned long long> epoch{1};
+    std::mutex mu;
+    struct Entry { unsigned long long epoch = 0; size_t free_b = 0, total_b = 0; } dev[64];
+    static MemInfoCache& get() {
+        static MemInfoCache c;
+        return c;
+    }
+    void touch() { epoch.fetch_add(1, std::memory_order_relaxed); }
+    cudaError_t query(size_t* free_b, size_t* total_b) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return cudaMemGetInfo(free_b, total_b);
+        std::lock_guard<std::mutex> lk(mu);
+        const unsigned long long now = epoch.load(std::memory_order_relaxed);
+        if (dev[d].epoch != now) {
+            cudaError_t e = cudaMemGetInfo(&dev[d].free_b, &dev[d].total_b);
+            if (e != cudaSuccess) return e;
+            dev[d].epoch = now;
+        }
+        *free_b = dev[d].free_b;
+        *total_b = dev[d].total_b;
+        return cudaSuccess;
+    }
+};
+
 struct DevBuf {  // RAII device allocation
     void* p = nullptr;
     size_t bytes = 0;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            cudaFree(p);
+            MemInfoCache::get().touch();
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -72,6 +106,7 @@ struct DevBuf {  // RAII device allocation
         if (n <= bytes) return cudaSuccess;
         release();
         cudaError_t e = cudaMalloc(&p, n);
+        MemInfoCache::get().touch();
         if (e == cudaSuccess) bytes = n;
         return e;
     }
@@ -530,7 +565,7 @@ long long auto_capacity(int dim, int fdim, int64_t P, int64_t maxEval, long long
         cap = std::max<long long>(need, 1024);
     }
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    if (MemInfoCache::get().query(&free_b, &total_b) == cudaSuccess) {
         const size_t per = Pool::bytes_per_region(dim, fdim) + extra_per_region;
         const long long fit = (long long)((free_b * 0.85) / per);
         cap = std::min(cap, std::max<long long>(fit, 1024));
