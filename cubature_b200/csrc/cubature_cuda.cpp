@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -28,6 +29,7 @@
 #include "integrands.h"
 #include "pool_kernels.h"
 #include "iter_exact.h"
+#include "iter_vec.h"
 
 // ---- host-side sharding arithmetic of the multi-GPU path (also exported for CPU-only tests) --------
 extern "C" int64_t cubature_cuda_shard_count(int64_t n, int nranks, int rank) {
@@ -350,6 +352,7 @@ struct Workspace {
     DevBuf d_list, d_stage_val, d_stage_err, d_partial, d_small;
     DevBuf g_send, g_recv, g_dense;  // sharded vector select: padded send block, gathered blocks, dense [f + 1][Nglobal]
     DevBuf d_exact;                  // device-resident loop (iter_exact.h): control block, exact sums, histograms
+    DevBuf d_vec;                    // device-resident loop of vector integrands (iter_vec.h)
     PinnedBuf h_list, h_stage, h_small, h_exact;
     long long stage_stride = 0;
 };
@@ -457,7 +460,7 @@ struct Session {
 
     // Launches the rule kernel for `work`; for fdim > 1 a BISECT request is split into the stand-alone
     // bisect kernel + CHILDREN mode.  Rule-kernel time is accumulated with a pair of events.
-    int launch_rule(const PoolView& pool, HostWork work) {
+    int launch_rule(const PoolView& pool, HostWork work, bool errmax_rows = true) {
         if (work.n_items <= 0) return CUB_OK;
         if (ev_used + 2 > evpool.size()) {
             if (evpool.size() >= 512) {
@@ -500,7 +503,7 @@ struct Session {
             const unsigned grid = (unsigned)std::min<long long>((threads + 127) / 128, (long long)n_sms * kern->gk_blocks_per_sm);
             e = cudaLaunchKernel((const void*)kern->gk_separable, dim3(grid), dim3(128), args, 0, stream);
             ++launches;
-            if (e == cudaSuccess && fdim > 1) {
+            if (e == cudaSuccess && fdim > 1 && errmax_rows) {
                 pk_errmax_rows(pool, fdim, work.list, work.n_items, work.base, work.mode, stream);
                 ++launches;
             }
@@ -652,6 +655,8 @@ void push_batch(cub_trace_t* tr, int64_t nR) {
 }
 
 // ---- HEAP_EXACT: Rule.cubature replayed on the host, rule evaluation + bisection on the GPU --------
+int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                         LoopResult* res);
 int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt,
                          double* out, LoopResult* res) {
     const int f = S.fdim;
@@ -1798,13 +1803,15 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
 // k_exact_select, the bisect + rule kernel (sized by the control block).  The host enqueues `ahead` iterations, then reads
 // the 256-byte control block once; launches queued behind the end of the loop (or a pause) retire at once.  Pauses:
 // LS_GROW (the pool has to grow: host work), LS_HANDOFF (multi-GPU: time to deal the pool out to the ranks).
-struct ExactBufs {
+struct LoopCtl {  // the control block of a device-resident loop (iter_exact.h) as the host sees it
     long long* d_ctl = nullptr;
     long long* h_ctl = nullptr;            // pinned: the control block as the host last wrote / finally read it
     long long* h_snap[2] = {nullptr, nullptr};  // pinned: snapshots taken behind the batches in flight
+    int64_t batches_logged = 0;
+};
+struct ExactBufs : LoopCtl {
     IterXParams p{};
     int max_select_blocks = 1, max_decide_blocks = 1;
-    int64_t batches_logged = 0;
 };
 
 int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm) {
@@ -1855,7 +1862,10 @@ void exact_bind_pool(Session& S, ExactBufs& X) {
 // queued (two snapshot buffers, one event each).  A host thread that is descheduled for milliseconds -- seen on shared boxes
 // as 10 - 40 ms added to single steps of a 118 ms job when every visit was a stream synchronisation -- then costs nothing;
 // the price is at most two batches of launches that find the loop finished and retire at once.
-int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit) {
+// enqueue_iter(n_upper): queue one iteration (selection kernels + rule launch) for a pool of at most n_upper regions;
+// rebind(): the pool has been re-allocated.
+int loop_run(Session& S, LoopCtl& X, cub_trace_t* trace, long long cap_limit, const std::function<int(long long)>& enqueue_iter,
+             const std::function<int()>& rebind, bool scalar_stamps) {
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     const bool timing = getenv("CUBATURE_TIMING") != nullptr;
@@ -1882,30 +1892,7 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
     auto enqueue_batch = [&](int slot) -> int {
         for (int it = 0; it < batch; ++it) {
             cudaGetLastError();
-            // the decide kernel first folds what the previous iteration changed: at most 2 n_upper children (written by the
-            // rule launch before it; n_upper already counts them) and half as many popped parents, 8 per thread
-            long long Gd = (3 * n_upper / 2 + 8 * 256 - 1) / (8 * 256);
-            Gd = std::max<long long>(1, std::min<long long>(Gd, X.max_decide_blocks));
-            cudaError_t e = ix_decide(X.p, (int)Gd, S.n_sms, S.stream);
-            if (e != cudaSuccess) {
-                cub_set_message(S.msg, "decide kernel launch failed: %s", cudaGetErrorString(e));
-                return CUB_ERR_CUDA;
-            }
-            long long G = (n_upper + 4095) / 4096;
-            G = std::max<long long>(1, std::min<long long>(G, X.max_select_blocks));
-            e = ix_select(X.p, (int)G, S.stream);
-            if (e != cudaSuccess) {
-                cub_set_message(S.msg, "select kernel launch failed (%lld CTAs of at most %d): %s", G, X.max_select_blocks, cudaGetErrorString(e));
-                return CUB_ERR_CUDA;
-            }
-            S.launches += 2;
-            HostWork w{};
-            w.list = X.p.list;
-            w.dyn = X.d_ctl;
-            w.n_items = 2 * std::min<long long>(n_upper, pool.cap);  // upper bound: sizes the grid only
-            w.base = 0;
-            w.mode = MODE_BISECT;
-            const int rc = S.launch_rule(pool.view(), w);
+            const int rc = enqueue_iter(n_upper);
             if (rc != CUB_OK) return rc;
             n_upper = std::min<long long>(2 * n_upper, pool.cap);
         }
@@ -1955,14 +1942,16 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
                 return CUB_ERR_POOL_EXHAUSTED;
             }
             cudaError_t e = pool.grow(nc, N, S.stream);
-            if (e == cudaSuccess) e = W.sel.ensure_scalar(pool.cap);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", N, cudaGetErrorString(e));
                 return CUB_ERR_POOL_EXHAUSTED;
             }
             ++grows;
-            exact_bind_pool(S, X);
+            {
+                const int rc2 = rebind();
+                if (rc2 != CUB_OK) return rc2;
+            }
             X.h_ctl[LC_CAP] = pool.cap;
             X.h_ctl[LC_STATE] = LS_RUN;
             CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl + LC_CAP, X.h_ctl + LC_CAP, 8, cudaMemcpyHostToDevice, S.stream), S.msg);
@@ -1972,11 +1961,11 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
         }
         break;
     }
-    if (timing)
+    if (timing && scalar_stamps)
         fprintf(stderr, "[cubature] decide kernel of the last iteration (us): streaming + arrival %.1f, fold %.1f, exchange %.1f, decision %.1f\n",
                 (X.h_ctl[LC_STAMP] - X.h_ctl[LC_STAMP + 4]) * 1e-3, (X.h_ctl[LC_STAMP + 1] - X.h_ctl[LC_STAMP]) * 1e-3,
                 (X.h_ctl[LC_STAMP + 2] - X.h_ctl[LC_STAMP + 1]) * 1e-3, (X.h_ctl[LC_STAMP + 3] - X.h_ctl[LC_STAMP + 2]) * 1e-3);
-    if (timing) {
+    if (timing && scalar_stamps) {
         const long long* t = X.h_ctl + LC_STAMP + 5;
         fprintf(stderr, "[cubature] select kernel of the last cut (us, CTA 0): binade histogram %.1f, walk %.1f, levels", (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3);
         long long prev = t[2];
@@ -1992,6 +1981,47 @@ int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit)
                 (long long)X.h_ctl[LC_ITER], (long long)X.h_ctl[LC_NSELECT], visits, grows,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     return CUB_OK;
+}
+
+int exact_run(Session& S, ExactBufs& X, cub_trace_t* trace, long long cap_limit) {
+    Pool& pool = S.ws->pool;
+    auto enqueue_iter = [&](long long n_upper) -> int {
+        // the decide kernel first folds what the previous iteration changed: at most 2 n_upper children (written by the
+        // rule launch before it; n_upper already counts them) and half as many popped parents, 8 per thread
+        long long Gd = (3 * n_upper / 2 + 8 * 256 - 1) / (8 * 256);
+        Gd = std::max<long long>(1, std::min<long long>(Gd, X.max_decide_blocks));
+        cudaError_t e = ix_decide(X.p, (int)Gd, S.n_sms, S.stream);
+        if (e != cudaSuccess) {
+            cub_set_message(S.msg, "decide kernel launch failed: %s", cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        long long G = (n_upper + 4095) / 4096;
+        G = std::max<long long>(1, std::min<long long>(G, X.max_select_blocks));
+        e = ix_select(X.p, (int)G, S.stream);
+        if (e != cudaSuccess) {
+            cub_set_message(S.msg, "select kernel launch failed (%lld CTAs of at most %d): %s", G, X.max_select_blocks, cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        S.launches += 2;
+        HostWork w{};
+        w.list = X.p.list;
+        w.dyn = X.d_ctl;
+        w.n_items = 2 * std::min<long long>(n_upper, pool.cap);  // upper bound: sizes the grid only
+        w.base = 0;
+        w.mode = MODE_BISECT;
+        return S.launch_rule(pool.view(), w);
+    };
+    auto rebind = [&]() -> int {
+        cudaError_t e = S.ws->sel.ensure_scalar(pool.cap);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cub_set_message(S.msg, "region pool exhausted at %lld regions (%s)", (long long)X.h_ctl[LC_N], cudaGetErrorString(e));
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+        exact_bind_pool(S, X);
+        return CUB_OK;
+    };
+    return loop_run(S, X, trace, cap_limit, enqueue_iter, rebind, true);
 }
 
 int exact_finish(Session& S, ExactBufs& X, double* out, LoopResult* res, cub_trace_t* trace) {
@@ -2081,6 +2111,171 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     rc = exact_finish(S, X, out, res, trace);
     if (timing) fprintf(stderr, "[cubature] root launch + control block %.3f ms, loop %.3f ms, finish %.3f ms (host clock)\n", t_run0 - t_root, t_run1 - t_run0, since() - t_run1);
     return rc;
+}
+
+// ---- DEVICE mode, vector integrands (fdim > 1): device-resident loop (iter_vec.cu) ------------------------------------------
+// One iteration of Rule.cubature (Rule.java:72-142) = the cooperative iteration kernel (totals, convergence, batch cut on the
+// per-component residual, compaction, bisection) + the rule launch it sizes; same control block, same enqueue-ahead host
+// loop as the scalar path.
+struct VecBufs : LoopCtl {
+    IterVParams p{};
+    int max_blocks = 1;
+};
+
+int vec_setup(Session& S, VecBufs& X, double relTol, double absTol, int norm) {
+    Workspace& W = *S.ws;
+    const int f = S.fdim;
+    const int maxG = iv_max_blocks(S.n_sms, f);
+    int gc = IV_GC_ROWS / f;
+    gc = std::max(1, std::min(gc, maxG));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t ctl_b = up((size_t)(LC_WORDS + LC_LOG_CAP) * 8), partial_b = up((size_t)2 * f * maxG * 8), totals_b = up((size_t)4 * f * 8),
+                 blk_b = up(((size_t)4 * maxG + 8) * 8), bar_b = 256, bpart_b = up((size_t)gc * IV_NB * f * 8), bcpart_b = up((size_t)gc * IV_NB * 8),
+                 bsum_b = up((size_t)IV_NB * f * 8), bcnt_b = up((size_t)IV_NB * 8), sab_b = up((size_t)2 * f * 8), chi_b = up((size_t)IV_CMAX * 8),
+                 clo_b = up((size_t)IV_CMAX * 4), cres_b = up((size_t)IV_CMAX * f * 8), cbase_b = up((size_t)IV_CHUNKS * f * 8), st_b = 256;
+    const size_t total = ctl_b + partial_b + totals_b + blk_b + bar_b + bpart_b + bcpart_b + bsum_b + bcnt_b + sab_b + chi_b + clo_b + cres_b + cbase_b + st_b;
+    CUB_CUDA_CHECK(W.d_vec.ensure(total), S.msg);
+    CUB_CUDA_CHECK(W.h_exact.ensure(3 * (size_t)(LC_WORDS + LC_LOG_CAP) * 8 + (size_t)2 * f * 8), S.msg);
+    unsigned char* q = W.d_vec.as<unsigned char>();
+    // the control block, the barrier words and the selection state start from zero; the rest is written before it is read
+    CUB_CUDA_CHECK(cudaMemsetAsync(q, 0, ctl_b, S.stream), S.msg);
+    X.d_ctl = (long long*)q;
+    q += ctl_b;
+    X.p.partial = (double*)q;
+    q += partial_b;
+    X.p.totals = (double*)q;
+    q += totals_b;
+    X.p.blk = (unsigned long long*)q;
+    q += blk_b;
+    X.p.bar = (unsigned long long*)q;
+    CUB_CUDA_CHECK(cudaMemsetAsync(q, 0, bar_b, S.stream), S.msg);
+    q += bar_b;
+    X.p.bsum_part = (double*)q;
+    q += bpart_b;
+    X.p.bcnt_part = (unsigned long long*)q;
+    q += bcpart_b;
+    X.p.bsum = (double*)q;
+    q += bsum_b;
+    X.p.bcnt = (unsigned long long*)q;
+    q += bcnt_b;
+    X.p.sabove = (double*)q;
+    q += sab_b;
+    X.p.cand_hi = (unsigned long long*)q;
+    q += chi_b;
+    X.p.cand_lo = (unsigned*)q;
+    q += clo_b;
+    X.p.cres = (double*)q;
+    q += cres_b;
+    X.p.cbase = (double*)q;
+    q += cbase_b;
+    X.p.state = (IvState*)q;
+    CUB_CUDA_CHECK(cudaMemsetAsync(q, 0, st_b, S.stream), S.msg);
+    X.h_ctl = W.h_exact.as<long long>();
+    X.h_snap[0] = X.h_ctl + (LC_WORDS + LC_LOG_CAP);
+    X.h_snap[1] = X.h_ctl + 2 * (LC_WORDS + LC_LOG_CAP);
+    X.p.ctl = X.d_ctl;
+    X.p.dim = S.dim;
+    X.p.fdim = f;
+    X.p.need_errmax = (S.dim == 1 && S.integ->separable) ? 1 : 0;  // cub_gk_separable leaves errmax / splitdim to the loop
+    X.p.gc_max = gc;
+    X.p.absTol = absTol;
+    X.p.relTol = relTol;
+    X.p.norm = norm;
+    X.max_blocks = maxG;
+    return CUB_OK;
+}
+
+int vec_bind_pool(Session& S, VecBufs& X) {
+    Workspace& W = *S.ws;
+    cudaError_t e = W.sel.idxA.ensure((size_t)4 * W.pool.cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cub_set_message(S.msg, "region pool exhausted (%s)", cudaGetErrorString(e));
+        return CUB_ERR_POOL_EXHAUSTED;
+    }
+    X.p.pool = W.pool.view();
+    X.p.list = W.sel.idxA.as<int>();
+    return CUB_OK;
+}
+
+int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                         LoopResult* res) {
+    const int f = S.fdim;
+    const int64_t P = S.P;
+    cub_trace_t* trace = opt ? opt->trace : nullptr;
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    const size_t extra = 4;
+    const long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
+    int rc = set_root(S, pool);
+    if (rc != CUB_OK) return rc;
+    VecBufs X;
+    rc = vec_setup(S, X, relTol, absTol, norm);
+    if (rc != CUB_OK) return rc;
+    rc = vec_bind_pool(S, X);
+    if (rc != CUB_OK) return rc;
+    {
+        HostWork w{};
+        w.n_items = 1;
+        w.base = 0;
+        w.mode = MODE_PLAIN;
+        rc = S.launch_rule(pool.view(), w, false);  // Rule.java:64-69: the root region
+        if (rc != CUB_OK) return rc;
+    }
+    long long* h = X.h_ctl;
+    memset(h, 0, (size_t)LC_WORDS * 8);
+    h[LC_DYN_N] = 1;  // the first iteration kernel finds the root region as item 0 of an identity batch (slot 0)
+    h[LC_N] = 1;
+    h[LC_NGLOBAL] = 1;
+    h[LC_NUMEVAL] = P;
+    h[LC_CAP] = pool.cap;
+    h[LC_MAXEVAL] = maxEval;
+    h[LC_P] = P;
+    h[LC_MAXITER] = kMaxIterations;
+    CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, h, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+    S.h2d_bytes += LC_WORDS * 8;
+    auto enqueue_iter = [&](long long n_upper) -> int {
+        long long G = (n_upper + 1023) / 1024;
+        G = std::max<long long>(1, std::min<long long>(G, X.max_blocks));
+        cudaError_t e = iv_iter(X.p, (int)G, S.stream);
+        if (e != cudaSuccess) {
+            cub_set_message(S.msg, "iteration kernel launch failed (%lld CTAs of at most %d): %s", G, X.max_blocks, cudaGetErrorString(e));
+            return CUB_ERR_CUDA;
+        }
+        S.launches += 1;
+        HostWork w{};
+        w.list = X.p.list;
+        w.dyn = X.d_ctl;
+        w.n_items = 2 * std::min<long long>(n_upper, pool.cap);  // upper bound: sizes the grid only
+        w.base = 0;
+        w.mode = MODE_CHILDREN;  // the iteration kernel has bisected the parents
+        return S.launch_rule(pool.view(), w, false);
+    };
+    auto rebind = [&]() -> int { return vec_bind_pool(S, X); };
+    rc = loop_run(S, X, trace, cap, enqueue_iter, rebind, false);
+    if (rc != CUB_OK) return rc;
+    const long long state = X.h_ctl[LC_STATE];
+    if (state == LS_ERROR) {
+        cub_set_message(S.msg, "internal: the batch selection of the vector loop failed (code %lld)", (long long)X.h_ctl[LC_DBG0]);
+        return CUB_ERR_CUDA;
+    }
+    if (state == LS_GUARD) cub_set_message(S.msg, "stopped after %lld iterations without convergence", (long long)X.h_ctl[LC_ITER]);
+    // the totals of the last decision: val[f] then err[f]
+    double* h_tot = (double*)(X.h_ctl + 3 * (LC_WORDS + LC_LOG_CAP));
+    CUB_CUDA_CHECK(cudaMemcpyAsync(h_tot, X.p.totals, (size_t)2 * f * 8, cudaMemcpyDeviceToHost, S.stream), S.msg);
+    CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);
+    S.d2h_bytes += (int64_t)2 * f * 8;
+    for (int j = 0; j < 2 * f; ++j) out[j] = h_tot[j];
+    S.flush_rule_timer();
+    res->converged = state == LS_CONVERGED ? 1 : 0;
+    res->num_eval = X.h_ctl[LC_NUMEVAL];
+    res->num_regions = X.h_ctl[LC_NGLOBAL];
+    res->iterations = X.h_ctl[LC_ITER];
+    res->ambiguous = X.h_ctl[LC_AMBIG];
+    S.local_regions_evaluated = 1 + X.h_ctl[LC_EVAL_LOCAL];
+    fill_trace_regions(S, pool, nullptr, X.h_ctl[LC_N], trace);
+    return CUB_OK;
 }
 
 // Multi-GPU (section 8e), scalar integrands, NVLink peers: replicated phase on every rank, ranked deal, then the same
@@ -2411,7 +2606,9 @@ int integrate_impl(cub_integrand_t* integrand, int dim, const double* xmin, cons
         ExactBufs X;
         bool handoff = false;
         rc = integrate_device_exact(S, relTol, absTol, norm, maxEval, options, out, &res, X, 0, 0, &handoff);
-    } else
+    } else if (S.fdim > 1 && !legacy_loop())
+        rc = integrate_device_vec(S, relTol, absTol, norm, maxEval, options, out, &res);
+    else
         rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, options, out, &res);
     const double t_body = call_ms();
     cudaEventRecord(S.ev1, S.stream);
