@@ -12,6 +12,7 @@ No CPU path exists here: without the CUDA library or without a GPU every call ra
 """
 import ctypes as C
 import enum
+import os
 
 import numpy as np
 
@@ -220,7 +221,7 @@ class Cubature:
     @staticmethod
     def integrate_ex(integrand, xmin, xmax, relTol, absTol, norm=CubatureError.INDIVIDUAL, maxEval=0, transform=None,
                      select=Select.DEVICE, device=-1, pool_capacity=0, trace_regions=0, trace_batches=0, comm=None,
-                     shard_min_regions=0, strict_all=False):
+                     shard_min_regions=0, strict_all=False, checkpoint_save=None, checkpoint_load=None):
         """-> (result[2][fdim], Stats, Trace or None)."""
         L = _ffi.lib()
         if xmin is None or len(xmin) == 0:
@@ -241,6 +242,8 @@ class Cubature:
         opt.comm = comm._h if comm is not None else None
         opt.shard_min_regions = shard_min_regions
         opt.strict_all = 1 if strict_all else 0
+        opt.checkpoint_save = None if checkpoint_save is None else os.fsencode(checkpoint_save)
+        opt.checkpoint_load = None if checkpoint_load is None else os.fsencode(checkpoint_load)
         tr = None
         keep = []
         if trace_regions or trace_batches:
@@ -274,6 +277,29 @@ class Cubature:
             trace = Trace(keep[0][:nb].tolist(), keep[1][:nr], keep[2][:nr], keep[3][:nr], keep[4][:nr], keep[5][:nr])
             trace.n_batches, trace.n_regions = int(tr.n_batches), int(tr.n_regions)
         return out, Stats(st), trace
+
+
+def checkpoint_info(path):
+    """Header of a pool checkpoint (no GPU needed) -> dict."""
+    info = _ffi.CubCheckpointInfo()
+    _check(_ffi.lib().cubature_cuda_checkpoint_info(os.fsencode(path), C.byref(info)))
+    return {"dim": info.dim, "fdim": info.fdim, "family": info.family, "n_regions": info.n_regions, "num_eval": info.num_eval,
+            "iterations": info.iterations, "transform": list(info.transform)[:info.dim], "shift": list(info.shift)[:info.dim]}
+
+
+def checkpoint_regions(path, first=0, count=None):
+    """Regions [first, first + count) of a pool checkpoint (no GPU needed) -> (centers, halfwidths, val, err, split_dim)."""
+    info = checkpoint_info(path)
+    n = info["n_regions"] - first if count is None else count
+    n = max(0, min(n, info["n_regions"] - first))
+    c, h = np.zeros((n, info["dim"])), np.zeros((n, info["dim"]))
+    v, e = np.zeros((n, info["fdim"])), np.zeros((n, info["fdim"]))
+    sd = np.zeros(n, dtype=np.int32)
+    got = _ffi.lib().cubature_cuda_checkpoint_regions(os.fsencode(path), int(first), int(n), _dp(c), _dp(h), _dp(v), _dp(e),
+                                                      sd.ctypes.data_as(_ffi.c_int32_p))
+    if got < 0:
+        _check(int(got))
+    return c[:got], h[:got], v[:got], e[:got], sd[:got]
 
 
 def fp64_peak_tflops(device=-1):

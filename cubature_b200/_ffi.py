@@ -40,6 +40,22 @@ class CubOptions(C.Structure):
         ("trace", C.POINTER(CubTrace)),
         ("comm", C.c_void_p),
         ("shard_min_regions", C.c_int64),
+        ("checkpoint_save", C.c_char_p),
+        ("checkpoint_load", C.c_char_p),
+    ]
+
+
+class CubCheckpointInfo(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("fdim", C.c_int32),
+        ("family", C.c_int32),
+        ("reserved", C.c_int32),
+        ("n_regions", C.c_int64),
+        ("num_eval", C.c_int64),
+        ("iterations", C.c_int64),
+        ("transform", C.c_int32 * 12),
+        ("shift", C.c_double * 12),
     ]
 
 
@@ -70,6 +86,8 @@ SIGNATURES = {
     "cubature_cuda_points_per_region": (C.c_int64, [C.c_int]),
     "cubature_cuda_converged": (C.c_int, [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int]),
     "cubature_cuda_rule_points": (C.c_int, [C.c_int, c_double_p, c_double_p, c_double_p]),
+    "cubature_cuda_checkpoint_info": (C.c_int, [C.c_char_p, C.POINTER(CubCheckpointInfo)]),
+    "cubature_cuda_checkpoint_regions": (C.c_int64, [C.c_char_p, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "cubature_cuda_integrand_builtin": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "cubature_cuda_integrand_nvrtc": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_size_t,
                                                 C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),

@@ -30,6 +30,7 @@
 #include "pool_kernels.h"
 #include "iter_exact.h"
 #include "iter_vec.h"
+#include "checkpoint.h"
 
 // ---- host-side sharding arithmetic of the multi-GPU path (also exported for CPU-only tests) --------
 extern "C" int64_t cubature_cuda_shard_count(int64_t n, int nranks, int rank) {
@@ -1798,6 +1799,123 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
     return CUB_OK;
 }
 
+// ---- pool checkpoint (checkpoint.h): dump / upload of the structure-of-arrays pool ------------------------------------------
+int checkpoint_write(Session& S, Pool& pool, long long n, int64_t num_eval, int64_t iterations, const char* path) {
+    FILE* fp = fopen(path, "wb");
+    if (!fp) {
+        cub_set_message(S.msg, "cannot write the pool checkpoint %s", path);
+        return CUB_ERR_BAD_ARGS;
+    }
+    CkptHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "CUBCKPT1", 8);
+    h.version = 1;
+    h.dim = S.dim;
+    h.fdim = S.fdim;
+    h.family = S.integ->family;
+    h.n_regions = n;
+    h.num_eval = num_eval;
+    h.iterations = iterations;
+    for (int d = 0; d < S.dim; ++d) {
+        h.transform[d] = S.tr.code[d];
+        h.shift[d] = S.tr.shift[d];
+        h.tmin[d] = S.tr.tmin[d];
+        h.tmax[d] = S.tr.tmax[d];
+    }
+    h.integrand_hash = ckpt_integrand_hash(S.integ);
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1;  // placeholder: rewritten with the payload checksum
+    std::vector<double> row((size_t)n);
+    uint64_t sum = 0x452821e638d01377ULL;
+    auto dump = [&](const DevBuf& buf, int nrows, size_t elt) {
+        for (int r = 0; r < nrows && ok; ++r) {
+            if (cudaMemcpy(row.data(), (const char*)buf.p + (size_t)r * pool.cap * elt, (size_t)n * elt, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                ok = false;
+                break;
+            }
+            sum = ckpt_mix(sum, row.data(), (size_t)n * elt);
+            ok = fwrite(row.data(), elt, (size_t)n, fp) == (size_t)n;
+            S.d2h_bytes += (int64_t)n * (int64_t)elt;
+        }
+    };
+    dump(pool.center, S.dim, 8);
+    dump(pool.halfw, S.dim, 8);
+    dump(pool.val, S.fdim, 8);
+    dump(pool.err, S.fdim, 8);
+    dump(pool.errmax, 1, 8);
+    dump(pool.splitdim, 1, 4);
+    h.payload_checksum = sum;
+    ckpt_seal_header(&h);
+    ok = ok && fseek(fp, 0, SEEK_SET) == 0 && fwrite(&h, sizeof h, 1, fp) == 1;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) {
+        cudaGetLastError();
+        cub_set_message(S.msg, "writing the pool checkpoint %s failed", path);
+        return CUB_ERR_CUDA;
+    }
+    return CUB_OK;
+}
+
+// Reads a checkpoint of this very problem (integrand, box, transform) into the pool (allocated for at least min_cap regions).
+int checkpoint_load(Session& S, Pool& pool, const char* path, long long min_cap, bool exact_cap, CkptHeader* h) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) {
+        cub_set_message(S.msg, "cannot read the pool checkpoint %s", path);
+        return CUB_ERR_BAD_ARGS;
+    }
+    int rc = ckpt_read_header(fp, h, S.msg);
+    if (rc == CUB_OK) {
+        bool same = h->dim == S.dim && h->fdim == S.fdim && h->integrand_hash == ckpt_integrand_hash(S.integ);
+        for (int d = 0; d < S.dim && same; ++d)
+            same = h->transform[d] == S.tr.code[d] && h->shift[d] == S.tr.shift[d] && h->tmin[d] == S.tr.tmin[d] && h->tmax[d] == S.tr.tmax[d];
+        if (!same) {
+            cub_set_message(S.msg, "the pool checkpoint belongs to another problem (integrand, box or transform differ)");
+            rc = CUB_ERR_BAD_ARGS;
+        }
+    }
+    if (rc == CUB_OK && h->n_regions >= (int64_t)std::numeric_limits<int>::max() / 2) {
+        cub_set_message(S.msg, "the pool checkpoint holds %lld regions: more than one GPU's slot range", (long long)h->n_regions);
+        rc = CUB_ERR_POOL_EXHAUSTED;
+    }
+    if (rc != CUB_OK) {
+        fclose(fp);
+        return rc;
+    }
+    const long long n = h->n_regions;
+    cudaError_t e = pool.alloc(S.dim, S.fdim, std::max<long long>(min_cap, n + 1), exact_cap);
+    if (e == cudaSuccess && pool.cap < n + 1) e = pool.alloc(S.dim, S.fdim, n + 1, true);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fclose(fp);
+        cub_set_message(S.msg, "region pool exhausted: the checkpoint's %lld regions do not fit (%s)", n, cudaGetErrorString(e));
+        return CUB_ERR_POOL_EXHAUSTED;
+    }
+    std::vector<double> row((size_t)n);
+    uint64_t sum = 0x452821e638d01377ULL;
+    bool ok = true;
+    auto load = [&](DevBuf& buf, int nrows, size_t elt) {
+        for (int r = 0; r < nrows && ok; ++r) {
+            ok = fread(row.data(), elt, (size_t)n, fp) == (size_t)n;
+            if (!ok) break;
+            sum = ckpt_mix(sum, row.data(), (size_t)n * elt);
+            ok = cudaMemcpy((char*)buf.p + (size_t)r * pool.cap * elt, row.data(), (size_t)n * elt, cudaMemcpyHostToDevice) == cudaSuccess;
+            S.h2d_bytes += (int64_t)n * (int64_t)elt;
+        }
+    };
+    load(pool.center, S.dim, 8);
+    load(pool.halfw, S.dim, 8);
+    load(pool.val, S.fdim, 8);
+    load(pool.err, S.fdim, 8);
+    load(pool.errmax, 1, 8);
+    load(pool.splitdim, 1, 4);
+    fclose(fp);
+    if (!ok || sum != h->payload_checksum) {
+        cudaGetLastError();
+        cub_set_message(S.msg, "the pool checkpoint %s is truncated or damaged", path);
+        return CUB_ERR_BAD_ARGS;
+    }
+    return CUB_OK;
+}
+
 // ---- DEVICE mode, scalar integrands: device-resident loop on exact running sums (iter_exact.cu) -------------------------
 // One iteration of Rule.cubature (Rule.java:72-142) = three launches with no host decision in between: k_exact_decide,
 // k_exact_select, the bisect + rule kernel (sized by the control block).  The host enqueues `ahead` iterations, then reads
@@ -2067,17 +2185,25 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     const size_t extra = 24 + (size_t)8 * f + 1;
     const long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
     const double t_cap = since();
-    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
+    const char* ck_load = opt ? opt->checkpoint_load : nullptr;
+    CkptHeader ck;
+    int rc = CUB_OK;
+    if (ck_load) {
+        rc = checkpoint_load(S, pool, ck_load, cap, opt && opt->pool_capacity > 0, &ck);
+        if (rc != CUB_OK) return rc;
+    } else {
+        CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
+    }
     CUB_CUDA_CHECK(W.sel.ensure_scalar(pool.cap), S.msg);
     const double t_alloc = since();
-    int rc = set_root(S, pool);
+    if (!ck_load) rc = set_root(S, pool);
     if (rc != CUB_OK) return rc;
     const double t_root = since();
     rc = exact_setup(S, X, relTol, absTol, norm);
     if (rc != CUB_OK) return rc;
     exact_bind_pool(S, X);
     if (timing) fprintf(stderr, "[cubature] start-up (host ms): capacity %.3f, buffers %.3f, root box %.3f, loop state %.3f\n", t_cap, t_alloc - t_cap, t_root - t_alloc, since() - t_root);
-    {
+    if (!ck_load) {
         HostWork w{};
         w.n_items = 1;
         w.base = 0;
@@ -2091,6 +2217,14 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     h[LC_N] = 1;
     h[LC_NGLOBAL] = 1;
     h[LC_NUMEVAL] = P;
+    if (ck_load) {  // resume: the pool comes from the file, the exact sums are rebuilt from it, nothing is pending
+        ix_rebuild(pool.view(), ck.n_regions, X.p.acc, S.n_sms, S.stream);
+        S.launches += 1;
+        h[LC_DYN_N] = 0;
+        h[LC_N] = h[LC_NGLOBAL] = ck.n_regions;
+        h[LC_NUMEVAL] = ck.num_eval;
+        h[LC_ITER] = ck.iterations;
+    }
     h[LC_CAP] = pool.cap;
     h[LC_MAXEVAL] = maxEval;
     h[LC_P] = P;
@@ -2109,6 +2243,7 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     if (handoff) *handoff = false;
     const double t_run1 = since();
     rc = exact_finish(S, X, out, res, trace);
+    if (rc == CUB_OK && opt && opt->checkpoint_save) rc = checkpoint_write(S, pool, X.h_ctl[LC_N], X.h_ctl[LC_NUMEVAL], X.h_ctl[LC_ITER], opt->checkpoint_save);
     if (timing) fprintf(stderr, "[cubature] root launch + control block %.3f ms, loop %.3f ms, finish %.3f ms (host clock)\n", t_run0 - t_root, t_run1 - t_run0, since() - t_run1);
     return rc;
 }
@@ -2132,8 +2267,8 @@ int vec_setup(Session& S, VecBufs& X, double relTol, double absTol, int norm) {
     const size_t ctl_b = up((size_t)(LC_WORDS + LC_LOG_CAP) * 8), partial_b = up((size_t)2 * f * maxG * 8), totals_b = up((size_t)4 * f * 8),
                  blk_b = up(((size_t)4 * maxG + 8) * 8), bar_b = 256, bpart_b = up((size_t)gc * IV_NB * f * 8), bcpart_b = up((size_t)gc * IV_NB * 8),
                  bsum_b = up((size_t)IV_NB * f * 8), bcnt_b = up((size_t)IV_NB * 8), sab_b = up((size_t)2 * f * 8), chi_b = up((size_t)IV_CMAX * 8),
-                 clo_b = up((size_t)IV_CMAX * 4), cres_b = up((size_t)IV_CMAX * f * 8), cbase_b = up((size_t)IV_CHUNKS * f * 8), st_b = 256;
-    const size_t total = ctl_b + partial_b + totals_b + blk_b + bar_b + bpart_b + bcpart_b + bsum_b + bcnt_b + sab_b + chi_b + clo_b + cres_b + cbase_b + st_b;
+                 clo_b = up((size_t)IV_CMAX * 4), shi_b = chi_b, slo_b = clo_b, cres_b = up((size_t)IV_CMAX * f * 8), cbase_b = up((size_t)IV_CHUNKS * f * 8), st_b = 256;
+    const size_t total = ctl_b + partial_b + totals_b + blk_b + bar_b + bpart_b + bcpart_b + bsum_b + bcnt_b + sab_b + chi_b + clo_b + shi_b + slo_b + cres_b + cbase_b + st_b;
     CUB_CUDA_CHECK(W.d_vec.ensure(total), S.msg);
     CUB_CUDA_CHECK(W.h_exact.ensure(3 * (size_t)(LC_WORDS + LC_LOG_CAP) * 8 + (size_t)2 * f * 8), S.msg);
     unsigned char* q = W.d_vec.as<unsigned char>();
@@ -2164,6 +2299,10 @@ int vec_setup(Session& S, VecBufs& X, double relTol, double absTol, int norm) {
     q += chi_b;
     X.p.cand_lo = (unsigned*)q;
     q += clo_b;
+    X.p.sort_hi = (unsigned long long*)q;
+    q += shi_b;
+    X.p.sort_lo = (unsigned*)q;
+    q += slo_b;
     X.p.cres = (double*)q;
     q += cres_b;
     X.p.cbase = (double*)q;
@@ -2207,15 +2346,22 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     Pool& pool = W.pool;
     const size_t extra = 4;
     const long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
-    CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
-    int rc = set_root(S, pool);
+    const char* ck_load = opt ? opt->checkpoint_load : nullptr;
+    CkptHeader ck;
+    int rc = CUB_OK;
+    if (ck_load) {
+        rc = checkpoint_load(S, pool, ck_load, cap, opt && opt->pool_capacity > 0, &ck);
+    } else {
+        CUB_CUDA_CHECK(pool.alloc(S.dim, f, cap, opt && opt->pool_capacity > 0), S.msg);
+        rc = set_root(S, pool);
+    }
     if (rc != CUB_OK) return rc;
     VecBufs X;
     rc = vec_setup(S, X, relTol, absTol, norm);
     if (rc != CUB_OK) return rc;
     rc = vec_bind_pool(S, X);
     if (rc != CUB_OK) return rc;
-    {
+    if (!ck_load) {
         HostWork w{};
         w.n_items = 1;
         w.base = 0;
@@ -2229,6 +2375,12 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     h[LC_N] = 1;
     h[LC_NGLOBAL] = 1;
     h[LC_NUMEVAL] = P;
+    if (ck_load) {  // resume: the pool (errmax included) comes from the file
+        h[LC_DYN_N] = 0;
+        h[LC_N] = h[LC_NGLOBAL] = ck.n_regions;
+        h[LC_NUMEVAL] = ck.num_eval;
+        h[LC_ITER] = ck.iterations;
+    }
     h[LC_CAP] = pool.cap;
     h[LC_MAXEVAL] = maxEval;
     h[LC_P] = P;
@@ -2236,7 +2388,8 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, h, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
     S.h2d_bytes += LC_WORDS * 8;
     auto enqueue_iter = [&](long long n_upper) -> int {
-        long long G = (n_upper + 1023) / 1024;
+        // one CTA per 1 024 regions, and enough warps for one row of the totals each (2 f rows, 8 warps per CTA)
+        long long G = std::max<long long>((n_upper + 1023) / 1024, (2 * (long long)f + 7) / 8);
         G = std::max<long long>(1, std::min<long long>(G, X.max_blocks));
         cudaError_t e = iv_iter(X.p, (int)G, S.stream);
         if (e != cudaSuccess) {
@@ -2255,6 +2408,13 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     auto rebind = [&]() -> int { return vec_bind_pool(S, X); };
     rc = loop_run(S, X, trace, cap, enqueue_iter, rebind, false);
     if (rc != CUB_OK) return rc;
+    if (getenv("CUBATURE_TIMING")) {
+        const long long* t = X.h_ctl + LC_STAMP;
+        auto us = [&](int a, int b2) { return t[b2] > t[a] ? (t[b2] - t[a]) * 1e-3 : 0.0; };
+        fprintf(stderr, "[cubature] vector iteration kernel, last iteration / last cut (us, CTA 0): errmax + barrier %.1f, partials %.1f, totals %.1f, decisions %.1f; "
+                        "last of %lld narrowing levels: sums %.1f, reduce %.1f, pick %.1f; gather %.1f, sort %.1f, residuals + predicate %.1f, counts %.1f, list %.1f, bisect %.1f\n",
+                us(0, 1), us(1, 2), us(2, 3), us(3, 4), (long long)t[13], us(15, 5), us(5, 6), us(6, 7), t[13] ? us(7, 8) : us(4, 8), us(8, 14), us(14, 9), us(9, 10), us(10, 11), us(11, 12));
+    }
     const long long state = X.h_ctl[LC_STATE];
     if (state == LS_ERROR) {
         cub_set_message(S.msg, "internal: the batch selection of the vector loop failed (code %lld)", (long long)X.h_ctl[LC_DBG0]);
@@ -2275,6 +2435,7 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     res->ambiguous = X.h_ctl[LC_AMBIG];
     S.local_regions_evaluated = 1 + X.h_ctl[LC_EVAL_LOCAL];
     fill_trace_regions(S, pool, nullptr, X.h_ctl[LC_N], trace);
+    if (opt && opt->checkpoint_save) return checkpoint_write(S, pool, X.h_ctl[LC_N], X.h_ctl[LC_NUMEVAL], X.h_ctl[LC_ITER], opt->checkpoint_save);
     return CUB_OK;
 }
 
@@ -2593,6 +2754,11 @@ int integrate_impl(cub_integrand_t* integrand, int dim, const double* xmin, cons
     const double t_open = call_ms();
     LoopResult res;
     cudaEventRecord(S.ev0, S.stream);
+    const bool wants_ckpt = options && (options->checkpoint_save || options->checkpoint_load);
+    if (wants_ckpt && (select == CUB_SELECT_HEAP_EXACT || (options->comm && options->comm->nranks > 1) || legacy_loop())) {
+        cub_set_message(S.msg, "pool checkpoints need the device-resident loop on one GPU (select = DEVICE, no communicator)");
+        return CUB_ERR_UNSUPPORTED;
+    }
     if (select == CUB_SELECT_HEAP_EXACT)
         rc = integrate_heap_exact(S, relTol, absTol, norm, maxEval, options, out, &res);
     else if (options && options->comm && options->comm->nranks > 1) {

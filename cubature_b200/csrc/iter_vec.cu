@@ -34,6 +34,17 @@ __device__ __forceinline__ iv_u128 iv_comp(unsigned long long key, long long slo
     return ((iv_u128)key << 32) | (iv_u128)(0xffffffffu - (unsigned)slot);
 }
 
+__device__ __forceinline__ unsigned long long iv_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// phase time stamps of the last iteration (CUBATURE_TIMING): CTA 0, thread 0
+#define IV_STAMP(k)                                                                         \
+    do {                                                                                    \
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.ctl[LC_STAMP + (k)] = (long long)iv_timer_ns(); \
+    } while (0)
+
 __device__ __forceinline__ void iv_gsync(unsigned long long* bar, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -70,6 +81,15 @@ struct IvBucketAcc {
         return E[j] - (__ldcg(&sab[j]) + s);
     }
 };
+// the same from suffix sums staged in shared memory
+struct IvSuffixAcc {
+    const double* v;
+    const double* E;
+    const double* sab;
+    const double* ssq;  // suffix sum of the buckets q .. IV_NB-1
+    __device__ double val(int j) const { return v[j]; }
+    __device__ double err(int j) const { return E[j] - (sab[j] + ssq[j]); }
+};
 // residual after popping the sorted candidates 0 .. k
 struct IvCandAcc {
     const double* v;      // shared
@@ -81,9 +101,39 @@ struct IvCandAcc {
     __device__ double err(int j) const { return (cbase[j] - crow[j]) + add * E[j]; }
 };
 
+// Rule.converged evaluated by a whole warp (every lane calls with the same arguments, every lane gets the result).
+// INDIVIDUAL / PAIRED test the components (pairs) independently and combine them with OR (the reference's ANY, Rule.java:
+// 172-213) or AND (strict-ALL extension): lanes take the units in turn and evaluate each with cub_converged itself on a
+// one-unit view, so the arithmetic is literally the reference's.  The other norms carry ordered sums: lane 0 evaluates.
+template <class Acc>
+struct IvShiftAcc {
+    const Acc& a;
+    int j0;
+    __device__ double val(int j) const { return a.val(j0 + j); }
+    __device__ double err(int j) const { return a.err(j0 + j); }
+};
+template <class Acc>
+__device__ __forceinline__ bool iv_conv_warp(int f, const Acc& ee, double absTol, double relTol, int norm) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int n = norm & 7;
+    if (n <= 1) {
+        const int width = n == 0 ? 1 : 2;
+        const int units = (f + width - 1) / width;
+        const bool strict = (norm & 8) != 0;
+        bool mine = strict;
+        for (int u = (int)lane; u < units; u += 32) {
+            const int j0 = u * width, len = f - j0 < width ? f - j0 : width;
+            const bool c = cub_converged(len, IvShiftAcc<Acc>{ee, j0}, absTol, relTol, norm);
+            mine = strict ? (mine && c) : (mine || c);
+        }
+        return strict ? __all_sync(0xffffffffu, mine) != 0 : __any_sync(0xffffffffu, mine) != 0;
+    }
+    int r = 0;
+    if (lane == 0) r = cub_converged(f, ee, absTol, relTol, norm) ? 1 : 0;
+    return __shfl_sync(0xffffffffu, r, 0) != 0;
+}
+
 struct IvShared {
-    unsigned long long k_hi[IV_CMAX];
-    unsigned k_lo[IV_CMAX];
     unsigned char sidx[IV_TILE];
     unsigned long long red_a[IV_THREADS], red_b[IV_THREADS], red_c[IV_THREADS];
     unsigned s_cnt[IV_NB];
@@ -113,7 +163,9 @@ __device__ __forceinline__ void iv_bisect_one(const PoolView& pool, int dim, lon
 }
 
 __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
-    extern __shared__ double tv[];  // [4 f]: Sum val, Sum err, val / err of the smallest region
+    extern __shared__ double tv[];  // [4 f]: Sum val, Sum err, val / err of the smallest region; then [IV_NB + 1][f] if f <= IV_SS_FMAX
+    const bool use_ss = p.fdim <= IV_SS_FMAX;
+    double* const ss = tv + 4 * p.fdim;
     __shared__ IvShared S;
     long long* ctl = p.ctl;
     const int tid = threadIdx.x, b = blockIdx.x, Gs = gridDim.x, f = p.fdim;
@@ -129,24 +181,33 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     c_iter = ctl[LC_ITER], c_maxiter = ctl[LC_MAXITER];
     const PoolView& pool = p.pool;
     unsigned long long* const bar = p.bar;
+    IV_STAMP(0);
     // ---- errmax of the regions the last rule launch wrote (separable GK15 path), by the whole grid ---------------------
-    if (p.need_errmax) {
+    if (p.need_errmax) {  // one warp per item: lanes over the components
         const long long n_items = ctl[LC_DYN_N], use_list = ctl[LC_DYN_LIST], base = ctl[LC_DYN_BASE];
-        for (long long i = (long long)b * IV_THREADS + tid; i < n_items; i += (long long)Gs * IV_THREADS) {
+        for (long long i = (long long)b * IV_WARPS + warp; i < n_items; i += (long long)Gs * IV_WARPS) {
             const long long pi = i >> 1;
             const long long slot = (i & 1) ? base + pi : (use_list ? (long long)p.list[pi] : pi);
             double emax = 0.0;
-            for (int j = 0; j < f; ++j) {
+            for (int j = (int)lane; j < f; j += 32) {
                 const double e = pool.err[(long long)j * pool.cap + slot];
+                if (e > emax) emax = e;  // NaN never wins (Rule.java:281-289)
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double e = __shfl_xor_sync(0xffffffffu, emax, o);
                 if (e > emax) emax = e;
             }
-            pool.errmax[slot] = emax;
-            pool.splitdim[slot] = 0;
+            if (lane == 0) {
+                pool.errmax[slot] = emax;
+                pool.splitdim[slot] = 0;
+            }
         }
     }
     // every CTA of the grid has read the loop state before anybody changes it
     iv_gsync(bar, (unsigned long long)Gs);
-    long long Gp_ll = (N + 1023) / 1024;
+    IV_STAMP(1);
+    long long Gp_ll = (N + 1023) / 1024;  // CTAs that take part: one per 1 024 regions, at least one warp per row of the totals
+    if (Gp_ll < (2 * f + IV_WARPS - 1) / IV_WARPS) Gp_ll = (2 * f + IV_WARPS - 1) / IV_WARPS;
     if (Gp_ll > Gs) Gp_ll = Gs;
     if (Gp_ll < 1) Gp_ll = 1;
     const int Gp = (int)Gp_ll;
@@ -158,21 +219,29 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         long long hi = lo + per;
         if (hi > N) hi = N;
         if (lo > hi) hi = lo;
-        // ---- A: chunk partials ------------------------------------------------------------------------------------
-        for (int row = warp; row < 2 * f; row += IV_WARPS) {
+        // ---- A: partial sums of (row, chunk) items, one warp per item; the chunking depends on N alone --------------------
+        long long nch_ll = (N + 1023) / 1024;
+        if (nch_ll > Gp) nch_ll = Gp;
+        const int nch = (int)nch_ll;
+        const long long perA = (N + nch - 1) / nch;
+        for (long long item = (long long)b * IV_WARPS + warp; item < (long long)2 * f * nch; item += (long long)Gp * IV_WARPS) {
+            const int row = (int)(item / nch), c = (int)(item - (long long)row * nch);
             const double* src = row < f ? pool.val + (long long)row * pool.cap : pool.err + (long long)(row - f) * pool.cap;
+            const long long a_lo = perA * c;
+            long long a_hi = a_lo + perA;
+            if (a_hi > N) a_hi = N;
             double s = 0.0;  // fixed order: lane l adds elements l, l + 32, ... of the chunk, then a shuffle tree
-            long long i = lo + lane;
-            for (; i + 96 < hi; i += 128) {
-                const double a0 = src[i], a1 = src[i + 32], a2 = src[i + 64], a3 = src[i + 96];
-                s += a0;
-                s += a1;
-                s += a2;
-                s += a3;
+            long long i = a_lo + lane;
+            for (; i + 224 < a_hi; i += 256) {
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = src[i + 32 * u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += a[u];
             }
-            for (; i < hi; i += 32) s += src[i];
+            for (; i < a_hi; i += 32) s += src[i];
             for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-            if (lane == 0) p.partial[(long long)row * Gs + b] = s;
+            if (lane == 0) p.partial[(long long)row * Gs + c] = s;
         }
         {
             unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;  // smallest errmax (highest slot among ties), largest
@@ -206,11 +275,13 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
             }
         }
         IV_SYNC();
+        IV_STAMP(2);
         // ---- totals in CTA order (spread over the grid), the smallest region's vectors (CTA 0) ---------------------------
-        for (long long g = (long long)b * IV_THREADS + tid; g < 2 * f; g += (long long)Gp * IV_THREADS) {
-            double s = 0.0;
-            for (int c = 0; c < Gp; ++c) s += __ldcg(&p.partial[g * Gs + c]);
-            p.totals[g] = s;
+        for (long long g = (long long)b * IV_WARPS + warp; g < 2 * f; g += (long long)Gp * IV_WARPS) {
+            double s = 0.0;  // lane l adds chunks l, l + 32, ..., then a shuffle tree: fixed order
+            for (int c = (int)lane; c < nch; c += 32) s += __ldcg(&p.partial[g * Gs + c]);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) p.totals[g] = s;
         }
         if (b == 0) {
             unsigned long long mn = ~0ULL, ms = 0ULL, mx = 0ULL;
@@ -250,9 +321,11 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                 p.state->M = 0ULL;
                 p.state->K = 0ULL;
                 p.state->fail = 0ULL;
+                p.state->kmin[0] = p.state->kmin[1] = p.state->kmin[2] = ~0ULL;
             }
         }
         IV_SYNC();
+        IV_STAMP(3);
         // ---- B: decisions, redundantly in every CTA (identical inputs) ----------------------------------------------------
         for (int j = tid; j < 4 * f; j += IV_THREADS) tv[j] = __ldcg(&p.totals[j]);
         __syncthreads();
@@ -263,21 +336,21 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         const long long numEval = c_numEval, maxEval = c_maxEval, P = c_P;
         const double eps = 2.220446049250313e-16;
         const double band = 4.0 * eps * sqrt(3.0 * (double)N);  // rounding band of the reference's drifting sums (diagnostic)
-        if (lane == 0 && warp < 6) {  // six predicate evaluations side by side, one per warp
+        if (warp < 6) {  // six predicate evaluations side by side, one per warp
             bool r;
             if (warp == 0)
-                r = cub_converged(f, IvBandAcc{tV, tE, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
             else if (warp == 1)
-                r = cub_converged(f, IvBandAcc{tV, tE, tE, 1.0 + band, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0 + band, 0.0}, p.absTol, p.relTol, p.norm);
             else if (warp == 2)
-                r = cub_converged(f, IvBandAcc{tV, tE, tE, 1.0 - band, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0 - band, 0.0}, p.absTol, p.relTol, p.norm);
             else if (warp == 3)
-                r = cub_converged(f, IvBandAcc{tV, le, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
             else if (warp == 4)
-                r = cub_converged(f, IvBandAcc{tV, le, tE, 1.0, band}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, band}, p.absTol, p.relTol, p.norm);
             else
-                r = cub_converged(f, IvBandAcc{tV, le, tE, 1.0, -band}, p.absTol, p.relTol, p.norm);
-            S.s_pred[warp] = r ? 1 : 0;
+                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, -band}, p.absTol, p.relTol, p.norm);
+            if (lane == 0) S.s_pred[warp] = r ? 1 : 0;
         }
         __syncthreads();
         if (tid == 0) {
@@ -322,6 +395,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         }
         __syncthreads();
         const int action = S.action;
+        IV_STAMP(4);
         long long K = 0;
         int use_list = 0, amb_total = S.amb;
         if (action == IV_ACT_POPALL) {
@@ -330,6 +404,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
             // ---- C: the batch cut ------------------------------------------------------------------------------------
             const long long Kcap = S.Kcap;
             const int count_only = S.count_only;
+            if (b == 0 && tid == 0) p.ctl[LC_STAMP + 13] = 0;
             unsigned long long Cabove = 0;
             int sab_par = 0;
             bool match_all = N <= IV_CMAX;
@@ -344,6 +419,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                 if (Gc < 1) Gc = 1;
                 const long long perC = (N + Gc - 1) / Gc;
                 for (;;) {
+                    IV_STAMP(15);
                     // -- per-CTA bucket sums of the regions that match the prefix --
                     if (b < Gc) {
                         const long long clo = perC * b;
@@ -400,31 +476,51 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         if (tid < IV_NB) p.bcnt_part[(long long)b * IV_NB + tid] = (unsigned long long)S.s_cnt[tid];
                     }
                     IV_SYNC();
+                    IV_STAMP(5);
                     // -- bucket sums of the partition, in CTA order --
-                    for (long long x = (long long)b * IV_THREADS + tid; x < (long long)IV_NB * f + IV_NB; x += (long long)Gp * IV_THREADS) {
+                    for (long long x = (long long)b * IV_WARPS + warp; x < (long long)IV_NB * f + IV_NB; x += (long long)Gp * IV_WARPS) {
                         if (x < (long long)IV_NB * f) {
-                            double sacc = 0.0;
-                            for (int c = 0; c < Gc; ++c) sacc += __ldcg(&p.bsum_part[(long long)c * IV_NB * f + x]);
-                            p.bsum[x] = sacc;
+                            double sacc = 0.0;  // lane l adds CTAs l, l + 32, ..., then a shuffle tree: fixed order
+                            for (int c = (int)lane; c < Gc; c += 32) sacc += __ldcg(&p.bsum_part[(long long)c * IV_NB * f + x]);
+                            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+                            if (lane == 0) p.bsum[x] = sacc;
                         } else {
                             const int q = (int)(x - (long long)IV_NB * f);
                             unsigned long long cacc = 0;
-                            for (int c = 0; c < Gc; ++c) cacc += __ldcg(&p.bcnt_part[(long long)c * IV_NB + q]);
-                            p.bcnt[q] = cacc;
+                            for (int c = (int)lane; c < Gc; c += 32) cacc += __ldcg(&p.bcnt_part[(long long)c * IV_NB + q]);
+                            for (int o = 16; o > 0; o >>= 1) cacc += __shfl_down_sync(0xffffffffu, cacc, o);
+                            if (lane == 0) p.bcnt[q] = cacc;
                         }
                     }
                     IV_SYNC();
+                    IV_STAMP(6);
                     // -- the bucket in which the batch ends: buckets in descending order, the first non-empty one at which
                     //    the budget runs out or the residual passes (every CTA, same numbers) --
                     const double* sab = p.sabove + (long long)sab_par * f;
-                    if (tid < IV_NB) {
-                        const int q = tid;
+                    if (use_ss) {  // suffix sums over the buckets (the order of IvBucketAcc) and the popped sum, in shared memory
+                        for (int j = tid; j < f; j += IV_THREADS) {
+                            double bq[IV_NB];
+#pragma unroll
+                            for (int t = 0; t < IV_NB; ++t) bq[t] = __ldcg(&p.bsum[(long long)t * f + j]);
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int t = IV_NB - 1; t >= 0; --t) {
+                                sacc += bq[t];
+                                ss[t * f + j] = sacc;
+                            }
+                            ss[IV_NB * f + j] = __ldcg(&sab[j]);
+                        }
+                        __syncthreads();
+                    }
+                    for (int q = warp; q < IV_NB; q += IV_WARPS) {  // one warp per bucket
                         unsigned long long cq = Cabove;
                         for (int t = IV_NB - 1; t >= q; --t) cq += __ldcg(&p.bcnt[t]);
+                        const bool nonempty = __ldcg(&p.bcnt[q]) > 0ULL;
                         bool stop = cq >= (unsigned long long)Kcap;
-                        if (!stop && !count_only && __ldcg(&p.bcnt[q]) > 0ULL)
-                            stop = cub_converged(f, IvBucketAcc{tV, tE, sab, p.bsum, f, q}, p.absTol, p.relTol, p.norm);
-                        S.s_stop[q] = (stop && __ldcg(&p.bcnt[q]) > 0ULL) ? 1 : 0;
+                        if (!stop && !count_only && nonempty)
+                            stop = use_ss ? iv_conv_warp(f, IvSuffixAcc{tV, tE, ss + IV_NB * f, ss + q * f}, p.absTol, p.relTol, p.norm)
+                                          : iv_conv_warp(f, IvBucketAcc{tV, tE, sab, p.bsum, f, q}, p.absTol, p.relTol, p.norm);
+                        if (lane == 0) S.s_stop[q] = (stop && nonempty) ? 1 : 0;
                     }
                     __syncthreads();
                     if (tid == 0) {
@@ -448,11 +544,17 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         double* nsab = p.sabove + (long long)(sab_par ^ 1) * f;
                         for (int j = tid; j < f; j += IV_THREADS) {
                             double sacc = 0.0;
-                            for (int t = IV_NB - 1; t > chosen; --t) sacc += __ldcg(&p.bsum[(long long)t * f + j]);
+                            if (use_ss) {
+                                if (chosen < IV_NB - 1) sacc = ss[(chosen + 1) * f + j];
+                            } else {
+                                for (int t = IV_NB - 1; t > chosen; --t) sacc += __ldcg(&p.bsum[(long long)t * f + j]);
+                            }
                             nsab[j] = __ldcg(&sab[j]) + sacc;
                         }
                     }
                     sab_par ^= 1;
+                    IV_STAMP(7);
+                    if (b == 0 && tid == 0) p.ctl[LC_STAMP + 13] += 1;  // narrowing levels run
                     prefix = (prefix << 4) | (iv_u128)chosen;
                     sh = s;
                     if (cnt_in <= (unsigned long long)IV_CMAX || s == 0) break;
@@ -473,94 +575,95 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                 }
             }
             IV_SYNC();
-            // -- CTA 0: sort, running residuals, the predicate for every batch size --
-            if (b == 0) {
-                const double* sab = p.sabove + (long long)sab_par * f;
-                const unsigned long long Mll = __ldcg(&p.state->M);
-                const int M = (int)(Mll < (unsigned long long)IV_CMAX ? Mll : (unsigned long long)IV_CMAX);
-                int M2 = 2;
-                while (M2 < M) M2 <<= 1;
-                for (int i = tid; i < M2; i += IV_THREADS) {
-                    S.k_hi[i] = i < M ? __ldcg(&p.cand_hi[i]) : 0ULL;
-                    S.k_lo[i] = i < M ? __ldcg(&p.cand_lo[i]) : 0u;
+            IV_STAMP(8);
+            // -- sort the candidates by rank counting, one warp per candidate over the whole grid (the composite keys are
+            //    distinct): candidate i goes to position #{keys greater than its own} of the sorted arrays --
+            const unsigned long long Mll = __ldcg(&p.state->M);
+            const int M = (int)(Mll < (unsigned long long)IV_CMAX ? Mll : (unsigned long long)IV_CMAX);
+            for (int i = warp * Gp + b; i < M; i += IV_WARPS * Gp) {
+                const unsigned long long mh = __ldcg(&p.cand_hi[i]);
+                const unsigned ml = __ldcg(&p.cand_lo[i]);
+                int greater = 0;
+                for (int q = (int)lane; q < M; q += 32) {
+                    const unsigned long long qh = __ldcg(&p.cand_hi[q]);
+                    const unsigned ql = __ldcg(&p.cand_lo[q]);
+                    greater += (qh > mh || (qh == mh && ql > ml)) ? 1 : 0;
                 }
-                __syncthreads();
-                for (int kk = 2; kk <= M2; kk <<= 1) {  // bitonic sort, descending (padding keys are the smallest)
-                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                        for (int i = tid; i < M2; i += IV_THREADS) {
-                            const int l = i ^ jj;
-                            if (l > i) {
-                                const unsigned long long ah = S.k_hi[i], bh = S.k_hi[l];
-                                const unsigned al = S.k_lo[i], bl = S.k_lo[l];
-                                const bool a_lt_b = ah < bh || (ah == bh && al < bl);
-                                const bool desc = (i & kk) == 0;
-                                if (desc ? a_lt_b : !a_lt_b && !(ah == bh && al == bl)) {
-                                    S.k_hi[i] = bh;
-                                    S.k_lo[i] = bl;
-                                    S.k_hi[l] = ah;
-                                    S.k_lo[l] = al;
-                                }
-                            }
+                for (int o = 16; o > 0; o >>= 1) greater += __shfl_xor_sync(0xffffffffu, greater, o);
+                if (lane == 0) {
+                    p.sort_hi[greater] = mh;
+                    p.sort_lo[greater] = ml;
+                }
+            }
+            if (b == 0 && tid == 0 && (Mll > (unsigned long long)IV_CMAX || M < 1)) p.state->fail = 2ULL;
+            IV_SYNC();
+            IV_STAMP(14);
+            const double* sab_f = p.sabove + (long long)sab_par * f;
+            const int cs = (M + IV_CHUNKS - 1) / IV_CHUNKS > 0 ? (M + IV_CHUNKS - 1) / IV_CHUNKS : 1;  // candidates per chunk
+            if (!count_only) {
+                // -- chunk-local running sums of err over the sorted candidates: one thread per (chunk, component), whole grid --
+                for (long long item = (long long)b * IV_THREADS + tid; item < (long long)IV_CHUNKS * f; item += (long long)Gp * IV_THREADS) {
+                    const int w = (int)(item / f), j = (int)(item - (long long)w * f);
+                    const int k0 = w * cs, k1 = (k0 + cs < M ? k0 + cs : M);
+                    const double* src = pool.err + (long long)j * pool.cap;
+                    double run = 0.0;
+                    int k = k0;
+                    for (; k + 8 <= k1; k += 8) {
+                        double a[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) a[u] = src[0xffffffffu - __ldcg(&p.sort_lo[k + u])];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            run += a[u];
+                            p.cres[(long long)(k + u) * f + j] = run;
                         }
-                        __syncthreads();
                     }
-                }
-                const int cs = (M + IV_CHUNKS - 1) / IV_CHUNKS;  // candidates per chunk (>= 1 when M >= 1)
-                {   // chunk-local running sums of err over the sorted candidates, one chunk per warp
-                    const int k0 = warp * cs, k1 = (k0 + cs < M ? k0 + cs : M);
-                    for (int j = (int)lane; j < f; j += 32) {
-                        const double* src = pool.err + (long long)j * pool.cap;
-                        double run = 0.0;
-                        for (int k = k0; k < k1; ++k) {
-                            run += src[0xffffffffu - S.k_lo[k]];
-                            p.cres[(long long)k * f + j] = run;
-                        }
-                        p.cbase[(long long)warp * f + j] = run;  // the chunk's total for now
+                    for (; k < k1; ++k) {
+                        run += src[0xffffffffu - __ldcg(&p.sort_lo[k])];
+                        p.cres[(long long)k * f + j] = run;
                     }
+                    p.cbase[(long long)w * f + j] = run;  // the chunk's total for now
                 }
-                __syncthreads();
-                for (int j = tid; j < f; j += IV_THREADS) {  // residual before the first candidate of every chunk
-                    double popped = __ldcg(&sab[j]);
+                IV_SYNC();
+                // -- residual before the first candidate of every chunk --
+                for (long long j = (long long)b * IV_THREADS + tid; j < f; j += (long long)Gp * IV_THREADS) {
+                    double popped = __ldcg(&sab_f[j]);
                     for (int w = 0; w < IV_CHUNKS; ++w) {
-                        const double t = p.cbase[(long long)w * f + j];
+                        const double t = __ldcg(&p.cbase[(long long)w * f + j]);
                         p.cbase[(long long)w * f + j] = tE[j] - popped;
                         popped += t;
                     }
                 }
-                if (tid < 3) S.kmin[tid] = ~0ULL;
-                __syncthreads();
-                if (!count_only) {
-                    for (int k = tid; k < M; k += IV_THREADS) {
-                        const int w = k / cs;
-                        const double* cb = p.cbase + (long long)w * f;
-                        const double* cr = p.cres + (long long)k * f;
-                        if (cub_converged(f, IvCandAcc{tV, tE, cb, cr, 0.0}, p.absTol, p.relTol, p.norm)) atomicMin(&S.kmin[0], (unsigned long long)k);
-                        if (cub_converged(f, IvCandAcc{tV, tE, cb, cr, band}, p.absTol, p.relTol, p.norm)) atomicMin(&S.kmin[1], (unsigned long long)k);
-                        if (cub_converged(f, IvCandAcc{tV, tE, cb, cr, -band}, p.absTol, p.relTol, p.norm)) atomicMin(&S.kmin[2], (unsigned long long)k);
-                    }
+                IV_SYNC();
+                // -- the predicate for every batch size (and its sensitivity to the rounding band), spread over the grid --
+                for (long long item = (long long)warp * Gp + b; item < (long long)3 * M; item += (long long)IV_WARPS * Gp) {  // one warp per item
+                    const int k = (int)(item / 3), v = (int)(item - (long long)k * 3);
+                    const int w = k / cs;
+                    const double add = v == 0 ? 0.0 : (v == 1 ? band : -band);
+                    const bool c = iv_conv_warp(f, IvCandAcc{tV, tE, p.cbase + (long long)w * f, p.cres + (long long)k * f, add}, p.absTol, p.relTol, p.norm);
+                    if (c && lane == 0) atomicMin(&p.state->kmin[v], (unsigned long long)k);
                 }
-                __syncthreads();
-                if (tid == 0) {
-                    const unsigned long long room = (unsigned long long)Kcap - Cabove;  // >= 1: the budget did not end above
-                    unsigned long long kk[3];
-                    for (int q = 0; q < 3; ++q) {
-                        unsigned long long take = S.kmin[q] == ~0ULL ? (unsigned long long)M : S.kmin[q] + 1ULL;
-                        if (take > room) take = room;
-                        if (take > (unsigned long long)M) take = (unsigned long long)M;
-                        if (take < 1ULL) take = 1ULL;
-                        kk[q] = take;
-                    }
-                    if (kk[1] != kk[0] || kk[2] != kk[0]) S.amb = 1;
-                    else S.amb = 0;
-                    const int kp = (int)kk[0] - 1;
-                    p.state->thr_hi = S.k_hi[kp];
-                    p.state->thr_lo = (unsigned long long)S.k_lo[kp];
-                    p.state->K = Cabove + kk[0];
-                    p.state->pad[0] = (unsigned long long)S.amb;
-                    if (Mll > (unsigned long long)IV_CMAX || M < 1) p.state->fail = 2ULL;
+                IV_SYNC();
+            }
+            if (b == 0 && tid == 0 && M >= 1) {
+                const unsigned long long room = (unsigned long long)Kcap - Cabove;  // >= 1: the budget did not end above
+                unsigned long long kk[3];
+                for (int q = 0; q < 3; ++q) {
+                    const unsigned long long km = __ldcg(&p.state->kmin[q]);
+                    unsigned long long take = km == ~0ULL ? (unsigned long long)M : km + 1ULL;
+                    if (take > room) take = room;
+                    if (take > (unsigned long long)M) take = (unsigned long long)M;
+                    if (take < 1ULL) take = 1ULL;
+                    kk[q] = take;
                 }
+                const int kp = (int)kk[0] - 1;
+                p.state->thr_hi = __ldcg(&p.sort_hi[kp]);
+                p.state->thr_lo = (unsigned long long)__ldcg(&p.sort_lo[kp]);
+                p.state->K = Cabove + kk[0];
+                p.state->pad[0] = (kk[1] != kk[0] || kk[2] != kk[0]) ? 1ULL : 0ULL;
             }
             IV_SYNC();
+            IV_STAMP(9);
             if (__ldcg(&p.state->fail)) {
                 if (b == 0 && tid == 0) {
                     ctl[LC_DBG0] = (long long)__ldcg(&p.state->fail);
@@ -587,6 +690,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                 if (tid == 0) p.blk[3 * Gs + b] = S.red_a[0];
             }
             IV_SYNC();
+            IV_STAMP(10);
             {
                 unsigned long long before = 0;
                 for (int c = tid; c < b; c += IV_THREADS) before += __ldcg(&p.blk[3 * Gs + c]);
@@ -620,6 +724,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                 }
             }
             IV_SYNC();
+            IV_STAMP(11);
             if (__ldcg(&p.state->fail)) {
                 if (b == 0 && tid == 0) {
                     ctl[LC_STATE] = LS_ERROR;
@@ -641,6 +746,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         // ---- bisection (Region.cut): the left child takes the parent's slot, the right child slot N + i -------------------------
         for (long long i = (long long)b * IV_THREADS + tid; i < K; i += (long long)Gp * IV_THREADS)
             iv_bisect_one(pool, p.dim, use_list ? (long long)p.list[i] : i, N + i);
+        IV_STAMP(12);
         if (b == 0 && tid == 0) {
             ctl[LC_DYN_N] = 2 * K;
             ctl[LC_DYN_LIST] = use_list;
@@ -674,7 +780,7 @@ done:
 
 }  // namespace
 
-size_t iv_dyn_smem(int fdim) { return (size_t)4 * fdim * sizeof(double); }
+size_t iv_dyn_smem(int fdim) { return ((size_t)4 * fdim + (fdim <= IV_SS_FMAX ? (size_t)(IV_NB + 1) * fdim : 0)) * sizeof(double); }
 
 static int g_iv_blocks_per_sm = -1, g_iv_fdim = -1;
 int iv_max_blocks(int n_sms, int fdim) {

@@ -15,6 +15,7 @@
 #define IV_NB 16          // buckets per narrowing level (4 bits of the composite key)
 #define IV_CMAX 1024      // candidates the final stage sorts in one CTA
 #define IV_CHUNKS 8       // k-chunks of the candidates' running sums (one per warp)
+#define IV_SS_FMAX 256     // up to this fdim the bucket suffix sums of a level are staged in shared memory
 #define IV_GC_ROWS 16384  // narrowing: at most this many (CTA, component) pairs of per-bucket partial sums per bucket
 
 // selection state shared by the CTAs through global memory (written by CTA 0, read by all after a grid barrier)
@@ -24,7 +25,8 @@ struct IvState {
     unsigned long long K;       // batch size
     unsigned long long M;       // candidates gathered
     unsigned long long fail;
-    unsigned long long pad[3];
+    unsigned long long kmin[3];  // smallest candidate index at which the predicate holds (exact, + band, - band)
+    unsigned long long pad[3];   // [0] the decision lies within the rounding band
 };
 
 struct IterVParams {
@@ -44,6 +46,8 @@ struct IterVParams {
     double* sabove;           // [2][f] err sums of the regions above the current bucket (double-buffered by level)
     unsigned long long* cand_hi;  // [IV_CMAX] candidates (composite keys), unsorted
     unsigned* cand_lo;        // [IV_CMAX]
+    unsigned long long* sort_hi;  // [IV_CMAX] the candidates in descending order
+    unsigned* sort_lo;        // [IV_CMAX]
     double* cres;             // [IV_CMAX][f] chunk-local running sums of err over the sorted candidates
     double* cbase;            // [IV_CHUNKS][f] residual before the first candidate of a chunk
     IvState* state;

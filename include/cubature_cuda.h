@@ -107,7 +107,21 @@ typedef struct cub_options {
     cub_comm_t* comm;       /* NULL = single GPU; else shard the pool over comm's ranks (DEVICE mode)*/
     int64_t shard_min_regions; /* replicate the loop on every rank until the pool holds this many
                                   regions, then shard (0 = default 32768 * nranks)                   */
+    const char* checkpoint_save; /* NULL, or a path: when the call returns (converged, or stopped by maxEval) the region
+                                    pool and the loop counters are written to this file (DEVICE mode, one GPU)          */
+    const char* checkpoint_load; /* NULL, or a checkpoint written by an earlier call with the same integrand, box and
+                                    transform: the loop continues from that pool instead of the root box (Rule.java:62-69);
+                                    relTol / absTol / norm / maxEval are this call's (maxEval counts the evaluations of
+                                    the checkpointed run too)                                                           */
 } cub_options_t;
+
+/* What a pool checkpoint holds (host-only readers: no GPU needed). */
+typedef struct cub_checkpoint_info {
+    int32_t dim, fdim, family, reserved;
+    int64_t n_regions, num_eval, iterations;
+    int32_t transform[12];
+    double shift[12];
+} cub_checkpoint_info_t;
 
 typedef struct cub_stats {
     int32_t struct_size;     /* = sizeof(cub_stats_t)                                               */
@@ -145,6 +159,14 @@ int cubature_cuda_converged(int fdim, const double* val, const double* err, doub
  * RuleGaussKronrod_1d.java:60-84): points[P][dim] row-major, P = cubature_cuda_points_per_region(dim).  Host-only utility
  * for plotting evaluation positions (the reference's examples/PlotEvalPositions.java) from a cub_trace_t region dump. */
 int cubature_cuda_rule_points(int dim, const double* center, const double* halfwidth, double* points);
+
+/* Pool checkpoints (cub_options_t.checkpoint_save / checkpoint_load): header of a file, and regions [first, first + count)
+ * of it in the layout of cub_trace_t (centers, halfwidths [count][dim]; val, err [count][fdim]; split_dim [count]; any of
+ * the five may be NULL).  checkpoint_regions returns the number of regions copied or a negative status.  Together with
+ * cubature_cuda_rule_points this reproduces examples/PlotEvalPositions.java:28-54 (tools/eval_positions.py). */
+int cubature_cuda_checkpoint_info(const char* path, cub_checkpoint_info_t* info);
+int64_t cubature_cuda_checkpoint_regions(const char* path, int64_t first, int64_t count, double* centers, double* halfwidths,
+                                         double* val, double* err, int32_t* split_dim);
 
 /* Built-in integrand family -> device plugin. */
 int cubature_cuda_integrand_builtin(int family_id, int dim, int fdim, const double* params, size_t nparams,

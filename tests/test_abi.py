@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -252,3 +253,56 @@ def test_java_shim_descriptors_match_header():
         assert len(lay) == len(args), (name, lay, args)
         for j, (l, a) in enumerate(zip(lay, args)):
             assert l == c_class(a), (name, j, l, a)
+
+
+def _ckpt_mix(h, data):
+    """checkpoint.cpp: ckpt_mix (word-wise multiply-xorshift)."""
+    M = (1 << 64) - 1
+    n = len(data)
+    i = 0
+    while i + 8 <= n:
+        w = int.from_bytes(data[i:i + 8], "little")
+        h = ((h ^ w) * 0x9e3779b97f4a7c15) & M
+        h ^= h >> 29
+        i += 8
+    tail = int.from_bytes(data[i:], "little") if i < n else 0
+    h = ((h ^ tail ^ n) * 0xbf58476d1ce4e5b9) & M
+    return h ^ (h >> 31)
+
+
+def test_checkpoint_readers_on_a_hand_written_file(cb, tmp_path):
+    """Pool checkpoint format (checkpoint.h): a file assembled here byte by byte is read back by the host-only readers
+    cubature_cuda_checkpoint_info / _regions; a damaged header is rejected."""
+    import struct
+    dim, fdim, n = 2, 3, 5
+    rng = np.random.default_rng(3)
+    centers, halfw = rng.random((dim, n)), rng.random((dim, n))
+    val, err = rng.standard_normal((fdim, n)), rng.random((fdim, n))
+    errmax = err.max(axis=0)
+    split = np.arange(n, dtype=np.int32) % dim
+    payload = b"".join(a.astype("<f8").tobytes() for a in (centers, halfw, val, err, errmax)) + split.astype("<i4").tobytes()
+    head = b"CUBCKPT1" + struct.pack("<4i3q", 1, dim, fdim, 4, n, 12345, 7) + struct.pack("<12i", *([1, 0] + [0] * 10))
+    head += struct.pack("<12d", *([0.5] + [0.0] * 11)) + struct.pack("<12d", *([0.0] * 12)) + struct.pack("<12d", *([1.0] * 12))
+    head += struct.pack("<2Q", 0xabcdef, 0x1234)
+    head += struct.pack("<Q", _ckpt_mix(0x13198a2e03707344, head))
+    path = tmp_path / "pool.ckpt"
+    path.write_bytes(head + payload)
+    info = cb.checkpoint_info(str(path))
+    assert (info["dim"], info["fdim"], info["n_regions"], info["num_eval"], info["iterations"]) == (dim, fdim, n, 12345, 7)
+    assert info["transform"] == [1, 0] and info["shift"][0] == 0.5
+    c, h, v, e, sd = cb.checkpoint_regions(str(path), 1, 3)
+    assert np.array_equal(c, centers.T[1:4]) and np.array_equal(h, halfw.T[1:4])
+    assert np.array_equal(v, val.T[1:4]) and np.array_equal(e, err.T[1:4]) and np.array_equal(sd, split[1:4])
+    # tools/eval_positions.py: the rule's points of every checkpointed box (examples/PlotEvalPositions.java:28-54)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import eval_positions
+    pts, reg = eval_positions.eval_positions(str(path))
+    assert pts.shape == (n * cb.points_per_region(dim), dim) and reg[0] == 0 and reg[-1] == n - 1
+    for i in range(n):
+        q = pts[reg == i]
+        assert np.all(np.abs(q - centers.T[i]) <= halfw.T[i] * (1 + 1e-15)) and np.array_equal(q[0], centers.T[i])
+    bad = bytearray(head + payload)
+    bad[20] ^= 1
+    path.write_bytes(bytes(bad))
+    with pytest.raises(Exception):
+        cb.checkpoint_info(str(path))

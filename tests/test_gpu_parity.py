@@ -477,3 +477,43 @@ def test_large_tie_group_cut_by_max_eval_tiles_the_domain(cb, oracle):
     assert sum(t.n_regions for _, _, t in outs) == o.num_regions and outs[0][2].batches == o.batches
     assert float(np.sum(np.prod(2.0 * allh, axis=1))) == 1.0
     assert len(np.unique(np.concatenate([allc, allh], axis=1), axis=0)) == o.num_regions
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["scalar", "vector"])
+def test_checkpoint_resume_equals_uninterrupted_run(cb, tmp_path, kind):
+    """Pool checkpoint / resume: a run stopped by maxEval exactly at an iteration boundary, saved,
+    and resumed without a budget retraces the uninterrupted run -- same batches, same counts, same bits (the resumed loop
+    sees the same pool in the same slots; scalar integrands rebuild their exact sums from it)."""
+    import cases
+    if kind == "scalar":
+        dim, fdim, norm = 3, 1, cb.CubatureError.INDIVIDUAL
+        ig = cb.Integrand.builtin(cases.GENZ["gaussian"], dim, 1, cases.genz_params("gaussian", dim))
+        lo, hi, rel, tr = [0.0] * dim, [1.0] * dim, 1e-7, None
+    else:
+        dim, fdim, norm = 2, 4, cb.CubatureError.PAIRED
+        ig = cb.Integrand.builtin(cb.Family.CEXP, dim, fdim, [0.5, 1.5])
+        lo, hi, rel, tr = [0.0] * dim, [float("inf")] * dim, 1e-6, [1] * dim
+    nan = float("nan")
+    P = cb.points_per_region(dim)
+    ra, sa, ta = cb.Cubature.integrate_ex(ig, lo, hi, rel, nan, norm, 0, transform=tr, trace_batches=4096)
+    assert sa.converged and len(ta.batches) >= 6
+    k = len(ta.batches) // 2
+    stop_at = P + P * sum(ta.batches[:k])  # numEval after k iterations (Rule.java:69,127)
+    path = str(tmp_path / "pool.ckpt")
+    rb, sb, tb = cb.Cubature.integrate_ex(ig, lo, hi, rel, nan, norm, stop_at, transform=tr, trace_batches=4096, checkpoint_save=path)
+    assert not sb.converged and sb.num_eval == stop_at and tb.batches == ta.batches[:k]
+    info = cb.checkpoint_info(path)
+    assert info["n_regions"] == sb.num_regions and info["num_eval"] == stop_at and info["iterations"] == k and info["fdim"] == fdim
+    rc, sc, tc = cb.Cubature.integrate_ex(ig, lo, hi, rel, nan, norm, 0, transform=tr, trace_batches=4096, checkpoint_load=path)
+    assert sc.converged and tc.batches == ta.batches[k:]
+    assert sc.num_eval == sa.num_eval and sc.num_regions == sa.num_regions and sc.iterations == sa.iterations
+    assert np.array_equal(rc, ra)
+    # a resumed call with no budget left returns the checkpointed totals
+    rd, sd, _ = cb.Cubature.integrate_ex(ig, lo, hi, rel, nan, norm, stop_at, transform=tr, checkpoint_load=path)
+    assert np.array_equal(rd, rb) and sd.num_regions == sb.num_regions and not sd.converged
+    # a checkpoint of another problem is refused
+    other = cb.Integrand.builtin(cases.GENZ["gaussian"], dim, 1, cases.genz_params("product_peak", dim)) if kind == "scalar" else \
+        cb.Integrand.builtin(cb.Family.CEXP, dim, fdim, [0.5, 2.5])
+    with pytest.raises(Exception, match="another problem"):
+        cb.Cubature.integrate_ex(other, lo, hi, rel, nan, norm, 0, transform=tr, checkpoint_load=path)
