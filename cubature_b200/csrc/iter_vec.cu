@@ -59,61 +59,53 @@ __device__ __forceinline__ void iv_gsync(unsigned long long* bar, unsigned long 
     __syncthreads();
 }
 
-struct IvBandAcc {  // err_j * scale + add * base_j (shared-memory vectors)
-    const double* v;
-    const double* e;
-    const double* base;
-    double scale, add;
-    __device__ double val(int j) const { return v[j]; }
-    __device__ double err(int j) const { return e[j] * scale + add * base[j]; }
-};
-// residual after popping the buckets q .. IV_NB-1 of a narrowing level on top of `sab`
-struct IvBucketAcc {
-    const double* v;      // shared
-    const double* E;      // shared
-    const double* sab;    // global
-    const double* bsum;   // global [IV_NB][f]
-    int f, q;
-    __device__ double val(int j) const { return v[j]; }
-    __device__ double err(int j) const {
-        double s = 0.0;
-        for (int t = IV_NB - 1; t >= q; --t) s += __ldcg(&bsum[(long long)t * f + j]);
-        return E[j] - (__ldcg(&sab[j]) + s);
+// One accessor type for every residual the kernel tests, and ONE out-of-line instantiation of Rule.converged for it: the
+// predicate is evaluated at eleven places, and inlined per accessor type the kernel grew to 46 000 instructions (740 KB) --
+// every phase of every iteration then started with instruction-cache misses (51 us for a pass that computes for 5 us).
+struct IvAcc {
+    int kind, j0, f, q;
+    const double* v;  // Sum val (shared)
+    const double* a;
+    const double* b;
+    const double* c;
+    double s, t;
+    __device__ double val(int j) const { return v[j0 + j]; }
+    __device__ double err(int jj) const {
+        const int j = j0 + jj;
+        switch (kind) {
+            case 0:  // a_j * s + t * b_j (shared vectors)
+                return a[j] * s + t * b[j];
+            case 1: {  // residual after popping the buckets q .. IV_NB-1 of a level: a = Sum err (shared), b = popped sum, c = bucket sums (global)
+                double x = 0.0;
+                for (int u = IV_NB - 1; u >= q; --u) x += __ldcg(&c[(long long)u * f + j]);
+                return a[j] - (__ldcg(&b[j]) + x);
+            }
+            case 2:  // the same from suffix sums staged in shared memory: b = popped sum, c = suffix sum of the buckets q ..
+                return a[j] - (b[j] + c[j]);
+            default:  // residual after popping the sorted candidates 0 .. k: b = residual before k's chunk, c = chunk-local running sum (global)
+                return (b[j] - c[j]) + t * a[j];
+        }
     }
 };
-// the same from suffix sums staged in shared memory
-struct IvSuffixAcc {
-    const double* v;
-    const double* E;
-    const double* sab;
-    const double* ssq;  // suffix sum of the buckets q .. IV_NB-1
-    __device__ double val(int j) const { return v[j]; }
-    __device__ double err(int j) const { return E[j] - (sab[j] + ssq[j]); }
-};
-// residual after popping the sorted candidates 0 .. k
-struct IvCandAcc {
-    const double* v;      // shared
-    const double* E;      // shared
-    const double* cbase;  // global: residual before the first candidate of k's chunk
-    const double* crow;   // global: chunk-local running sum, row k
-    double add;
-    __device__ double val(int j) const { return v[j]; }
-    __device__ double err(int j) const { return (cbase[j] - crow[j]) + add * E[j]; }
-};
+__device__ __forceinline__ IvAcc iv_band_acc(const double* V, const double* e, const double* base, double scale, double add) {
+    return IvAcc{0, 0, 0, 0, V, e, base, nullptr, scale, add};
+}
+__device__ __forceinline__ IvAcc iv_bucket_acc(const double* V, const double* E, const double* sab, const double* bsum, int f, int q) {
+    return IvAcc{1, 0, f, q, V, E, sab, bsum, 0.0, 0.0};
+}
+__device__ __forceinline__ IvAcc iv_suffix_acc(const double* V, const double* E, const double* sab, const double* ssq) {
+    return IvAcc{2, 0, 0, 0, V, E, sab, ssq, 0.0, 0.0};
+}
+__device__ __forceinline__ IvAcc iv_cand_acc(const double* V, const double* E, const double* cbase, const double* crow, double add) {
+    return IvAcc{3, 0, 0, 0, V, E, cbase, crow, 0.0, add};
+}
+__device__ __noinline__ bool iv_conv(int f, IvAcc acc, double absTol, double relTol, int norm) { return cub_converged(f, acc, absTol, relTol, norm); }
 
 // Rule.converged evaluated by a whole warp (every lane calls with the same arguments, every lane gets the result).
 // INDIVIDUAL / PAIRED test the components (pairs) independently and combine them with OR (the reference's ANY, Rule.java:
 // 172-213) or AND (strict-ALL extension): lanes take the units in turn and evaluate each with cub_converged itself on a
 // one-unit view, so the arithmetic is literally the reference's.  The other norms carry ordered sums: lane 0 evaluates.
-template <class Acc>
-struct IvShiftAcc {
-    const Acc& a;
-    int j0;
-    __device__ double val(int j) const { return a.val(j0 + j); }
-    __device__ double err(int j) const { return a.err(j0 + j); }
-};
-template <class Acc>
-__device__ __forceinline__ bool iv_conv_warp(int f, const Acc& ee, double absTol, double relTol, int norm) {
+__device__ __forceinline__ bool iv_conv_warp(int f, IvAcc ee, double absTol, double relTol, int norm) {
     const unsigned lane = threadIdx.x & 31u;
     const int n = norm & 7;
     if (n <= 1) {
@@ -122,24 +114,27 @@ __device__ __forceinline__ bool iv_conv_warp(int f, const Acc& ee, double absTol
         const bool strict = (norm & 8) != 0;
         bool mine = strict;
         for (int u = (int)lane; u < units; u += 32) {
-            const int j0 = u * width, len = f - j0 < width ? f - j0 : width;
-            const bool c = cub_converged(len, IvShiftAcc<Acc>{ee, j0}, absTol, relTol, norm);
+            IvAcc one = ee;
+            one.j0 = u * width;
+            const int len = f - one.j0 < width ? f - one.j0 : width;
+            const bool c = iv_conv(len, one, absTol, relTol, norm);
             mine = strict ? (mine && c) : (mine || c);
         }
         return strict ? __all_sync(0xffffffffu, mine) != 0 : __any_sync(0xffffffffu, mine) != 0;
     }
     int r = 0;
-    if (lane == 0) r = cub_converged(f, ee, absTol, relTol, norm) ? 1 : 0;
+    if (lane == 0) r = iv_conv(f, ee, absTol, relTol, norm) ? 1 : 0;
     return __shfl_sync(0xffffffffu, r, 0) != 0;
 }
 
 struct IvShared {
-    unsigned char sidx[IV_TILE];
+    unsigned char sidx[IV_TILE];    // digits of the tile's matching regions ...
+    unsigned short midx[IV_TILE];   // ... and their index inside the tile, in slot order
     unsigned long long red_a[IV_THREADS], red_b[IV_THREADS], red_c[IV_THREADS];
     unsigned s_cnt[IV_NB];
     int s_pred[8];
     int s_stop[IV_NB];
-    int action, state, count_only, chosen, amb, tile_any;
+    int action, state, count_only, chosen, amb;
     long long Kcap;
     unsigned long long kmin[3];
     unsigned wcnt[IV_WARPS + 1];
@@ -339,17 +334,17 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         if (warp < 6) {  // six predicate evaluations side by side, one per warp
             bool r;
             if (warp == 0)
-                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm);
             else if (warp == 1)
-                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0 + band, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 + band, 0.0), p.absTol, p.relTol, p.norm);
             else if (warp == 2)
-                r = iv_conv_warp(f, IvBandAcc{tV, tE, tE, 1.0 - band, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 - band, 0.0), p.absTol, p.relTol, p.norm);
             else if (warp == 3)
-                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, 0.0}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm);
             else if (warp == 4)
-                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, band}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, band), p.absTol, p.relTol, p.norm);
             else
-                r = iv_conv_warp(f, IvBandAcc{tV, le, tE, 1.0, -band}, p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, -band), p.absTol, p.relTol, p.norm);
             if (lane == 0) S.s_pred[warp] = r ? 1 : 0;
         }
         __syncthreads();
@@ -430,50 +425,77 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         for (int x = tid; x < IV_NB * f; x += IV_THREADS) part[x] = 0.0;
                         if (tid < IV_NB) S.s_cnt[tid] = 0u;
                         __syncthreads();
+                        if (b == 0 && tid == 0) p.ctl[27] = (long long)iv_timer_ns();
                         for (long long t_lo = clo; t_lo < chi; t_lo += IV_TILE) {
                             const int tn = (int)(chi - t_lo < IV_TILE ? chi - t_lo : IV_TILE);
-                            if (tid == 0) S.tile_any = 0;
-                            __syncthreads();
-                            bool any = false;
-                            for (int i = tid; i < tn; i += IV_THREADS) {
-                                const iv_u128 c = iv_comp(iv_key(pool.errmax[t_lo + i]), t_lo + i);
-                                unsigned char d = 255;
-                                if ((c >> (s + 4)) == prefix) {
-                                    d = (unsigned char)((unsigned)(c >> s) & (IV_NB - 1));
-                                    atomicAdd(&S.s_cnt[d], 1u);
-                                    any = true;
+                            // the tile's matching regions, in slot order: local index and digit (ordered compaction: ballots + a
+                            // scan over the warps' counts per round of IV_THREADS elements)
+                            int nm = 0;
+                            for (int r0 = 0; r0 < tn; r0 += IV_THREADS) {
+                                const int i = r0 + tid;
+                                unsigned d = 255u;
+                                if (i < tn) {
+                                    const iv_u128 c = iv_comp(iv_key(pool.errmax[t_lo + i]), t_lo + i);
+                                    if ((c >> (s + 4)) == prefix) {
+                                        d = (unsigned)(c >> s) & (IV_NB - 1);
+                                        atomicAdd(&S.s_cnt[d], 1u);
+                                    }
                                 }
-                                S.sidx[i] = d;
+                                const unsigned bal = __ballot_sync(0xffffffffu, d != 255u);
+                                if (lane == 0) S.wcnt[warp] = (unsigned)__popc(bal);
+                                __syncthreads();
+                                unsigned off = 0, tot = 0;
+                                for (int w = 0; w < IV_WARPS; ++w) {
+                                    if (w < warp) off += S.wcnt[w];
+                                    tot += S.wcnt[w];
+                                }
+                                if (d != 255u) {
+                                    const int at = nm + (int)off + __popc(bal & ((1u << lane) - 1u));
+                                    S.midx[at] = (unsigned short)i;
+                                    S.sidx[at] = (unsigned char)d;
+                                }
+                                nm += (int)tot;
+                                __syncthreads();
                             }
-                            if (any) S.tile_any = 1;
-                            __syncthreads();
-                            if (S.tile_any) {
+                            if (b == 0 && tid == 0) p.ctl[28] = (long long)iv_timer_ns();
+                            if (nm > 0) {
                                 for (int j = warp; j < f; j += IV_WARPS) {
                                     const double* src = pool.err + (long long)j * pool.cap + t_lo;
                                     double acc[IV_NB];
 #pragma unroll
                                     for (int q = 0; q < IV_NB; ++q) acc[q] = 0.0;
-                                    for (int i = (int)lane; i < tn; i += 32) {
-                                        const unsigned d = S.sidx[i];
-                                        if (d != 255u) {
-                                            const double e = src[i];
+                                    for (int m0 = 0; m0 < nm; m0 += 8 * 32) {  // lane l takes the matches l, l + 32, ...: eight loads in flight
+                                        double e[8];
+                                        unsigned dg[8];
 #pragma unroll
-                                            for (int q = 0; q < IV_NB; ++q) acc[q] += (d == (unsigned)q) ? e : 0.0;
+                                        for (int u = 0; u < 8; ++u) {
+                                            const int m = m0 + 32 * u + (int)lane;
+                                            const bool in = m < nm;
+                                            dg[u] = in ? (unsigned)S.sidx[m] : 255u;
+                                            e[u] = in ? src[S.midx[m]] : 0.0;
                                         }
+#pragma unroll
+                                        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                                            for (int q = 0; q < IV_NB; ++q) acc[q] += (dg[u] == (unsigned)q) ? e[u] : 0.0;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) {  // sixteen shuffle trees side by side
+#pragma unroll
+                                        for (int q = 0; q < IV_NB; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
                                     }
                                     double mine = 0.0;
 #pragma unroll
-                                    for (int q = 0; q < IV_NB; ++q) {
-                                        double v = acc[q];
-                                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                                        if ((int)lane == q) mine = v;
-                                    }
+                                    for (int q = 0; q < IV_NB; ++q)
+                                        if ((int)lane == q) mine = acc[q];
                                     if (lane < IV_NB) part[(long long)lane * f + j] += mine;  // cell owned by this warp
                                 }
                             }
                             __syncthreads();
                         }
                         if (tid < IV_NB) p.bcnt_part[(long long)b * IV_NB + tid] = (unsigned long long)S.s_cnt[tid];
+                        if (b == 0 && tid == 0) p.ctl[29] = (long long)iv_timer_ns();
                     }
                     IV_SYNC();
                     IV_STAMP(5);
@@ -497,7 +519,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     // -- the bucket in which the batch ends: buckets in descending order, the first non-empty one at which
                     //    the budget runs out or the residual passes (every CTA, same numbers) --
                     const double* sab = p.sabove + (long long)sab_par * f;
-                    if (use_ss) {  // suffix sums over the buckets (the order of IvBucketAcc) and the popped sum, in shared memory
+                    if (use_ss) {  // suffix sums over the buckets (the order of IvAcc kind 1) and the popped sum, in shared memory
                         for (int j = tid; j < f; j += IV_THREADS) {
                             double bq[IV_NB];
 #pragma unroll
@@ -518,8 +540,8 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         const bool nonempty = __ldcg(&p.bcnt[q]) > 0ULL;
                         bool stop = cq >= (unsigned long long)Kcap;
                         if (!stop && !count_only && nonempty)
-                            stop = use_ss ? iv_conv_warp(f, IvSuffixAcc{tV, tE, ss + IV_NB * f, ss + q * f}, p.absTol, p.relTol, p.norm)
-                                          : iv_conv_warp(f, IvBucketAcc{tV, tE, sab, p.bsum, f, q}, p.absTol, p.relTol, p.norm);
+                            stop = use_ss ? iv_conv_warp(f, iv_suffix_acc(tV, tE, ss + IV_NB * f, ss + q * f), p.absTol, p.relTol, p.norm)
+                                          : iv_conv_warp(f, iv_bucket_acc(tV, tE, sab, p.bsum, f, q), p.absTol, p.relTol, p.norm);
                         if (lane == 0) S.s_stop[q] = (stop && nonempty) ? 1 : 0;
                     }
                     __syncthreads();
@@ -540,7 +562,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     }
                     for (int t = IV_NB - 1; t > chosen; --t) Cabove += __ldcg(&p.bcnt[t]);
                     const unsigned long long cnt_in = __ldcg(&p.bcnt[chosen]);
-                    if (b == 0) {  // the buckets above the chosen one join the popped sum (same order as IvBucketAcc)
+                    if (b == 0) {  // the buckets above the chosen one join the popped sum (same order as IvAcc kind 1)
                         double* nsab = p.sabove + (long long)(sab_par ^ 1) * f;
                         for (int j = tid; j < f; j += IV_THREADS) {
                             double sacc = 0.0;
@@ -640,7 +662,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     const int k = (int)(item / 3), v = (int)(item - (long long)k * 3);
                     const int w = k / cs;
                     const double add = v == 0 ? 0.0 : (v == 1 ? band : -band);
-                    const bool c = iv_conv_warp(f, IvCandAcc{tV, tE, p.cbase + (long long)w * f, p.cres + (long long)k * f, add}, p.absTol, p.relTol, p.norm);
+                    const bool c = iv_conv_warp(f, iv_cand_acc(tV, tE, p.cbase + (long long)w * f, p.cres + (long long)k * f, add), p.absTol, p.relTol, p.norm);
                     if (c && lane == 0) atomicMin(&p.state->kmin[v], (unsigned long long)k);
                 }
                 IV_SYNC();
