@@ -2415,11 +2415,6 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
                         "last of %lld narrowing levels: sums %.1f, reduce %.1f, pick %.1f; gather %.1f, sort %.1f, residuals + predicate %.1f, counts %.1f, list %.1f, bisect %.1f\n",
                 us(0, 1), us(1, 2), us(2, 3), us(3, 4), (long long)t[13], us(15, 5), us(5, 6), us(6, 7), t[13] ? us(7, 8) : us(4, 8), us(8, 14), us(14, 9), us(9, 10), us(10, 11), us(11, 12));
     }
-    if (getenv("CUBATURE_TIMING")) {
-        const long long* t = X.h_ctl;
-        fprintf(stderr, "[cubature] (debug) last level of CTA 0: zero %.1f, digits %.1f, rows %.1f, barrier %.1f us\n", (t[27] - t[LC_STAMP + 15]) * 1e-3,
-                (t[28] - t[27]) * 1e-3, (t[29] - t[28]) * 1e-3, (t[LC_STAMP + 5] - t[29]) * 1e-3);
-    }
     const long long state = X.h_ctl[LC_STATE];
     if (state == LS_ERROR) {
         cub_set_message(S.msg, "internal: the batch selection of the vector loop failed (code %lld)", (long long)X.h_ctl[LC_DBG0]);

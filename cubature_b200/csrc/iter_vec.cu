@@ -132,6 +132,7 @@ struct IvShared {
     unsigned short midx[IV_TILE];   // ... and their index inside the tile, in slot order
     unsigned long long red_a[IV_THREADS], red_b[IV_THREADS], red_c[IV_THREADS];
     unsigned s_cnt[IV_NB];
+    unsigned long long bc[IV_NB];  // bucket counts of the partition at the current level
     int s_pred[8];
     int s_stop[IV_NB];
     int action, state, count_only, chosen, amb;
@@ -425,7 +426,6 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         for (int x = tid; x < IV_NB * f; x += IV_THREADS) part[x] = 0.0;
                         if (tid < IV_NB) S.s_cnt[tid] = 0u;
                         __syncthreads();
-                        if (b == 0 && tid == 0) p.ctl[27] = (long long)iv_timer_ns();
                         for (long long t_lo = clo; t_lo < chi; t_lo += IV_TILE) {
                             const int tn = (int)(chi - t_lo < IV_TILE ? chi - t_lo : IV_TILE);
                             // the tile's matching regions, in slot order: local index and digit (ordered compaction: ballots + a
@@ -457,7 +457,6 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                                 nm += (int)tot;
                                 __syncthreads();
                             }
-                            if (b == 0 && tid == 0) p.ctl[28] = (long long)iv_timer_ns();
                             if (nm > 0) {
                                 for (int j = warp; j < f; j += IV_WARPS) {
                                     const double* src = pool.err + (long long)j * pool.cap + t_lo;
@@ -495,7 +494,6 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                             __syncthreads();
                         }
                         if (tid < IV_NB) p.bcnt_part[(long long)b * IV_NB + tid] = (unsigned long long)S.s_cnt[tid];
-                        if (b == 0 && tid == 0) p.ctl[29] = (long long)iv_timer_ns();
                     }
                     IV_SYNC();
                     IV_STAMP(5);
@@ -519,6 +517,8 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     // -- the bucket in which the batch ends: buckets in descending order, the first non-empty one at which
                     //    the budget runs out or the residual passes (every CTA, same numbers) --
                     const double* sab = p.sabove + (long long)sab_par * f;
+                    if (tid < IV_NB) S.bc[tid] = __ldcg(&p.bcnt[tid]);
+                    if (!use_ss) __syncthreads();
                     if (use_ss) {  // suffix sums over the buckets (the order of IvAcc kind 1) and the popped sum, in shared memory
                         for (int j = tid; j < f; j += IV_THREADS) {
                             double bq[IV_NB];
@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     }
                     for (int q = warp; q < IV_NB; q += IV_WARPS) {  // one warp per bucket
                         unsigned long long cq = Cabove;
-                        for (int t = IV_NB - 1; t >= q; --t) cq += __ldcg(&p.bcnt[t]);
-                        const bool nonempty = __ldcg(&p.bcnt[q]) > 0ULL;
+                        for (int t = IV_NB - 1; t >= q; --t) cq += S.bc[t];
+                        const bool nonempty = S.bc[q] > 0ULL;
                         bool stop = cq >= (unsigned long long)Kcap;
                         if (!stop && !count_only && nonempty)
                             stop = use_ss ? iv_conv_warp(f, iv_suffix_acc(tV, tE, ss + IV_NB * f, ss + q * f), p.absTol, p.relTol, p.norm)
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     if (tid == 0) {
                         int chosen = -1, lowest = -1;
                         for (int q = IV_NB - 1; q >= 0; --q) {
-                            if (__ldcg(&p.bcnt[q]) > 0ULL) lowest = q;
+                            if (S.bc[q] > 0ULL) lowest = q;
                             if (chosen < 0 && S.s_stop[q]) chosen = q;
                         }
                         if (chosen < 0) chosen = lowest;
@@ -560,8 +560,8 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         if (b == 0 && tid == 0) p.state->fail = 1ULL;
                         break;
                     }
-                    for (int t = IV_NB - 1; t > chosen; --t) Cabove += __ldcg(&p.bcnt[t]);
-                    const unsigned long long cnt_in = __ldcg(&p.bcnt[chosen]);
+                    for (int t = IV_NB - 1; t > chosen; --t) Cabove += S.bc[t];
+                    const unsigned long long cnt_in = S.bc[chosen];
                     if (b == 0) {  // the buckets above the chosen one join the popped sum (same order as IvAcc kind 1)
                         double* nsab = p.sabove + (long long)(sab_par ^ 1) * f;
                         for (int j = tid; j < f; j += IV_THREADS) {
@@ -624,8 +624,10 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
             const int cs = (M + IV_CHUNKS - 1) / IV_CHUNKS > 0 ? (M + IV_CHUNKS - 1) / IV_CHUNKS : 1;  // candidates per chunk
             if (!count_only) {
                 // -- chunk-local running sums of err over the sorted candidates: one thread per (chunk, component), whole grid --
-                for (long long item = (long long)b * IV_THREADS + tid; item < (long long)IV_CHUNKS * f; item += (long long)Gp * IV_THREADS) {
-                    const int w = (int)(item / f), j = (int)(item - (long long)w * f);
+                const int jblocks = (f + 31) / 32;
+                for (long long g = (long long)warp * Gp + b; g < (long long)IV_CHUNKS * jblocks; g += (long long)IV_WARPS * Gp) {  // one warp per (chunk, 32 components)
+                    const int w = (int)(g / jblocks), j = (int)(g - (long long)w * jblocks) * 32 + (int)lane;
+                    if (j >= f) continue;
                     const int k0 = w * cs, k1 = (k0 + cs < M ? k0 + cs : M);
                     const double* src = pool.err + (long long)j * pool.cap;
                     double run = 0.0;

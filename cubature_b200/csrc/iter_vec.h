@@ -14,7 +14,7 @@
 #define IV_THREADS 256
 #define IV_NB 16          // buckets per narrowing level (4 bits of the composite key)
 #define IV_CMAX 1024      // candidates the final stage sorts in one CTA
-#define IV_CHUNKS 8       // k-chunks of the candidates' running sums (one per warp)
+#define IV_CHUNKS 32      // k-chunks of the candidates' running sums
 #define IV_SS_FMAX 256     // up to this fdim the bucket suffix sums of a level are staged in shared memory
 #define IV_GC_ROWS 16384  // narrowing: at most this many (CTA, component) pairs of per-bucket partial sums per bucket
 
