@@ -196,7 +196,7 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def time_to_tol_block(cb, cases, dist, local_rank, comm, world):
+def time_to_tol_block(cb, cases, dist, local_rank, comm, world, shard_min=0):
     """BASELINE's second headline: wall time to relTol 1e-8 for the six Genz families at dim 5 (config C3), at this number of
     GPUs (a pool is only sharded once it is large enough, so small problems run replicated).  Outside the timed region of the
     regions/s metric.  Per family: second call (the first one compiles the rule kernel), device time = max over ranks."""
@@ -207,14 +207,14 @@ def time_to_tol_block(cb, cases, dist, local_rank, comm, world):
         p = cases.genz_params(name, dim)
         ig = cb.Integrand.builtin(fam, dim, 1, p)
         args = ([0.0] * dim, [1.0] * dim, 1e-8, NAN, cb.CubatureError.INDIVIDUAL, 0)
-        cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm)
+        cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm, shard_min_regions=shard_min)
         best = None
         for _ in range(3):
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            r, st, _ = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm)
+            r, st, _ = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm, shard_min_regions=shard_min)
             wall = (time.perf_counter() - t0) * 1e3
             t = torch.tensor([st.device_ms, wall, st.rule_ms], dtype=torch.float64, device="cuda")
             if dist is not None:
@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-time-to-tol", action="store_true", help="skip the time-to-relTol-1e-8 block (six Genz families, dim 5)")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--shard-min", type=float, default=0, help="regions at which a pool is dealt out to the ranks (0 = library default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 1)
@@ -308,7 +309,8 @@ def main():
 
     def step():
         t0 = time.perf_counter()
-        r, st, _ = cb.Cubature.integrate_ex(ig, xmin, xmax, 1e-13, NAN, cb.CubatureError.INDIVIDUAL, max_eval, device=local_rank, comm=comm)
+        r, st, _ = cb.Cubature.integrate_ex(ig, xmin, xmax, 1e-13, NAN, cb.CubatureError.INDIVIDUAL, max_eval, device=local_rank, comm=comm,
+                                            shard_min_regions=int(args.shard_min))
         return r, st, time.perf_counter() - t0
 
     def barrier():
@@ -345,7 +347,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ambiguous_last = st.ambiguous_decisions
     import cases
-    ttt = None if args.no_time_to_tol else time_to_tol_block(cb, cases, dist, local_rank, comm, world)
+    ttt = None if args.no_time_to_tol else time_to_tol_block(cb, cases, dist, local_rank, comm, world, int(args.shard_min))
     parity = None if args.no_parity_check else parity_block(cb, cases, dist, local_rank, comm, world, rank)
 
     t_dev = torch.tensor([sum(dev_ms), sum(wall_s) * 1e3, sum(rule_ms)], dtype=torch.float64, device="cuda")

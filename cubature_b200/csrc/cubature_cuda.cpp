@@ -643,6 +643,18 @@ int integrate_device_fused(Session& S, double relTol, double absTol, int norm, i
 int integrate_sharded_peer(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
                            LoopResult* res, const LoopState& st0);
 
+// When is a pool dealt out to the ranks?  Dealing costs a ranked sort of the pool (1 ms at 1e5 regions, 8 ms at 8e6) and every
+// sharded iteration a few peer exchanges (50 - 100 us), which only pays once a rule launch is longer than that: above about
+// 1e6 regions per iteration.  A job whose evaluation budget says it will grow far beyond that (BASELINE config C5: 3.4e8
+// regions) is dealt out early, while the pool is small and the deal is cheap; a job without such a budget (tolerance-driven,
+// config C3: 1e3 ... 4e6 regions) stays replicated -- every rank computes the identical result, as fast as one GPU -- until
+// it has proven large (2^23 regions).  Measured on 2 B200 (profiles/r02/summary.md): C5 59.4 ms either way; C3 corner peak
+// 10.9 ms dealt out at 65 536 regions, 8.2 ms replicated (one GPU: 8.1 ms).
+long long default_shard_min(int R, int64_t maxEval, int64_t P) {
+    const bool known_large = maxEval > 0 && maxEval / (2 * P) >= (1LL << 24);
+    return known_large ? 32768LL * R : (1LL << 23);
+}
+
 // CUBATURE_LOOP=legacy: the round-1 loop (k_iter_coop on floating-point sums, one host visit per iteration)
 bool legacy_loop() {
     static const bool v = [] { const char* e = getenv("CUBATURE_LOOP"); return e && strcmp(e, "legacy") == 0; }();
@@ -853,7 +865,7 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
     // (measured on 4 and 8 B200: sharding later, at 2^21 regions, is slower -- ranking 2^21 regions for the
     // deal costs more than the cheaper replicated iterations save)
-    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
+    long long shard_min = opt && opt->shard_min_regions > 0 ? opt->shard_min_regions : default_shard_min(R, maxEval, P);
     if (R > 1 && !(opt && opt->pool_capacity > 0) && maxEval > 0) {
         // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
         const long long total = maxEval / (2 * P) + 8;
@@ -2457,7 +2469,7 @@ int integrate_sharded_exact(Session& S, double relTol, double absTol, int norm, 
     }
     const size_t extra = 24 + (size_t)8 * f + 1;
     long long cap = auto_capacity(S.dim, f, P, maxEval, opt->pool_capacity, extra);
-    const long long shard_min = opt->shard_min_regions > 0 ? opt->shard_min_regions : 32768LL * R;
+    const long long shard_min = opt->shard_min_regions > 0 ? opt->shard_min_regions : default_shard_min(R, maxEval, S.P);
     if (!(opt->pool_capacity > 0) && maxEval > 0) {
         // a rank holds about 1/R of the final pool (plus imbalance head-room), but at least the replicated phase
         const long long total = maxEval / (2 * P) + 8;

@@ -106,7 +106,8 @@ typedef struct cub_options {
     cub_trace_t* trace;     /* NULL = no trace                                                      */
     cub_comm_t* comm;       /* NULL = single GPU; else shard the pool over comm's ranks (DEVICE mode)*/
     int64_t shard_min_regions; /* replicate the loop on every rank until the pool holds this many
-                                  regions, then shard (0 = default 32768 * nranks)                   */
+                                  regions, then shard (0 = default: 32768 * nranks when maxEval allows more than
+                                  2^24 regions, else 2^23 -- small jobs stay replicated)               */
     const char* checkpoint_save; /* NULL, or a path: when the call returns (converged, or stopped by maxEval) the region
                                     pool and the loop counters are written to this file (DEVICE mode, one GPU)          */
     const char* checkpoint_load; /* NULL, or a checkpoint written by an earlier call with the same integrand, box and
