@@ -76,6 +76,7 @@ class CubStats(C.Structure):
         ("wall_ms", C.c_double),
         ("jit_ms", C.c_double),
         ("message", C.c_char * 256),
+        ("rebalances", C.c_int64),
     ]
 
 

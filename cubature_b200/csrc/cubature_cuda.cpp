@@ -626,7 +626,7 @@ const long long kDeviceSizedMaxRegions = 1 << 20;  // below this the rule kernel
 
 struct LoopResult {
     int converged = 0;
-    int64_t num_eval = 0, num_regions = 0, iterations = 0, ambiguous = 0;
+    int64_t num_eval = 0, num_regions = 0, iterations = 0, ambiguous = 0, rebalances = 0;
 };
 
 // state handed from the replicated (single-GPU style) phase to the sharded phase of a multi-GPU run
@@ -2451,6 +2451,107 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     return CUB_OK;
 }
 
+// ---- periodic rebalancing of a sharded pool -----------------------------------------------------------
+// The decide kernel has paused every rank at the same iteration (LS_REBALANCE) with every rank's region count in the control
+// block.  Every rank derives the same plan from the counts: shards above their target (Ntot / R, the first Ntot % R ranks one
+// more) give away the regions in their last slots, shards below it append what they are missing; the surplus regions form one
+// stream in donor-rank order, the receivers take consecutive pieces of it in rank order.  Transport: NCCL all-gather of
+// bounded SoA blocks (the only collective the communicator loads; a rebalance is rare and outside the loop).  Regions are
+// self-contained (box, val, err, errmax, split dimension), children are addable to any owner: the partition, the exact sums
+// and therefore every later decision are unchanged; only the (rank, slot) order of exactly tied regions can differ.
+int rebalance_shards(Session& S, ExactBufs& X, cub_comm* comm, int R, int rank) {
+    Workspace& W = *S.ws;
+    Pool& pool = W.pool;
+    const int f = S.fdim, dim = S.dim;
+    std::vector<long long> cnt(R), target(R), surplus(R), deficit(R), sur_before(R + 1, 0), def_before(R + 1, 0);
+    long long Ntot = 0, maxS = 0;
+    for (int r = 0; r < R; ++r) Ntot += (cnt[r] = X.h_ctl[LC_RANKN + r]);
+    for (int r = 0; r < R; ++r) {
+        target[r] = Ntot / R + (r < Ntot % R ? 1 : 0);
+        surplus[r] = std::max<long long>(0, cnt[r] - target[r]);
+        deficit[r] = std::max<long long>(0, target[r] - cnt[r]);
+        sur_before[r + 1] = sur_before[r] + surplus[r];
+        def_before[r + 1] = def_before[r] + deficit[r];
+        maxS = std::max(maxS, surplus[r]);
+    }
+    if (cnt[rank] != X.h_ctl[LC_N]) {
+        cub_set_message(S.msg, "internal: rebalance: this rank holds %lld regions, the exchange says %lld", (long long)X.h_ctl[LC_N], cnt[rank]);
+        return CUB_ERR_CUDA;
+    }
+    long long N = cnt[rank];
+    const long long N_new = N - surplus[rank] + deficit[rank];
+    if (N_new + 1 > pool.cap) {
+        cudaError_t e = pool.grow(std::max<long long>(pool.cap + pool.cap / 4, N_new + 1), N, S.stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cub_set_message(S.msg, "region pool exhausted while rebalancing (%lld regions, %s)", N_new, cudaGetErrorString(e));
+            return CUB_ERR_POOL_EXHAUSTED;
+        }
+    }
+    const int drows = 2 * dim + 2 * f + 1;                     // double rows of a region
+    const long long CH = std::min<long long>(maxS, 1 << 18);   // regions per rank and round
+    const size_t blk = (size_t)CH * ((size_t)drows * 8 + 4);   // one rank's block: drows rows of CH doubles, then CH ints
+    CUB_CUDA_CHECK(W.g_send.ensure(blk), S.msg);
+    CUB_CUDA_CHECK(W.g_recv.ensure(blk * (size_t)R), S.msg);
+    struct Row { DevBuf* buf; int nrows; size_t elt; };
+    Row rows[6] = {{&pool.center, dim, 8}, {&pool.halfw, dim, 8}, {&pool.val, f, 8}, {&pool.err, f, 8}, {&pool.errmax, 1, 8}, {&pool.splitdim, 1, 4}};
+    const long long my_tail = N - surplus[rank];  // first slot this rank gives away
+    for (long long c0 = 0; c0 < maxS; c0 += CH) {
+        const long long mine = std::max<long long>(0, std::min<long long>(CH, surplus[rank] - c0));  // elements of this round I contribute
+        {   // pack: row-major block, row pitch CH
+            size_t off = 0;
+            for (const Row& rw : rows) {
+                if (mine > 0)
+                    CUB_CUDA_CHECK(cudaMemcpy2DAsync(W.g_send.as<unsigned char>() + off, (size_t)CH * rw.elt,
+                                                     (const unsigned char*)rw.buf->p + (size_t)(my_tail + c0) * rw.elt, (size_t)pool.cap * rw.elt,
+                                                     (size_t)mine * rw.elt, rw.nrows, cudaMemcpyDeviceToDevice, S.stream), S.msg);
+                off += (size_t)CH * rw.elt * rw.nrows;
+            }
+        }
+        int rc = cub_comm_allgather(comm, W.g_send.p, blk, W.g_recv.p, S.stream);
+        if (rc != CUB_OK) return rc;
+        if (deficit[rank] > 0) {
+            // my piece of the surplus stream: [def_before[rank], def_before[rank] + deficit[rank]); this round carries the
+            // elements [c0, c0 + CH) of every donor's tail = stream positions sur_before[d] + c0 ...
+            const long long want_lo = def_before[rank], want_hi = want_lo + deficit[rank];
+            for (int d = 0; d < R; ++d) {
+                const long long have = std::max<long long>(0, std::min<long long>(CH, surplus[d] - c0));
+                if (have <= 0) continue;
+                const long long s_lo = sur_before[d] + c0, s_hi = s_lo + have;
+                const long long lo = std::max(s_lo, want_lo), hi = std::min(s_hi, want_hi);
+                if (lo >= hi) continue;
+                const long long src_e = lo - s_lo;                       // element inside donor d's block
+                const long long dst_slot = (N - surplus[rank]) + (lo - want_lo);  // receivers have no surplus: N + position in my piece
+                size_t off = 0;
+                for (const Row& rw : rows) {
+                    CUB_CUDA_CHECK(cudaMemcpy2DAsync((unsigned char*)rw.buf->p + (size_t)dst_slot * rw.elt, (size_t)pool.cap * rw.elt,
+                                                     W.g_recv.as<const unsigned char>() + (size_t)d * blk + off + (size_t)src_e * rw.elt, (size_t)CH * rw.elt,
+                                                     (size_t)(hi - lo) * rw.elt, rw.nrows, cudaMemcpyDeviceToDevice, S.stream), S.msg);
+                    off += (size_t)CH * rw.elt * rw.nrows;
+                }
+            }
+        }
+        CUB_CUDA_CHECK(cudaStreamSynchronize(S.stream), S.msg);  // the send block is reused by the next round
+    }
+    S.launches += 0;
+    CUB_CUDA_CHECK(W.sel.ensure_scalar(pool.cap), S.msg);
+    exact_bind_pool(S, X);
+    ix_rebuild(pool.view(), N_new, X.p.acc, S.n_sms, S.stream);
+    S.launches += 1;
+    X.h_ctl[LC_N] = N_new;
+    X.h_ctl[LC_DYN_N] = 0;
+    X.h_ctl[LC_SUB_K] = 0;
+    X.h_ctl[LC_CAP] = pool.cap;
+    X.h_ctl[LC_STATE] = LS_RUN;
+    X.h_ctl[LC_REBAL_COUNT] += 1;
+    CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, X.h_ctl, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
+    S.h2d_bytes += LC_WORDS * 8;
+    if (getenv("CUBATURE_TIMING"))
+        fprintf(stderr, "[cubature rank %d] rebalance %lld: %lld -> %lld regions (partition %lld, fullest shard %lld)\n", rank, (long long)X.h_ctl[LC_REBAL_COUNT], N, N_new,
+                Ntot, *std::max_element(cnt.begin(), cnt.end()));
+    return CUB_OK;
+}
+
 // Multi-GPU (section 8e), scalar integrands, NVLink peers: replicated phase on every rank, ranked deal, then the same
 // device-resident loop on the rank's shard; the decide / select kernels exchange bins and histograms with the other ranks
 // through peer-mapped buffers (iter_exact.cu), no NCCL call and no host decision inside the loop.
@@ -2509,6 +2610,10 @@ int integrate_sharded_exact(Session& S, double relTol, double absTol, int norm, 
         X.h_ctl[LC_CAP] = pool.cap;
         X.h_ctl[LC_STOP_AT] = 0;
         X.h_ctl[LC_STATE] = LS_RUN;
+        {   // rebalance trigger: partitions of at least 2^20 regions per rank (CUBATURE_REBALANCE_MIN overrides; 0 = never)
+            const char* e = getenv("CUBATURE_REBALANCE_MIN");
+            X.h_ctl[LC_REBAL_MIN] = e ? atoll(e) : (long long)R << 20;
+        }
         X.h_ctl[LC_SEQ] = (long long)comm->seq;
         X.h_ctl[LC_DBG1] = 0;
         if (cudaMemcpyAsync(X.d_ctl, X.h_ctl, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream) != cudaSuccess) rc = CUB_ERR_CUDA;
@@ -2516,6 +2621,11 @@ int integrate_sharded_exact(Session& S, double relTol, double absTol, int norm, 
     }
     const double t_deal = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     if (rc == CUB_OK) rc = exact_run(S, X, trace, cap);
+    while (rc == CUB_OK && X.h_ctl[LC_STATE] == LS_REBALANCE) {
+        rc = rebalance_shards(S, X, comm, R, rank);
+        if (rc == CUB_OK) rc = exact_run(S, X, trace, cap);
+    }
+    res->rebalances = X.h_ctl[LC_REBAL_COUNT];
     if (rc == CUB_OK && X.h_ctl[LC_STATE] == LS_ERROR) {
         comm->poisoned = true;  // the ranks no longer agree on the exchange sequence
         return exact_finish(S, X, out, res, trace);
@@ -2806,6 +2916,7 @@ int integrate_impl(cub_integrand_t* integrand, int dim, const double* xmin, cons
         stats->iterations = res.iterations;
         stats->regions_evaluated = select == CUB_SELECT_DEVICE ? S.local_regions_evaluated : (S.P > 0 ? res.num_eval / S.P : 0);
         stats->ambiguous_decisions = res.ambiguous;
+        stats->rebalances = res.rebalances;
         stats->gpu_launches = S.launches;
         stats->h2d_bytes = S.h2d_bytes;
         stats->d2h_bytes = S.d2h_bytes;

@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
             Ntot = 0;
             for (int r = 0; r < p.R; ++r) {
                 Ntot += S.hdr[r][0];
+                ctl[LC_RANKN + r] = (long long)S.hdr[r][0];
                 minkey = S.hdr[r][1] < minkey ? S.hdr[r][1] : minkey;
                 topkey = S.hdr[r][10] > topkey ? S.hdr[r][10] : topkey;
                 for (int q = 0; q < 5; ++q) misc[q] += S.hdr[r][2 + q];
@@ -502,6 +503,17 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     if (c0) {
         ix_finish(p, LS_CONVERGED, 0);
         return;
+    }
+    // ---- sharded pool: the loop pauses for a rebalance when the fullest shard exceeds 1.25 x the mean.  Every
+    // rank sees the same counts, so every rank pauses at the same iteration; the host moves the surplus (cubature_cuda.cpp:
+    // rebalance_shards), rebuilds the sums and resumes -- this launch has folded everything, a resumed one starts from scratch
+    if (p.R > 1 && ctl[LC_REBAL_MIN] > 0 && Nglobal >= ctl[LC_REBAL_MIN]) {
+        unsigned long long nmax = 0;
+        for (int r = 0; r < p.R; ++r) nmax = S.hdr[r][0] > nmax ? S.hdr[r][0] : nmax;
+        if (4ULL * nmax * (unsigned long long)p.R > 5ULL * Ntot) {
+            ix_finish(p, LS_REBALANCE, 0);
+            return;
+        }
     }
     // ---- the whole pool is popped when the residual left by the smallest region alone does not pass (monotone) -------
     const double err_min = __longlong_as_double((long long)minkey);

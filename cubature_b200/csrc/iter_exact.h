@@ -41,11 +41,15 @@ enum {
     LC_DBG0 = 24,
     LC_DBG1 = 25,
     LC_SUB_K = 26,  // popped parents whose (val, err) copies the next decide kernel has to subtract from the sums
+    LC_REBAL_MIN = 27,    // sharded pool: pause for a rebalance (LS_REBALANCE) when the partition holds at least this many regions
+                          //   and the fullest shard exceeds 1.25 x the mean (0: never; host)
+    LC_REBAL_COUNT = 28,  // rebalances so far (host)
     LC_STAMP = 32,  // [16] time stamps (CUBATURE_TIMING): [0..4] decide kernel, [5..15] select kernel (CTA 0)
-    LC_WORDS = 48,
+    LC_RANKN = 48,  // [PK_MAX_RANKS] regions of every rank's shard at the last decision (sharded pool)
+    LC_WORDS = 64,
 };
 #define LC_LOG_CAP 1024  // batch-size log [LC_WORDS .. LC_WORDS + LC_LOG_CAP): 2 K of iteration i at i % LC_LOG_CAP
-enum { LS_RUN = 0, LS_CONVERGED = 1, LS_MAXEVAL = 2, LS_GROW = 3, LS_ERROR = 4, LS_GUARD = 5, LS_HANDOFF = 6 };
+enum { LS_RUN = 0, LS_CONVERGED = 1, LS_MAXEVAL = 2, LS_GROW = 3, LS_ERROR = 4, LS_GUARD = 5, LS_HANDOFF = 6, LS_REBALANCE = 7 };
 enum { LE_NONE = 0, LE_PEER_TIMEOUT = 1, LE_PEER_ABORT = 2, LE_INTERNAL = 3 };
 
 // selection state handed from the decide kernel to the select kernel (device memory)

@@ -142,6 +142,7 @@ typedef struct cub_stats {
     double wall_ms;          /* host wall clock of the call                                          */
     double jit_ms;           /* NVRTC compile + module load done inside this call (0 when cached)    */
     char message[256];       /* human-readable detail for errors                                     */
+    int64_t rebalances;      /* sharded pool: how often surplus regions were moved between the ranks' shards */
 } cub_stats_t;
 
 /* Library / ABI version: major*1000 + minor. */

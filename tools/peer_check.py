@@ -94,6 +94,40 @@ for name, dim, rel, max_eval, smin in CASES:
                     print("   first batch difference at iteration", i, a, b, "of", len(t1.batches), len(t2.batches))
                     break
     bad += int(flag.item())
+# periodic rebalancing: pools dealt out very early, whose shards then grow unevenly; with a low trigger the
+# loop pauses, moves the surplus regions and goes on -- results still bit-identical to one GPU
+REBAL = [
+    ("product_peak", 4, 1e-9, 0, 8),
+    ("corner_peak", 3, 1e-11, int(4e8), 4),
+    ("gaussian", 3, 1e-10, 0, 4),
+    ("c0", 3, 1e-7, int(3e8), 4),
+]
+if not os.environ.get("PEER_CASES"):
+    os.environ["CUBATURE_REBALANCE_MIN"] = "2000"
+    total_rebalances = 0
+    for name, dim, rel, max_eval, smin in REBAL:
+        p = cases.genz_params(name, dim)
+        ig = cb.Integrand.builtin(cases.GENZ[name], dim, 1, p)
+        args = ([0.0] * dim, [1.0] * dim, rel, NAN, cb.CubatureError.INDIVIDUAL, max_eval)
+        r1, s1, t1 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, trace_batches=4096)
+        dist.barrier()
+        r2, s2, t2 = cb.Cubature.integrate_ex(ig, *args, device=local_rank, comm=comm, shard_min_regions=smin, trace_batches=4096)
+        ok = (t1.batches == t2.batches and s1.num_eval == s2.num_eval and s1.num_regions == s2.num_regions and s1.converged == s2.converged
+              and r1[0][0] == r2[0][0] and r1[1][0] == r2[1][0])
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        shares = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(shares, torch.tensor([s2.regions_evaluated], dtype=torch.int64, device="cuda"))
+        if rank == 0:
+            ev = [int(x.item()) for x in shares]
+            print("rebalance %-14s d=%d rel=%g maxEval=%d shard_min=%d: %s  regions=%d iters=%d  rebalances=%d  regions evaluated per rank max/mean=%.3f"
+                  % (name, dim, rel, max_eval, smin, "OK" if flag.item() == 0 else "MISMATCH", s2.num_regions, s2.iterations, s2.rebalances,
+                     max(ev) * len(ev) / max(1, sum(ev))), flush=True)
+        total_rebalances += s2.rebalances
+        bad += int(flag.item())
+    del os.environ["CUBATURE_REBALANCE_MIN"]
+    if rank == 0:
+        print("REBALANCES %d" % total_rebalances, flush=True)
 comm.close()
 dist.destroy_process_group()
 sys.exit(1 if bad else 0)
