@@ -393,7 +393,7 @@ def main():
                    "regions_per_step": regions, "points_per_region": P, "l2": "pool per step >> 126 MB L2, no flush needed",
                    "parallelism": ("pool sharded over %d GPUs; the decide / select kernels of every iteration exchange sums and histograms over "
                                    "NVLink peer memory (no NCCL call and no host decision in the loop)" % world) if world > 1 else "1 GPU",
-                   "loop": "device-resident: decide / select / rule enqueued ahead in batches of 8 iterations, host reads a 384-byte control block "
+                   "loop": "device-resident: decide / select / rule enqueued ahead in batches of 8 iterations, host reads a 512-byte control block "
                            "behind each batch while the next is queued",
                    "cpu_arm": "cpu_baseline and --impl reference time the CPU restatement of the reference on a bounded sample of this job "
                               "(maxEval=%d instead of %d): a stated baseline, not the target" % (int(args.cpu_sample), max_eval)},

@@ -35,6 +35,13 @@ final class Native {
     static final MethodHandle INTEGRATE = h("cubature_cuda_integrate",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT,
                     JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+    /* int cubature_cuda_checkpoint_info(const char*, cub_checkpoint_info_t*) */
+    static final MethodHandle CHECKPOINT_INFO = h("cubature_cuda_checkpoint_info", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    /* int64_t cubature_cuda_checkpoint_regions(const char*, int64_t, int64_t, double*, double*, double*, double*, int32_t*) */
+    static final MethodHandle CHECKPOINT_REGIONS = h("cubature_cuda_checkpoint_regions",
+            FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    /* int cubature_cuda_rule_points(int, const double*, const double*, double*) */
+    static final MethodHandle RULE_POINTS = h("cubature_cuda_rule_points", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     /* const char* cubature_cuda_strerror(int) */
     static final MethodHandle STRERROR = h("cubature_cuda_strerror", FunctionDescriptor.of(ADDRESS, JAVA_INT));
 

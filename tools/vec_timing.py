@@ -14,8 +14,8 @@ CASES = {
 for name in (sys.argv[1:] or ["C2", "C4"]):
     fam, dim, fdim, p, lo, hi, rel, ab, norm, tr = CASES[name]
     ig = cb.Integrand.builtin(fam, dim, fdim, p)
-    for rep in range(3):
+    for rep in range(int(os.environ.get("CALLS", "3"))):
         t0 = time.perf_counter()
-        r, st, _ = cb.Cubature.integrate_ex(ig, lo, hi, rel, ab, norm, 0, transform=tr)
+        r, st, _ = cb.Cubature.integrate_ex(ig, lo, hi, rel, ab, norm, 0, transform=tr, pool_capacity=int(float(os.environ.get("POOL_CAP", "0"))))
         print("%s call %d: wall %.2f ms device %.2f ms rule %.2f ms iterations %d regions %d launches %d ambiguous %d" % (
             name, rep, (time.perf_counter() - t0) * 1e3, st.device_ms, st.rule_ms, st.iterations, st.num_regions, st.gpu_launches, st.ambiguous_decisions), flush=True)
