@@ -345,6 +345,18 @@ def main():
         h2d += st.h2d_bytes
         d2h += st.d2h_bytes
     clocks = sampler.stop() if rank == 0 else None
+    # one more (untimed) step with the batch log: algorithmic HBM bytes of the iteration kernels (decide / select)
+    _, st_log, tr_log = cb.Cubature.integrate_ex(ig, xmin, xmax, 1e-13, NAN, cb.CubatureError.INDIVIDUAL, max_eval, device=local_rank, comm=comm,
+                                                 shard_min_regions=int(args.shard_min), trace_batches=4096)
+    iter_bytes, n_cut, n_now = 0.0, 0, 1
+    for nr in tr_log.batches:
+        k = nr // 2
+        if k >= n_now:   # the whole pool is popped: the decide kernel adds 2 K children (16 B each), nothing else streams
+            iter_bytes += 16.0 * 2 * k
+        else:            # a batch is cut: + three passes over errmax / err, compaction (err, list, parent copies), parents subtracted
+            iter_bytes += 16.0 * 2 * k + 3 * 8.0 * n_now + (8.0 * n_now + 4.0 * k + 32.0 * k) + 16.0 * k
+            n_cut += 1
+        n_now += k
     ambiguous_last = st.ambiguous_decisions
     import cases
     ttt = None if args.no_time_to_tol else time_to_tol_block(cb, cases, dist, local_rank, comm, world, int(args.shard_min))
@@ -416,6 +428,13 @@ def main():
                      "rule_regions_per_s_per_gpu": rule_regions_per_s,
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
                              "frac": rule_regions_per_s * BYTES_REGION / 1e9 / hbm_peak}},
+        # the iteration kernels (k_exact_decide, k_exact_select): everything on the stream that is not a rule launch, launch gaps
+        # included; bytes = what the algorithm has to stream (partition-wide), divided by the ranks
+        "roofline_hbm": {"kernels": "k_exact_decide + k_exact_select", "non_rule_ms_per_step": (tot_dev_ms - tot_rule_ms) / steps,
+                         "algorithmic_bytes_per_step": iter_bytes, "iterations": len(tr_log.batches), "iterations_that_cut": n_cut,
+                         "achieved_gbs": iter_bytes / world / max(1e-9, (tot_dev_ms - tot_rule_ms) / steps * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                         "frac": iter_bytes / world / max(1e-9, (tot_dev_ms - tot_rule_ms) / steps * 1e-3) / 1e9 / hbm_peak,
+                         "ncu": "profiles/r02/ncu_decide_select_large_raw.csv: decide 2.7 TB/s, select 2.4-2.6 TB/s of DRAM traffic on 3e7-region launches"},
         "clocks": clocks,
         # rank 0's device time of every timed step (a late host thread on one rank shows up as one long step on all ranks)
         "rank0_step_ms": [round(float(v), 3) for v in dev_ms],
