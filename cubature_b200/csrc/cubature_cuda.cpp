@@ -1948,8 +1948,9 @@ int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm
     Workspace& W = *S.ws;
     const int maxG = ix_select_max_blocks(S.n_sms);
     const size_t ctl_b = (size_t)(LC_WORDS + LC_LOG_CAP) * 8, acc_b = (size_t)XA_WORDS * 8, hset_b = (size_t)IX_HSET_WORDS * 8,
-                 blk_b = ((size_t)3 * maxG + 8) * 8;
-    CUB_CUDA_CHECK(W.d_exact.ensure(ctl_b + 2 * acc_b + hset_b + 512 + blk_b), S.msg);
+                 blk_b = ((size_t)3 * maxG + 8 + 7) / 8 * 64, gcand_b = ((size_t)PK_MAX_RANKS * IX_GCAP + 16 + IX_GCAP) * 8;
+    static_assert(16 + IX_GCAP <= PK_XB_PAY, "a payload slot of the peer exchange must take a rank's candidates");
+    CUB_CUDA_CHECK(W.d_exact.ensure(ctl_b + 2 * acc_b + hset_b + 512 + blk_b + gcand_b), S.msg);
     CUB_CUDA_CHECK(W.h_exact.ensure(3 * ctl_b), S.msg);
     unsigned char* base = W.d_exact.as<unsigned char>();
     CUB_CUDA_CHECK(cudaMemsetAsync(base, 0, ctl_b + 2 * acc_b + hset_b + 512 + blk_b, S.stream), S.msg);
@@ -1964,6 +1965,8 @@ int exact_setup(Session& S, ExactBufs& X, double relTol, double absTol, int norm
     X.p.selx = (SelX*)(base + ctl_b + 2 * acc_b + hset_b);
     X.p.blk = (unsigned long long*)(base + ctl_b + 2 * acc_b + hset_b + 512);
     X.p.bar = X.p.blk + (size_t)3 * maxG + 4;
+    X.p.gcand = (unsigned long long*)(base + ctl_b + 2 * acc_b + hset_b + 512 + blk_b);
+    if (getenv("CUBATURE_GATHER_CANDIDATES") && getenv("CUBATURE_GATHER_CANDIDATES")[0] == '0') X.p.gcand = nullptr;  // A/B: one exchange per level
     X.p.absTol = absTol;
     X.p.relTol = relTol;
     X.p.norm = norm;

@@ -1021,9 +1021,9 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     }
     const unsigned long long top_mask = 0xfffULL << 52;  // sign + exponent
     const unsigned long long top_prefix = (unsigned long long)sx.binade << 52;
-    bool have_cand = false;
+    bool have_cand = false, gathered = false;
     unsigned long long above_def = 0;  // (thread-local) regions of this chunk that are certainly popped
-    long long M = 0;
+    long long M = 0, Mg = 0;
     for (int level = 0; level < IX_LEVELS; ++level) {
         const int shift = ix_level_shift(level), NB = ix_level_nb(level);
         const int copies = level <= 1 ? IX_HCOPIES : 1;
@@ -1084,13 +1084,16 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             }
             if (level == 1) have_cand = true;
         } else {
+            // the candidates: this rank's own, or (sharded pool, after the gather below) those of the whole partition
+            const unsigned long long* const ckeys = gathered ? p.gcand : p.cand_key;
+            const long long Mlist = gathered ? Mg : M;
             const long long cstride = (long long)G * IX_THREADS;
-            for (long long r0 = 0; r0 < M; r0 += cstride * (IX_ROUND / IX_THREADS)) {  // a CTA takes IX_ROUND candidates per round
-                const long long r1 = r0 + cstride * (IX_ROUND / IX_THREADS) < M ? r0 + cstride * (IX_ROUND / IX_THREADS) : M;
+            for (long long r0 = 0; r0 < Mlist; r0 += cstride * (IX_ROUND / IX_THREADS)) {  // a CTA takes IX_ROUND candidates per round
+                const long long r1 = r0 + cstride * (IX_ROUND / IX_THREADS) < Mlist ? r0 + cstride * (IX_ROUND / IX_THREADS) : Mlist;
                 unsigned cur = 0, run_c = 0;
                 unsigned long long run = 0;
                 for (long long q = r0 + (long long)b * IX_THREADS + tid; q < r1; q += cstride) {
-                    const unsigned long long k = p.cand_key[q];
+                    const unsigned long long k = gathered ? __ldcg(&ckeys[q]) : ckeys[q];
                     if ((k & mask) == prefix) {
                         const unsigned d = (unsigned)(k >> shift) & (unsigned)(NB - 1);
                         if (d != cur) {
@@ -1116,7 +1119,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
             }
         }
         ix_gsync(bar, ++nsync * (unsigned long long)G);
-        if (sharded) {  // this level's histogram of the whole partition: sum of the R local ones
+        if (sharded && !gathered) {  // this level's histogram of the whole partition: sum of the R local ones
             // (one CTA: the ranks' grids differ in size, and 1 536 words per peer are not worth slicing)
             const int words = 3 * IX_NB;
             if (b == 0) {
@@ -1141,6 +1144,50 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         const int fin = ix_pick(p, sx, &ps, gh, level, shc, shl, shh);
         if (level < 6) IX_SEL_STAMP(3 + level);
         if (fin) break;
+        if (sharded && level == 1 && p.gcand) {
+            // ---- sharded pool: instead of one histogram exchange per remaining level (up to four), the ranks all-gather
+            // their candidates once (the regions that match the 27 key bits decided so far: a few hundred per rank) and
+            // every rank finishes the select on the identical list.  Falls back to per-level exchanges when a rank holds
+            // more candidates than a payload slot takes.
+            unsigned long long* const stagec = p.gcand + (size_t)PK_MAX_RANKS * IX_GCAP;  // [16 + IX_GCAP] staging: header | keys
+            if (b == 0) {
+                const long long mc = M <= IX_GCAP ? M : 0;
+                if (tid < 16) stagec[tid] = tid == 0 ? (unsigned long long)M : 0ULL;
+                for (long long q = tid; q < mc; q += IX_THREADS) stagec[16 + q] = p.cand_key[q];
+                __threadfence();
+                __syncthreads();
+                const int f = ix_exchange(p, xseq, 0, stagec, 0, 16 + (int)mc);
+                if (f) atomicExch((unsigned long long*)&ctl[LC_DBG1], (unsigned long long)f);
+            }
+            ++xseq;
+            ix_gsync(bar, ++nsync * (unsigned long long)G);
+            if (__ldcg((const unsigned long long*)&ctl[LC_DBG1])) {
+                failed = (int)ctl[LC_DBG1];
+                break;
+            }
+            {
+                const unsigned long long* own = p.xbuf[p.rank];
+                bool fits = true;
+                long long tot = 0;
+                for (int r = 0; r < p.R; ++r) {
+                    const long long mr = (long long)__ldcg(&ix_pay((unsigned long long*)own, xseq - 1ULL, r)[0]);
+                    fits = fits && mr <= IX_GCAP;
+                    tot += mr;
+                }
+                if (fits) {  // uniform over the grid and over the ranks (same headers everywhere)
+                    long long base_r = 0;
+                    for (int r = 0; r < p.R; ++r) {  // concatenation in rank order
+                        const unsigned long long* pay = ix_pay((unsigned long long*)own, xseq - 1ULL, r);
+                        const long long mr = (long long)__ldcg(&pay[0]);
+                        for (long long q = (long long)b * IX_THREADS + tid; q < mr; q += (long long)G * IX_THREADS) p.gcand[base_r + q] = __ldcg(&pay[16 + q]);
+                        base_r += mr;
+                    }
+                    gathered = true;
+                    Mg = tot;
+                    ix_gsync(bar, ++nsync * (unsigned long long)G);
+                }
+            }
+        }
     }
     if (failed) {
         if (b == 0 && tid == 0) {

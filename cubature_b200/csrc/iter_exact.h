@@ -73,6 +73,7 @@ struct SelX {
 // levels: 8 + 8 bits (streamed), then 4 x 9 bits (candidates only) of the 52 fraction bits
 #define IX_LEVELS 6
 #define IX_NB 512
+#define IX_GCAP 8192  // sharded pool: candidates per rank that one payload slot of the peer exchange takes (16 + IX_GCAP <= PK_XB_PAY)
 #define IX_HSET_WORDS ((IX_LEVELS + 1) * 3 * IX_NB + 8)  // slot 0: binary exponents, slots 1..IX_LEVELS: fraction digits
 
 struct IterXParams {
@@ -85,6 +86,7 @@ struct IterXParams {
     unsigned long long* bar;   // [0] arrival counter of the select kernel's grid barrier (cleared by the decide kernel),
                                // [1] arrival counter of the decide kernel's CTAs
     unsigned long long* gbins; // [XA_WORDS] combined bins of the partition (sharded pool)
+    unsigned long long* gcand; // [PK_MAX_RANKS * IX_GCAP + 16 + IX_GCAP] sharded pool: the partition's candidates, staging (or null)
     unsigned long long* cand_key;  // [cap]
     int* cand_idx;                 // [cap]
     int* list;                     // [cap] popped slots
