@@ -1985,6 +1985,7 @@ void exact_bind_pool(Session& S, ExactBufs& X) {
     X.p.cand_key = W.sel.keysA.as<unsigned long long>();
     X.p.cand_idx = W.sel.idxB.as<int>();
     X.p.list = W.sel.idxA.as<int>();
+    X.p.kept = W.sel.idxB.as<int>();  // (the candidates are dead when the compaction lists the kept regions)
     X.p.stash_val = W.sel.keysB.as<double>();
     X.p.stash_err = W.sel.keysA.as<double>();
 }
@@ -2243,6 +2244,10 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     h[LC_CAP] = pool.cap;
     h[LC_MAXEVAL] = maxEval;
     h[LC_P] = P;
+    {   // batches that keep at most 1 / 4 of the shard reset the sums and re-add the kept regions (CUBATURE_READD_DIV; 0 = never)
+        static const long long readd_max = [] { const char* e = getenv("CUBATURE_READD_DIV"); return e ? atoll(e) : 4LL; }();
+        h[LC_READD_MAX] = readd_max;
+    }
     h[LC_STOP_AT] = stop_at_regions;
     h[LC_MAXITER] = kMaxIterations;
     h[LC_SEQ] = 1;

@@ -180,10 +180,10 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     // the children of the last batch enter the sums (item j of the rule launch: slot arithmetic of CUB_MODE_BISECT), the
     // popped parents leave them (their val / err were copied by the select kernel before the left children overwrote them)
     {
-        const long long n_add = ctl[LC_DYN_N], use_list = ctl[LC_DYN_LIST], base = ctl[LC_DYN_BASE], n_sub = ctl[LC_SUB_K];
+        const long long n_add = ctl[LC_DYN_N], use_list = ctl[LC_DYN_LIST], base = ctl[LC_DYN_BASE], n_sub = ctl[LC_SUB_K], n_readd = ctl[LC_READD];
         const long long n_pairs = n_add >> 1;  // (left, right) children of one parent; an odd item is the root region
         const long long first = (long long)blockIdx.x * IX_THREADS, stride = (long long)gridDim.x * IX_THREADS;
-        if (first < n_pairs + (n_add & 1) || first < n_sub) {
+        if (first < n_pairs + (n_add & 1) || first < n_sub || first < n_readd) {
             cub_acc_begin(p.acc, &win);
             CubAccKeys keys;
             cub_acc_keys_init(keys);
@@ -222,6 +222,11 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
                 cub_acc_region(&win, p.acc, keys, v0, e0, -1);
                 if (two) cub_acc_region(&win, p.acc, keys, v1, e1, -1);
             }
+            // a selection that popped almost everything has reset the sums: the few regions it kept enter them again
+            for (long long i0 = first + tid; i0 < n_readd; i0 += stride) {
+                const long long sl = (long long)p.kept[i0];
+                cub_acc_region(&win, p.acc, keys, val[sl], err[sl], 1);
+            }
             cub_acc_keys_store(&win, keys);
             cub_acc_end(p.acc, &win);
         }
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     if (tid == 0) {
         p.bar[1] = 0ULL;
         ctl[LC_SUB_K] = 0;
+        ctl[LC_READD] = 0;
         ctl[LC_STAMP] = (long long)ix_timer_ns();
     }
     const long long N = ctl[LC_N], Nglobal = ctl[LC_NGLOBAL], numEval = ctl[LC_NUMEVAL], maxEval = ctl[LC_MAXEVAL], P = ctl[LC_P];
@@ -1270,6 +1276,18 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         tie_take_local = __ldcg(&p.blk[2 * G]);
         K_local = __ldcg(&p.blk[2 * G + 1]);
     }
+    // A batch that takes almost the whole shard (BASELINE config C5: every cut leaves a handful of regions whose errors are
+    // below the unreachable tolerance): instead of copying (val, err) of the K popped parents for the next decide kernel to
+    // subtract (32 B written and 24 B read per region), this rank's sums are reset and the few kept regions are listed
+    // and added again.  Exact sums: the result is the same integers.  Only when the pool holds no non-finite value (their
+    // counters and sticky flags follow the reference's Inf - Inf = NaN history, which a reset would lose).
+    bool readd = false;
+    {
+        const long long kept_n = n - (long long)K_local, readd_max = ctl[LC_READD_MAX];
+        bool finite = true;
+        for (int q = 0; q < 5; ++q) finite = finite && __ldcg(&p.acc[XA_M_OFF + q]) == 0ULL;
+        readd = readd_max > 0 && kept_n * readd_max <= n && finite;  // at most n / LC_READD_MAX regions stay
+    }
     unsigned long long gt_base = 0, eq_base = 0;
     {
         unsigned long long a = 0, c = 0;
@@ -1326,18 +1344,21 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
 #pragma unroll
         for (int u = 0; u < IX_TILE_ITEMS; ++u) {
             const bool is_gt = (bg[u] >> lane) & 1u, is_eq = (be[u] >> lane) & 1u;
-            if (is_gt || is_eq) {
-                const unsigned long long gt_before = gt_base + sgt[u * IX_WARPS + warp] + (unsigned)__popc(bg[u] & lt_mask);
-                const unsigned long long eq_before = eq_base + seq[u * IX_WARPS + warp] + (unsigned)__popc(be[u] & lt_mask);
-                if (is_gt || eq_before < tie_take_local) {
-                    const long long i = t_lo + (long long)u * IX_THREADS + tid;
-                    const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
-                    p.list[pos] = (int)i;
+            const long long i = t_lo + (long long)u * IX_THREADS + tid;
+            // popped regions ahead of this one in slot order
+            const unsigned long long gt_before = gt_base + sgt[u * IX_WARPS + warp] + (unsigned)__popc(bg[u] & lt_mask);
+            const unsigned long long eq_before = eq_base + seq[u * IX_WARPS + warp] + (unsigned)__popc(be[u] & lt_mask);
+            const unsigned long long pos = gt_before + (eq_before < tie_take_local ? eq_before : tie_take_local);
+            if (is_gt || (is_eq && eq_before < tie_take_local)) {
+                p.list[pos] = (int)i;
+                if (!readd) {
                     // the parent leaves the running sums (RegionHeap.poll, RegionHeap.java:21-28): the next decide kernel subtracts
                     // this copy, the slot itself is about to be overwritten by the left child
                     p.stash_val[pos] = p.pool.val[i];
                     p.stash_err[pos] = err[i];
                 }
+            } else if (readd && i < hi) {
+                p.kept[(unsigned long long)i - pos] = (int)i;  // kept regions in slot order: i minus the popped ones ahead of it
             }
         }
         gt_base += sgt[64];
@@ -1354,7 +1375,17 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         ctl[LC_DYN_LIST] = 1;
         ctl[LC_DYN_BASE] = n;
         ctl[LC_K] = Kl;
-        ctl[LC_SUB_K] = Kl;
+        ctl[LC_SUB_K] = readd ? 0 : Kl;
+        ctl[LC_READD] = readd ? n - Kl : 0;
+        if (readd) {  // this rank's sums restart from zero (as when the whole pool is popped); the kept regions follow in the next decide
+            unsigned long long* tot = p.acc + XA_TOT_OFF;
+            for (int j = 0; j < 2 * XA_LIMBS; ++j) tot[j] = 0ULL;
+            tot[XA_TOT_MISC + 0] = 0ULL;
+            tot[XA_TOT_MISC + 1] = 0ULL;
+            tot[XA_TOT_MISC + 2] = tot[XA_TOT_MISC + 4] = (unsigned long long)(XA_LIMBS - 1);
+            tot[XA_TOT_MISC + 3] = tot[XA_TOT_MISC + 5] = 0ULL;
+            p.acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;
+        }
         ctl[LC_KGLOBAL] = Kg;
         ctl[LC_N] = n + Kl;
         ctl[LC_NGLOBAL] = Nglobal + Kg;

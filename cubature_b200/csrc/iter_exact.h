@@ -44,6 +44,9 @@ enum {
     LC_REBAL_MIN = 27,    // sharded pool: pause for a rebalance (LS_REBALANCE) when the partition holds at least this many regions
                           //   and the fullest shard exceeds 1.25 x the mean (0: never; host)
     LC_REBAL_COUNT = 28,  // rebalances so far (host)
+    LC_READD = 29,        // regions the last selection KEPT, listed in IterXParams::kept: the select kernel has reset this rank's sums
+                          //   and the next decide kernel adds these regions again instead of subtracting the popped ones
+    LC_READD_MAX = 30,    // a selection takes that path when it keeps at most 1 / LC_READD_MAX of the shard (0: never; host)
     LC_STAMP = 32,  // [16] time stamps (CUBATURE_TIMING): [0..4] decide kernel, [5..15] select kernel (CTA 0)
     LC_RANKN = 48,  // [PK_MAX_RANKS] regions of every rank's shard at the last decision (sharded pool)
     LC_WORDS = 64,
@@ -90,6 +93,7 @@ struct IterXParams {
     unsigned long long* cand_key;  // [cap]
     int* cand_idx;                 // [cap]
     int* list;                     // [cap] popped slots
+    int* kept;                     // [cap] slots the last selection kept (LC_READD; shares cand_idx's storage)
     double* stash_val;             // [cap] val / err of the popped regions in list order (stash_err shares cand_key's storage:
     double* stash_err;             //   the candidates are dead when the compaction writes it)
     double absTol, relTol;
