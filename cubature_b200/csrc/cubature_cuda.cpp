@@ -2244,8 +2244,9 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     h[LC_CAP] = pool.cap;
     h[LC_MAXEVAL] = maxEval;
     h[LC_P] = P;
-    {   // batches that keep at most 1 / 4 of the shard reset the sums and re-add the kept regions (CUBATURE_READD_DIV; 0 = never)
-        static const long long readd_max = [] { const char* e = getenv("CUBATURE_READD_DIV"); return e ? atoll(e) : 4LL; }();
+    {   // batches that keep at most this many sixteenths of the shard reset the sums and re-add the kept regions instead of
+        // copying and subtracting the popped ones (CUBATURE_READD_16THS; 0 = never)
+        static const long long readd_max = [] { const char* e = getenv("CUBATURE_READD_16THS"); return e ? atoll(e) : 10LL; }();
         h[LC_READD_MAX] = readd_max;
     }
     h[LC_STOP_AT] = stop_at_regions;

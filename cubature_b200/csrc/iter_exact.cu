@@ -1286,7 +1286,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
         const long long kept_n = n - (long long)K_local, readd_max = ctl[LC_READD_MAX];
         bool finite = true;
         for (int q = 0; q < 5; ++q) finite = finite && __ldcg(&p.acc[XA_M_OFF + q]) == 0ULL;
-        readd = readd_max > 0 && kept_n * readd_max <= n && finite;  // at most n / LC_READD_MAX regions stay
+        readd = readd_max > 0 && kept_n * 16 <= n * readd_max && finite;  // at most LC_READD_MAX / 16 of the shard stays
     }
     unsigned long long gt_base = 0, eq_base = 0;
     {

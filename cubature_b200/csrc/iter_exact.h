@@ -46,7 +46,7 @@ enum {
     LC_REBAL_COUNT = 28,  // rebalances so far (host)
     LC_READD = 29,        // regions the last selection KEPT, listed in IterXParams::kept: the select kernel has reset this rank's sums
                           //   and the next decide kernel adds these regions again instead of subtracting the popped ones
-    LC_READD_MAX = 30,    // a selection takes that path when it keeps at most 1 / LC_READD_MAX of the shard (0: never; host)
+    LC_READD_MAX = 30,    // a selection takes that path when it keeps at most LC_READD_MAX / 16 of the shard (0: never; host)
     LC_STAMP = 32,  // [16] time stamps (CUBATURE_TIMING): [0..4] decide kernel, [5..15] select kernel (CTA 0)
     LC_RANKN = 48,  // [PK_MAX_RANKS] regions of every rank's shard at the last decision (sharded pool)
     LC_WORDS = 64,
