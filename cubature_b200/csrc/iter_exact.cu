@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
         ctl[LC_STAMP] = (long long)ix_timer_ns();
     }
     const long long N = ctl[LC_N], Nglobal = ctl[LC_NGLOBAL], numEval = ctl[LC_NUMEVAL], maxEval = ctl[LC_MAXEVAL], P = ctl[LC_P];
+    // (everything the decisions below read, issued together: one L2 round trip instead of one per branch)
+    const long long c_stop_at = ctl[LC_STOP_AT], c_cap = ctl[LC_CAP], c_iter = ctl[LC_ITER], c_maxiter = ctl[LC_MAXITER], c_rebal_min = ctl[LC_REBAL_MIN];
     const bool budget_left = maxEval == 0 || numEval < maxEval;  // Rule.java:72
     // pops the evaluation budget allows (checked after every pop, Rule.java:133)
     long long Kcap = Nglobal;
@@ -260,11 +262,19 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     unsigned long long* tot = acc + XA_TOT_OFF;
     // ---- collect the deltas (and clear them for the next launch) -----------------------------------------------------
     if (tid < XA_CELLS) {
+        // (sixteen loads in flight, then the stores: interleaved, every load waited for the store before it -- a quarter of
+        // this kernel's latency on small pools)
         long long s = 0;
-        for (int r = 0; r < XA_REPL; ++r) {
-            unsigned long long* c = acc + XA_D_OFF + (size_t)r * XA_CELLS + tid;
-            s += (long long)__ldcg(c);  // written by the other CTAs' atomics: read at L2
-            *c = 0ULL;
+#pragma unroll 1
+        for (int r0 = 0; r0 < XA_REPL; r0 += 16) {
+            unsigned long long v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = __ldcg(acc + XA_D_OFF + (size_t)(r0 + r) * XA_CELLS + tid);  // written by the other CTAs' atomics: read at L2
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                s += (long long)v[r];
+                if (v[r]) acc[XA_D_OFF + (size_t)(r0 + r) * XA_CELLS + tid] = 0ULL;
+            }
         }
         S.dcell[tid] = s;
     }
@@ -369,12 +379,12 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     if (budget_left) {
         // pauses are taken before any exchange, so that a resumed launch starts the iteration from scratch on every rank (the
         // sums are up to date: a resumed launch finds nothing left to fold)
-        if (ctl[LC_STOP_AT] > 0 && Nglobal >= ctl[LC_STOP_AT]) {
+        if (c_stop_at > 0 && Nglobal >= c_stop_at) {
             if (tid == 0) ix_finish(p, LS_HANDOFF, 0);
             return;
         }
         const long long kmax = N < Kcap ? N : Kcap;
-        if (N + kmax > ctl[LC_CAP]) {
+        if (N + kmax > c_cap) {
             if (tid == 0) ix_finish(p, LS_GROW, 0);
             return;
         }
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
         ix_finish(p, LS_MAXEVAL, 0);
         return;
     }
-    if (ctl[LC_ITER] >= ctl[LC_MAXITER]) {
+    if (c_iter >= c_maxiter) {
         ix_finish(p, LS_GUARD, 0);
         return;
     }
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
     // ---- sharded pool: the loop pauses for a rebalance when the fullest shard exceeds 1.25 x the mean.  Every
     // rank sees the same counts, so every rank pauses at the same iteration; the host moves the surplus (cubature_cuda.cpp:
     // rebalance_shards), rebuilds the sums and resumes -- this launch has folded everything, a resumed one starts from scratch
-    if (p.R > 1 && ctl[LC_REBAL_MIN] > 0 && Nglobal >= ctl[LC_REBAL_MIN]) {
+    if (p.R > 1 && c_rebal_min > 0 && Nglobal >= c_rebal_min) {
         unsigned long long nmax = 0;
         for (int r = 0; r < p.R; ++r) nmax = S.hdr[r][0] > nmax ? S.hdr[r][0] : nmax;
         if (4ULL * nmax * (unsigned long long)p.R > 5ULL * Ntot) {
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(IX_THREADS, MIN_BLOCKS) k_exact_decide(IterXPa
         ctl[LC_EVAL_LOCAL] += 2 * N;
         ctl[LC_WORDS + (ctl[LC_NBATCH] % LC_LOG_CAP)] = 2 * Nglobal;
         ctl[LC_NBATCH] += 1;
-        ctl[LC_ITER] += 1;
+        ctl[LC_ITER] = c_iter + 1;
         // every region leaves the pool (one RegionHeap.poll per region): this rank's sums restart from zero; a non-finite
         // value that leaves turns the reference's running sum into NaN for good (Inf - Inf)
         acc[XA_M_OFF + XA_M_MINKEY] = ~0ULL;
@@ -635,11 +645,11 @@ __device__ int ix_pick(const IterXParams& p, const SelX& sx, PickShared* ps, con
         s_in[j] = 0;
         if (j < per_t) {
             const int jb = NB - 1 - (tid * per_t + j);
-            const unsigned long long c = __ldcg(&gh[jb]);
+            const unsigned long long c = __ldcg(&gh[jb]), r_lo = __ldcg(&gh[IX_NB + jb]), r_hi = __ldcg(&gh[2 * IX_NB + jb]);  // (together)
             c_in[j] = c;
             if (c) {
                 const unsigned long long base = implicit | frac | ((unsigned long long)jb << shift);
-                const xa_u128 r = (xa_u128)__ldcg(&gh[IX_NB + jb]) + ((xa_u128)__ldcg(&gh[2 * IX_NB + jb]) << 32);
+                const xa_u128 r = (xa_u128)r_lo + ((xa_u128)r_hi << 32);
                 s_in[j] = (xa_u128)c * base + r;
                 ct += c;
                 st += s_in[j];
@@ -861,7 +871,7 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     long long* ctl = p.ctl;
     if (ctl[LC_STATE] != LS_RUN || !ctl[LC_SELECT]) return;  // uniform over the grid
     IX_SEL_STAMP(0);
-    const long long n = ctl[LC_N];
+    const long long n = ctl[LC_N], c_readd_max = ctl[LC_READD_MAX];
     // CTAs that take part: one per 4096 regions (the grid is sized for the largest pool the host could not rule out)
     long long G_ll = (n + 4095) / 4096;
     if (G_ll > (long long)gridDim.x) G_ll = (long long)gridDim.x;
@@ -1283,10 +1293,13 @@ __global__ void __launch_bounds__(IX_THREADS, 4) k_exact_select(IterXParams p) {
     // counters and sticky flags follow the reference's Inf - Inf = NaN history, which a reset would lose).
     bool readd = false;
     {
-        const long long kept_n = n - (long long)K_local, readd_max = ctl[LC_READD_MAX];
-        bool finite = true;
-        for (int q = 0; q < 5; ++q) finite = finite && __ldcg(&p.acc[XA_M_OFF + q]) == 0ULL;
-        readd = readd_max > 0 && kept_n * 16 <= n * readd_max && finite;  // at most LC_READD_MAX / 16 of the shard stays
+        const long long kept_n = n - (long long)K_local, readd_max = c_readd_max;
+        if (readd_max > 0 && kept_n * 16 <= n * readd_max) {  // at most LC_READD_MAX / 16 of the shard stays
+            unsigned long long nonfinite = 0ULL;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) nonfinite |= __ldcg(&p.acc[XA_M_OFF + q]);  // (five loads in flight)
+            readd = nonfinite == 0ULL;
+        }
     }
     unsigned long long gt_base = 0, eq_base = 0;
     {
