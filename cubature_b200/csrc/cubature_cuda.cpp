@@ -668,8 +668,11 @@ void push_batch(cub_trace_t* tr, int64_t nR) {
 }
 
 // ---- HEAP_EXACT: Rule.cubature replayed on the host, rule evaluation + bisection on the GPU --------
+struct LoopState;
+int replicated_phase_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, long long stop_at_regions, LoopState* st0, long long cap);
 int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
-                         LoopResult* res);
+                         LoopResult* res, long long stop_at_regions = 0, LoopState* state_out = nullptr, long long cap_override = 0);
 int integrate_heap_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt,
                          double* out, LoopResult* res) {
     const int f = S.fdim;
@@ -874,7 +877,14 @@ int integrate_device(Session& S, double relTol, double absTol, int norm, int64_t
     // replicated phase: every rank runs the single-GPU device-driven loop on a full copy until the pool is
     // large enough to be dealt out (identical, deterministic kernels => identical pools on every rank)
     LoopState st0;
-    int rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
+    int rc;
+    if (legacy_loop()) {
+        rc = integrate_device_fused(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
+    } else if (f == 1) {  // the device-resident loops (the round-1 kernel k_iter_coop is not on any default path any more)
+        rc = replicated_phase_exact(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
+    } else {
+        rc = integrate_device_vec(S, relTol, absTol, norm, maxEval, opt, out, res, R > 1 ? shard_min : 0, &st0, cap);
+    }
     if (rc != CUB_OK || !st0.handoff) return rc;  // finished (converged / maxEval) before sharding: result already complete
     {
         const char* env = getenv("CUBATURE_PEER_LOOP");
@@ -2269,6 +2279,26 @@ int integrate_device_exact(Session& S, double relTol, double absTol, int norm, i
     return rc;
 }
 
+// The replicated phase of a sharded run on the exact loop: complete result, or the state at the hand-off.
+int replicated_phase_exact(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
+                           LoopResult* res, long long stop_at_regions, LoopState* st0, long long cap) {
+    ExactBufs X;
+    bool handoff = false;
+    const int rc = integrate_device_exact(S, relTol, absTol, norm, maxEval, opt, out, res, X, stop_at_regions, cap, &handoff);
+    if (rc == CUB_OK && handoff) {
+        st0->N = X.h_ctl[LC_N];
+        st0->numEval = X.h_ctl[LC_NUMEVAL];
+        st0->ops = 1.0 + 3.0 * (double)(X.h_ctl[LC_N] - 1);
+        st0->cap_hint = cap;
+        st0->handoff = true;
+        res->iterations = X.h_ctl[LC_ITER];
+        res->ambiguous = X.h_ctl[LC_AMBIG];
+        S.local_regions_evaluated = 1 + X.h_ctl[LC_EVAL_LOCAL];
+        S.flush_rule_timer();
+    }
+    return rc;
+}
+
 // ---- DEVICE mode, vector integrands (fdim > 1): device-resident loop (iter_vec.cu) ------------------------------------------
 // One iteration of Rule.cubature (Rule.java:72-142) = the cooperative iteration kernel (totals, convergence, batch cut on the
 // per-component residual, compaction, bisection) + the rule launch it sizes; same control block, same enqueue-ahead host
@@ -2288,8 +2318,9 @@ int vec_setup(Session& S, VecBufs& X, double relTol, double absTol, int norm) {
     const size_t ctl_b = up((size_t)(LC_WORDS + LC_LOG_CAP) * 8), partial_b = up((size_t)2 * f * maxG * 8), totals_b = up((size_t)4 * f * 8),
                  blk_b = up(((size_t)4 * maxG + 8) * 8), bar_b = 256, bpart_b = up((size_t)gc * IV_NB * f * 8), bcpart_b = up((size_t)gc * IV_NB * 8),
                  bsum_b = up((size_t)IV_NB * f * 8), bcnt_b = up((size_t)IV_NB * 8), sab_b = up((size_t)2 * f * 8), chi_b = up((size_t)IV_CMAX * 8),
-                 clo_b = up((size_t)IV_CMAX * 4), shi_b = chi_b, slo_b = clo_b, cres_b = up((size_t)IV_CMAX * f * 8), cbase_b = up((size_t)IV_CHUNKS * f * 8), st_b = 256;
-    const size_t total = ctl_b + partial_b + totals_b + blk_b + bar_b + bpart_b + bcpart_b + bsum_b + bcnt_b + sab_b + chi_b + clo_b + shi_b + slo_b + cres_b + cbase_b + st_b;
+                 clo_b = up((size_t)IV_CMAX * 4), shi_b = chi_b, slo_b = clo_b, cres_b = up((size_t)IV_CMAX * f * 8), cbase_b = up((size_t)IV_CHUNKS * f * 8), st_b = 256,
+                 wscr_b = up((size_t)maxG * (IV_THREADS / 32) * f * 8);
+    const size_t total = ctl_b + partial_b + totals_b + blk_b + bar_b + bpart_b + bcpart_b + bsum_b + bcnt_b + sab_b + chi_b + clo_b + shi_b + slo_b + cres_b + cbase_b + st_b + wscr_b;
     CUB_CUDA_CHECK(W.d_vec.ensure(total), S.msg);
     CUB_CUDA_CHECK(W.h_exact.ensure(3 * (size_t)(LC_WORDS + LC_LOG_CAP) * 8 + (size_t)2 * f * 8), S.msg);
     unsigned char* q = W.d_vec.as<unsigned char>();
@@ -2330,6 +2361,8 @@ int vec_setup(Session& S, VecBufs& X, double relTol, double absTol, int norm) {
     q += cbase_b;
     X.p.state = (IvState*)q;
     CUB_CUDA_CHECK(cudaMemsetAsync(q, 0, st_b, S.stream), S.msg);
+    q += st_b;
+    X.p.wscratch = (double*)q;
     X.h_ctl = W.h_exact.as<long long>();
     X.h_snap[0] = X.h_ctl + (LC_WORDS + LC_LOG_CAP);
     X.h_snap[1] = X.h_ctl + 2 * (LC_WORDS + LC_LOG_CAP);
@@ -2359,14 +2392,14 @@ int vec_bind_pool(Session& S, VecBufs& X) {
 }
 
 int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int64_t maxEval, const cub_options_t* opt, double* out,
-                         LoopResult* res) {
+                         LoopResult* res, long long stop_at_regions, LoopState* state_out, long long cap_override) {
     const int f = S.fdim;
     const int64_t P = S.P;
     cub_trace_t* trace = opt ? opt->trace : nullptr;
     Workspace& W = *S.ws;
     Pool& pool = W.pool;
     const size_t extra = 4;
-    const long long cap = auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
+    const long long cap = cap_override > 0 ? cap_override : auto_capacity(S.dim, f, P, maxEval, opt ? opt->pool_capacity : 0, extra);
     const char* ck_load = opt ? opt->checkpoint_load : nullptr;
     CkptHeader ck;
     int rc = CUB_OK;
@@ -2406,6 +2439,7 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
     h[LC_MAXEVAL] = maxEval;
     h[LC_P] = P;
     h[LC_MAXITER] = kMaxIterations;
+    h[LC_STOP_AT] = stop_at_regions;
     CUB_CUDA_CHECK(cudaMemcpyAsync(X.d_ctl, h, (size_t)LC_WORDS * 8, cudaMemcpyHostToDevice, S.stream), S.msg);
     S.h2d_bytes += LC_WORDS * 8;
     auto enqueue_iter = [&](long long n_upper) -> int {
@@ -2437,6 +2471,18 @@ int integrate_device_vec(Session& S, double relTol, double absTol, int norm, int
                 us(0, 1), us(1, 2), us(2, 3), us(3, 4), (long long)t[13], us(15, 5), us(5, 6), us(6, 7), t[13] ? us(7, 8) : us(4, 8), us(8, 14), us(14, 9), us(9, 10), us(10, 11), us(11, 12));
     }
     const long long state = X.h_ctl[LC_STATE];
+    if (state == LS_HANDOFF && state_out) {  // multi-GPU: time to deal the pool out to the ranks (the caller goes on)
+        state_out->N = X.h_ctl[LC_N];
+        state_out->numEval = X.h_ctl[LC_NUMEVAL];
+        state_out->ops = 1.0 + 3.0 * (double)(X.h_ctl[LC_N] - 1);
+        state_out->cap_hint = cap;
+        state_out->handoff = true;
+        res->iterations = X.h_ctl[LC_ITER];
+        res->ambiguous = X.h_ctl[LC_AMBIG];
+        S.local_regions_evaluated = 1 + X.h_ctl[LC_EVAL_LOCAL];
+        S.flush_rule_timer();
+        return CUB_OK;
+    }
     if (state == LS_ERROR) {
         cub_set_message(S.msg, "internal: the batch selection of the vector loop failed (code %lld)", (long long)X.h_ctl[LC_DBG0]);
         return CUB_ERR_CUDA;

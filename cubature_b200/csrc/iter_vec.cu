@@ -105,7 +105,18 @@ __device__ __noinline__ bool iv_conv(int f, IvAcc acc, double absTol, double rel
 // INDIVIDUAL / PAIRED test the components (pairs) independently and combine them with OR (the reference's ANY, Rule.java:
 // 172-213) or AND (strict-ALL extension): lanes take the units in turn and evaluate each with cub_converged itself on a
 // one-unit view, so the arithmetic is literally the reference's.  The other norms carry ordered sums: lane 0 evaluates.
-__device__ __forceinline__ bool iv_conv_warp(int f, IvAcc ee, double absTol, double relTol, int norm) {
+struct IvArr {  // flat vectors
+    const double* v;
+    const double* e;
+    __device__ double val(int j) const { return v[j]; }
+    __device__ double err(int j) const { return e[j]; }
+};
+__device__ __noinline__ bool iv_conv_arr(int f, const double* v, const double* e, double absTol, double relTol, int norm) {
+    return cub_converged(f, IvArr{v, e}, absTol, relTol, norm);
+}
+// scratch: this warp's [f] doubles in global memory (the norms with ordered sums: the lanes materialise the residual vector,
+// lane 0 walks the flat array -- through the generic accessor the walk took 90 ns per element)
+__device__ __forceinline__ bool iv_conv_warp(int f, IvAcc ee, double absTol, double relTol, int norm, double* scratch) {
     const unsigned lane = threadIdx.x & 31u;
     const int n = norm & 7;
     if (n <= 1) {
@@ -122,9 +133,13 @@ __device__ __forceinline__ bool iv_conv_warp(int f, IvAcc ee, double absTol, dou
         }
         return strict ? __all_sync(0xffffffffu, mine) != 0 : __any_sync(0xffffffffu, mine) != 0;
     }
+    for (int j = (int)lane; j < f; j += 32) scratch[j] = ee.err(j);
+    __syncwarp();
     int r = 0;
-    if (lane == 0) r = iv_conv(f, ee, absTol, relTol, norm) ? 1 : 0;
-    return __shfl_sync(0xffffffffu, r, 0) != 0;
+    if (lane == 0) r = iv_conv_arr(f, ee.v + ee.j0, scratch, absTol, relTol, norm) ? 1 : 0;
+    r = __shfl_sync(0xffffffffu, r, 0);
+    __syncwarp();  // the scratch vector is free again
+    return r != 0;
 }
 
 struct IvShared {
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
     const int tid = threadIdx.x, b = blockIdx.x, Gs = gridDim.x, f = p.fdim;
     const unsigned lane = tid & 31u;
     const int warp = tid >> 5;
+    double* const wscr = p.wscratch + ((long long)b * IV_WARPS + warp) * f;  // this warp's scratch vector
     if (ctl[LC_STATE] != LS_RUN) {  // finished or paused: this launch and the ones queued behind it do nothing
         if (b == 0 && tid == 0) ctl[LC_DYN_N] = 0;
         return;
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
     // the loop state as it is at launch: CTA 0 changes the control block at the end of this launch, so every CTA reads what
     // it needs before the first grid barrier
     const long long N = ctl[LC_N], c_numEval = ctl[LC_NUMEVAL], c_maxEval = ctl[LC_MAXEVAL], c_P = ctl[LC_P], c_cap = ctl[LC_CAP],
-                    c_iter = ctl[LC_ITER], c_maxiter = ctl[LC_MAXITER];
+                    c_iter = ctl[LC_ITER], c_maxiter = ctl[LC_MAXITER], c_stop_at = ctl[LC_STOP_AT];
     const PoolView& pool = p.pool;
     unsigned long long* const bar = p.bar;
     IV_STAMP(0);
@@ -335,17 +351,17 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
         if (warp < 6) {  // six predicate evaluations side by side, one per warp
             bool r;
             if (warp == 0)
-                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm, wscr);
             else if (warp == 1)
-                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 + band, 0.0), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 + band, 0.0), p.absTol, p.relTol, p.norm, wscr);
             else if (warp == 2)
-                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 - band, 0.0), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, tE, tE, 1.0 - band, 0.0), p.absTol, p.relTol, p.norm, wscr);
             else if (warp == 3)
-                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, 0.0), p.absTol, p.relTol, p.norm, wscr);
             else if (warp == 4)
-                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, band), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, band), p.absTol, p.relTol, p.norm, wscr);
             else
-                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, -band), p.absTol, p.relTol, p.norm);
+                r = iv_conv_warp(f, iv_band_acc(tV, le, tE, 1.0, -band), p.absTol, p.relTol, p.norm, wscr);
             if (lane == 0) S.s_pred[warp] = r ? 1 : 0;
         }
         __syncthreads();
@@ -362,6 +378,9 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
             if (!budget_left) {
                 action = IV_ACT_FINISH;
                 state = LS_MAXEVAL;
+            } else if (c_stop_at > 0 && N >= c_stop_at) {  // multi-GPU: the host deals the pool out to the ranks
+                action = IV_ACT_FINISH;
+                state = LS_HANDOFF;
             } else if (N + (N < Kcap ? N : Kcap) > c_cap) {
                 action = IV_ACT_FINISH;
                 state = LS_GROW;
@@ -540,8 +559,8 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                         const bool nonempty = S.bc[q] > 0ULL;
                         bool stop = cq >= (unsigned long long)Kcap;
                         if (!stop && !count_only && nonempty)
-                            stop = use_ss ? iv_conv_warp(f, iv_suffix_acc(tV, tE, ss + IV_NB * f, ss + q * f), p.absTol, p.relTol, p.norm)
-                                          : iv_conv_warp(f, iv_bucket_acc(tV, tE, sab, p.bsum, f, q), p.absTol, p.relTol, p.norm);
+                            stop = use_ss ? iv_conv_warp(f, iv_suffix_acc(tV, tE, ss + IV_NB * f, ss + q * f), p.absTol, p.relTol, p.norm, wscr)
+                                          : iv_conv_warp(f, iv_bucket_acc(tV, tE, sab, p.bsum, f, q), p.absTol, p.relTol, p.norm, wscr);
                         if (lane == 0) S.s_stop[q] = (stop && nonempty) ? 1 : 0;
                     }
                     __syncthreads();
@@ -664,7 +683,7 @@ __global__ void __launch_bounds__(IV_THREADS, 2) k_vec_iter(IterVParams p) {
                     const int k = (int)(item / 3), v = (int)(item - (long long)k * 3);
                     const int w = k / cs;
                     const double add = v == 0 ? 0.0 : (v == 1 ? band : -band);
-                    const bool c = iv_conv_warp(f, iv_cand_acc(tV, tE, p.cbase + (long long)w * f, p.cres + (long long)k * f, add), p.absTol, p.relTol, p.norm);
+                    const bool c = iv_conv_warp(f, iv_cand_acc(tV, tE, p.cbase + (long long)w * f, p.cres + (long long)k * f, add), p.absTol, p.relTol, p.norm, wscr);
                     if (c && lane == 0) atomicMin(&p.state->kmin[v], (unsigned long long)k);
                 }
                 IV_SYNC();

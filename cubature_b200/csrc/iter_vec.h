@@ -50,6 +50,7 @@ struct IterVParams {
     unsigned* sort_lo;        // [IV_CMAX]
     double* cres;             // [IV_CMAX][f] chunk-local running sums of err over the sorted candidates
     double* cbase;            // [IV_CHUNKS][f] residual before the first candidate of a chunk
+    double* wscratch;         // [maxG][8 warps][f] one residual vector per warp (norms with ordered sums)
     IvState* state;
     int* list;                // [cap] popped slots, ascending
     double absTol, relTol;
