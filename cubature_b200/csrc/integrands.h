@@ -39,8 +39,13 @@
 template <int DIM>
 DM_HD double cub_dot2(const double* a, const double* x, double init) {
     double s0 = init, s1 = 0.0;
+#if defined(CUB_DOT_DESCENDING) && CUB_DOT_DESCENDING
+    for (int i = ((DIM - 1) & ~1); i >= 0; i -= 2) s0 = dm_fma(a[i], x[i], s0);
+    for (int i = ((DIM - 2) | 1); i >= 1 && DIM > 1; i -= 2) s1 = dm_fma(a[i], x[i], s1);
+#else
     for (int i = 0; i < DIM; i += 2) s0 = dm_fma(a[i], x[i], s0);
     for (int i = 1; i < DIM; i += 2) s1 = dm_fma(a[i], x[i], s1);
+#endif
     return DIM > 1 ? s0 + s1 : s0;
 }
 template <int N>
@@ -68,10 +73,19 @@ struct GenzOscillatory {  // cos(2 pi u_0 + sum a_i x_i)
     DM_HD void eval(const double* x, double* f) const { f[0] = dm_cos(cub_dot2<DIM>(a, x, phase)); }
 };
 
-template <int DIM, bool FAST = true>
+// The two rational families come in three variants of the final reciprocal (MODE):
+//   0  IEEE division (the definition; what the oracle computes)
+//   1  the branch-free in-range reciprocal, leaving its exact range is recorded in `bad` (detmath.h: dm_rcp_flag)
+//   2  the in-range reciprocal without the check -- only for boxes box_safe() has accepted
+// box_safe(c, h): true only if EVERY point of the box c +- h (all rule points lie inside it) gives an argument far
+// inside the reciprocal's exact range, intermediate products included; conservative by hundreds of binades, so the
+// rounding of the bound itself is irrelevant; any NaN makes it false.  The scalar rule kernel asks once per region and
+// runs variant 2 (149 range checks per region become one), else variant 0 (rule_kernels.cuh: cub_gm_scalar).
+template <int DIM, int MODE = 1>
 struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 / prod(...)
     static const bool kSeparable = false;
-    typedef GenzProductPeak<DIM, false> Exact;  // always IEEE division (rule_kernels.cuh: cub_fast_failed)
+    typedef GenzProductPeak<DIM, 0> Exact;      // always IEEE division (rule_kernels.cuh: cub_fast_failed)
+    typedef GenzProductPeak<DIM, 2> Unchecked;  // in-range reciprocal, no check (after box_safe)
     double c[DIM], u[DIM];
     mutable int bad;
     DM_HD GenzProductPeak(const double* p, int) {
@@ -91,14 +105,31 @@ struct GenzProductPeak {  // prod 1 / (a_i^-2 + (x_i - u_i)^2), evaluated as 1 /
             double t = x[i] - u[i];
             d1 = d1 * dm_fma(t, t, c[i]);
         }
-        f[0] = FAST ? dm_rcp_flag(d0 * d1, &bad) : 1.0 / (d0 * d1);
+        f[0] = MODE == 1 ? dm_rcp_flag(d0 * d1, &bad) : (MODE == 2 ? dm_rcp_inrange(d0 * d1) : 1.0 / (d0 * d1));
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        // factor i lies in [c_i, c_i + (|bc_i - u_i| + bh_i)^2]; each chain's product must stay within 2^+-400
+        double lo0 = 1.0, lo1 = 1.0, up0 = 1.0, up1 = 1.0;
+        for (int i = 0; i < DIM; i += 2) {
+            const double d = dm_abs(bc[i] - u[i]) + dm_abs(bh[i]);
+            lo0 = lo0 * c[i];
+            up0 = up0 * dm_fma(d, d, c[i]);
+        }
+        for (int i = 1; i < DIM; i += 2) {
+            const double d = dm_abs(bc[i] - u[i]) + dm_abs(bh[i]);
+            lo1 = lo1 * c[i];
+            up1 = up1 * dm_fma(d, d, c[i]);
+        }
+        const double tiny = 3.8725919148493183e-121, huge = 2.5822498780869086e+120;  // 2^-400, 2^400
+        return lo0 > tiny && lo1 > tiny && up0 < huge && up1 < huge;
     }
 };
 
-template <int DIM, bool FAST = true>
+template <int DIM, int MODE = 1>
 struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
     static const bool kSeparable = false;
-    typedef GenzCornerPeak<DIM, false> Exact;  // always IEEE division (rule_kernels.cuh: cub_fast_failed)
+    typedef GenzCornerPeak<DIM, 0> Exact;      // always IEEE division (rule_kernels.cuh: cub_fast_failed)
+    typedef GenzCornerPeak<DIM, 2> Unchecked;  // in-range reciprocal, no check (after box_safe)
     double a[DIM];
     mutable int bad;
     DM_HD GenzCornerPeak(const double* p, int) {
@@ -108,7 +139,20 @@ struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
     DM_HD void eval(const double* x, double* f) const {
         const double s = cub_dot2<DIM>(a, x, 1.0);
         const double p = CubPow<DIM + 1>::of(s);  // s^(d+1) by square-and-multiply (fixed association)
-        f[0] = FAST ? dm_rcp_flag(p, &bad) : 1.0 / p;
+        f[0] = MODE == 1 ? dm_rcp_flag(p, &bad) : (MODE == 2 ? dm_rcp_inrange(p) : 1.0 / p);
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        // s = mid +- rad over the box, |terms| <= mag: |s| > 2^-40 mag >= 2^-40 (rounding: ~2^-50 mag) and |s| < mag, so
+        // 2^-40(d+1) < |s^(d+1)| < mag^(d+1) < 2^900
+        if (DIM + 1 > 22) return false;
+        double mid = 1.0, rad = 0.0, mag = 1.0;
+        for (int i = 0; i < DIM; ++i) {
+            mid = dm_fma(a[i], bc[i], mid);
+            rad = dm_fma(dm_abs(a[i]), dm_abs(bh[i]), rad);
+            mag = dm_fma(dm_abs(a[i]), dm_abs(bc[i]), mag);
+        }
+        mag = mag + rad;
+        return dm_abs(mid) - rad > 9.094947017729282e-13 * mag && mag < dm_pow2i(900 / (DIM + 1));
     }
 };
 

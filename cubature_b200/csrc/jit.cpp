@@ -317,6 +317,9 @@ int cub_jit_get_kernels(cub_integrand* integ, int has_transform, int device, Rul
         cudaFuncAttributes fa;
         if (k.gm_scalar && cudaFuncGetAttributes(&fa, (const void*)k.gm_scalar) == cudaSuccess && fa.maxThreadsPerBlock >= 32)
             k.gm_threads = fa.maxThreadsPerBlock;  // = __launch_bounds__(CUB_GM_THREADS, ..) of the compiled kernel
+        // tuning only: a kernel built with -DCUB_GM_MAXNREG carries no launch bounds; its CTA size is then given here
+        if (const char* t = getenv("CUBATURE_GM_THREADS"))
+            if (atoi(t) >= 32) k.gm_threads = atoi(t);
         int nb = 0;
         if (k.gm_scalar && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.gm_scalar, k.gm_threads, 0) == cudaSuccess && nb > 0)
             k.gm_blocks_per_sm = nb;

@@ -277,7 +277,10 @@ __device__ __forceinline__ void cub_gm_region(const F& fn, const CubTransform& t
             cp[d] = c[d] + r5;
             x[d] = cp[d];
         }
-        constexpr int LOW = CUB_DIM < 3 ? CUB_DIM : 3;  // bits flipped inside one unrolled block
+#ifndef CUB_GM_GRAY_LOW
+#define CUB_GM_GRAY_LOW 4  // (3: +2.9 % rule time on the d = 6 corner peak; 5, 6: spills, profiles/r02/summary.md section 6)
+#endif
+        constexpr int LOW = CUB_DIM < CUB_GM_GRAY_LOW ? CUB_DIM : CUB_GM_GRAY_LOW;  // bits flipped inside one unrolled block
         constexpr int BLOCK = 1 << LOW;
 #pragma unroll 1
         for (int blk = 0; blk < (1 << CUB_DIM) / BLOCK; ++blk) {
@@ -339,6 +342,36 @@ __device__ __forceinline__ CubRegionResult cub_gm_region_exact(const CubPoolView
     return CubRegionResult();
 }
 
+// Integrands whose fast path can be proved safe for a whole box (integrands.h: box_safe / Unchecked): the kernel asks
+// once per region and then runs the variant without any per-point check (the range checks were 1.5 of the ~21
+// instructions per integrand value); a region that cannot be proved safe goes to the exact variant.  Not used with a
+// variable transform (the box is in t-space, the integrand's argument is not).
+#ifndef CUB_GM_BOX_GUARD
+#define CUB_GM_BOX_GUARD 1
+#endif
+template <class F>
+__device__ auto cub_unchecked_probe(int) -> typename F::Unchecked;
+template <class F>
+__device__ F cub_unchecked_probe(long);
+typedef decltype(cub_unchecked_probe<CUB_INTEGRAND>(0)) CubUncheckedIntegrand;
+template <class A, class B>
+struct CubSameType {
+    static const bool value = false;
+};
+template <class A>
+struct CubSameType<A, A> {
+    static const bool value = true;
+};
+template <class F>
+__device__ __forceinline__ auto cub_box_safe(const F& f, const double* c, const double* h, int) -> decltype(f.box_safe(c, h)) {
+    return f.box_safe(c, h);
+}
+template <class F>
+__device__ __forceinline__ bool cub_box_safe(const F&, const double*, const double*, long) {
+    return false;
+}
+#define CUB_GM_HAS_BOX_GUARD (CUB_GM_BOX_GUARD && !CUB_HAS_TRANSFORM && !CubSameType<CubUncheckedIntegrand, CUB_INTEGRAND>::value)
+
 // K1, scalar integrand: one thread per region.
 #ifndef CUB_GM_MIN_BLOCKS
 #define CUB_GM_MIN_BLOCKS 5
@@ -348,12 +381,130 @@ __device__ __forceinline__ CubRegionResult cub_gm_region_exact(const CubPoolView
 #ifndef CUB_GM_THREADS
 #define CUB_GM_THREADS 128
 #endif
-extern "C" __global__ void __launch_bounds__(CUB_GM_THREADS, CUB_GM_MIN_BLOCKS)
+// Geometry pipeline (CUB_GM_PREFETCH, default on).  A tile starts with a chain of two dependent global loads (list
+// entry -> parent geometry) in front of ~2 800 instructions of FP64 work; with four warps per scheduler that chain
+// showed up as 15 % of the warps' time in "long scoreboard" (profiles/r02/ncu_gm_scalar_raw.csv).  Every thread
+// therefore fetches the geometry of ITS item of the CTA's next tile, and the list entry of the tile after that, with
+// cp.async into thread-private shared-memory cells (two buffers, [field][thread]: conflict-free) while it evaluates
+// the current tile; nothing but the tile counter stays live in registers across the evaluation.  The cells are
+// private to a thread, so no CTA barrier is needed, only cp.async.wait_all.  In BISECT mode the parents of the next
+// tile are written by nobody but that tile itself, so reading them ahead is safe.
+#ifndef CUB_GM_PREFETCH
+#define CUB_GM_PREFETCH 1
+#endif
+__device__ __forceinline__ void cub_cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cub_cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cub_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cub_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// (CUB_GM_MAXNREG: an explicit register cap instead of an occupancy target -- tuning only; the host then needs
+//  CUBATURE_GM_THREADS, because the kernel no longer carries its CTA size as an attribute)
+#if defined(CUB_GM_MAXNREG)
+#define CUB_GM_BOUNDS __maxnreg__(CUB_GM_MAXNREG)
+#elif CUB_GM_MIN_BLOCKS > 0
+#define CUB_GM_BOUNDS __launch_bounds__(CUB_GM_THREADS, CUB_GM_MIN_BLOCKS)
+#else
+#define CUB_GM_BOUNDS __launch_bounds__(CUB_GM_THREADS)
+#endif
+extern "C" __global__ void CUB_GM_BOUNDS
 cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubParams prm, const __grid_constant__ CubTransform tr) {
     // Persistent: the grid covers the machine once and every CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     // so a launch needs no host knowledge of the batch size (device-sized launches: CubWork::dyn).
     const CubWork work = cub_resolve(work_in);
     const long long n = work.n_items;
+#if CUB_GM_PREFETCH
+    __shared__ double s_geo[2][2 * CUB_DIM][CUB_GM_THREADS];  // centre[d], halfwidth[d] of the item's source region
+    __shared__ int s_split[2][CUB_GM_THREADS];                 // its split dimension (BISECT)
+    __shared__ int s_src[2][CUB_GM_THREADS];                   // the source region's slot
+    __shared__ int s_list[2][CUB_GM_THREADS];                  // list entry of the tile after the next
+    const int tid = threadIdx.x;
+    // item of this thread in the CTA's k-th tile, and where its geometry comes from: the slot itself (PLAIN) or the
+    // parent it is a child of (BISECT); `list` holds one entry per slot / per parent
+#define CUB_GM_ITEM(k) ((((long long)blockIdx.x + (long long)(k) * gridDim.x) * CUB_GM_THREADS) + tid)
+#define CUB_GM_LIST_INDEX(i) (work.mode == CUB_MODE_PLAIN ? (i) : ((i) >> 1))
+#define CUB_GM_SRC_NOLIST(i) (work.mode == CUB_MODE_PLAIN ? (int)(work.base + (i)) : (int)((i) >> 1))
+    // (CHILDREN mode -- boxes already written, not used with this kernel today -- reads the child's own slot)
+#define CUB_GM_SRC_FIX(src, i) \
+    if (work.mode == CUB_MODE_CHILDREN && ((i) & 1)) src = (int)(work.base + ((i) >> 1))
+#define CUB_GM_FETCH_GEOMETRY(src, buf)                                                                       \
+    do {                                                                                                      \
+        _Pragma("unroll") for (int d = 0; d < CUB_DIM; ++d) {                                                 \
+            cub_cp_async8(&s_geo[buf][d][tid], &pool.center[(long long)d * pool.cap + (src)]);                \
+            cub_cp_async8(&s_geo[buf][CUB_DIM + d][tid], &pool.halfw[(long long)d * pool.cap + (src)]);       \
+        }                                                                                                     \
+        if (work.mode == CUB_MODE_BISECT) cub_cp_async4(&s_split[buf][tid], &pool.splitdim[(src)]);           \
+    } while (0)
+    {  // prologue: tile 0's geometry and tile 1's list entry
+        const long long i0 = CUB_GM_ITEM(0);
+        if (i0 < n) {
+            int src0 = work.list ? work.list[CUB_GM_LIST_INDEX(i0)] : CUB_GM_SRC_NOLIST(i0);
+            CUB_GM_SRC_FIX(src0, i0);
+            s_src[0][tid] = src0;
+            CUB_GM_FETCH_GEOMETRY(src0, 0);
+        }
+        const long long i1 = CUB_GM_ITEM(1);
+        if (work.list && i1 < n) cub_cp_async4(&s_list[1][tid], &work.list[CUB_GM_LIST_INDEX(i1)]);
+        cub_cp_async_commit();
+    }
+    for (int k = 0; ((long long)blockIdx.x + (long long)k * gridDim.x) * CUB_GM_THREADS < n; ++k) {
+        const int b = k & 1;
+        const long long i = CUB_GM_ITEM(k);
+        const bool active = i < n;
+        cub_cp_async_wait_all();
+        double c[CUB_DIM], h[CUB_DIM];
+        int src = 0, s = 0;
+#pragma unroll
+        for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < CUB_DIM; ++d) {
+                c[d] = s_geo[b][d][tid];
+                h[d] = s_geo[b][CUB_DIM + d][tid];
+            }
+            src = s_src[b][tid];
+            if (work.mode == CUB_MODE_BISECT) s = s_split[b][tid];
+        }
+        {  // next tile's geometry, list entry of the one after
+            const long long i1 = CUB_GM_ITEM(k + 1);
+            if (i1 < n) {
+                int src1 = work.list ? s_list[b ^ 1][tid] : CUB_GM_SRC_NOLIST(i1);
+                CUB_GM_SRC_FIX(src1, i1);
+                s_src[b ^ 1][tid] = src1;
+                CUB_GM_FETCH_GEOMETRY(src1, b ^ 1);
+            }
+            const long long i2 = CUB_GM_ITEM(k + 2);
+            if (work.list && i2 < n) cub_cp_async4(&s_list[b][tid], &work.list[CUB_GM_LIST_INDEX(i2)]);
+            cub_cp_async_commit();
+        }
+        long long slot = src;
+        if (work.mode == CUB_MODE_BISECT) {
+            // Region.java:31-38; the left child replaces the parent, the right one goes to base + parent index.  Both
+            // children (adjacent lanes) hold their copy of the parent before either writes (__syncwarp).
+            const int right = (int)(i & 1);
+            if (active) {
+#pragma unroll
+                for (int d = 0; d < CUB_DIM; ++d) {
+                    if (d == s) {
+                        h[d] = h[d] * 0.5;
+                        c[d] = right ? c[d] + h[d] : c[d] - h[d];
+                    }
+                }
+                if (right) slot = work.base + (i >> 1);
+            }
+            __syncwarp();
+            if (active) {
+#pragma unroll
+                for (int d = 0; d < CUB_DIM; ++d) {
+                    pool.center[(long long)d * pool.cap + slot] = c[d];
+                    pool.halfw[(long long)d * pool.cap + slot] = h[d];
+                }
+            }
+        }
+#else
     for (long long tile = blockIdx.x; tile * CUB_GM_THREADS < n; tile += gridDim.x) {
         const long long i = tile * CUB_GM_THREADS + threadIdx.x;
         const bool active = i < n;
@@ -361,12 +512,23 @@ cub_gm_scalar(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPara
 #pragma unroll
         for (int d = 0; d < CUB_DIM; ++d) c[d] = h[d] = 0.0;
         const long long slot = cub_load_item(pool, work, i, active, c, h);
+#endif
         double result = 0.0, err = 0.0;
         int split = 0;
         if (active) {
             const CUB_INTEGRAND fn(prm.v, 1);
-            cub_gm_region(fn, tr, c, h, result, err, split);
-            if (cub_fast_failed(fn, 0)) {  // an argument left the fast path's exact range: redo with IEEE division
+            bool redo;
+            if (CUB_GM_HAS_BOX_GUARD) {  // (compile-time)
+                redo = !cub_box_safe(fn, c, h, 0);
+                if (!redo) {
+                    const CubUncheckedIntegrand fu(prm.v, 1);
+                    cub_gm_region(fu, tr, c, h, result, err, split);
+                }
+            } else {
+                cub_gm_region(fn, tr, c, h, result, err, split);
+                redo = cub_fast_failed(fn, 0);  // an argument left the fast path's exact range
+            }
+            if (redo) {  // redo with IEEE division
                 const CubRegionResult r = cub_gm_region_exact<CUB_INTEGRAND>(pool, slot, prm, tr, 0);
                 result = r.result;
                 err = r.err;
