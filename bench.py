@@ -39,7 +39,7 @@ DIM = 6
 P = 149
 F_REGION = 3643.0      # algorithmic flops per evaluated 6-D corner-peak region
 BYTES_REGION = 124.0   # algorithmic HBM bytes per evaluated region
-TRAFFIC_REGION = 185.0 # DRAM bytes per evaluated region of the bisecting rule launch, ncu --set full (profiles/r01_summary.md)
+TRAFFIC_REGION = 185.0 # DRAM bytes per evaluated region of the bisecting rule launch, ncu --set full (profiles/r02/late/ncu_gm_scalar_final_raw.csv: 3.44 GB read + 7.65 GB written for 5.99e7 regions)
 NAN = float("nan")
 
 
@@ -417,13 +417,13 @@ def main():
         "roofline": {"bound": "fp64", "kernel": "cub_gm_scalar", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp64_peak,
                      # DRAM bytes per average rule launch: TRAFFIC_REGION per evaluated region measured with `ncu --set full`
-                     # (dram__bytes_read.sum + dram__bytes_write.sum of one 6e7-region launch, profiles/r01_summary.md)
+                     # (dram__bytes_read.sum + dram__bytes_write.sum of one 6e7-region launch, profiles/r02/late/ncu_gm_scalar_final_raw.csv)
                      "traffic": TRAFFIC_REGION * regions / max(1, rule_launches_per_step),
                      "peak_source": "measured live: DFMA-chain microbenchmark (cubature_cuda_fp64_peak), best 10 ms launch; MEASURED_PEAKS.json has no FP64 entry",
                      "peak_sustained": fp64_sustained,
                      "peak_nominal": fp64_nominal, "frac_of_nominal": achieved_tflops / fp64_nominal if fp64_nominal else None,
                      "traffic_source": "constant: 185 B per evaluated region x regions per average launch, from the ncu --set full capture "
-                                       "profiles/r01b_ncu_gm_scalar_raw.csv (dram read + write of one bisecting launch); not measured in this run",
+                                       "profiles/r02/late/ncu_gm_scalar_final_raw.csv (dram read + write of one bisecting launch: 124 B written per child + its parent's geometry); not measured in this run",
                      "flops_per_region": F_REGION, "rule_kernel_ms_per_step": tot_rule_ms / steps,
                      "rule_regions_per_s_per_gpu": rule_regions_per_s,
                      "hbm": {"achieved_gbs": rule_regions_per_s * BYTES_REGION / 1e9, "peak_gbs": hbm_peak,
