@@ -378,9 +378,6 @@ __device__ __forceinline__ bool cub_box_safe(const F&, const double*, const doub
 #endif
 // (tried and dropped: per-thread coordinate tables in shared memory to raise occupancy -- slower at every
 //  CTA count, profiles/r01_summary.md)
-#ifndef CUB_GM_THREADS
-#define CUB_GM_THREADS 128
-#endif
 // Geometry pipeline (CUB_GM_PREFETCH, default on).  A tile starts with a chain of two dependent global loads (list
 // entry -> parent geometry) in front of ~2 800 instructions of FP64 work; with four warps per scheduler that chain
 // showed up as 15 % of the warps' time in "long scoreboard" (profiles/r02/ncu_gm_scalar_raw.csv).  Every thread
@@ -389,8 +386,11 @@ __device__ __forceinline__ bool cub_box_safe(const F&, const double*, const doub
 // the current tile; nothing but the tile counter stays live in registers across the evaluation.  The cells are
 // private to a thread, so no CTA barrier is needed, only cp.async.wait_all.  In BISECT mode the parents of the next
 // tile are written by nobody but that tile itself, so reading them ahead is safe.
-#ifndef CUB_GM_PREFETCH
-#define CUB_GM_PREFETCH 1
+#ifndef CUB_GM_THREADS
+#define CUB_GM_THREADS 128
+#endif
+#ifndef CUB_GM_PREFETCH  // (the cells must fit well inside the 48 KB of static shared memory: d <= 10 at 128 threads)
+#define CUB_GM_PREFETCH ((2 * 2 * CUB_DIM * 8 + 3 * 2 * 4) * CUB_GM_THREADS <= 44 * 1024)
 #endif
 __device__ __forceinline__ void cub_cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");

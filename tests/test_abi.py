@@ -62,6 +62,10 @@ def test_nvrtc_compiles_builtin_without_gpu(cb):
     assert cubin[:4] == b"\x7fELF" and b"cub_gm_scalar" in cubin and b"cub_rule_staged" in cubin
     ig1 = cb.Integrand.builtin(cb.Family.OSC_VEC, 1, 64)
     assert b"cub_gk_separable" in ig1.cubin()
+    # the largest dimensions: the scalar kernel's geometry cells no longer fit static shared memory and are compiled out
+    for dim in (10, 11, 12):
+        ig = cb.Integrand.builtin(cb.Family.GENZ_CORNER_PEAK, dim, 1, [0.3] * dim + [0.5] * dim)
+        assert b"cub_gm_scalar" in ig.cubin()
 
 
 def test_nvrtc_user_source_and_error_log(cb):
