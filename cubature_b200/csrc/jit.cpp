@@ -165,9 +165,13 @@ std::string cub_jit_translation_unit(const cub_integrand* integ, int has_transfo
     // CTAs per SM the scalar Genz-Malik kernel is compiled for (register budget 65536 / (128 * n)); measured on B200
     // (profiles/r01_summary.md, "power"): the rational families run best at 4 (128 registers, next to no spills: the
     // local-memory traffic of the 5- and 6-CTA variants drives the board into its power cap under a sustained load)
-    int min_blocks = 5;  // Gaussian, C0 and everything not listed (profiles/r01_summary.md, family sweep)
+    int min_blocks = 5;  // everything not listed (profiles/r01_summary.md, family sweep)
     if (integ->family == CUB_FAM_GENZ_CORNER_PEAK || integ->family == CUB_FAM_GENZ_PRODUCT_PEAK) min_blocks = 4;
     if (integ->family == CUB_FAM_GENZ_OSCILLATORY || integ->family == CUB_FAM_GENZ_DISCONTINUOUS) min_blocks = 4;
+    // with the Gray orbit in blocks of 16 (profiles/r02/late/families_call5.log): Gaussian 17 % (d = 6) / 2 % (d = 5) faster at
+    // 4 CTAs per SM (no spills instead of 156 bytes), C0 16 % faster at d = 5 and 5 % slower at d = 6
+    if (integ->family == CUB_FAM_GENZ_GAUSSIAN) min_blocks = 4;
+    if (integ->family == CUB_FAM_GENZ_C0 && integ->dim <= 5) min_blocks = 4;
     tu << "#ifndef CUB_GM_MIN_BLOCKS\n#define CUB_GM_MIN_BLOCKS " << min_blocks << "\n#endif\n";
     // branch-free reciprocal fast path of the rational built-in families (detmath.h: dm_rcp_flag; the kernel re-evaluates a
     // region with the IEEE division when an argument leaves the fast path's exact range)
