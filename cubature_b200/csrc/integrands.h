@@ -39,13 +39,8 @@
 template <int DIM>
 DM_HD double cub_dot2(const double* a, const double* x, double init) {
     double s0 = init, s1 = 0.0;
-#if defined(CUB_DOT_DESCENDING) && CUB_DOT_DESCENDING
-    for (int i = ((DIM - 1) & ~1); i >= 0; i -= 2) s0 = dm_fma(a[i], x[i], s0);
-    for (int i = ((DIM - 2) | 1); i >= 1 && DIM > 1; i -= 2) s1 = dm_fma(a[i], x[i], s1);
-#else
     for (int i = 0; i < DIM; i += 2) s0 = dm_fma(a[i], x[i], s0);
     for (int i = 1; i < DIM; i += 2) s1 = dm_fma(a[i], x[i], s1);
-#endif
     return DIM > 1 ? s0 + s1 : s0;
 }
 template <int N>
