@@ -151,9 +151,15 @@ struct GenzCornerPeak {  // (1 + sum a_i x_i)^-(d+1)
     }
 };
 
-template <int DIM>
+// The exponential families come in two variants (MODE): 1 dm_exp (the definition), 2 dm_exp_inrange -- the same bits
+// without the out-of-range handling, for boxes in which box_safe() has bounded the exponent's argument by 690 in
+// magnitude (dm_exp_inrange is exact to 700; any NaN makes box_safe false).  See the rational families above.
+#define CUB_EXP_SAFE 690.0
+template <int DIM, int MODE = 1>
 struct GenzGaussian {  // exp(-sum a_i^2 (x_i - u_i)^2)
     static const bool kSeparable = false;
+    typedef GenzGaussian<DIM, 1> Exact;
+    typedef GenzGaussian<DIM, 2> Unchecked;
     double a[DIM], u[DIM];
     DM_HD GenzGaussian(const double* p, int) {
         for (int i = 0; i < DIM; ++i) {
@@ -171,13 +177,23 @@ struct GenzGaussian {  // exp(-sum a_i^2 (x_i - u_i)^2)
             double t = a[i] * (x[i] - u[i]);
             s1 = dm_fma(t, t, s1);
         }
-        f[0] = dm_exp(-(s0 + s1));
+        f[0] = MODE == 2 ? dm_exp_inrange(-(s0 + s1)) : dm_exp(-(s0 + s1));
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) {
+            const double t = dm_abs(a[i]) * (dm_abs(bc[i] - u[i]) + dm_abs(bh[i]));
+            s = dm_fma(t, t, s);
+        }
+        return s < CUB_EXP_SAFE;
     }
 };
 
-template <int DIM>
+template <int DIM, int MODE = 1>
 struct GenzC0 {  // exp(-sum a_i |x_i - u_i|)
     static const bool kSeparable = false;
+    typedef GenzC0<DIM, 1> Exact;
+    typedef GenzC0<DIM, 2> Unchecked;
     double a[DIM], u[DIM];
     DM_HD GenzC0(const double* p, int) {
         for (int i = 0; i < DIM; ++i) {
@@ -188,13 +204,20 @@ struct GenzC0 {  // exp(-sum a_i |x_i - u_i|)
     DM_HD void eval(const double* x, double* f) const {
         double s = 0.0;
         for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], dm_abs(x[i] - u[i]), s);
-        f[0] = dm_exp(-s);
+        f[0] = MODE == 2 ? dm_exp_inrange(-s) : dm_exp(-s);
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(dm_abs(a[i]), dm_abs(bc[i] - u[i]) + dm_abs(bh[i]), s);
+        return s < CUB_EXP_SAFE;
     }
 };
 
-template <int DIM>
+template <int DIM, int MODE = 1>
 struct GenzDiscontinuous {  // 0 if x_0 > u_0 or x_1 > u_1, else exp(sum a_i x_i)
     static const bool kSeparable = false;
+    typedef GenzDiscontinuous<DIM, 1> Exact;
+    typedef GenzDiscontinuous<DIM, 2> Unchecked;
     double a[DIM], u0, u1;
     DM_HD GenzDiscontinuous(const double* p, int) {
         for (int i = 0; i < DIM; ++i) a[i] = p[i];
@@ -206,21 +229,36 @@ struct GenzDiscontinuous {  // 0 if x_0 > u_0 or x_1 > u_1, else exp(sum a_i x_i
         for (int i = 0; i < DIM; ++i) s = dm_fma(a[i], x[i], s);
         bool outside = x[0] > u0;
         if (DIM > 1) outside = outside || (x[DIM > 1 ? 1 : 0] > u1);
-        f[0] = outside ? 0.0 : dm_exp(s);
+        f[0] = outside ? 0.0 : (MODE == 2 ? dm_exp_inrange(s) : dm_exp(s));
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) s = dm_fma(dm_abs(a[i]), dm_abs(bc[i]) + dm_abs(bh[i]), s);
+        return s < CUB_EXP_SAFE;
     }
 };
 
 // ---- the reference's golden-vector integrand -----------------------------------------------------
 // TestCubature.java:442-455: sum += x*x left to right (Java never fuses), exp(-sigma*sum).
-template <int DIM>
+template <int DIM, int MODE = 1>
 struct GaussIso {
     static const bool kSeparable = false;
+    typedef GaussIso<DIM, 1> Exact;
+    typedef GaussIso<DIM, 2> Unchecked;
     double sigma;
     DM_HD GaussIso(const double* p, int) { sigma = p[0]; }
     DM_HD void eval(const double* x, double* f) const {
         double s = 0.0;
         for (int i = 0; i < DIM; ++i) s = s + x[i] * x[i];
-        f[0] = dm_exp(-sigma * s);
+        f[0] = MODE == 2 ? dm_exp_inrange(-sigma * s) : dm_exp(-sigma * s);
+    }
+    DM_HD bool box_safe(const double* bc, const double* bh) const {
+        double s = 0.0;
+        for (int i = 0; i < DIM; ++i) {
+            const double t = dm_abs(bc[i]) + dm_abs(bh[i]);
+            s = dm_fma(t, t, s);
+        }
+        return dm_abs(sigma) * s < CUB_EXP_SAFE;
     }
 };
 

@@ -24,6 +24,8 @@ def bg():
     dp = ctypes.POINTER(ctypes.c_double)
     L.bg_check.restype = ctypes.c_int
     L.bg_check.argtypes = [ctypes.c_int, dp, dp, dp, dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.bg_exp_pair.restype = None
+    L.bg_exp_pair.argtypes = [ctypes.c_double, dp]
     return L
 
 
@@ -47,7 +49,7 @@ def _check(bg, family, params, c, h, x):
     return bool(safe), bool(flag.value)
 
 
-@pytest.mark.parametrize("family", [3, 2])
+@pytest.mark.parametrize("family", [3, 2, 4, 5, 6, 10])
 def test_box_safe_implies_every_argument_in_range(bg, family):
     rng = np.random.default_rng(5)
     accepted = rejected = 0
@@ -58,6 +60,11 @@ def test_box_safe_implies_every_argument_in_range(bg, family):
             if trial % 5 == 0:
                 a = np.abs(a)
             params = np.concatenate([a, np.zeros(DIM)])
+        elif family in (4, 5, 6):  # exp families: a (any sign, scales around the guard's threshold), u
+            a = rng.uniform(-1, 1, DIM) * 10.0 ** rng.uniform(-2, 3.5)
+            params = np.concatenate([a, rng.uniform(0, 1, DIM)])
+        elif family == 10:
+            params = np.concatenate([[rng.uniform(-1, 1) * 10.0 ** rng.uniform(-2, 4)], np.zeros(2 * DIM - 1)])
         else:
             params = np.concatenate([10.0 ** rng.uniform(-1, 1, DIM) * (scale if trial % 2 else 1.0), rng.uniform(0, 1, DIM)])
         c = rng.uniform(-1, 2, DIM)
@@ -71,7 +78,7 @@ def test_box_safe_implies_every_argument_in_range(bg, family):
     assert accepted > 200 and rejected > 200  # both branches are exercised
 
 
-@pytest.mark.parametrize("family", [3, 2])
+@pytest.mark.parametrize("family", [3, 2, 4, 5, 6])
 def test_box_safe_accepts_the_benchmark_boxes(bg, family):
     """Genz parameters as the benchmarks use them on sub-boxes of [0,1]^d: the guard must not send them to the slow path."""
     rng = np.random.default_rng(6)
@@ -103,3 +110,14 @@ def test_box_safe_rejects_nan_zero_and_overflow(bg, family):
         assert not safe, p
     safe, _ = _check(bg, family, np.array([1.0, 1, 1, 1, 0.5, 0.5, 0.5, 0.5]), np.array([np.nan, 0.5, 0.5, 0.5]), h, x)
     assert not safe
+
+
+def test_exp_inrange_has_the_bits_of_exp(bg):
+    """dm_exp_inrange (no out-of-range selects, one scaling step) == dm_exp bit for bit on [-700, 700]."""
+    rng = np.random.default_rng(8)
+    xs = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-1, 1, 50000), 10.0 ** rng.uniform(-300, 2.8, 20000),
+                         -(10.0 ** rng.uniform(-300, 2.8, 20000)), [0.0, -0.0, 700.0, -700.0, 690.0, -690.0, 1e-320, -1e-320]])
+    out = np.zeros(2)
+    for x in xs:
+        bg.bg_exp_pair(float(x), _dp(out))
+        assert out.view(np.uint64)[0] == out.view(np.uint64)[1], x

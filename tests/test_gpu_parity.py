@@ -453,6 +453,37 @@ def test_fast_reciprocal_falls_back_to_ieee_division_out_of_range(cb, oracle, na
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gaussian", "c0", "discontinuous"])
+def test_exp_families_leave_the_guarded_range_region_by_region(cb, oracle, name):
+    """The exponential Genz families run dm_exp_inrange in boxes whose exponent argument is provably within +-690
+    (integrands.h: box_safe) and the full dm_exp elsewhere (out of line), region by region in the same launch: parameters
+    that put some boxes inside and some outside the guard, and parameters that underflow / overflow exp in every box, must
+    all give the oracle's bits (zeros, subnormals, inf and NaN included)."""
+    dim = 4
+    rng = np.random.default_rng(12)
+    n = 512
+    c = rng.uniform(0.3, 0.7, (n, dim))
+    h = rng.uniform(0.01, 0.2, (n, dim))
+    fam = cases.GENZ[name]
+    u = [0.5, 0.5, 0.5, 0.5]
+    if name == "gaussian":    # argument -(sum (a_i (x_i - u_i))^2): bound 4 (a * 0.4)^2 crosses 690 around a = 33
+        variants = [np.array([40.0, 40, 40, 40] + u), np.array([90.0, 30, 60, 45] + u), np.array([1e3, 1e3, 1e3, 1e3] + u), np.array([1e160, 1, 1, 1] + u)]
+    elif name == "c0":        # argument -(sum a_i |x_i - u_i|)
+        variants = [np.array([500.0, 500, 500, 500] + u), np.array([2000.0, 100, 900, 400] + u), np.array([-2000.0, 100, -900, 400] + u),
+                    np.array([1e300, 1e300, 1, 1] + u)]
+    else:                     # argument sum a_i x_i (overflows exp for positive a)
+        variants = [np.array([250.0, 250, 250, 250] + u), np.array([-250.0, -250, -250, -250] + u), np.array([900.0, -900, 400, -100] + u),
+                    np.array([1e200, 1e200, 1, 1] + u)]
+    for p in variants:
+        gv, ge, gs, _ = cb.Integrand.builtin(fam, dim, 1, p).eval_regions(c, h)
+        cv, ce, cs = oracle.eval_regions(fam, dim, 1, p, c, h)
+        for g, o in ((gv, cv), (ge, ce)):
+            gn, on = np.isnan(g), np.isnan(o)
+            assert np.array_equal(gn, on) and np.array_equal(g[~gn].view(np.uint64), o[~on].view(np.uint64))
+        assert np.array_equal(gs, cs)
+
+
+@pytest.mark.gpu
 def test_large_tie_group_cut_by_max_eval_tiles_the_domain(cb, oracle):
     """5e5 regions with exactly equal error estimates (an integrand the rule cannot see: all values 0) and a batch cut by
     maxEval inside that tie group: many CTAs of the iteration kernel must agree on the threshold key down to its last
