@@ -34,6 +34,7 @@ struct HostWork {
     double* stage_val;
     double* stage_err;
     long long stage_stride;
+    long long dyn_lo, dyn_hi;  // device-sized launches: batch sizes this kernel takes (rule_kernels.cuh: CubWork)
 };
 enum { MODE_PLAIN = 0, MODE_BISECT = 1, MODE_CHILDREN = 2 };
 

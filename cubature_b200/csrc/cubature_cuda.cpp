@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <climits>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -497,8 +498,31 @@ struct Session {
             const long long tiles = (work.n_items + threads - 1) / threads;
             static const int waves = [] { const char* e = getenv("CUBATURE_RULE_WAVES"); return e ? atoi(e) : 16; }();
             const unsigned grid = (unsigned)(waves > 0 ? std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm * waves) : tiles);
+            // Device-sized bisecting launches (the device-resident loops): a batch below `small` items goes to the
+            // point-parallel staged kernel instead (one thread per (region, point), then the serial sums: a few microseconds,
+            // where one thread per region costs the serial latency of a whole region, 10-25 us, however small the batch).
+            // Both kernels are enqueued; each reads the batch size from the control block and the other one retires at once.
+            // Same values, same sums in the same order: results are bit-identical.  CUBATURE_SMALL_BATCH=0 disables.
+            const char* small_env = getenv("CUBATURE_SMALL_BATCH");  // (read per launch: tools toggle it within one process)
+            const long long small = small_env ? atoll(small_env) : 2048LL;
+            const bool split_by_size = small >= 2 && work.dyn && work.mode == MODE_BISECT && !work.stage_val && kern->staged;
+            if (split_by_size) {
+                work.dyn_lo = small;
+                work.dyn_hi = LLONG_MAX;
+            }
             e = cudaLaunchKernel((const void*)kern->gm_scalar, dim3(grid), dim3(threads), args, 0, stream);
             ++launches;
+            if (split_by_size && e == cudaSuccess) {
+                work.dyn_lo = 0;
+                work.dyn_hi = small;
+                int rpb = 2;  // even: both children of a parent in one pass (rule_kernels.cuh: cub_rule_staged, BISECT)
+                const size_t per_region = ((size_t)P * 1 + 3 * (size_t)dim + 1) * 8 + 24;
+                const long long groups = (std::min<long long>(work.n_items, small) + rpb - 1) / rpb;
+                const unsigned sgrid = (unsigned)std::max<long long>(1, std::min<long long>(groups, (long long)n_sms * 8));
+                args[4] = &rpb;
+                e = cudaLaunchKernel((const void*)kern->staged, dim3(sgrid), dim3(256), args, per_region * rpb, stream);
+                ++launches;
+            }
         } else if (dim == 1 && (fdim == 1 || integ->separable)) {
             const long long threads = work.n_items * fdim;
             const unsigned grid = (unsigned)std::min<long long>((threads + 127) / 128, (long long)n_sms * kern->gk_blocks_per_sm);
@@ -510,7 +534,7 @@ struct Session {
             }
         } else {
             const int FS = fdim | 1;
-            const size_t per_region = ((size_t)P * FS + 3 * (size_t)dim + (size_t)fdim) * 8 + 8;
+            const size_t per_region = ((size_t)P * FS + 3 * (size_t)dim + (size_t)fdim) * 8 + 24;
             const size_t max_smem = (size_t)kern->staged_max_smem;
             if (per_region > max_smem) {
                 cub_set_message(msg, "fdim=%d at dim=%d needs %zu bytes of shared memory per region (max %zu)", fdim, dim,

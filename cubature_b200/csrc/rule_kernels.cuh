@@ -69,6 +69,10 @@ struct CubWork {
     double* stage_val;  // [CUB_FDIM][stage_stride]
     double* stage_err;  // [CUB_FDIM][stage_stride]
     long long stage_stride;
+    // device-sized launches only: this kernel takes the batch only if dyn_lo <= n_items < dyn_hi (dyn_hi == 0: always).
+    // The host enqueues the one-thread-per-region kernel for [T, inf) and the point-parallel staged kernel for [0, T):
+    // a small batch does not pay the serial latency of a whole region per thread.
+    long long dyn_lo, dyn_hi;
 };
 
 struct CubParams {
@@ -100,6 +104,7 @@ __device__ __forceinline__ CubWork cub_resolve(const CubWork& w) {
         r.n_items = w.dyn[0];
         if (!w.dyn[1]) r.list = nullptr;
         r.base = w.dyn[2];
+        if (w.dyn_hi > 0 && (r.n_items < w.dyn_lo || r.n_items >= w.dyn_hi)) r.n_items = 0;  // another kernel's batch
     }
     return r;
 }
@@ -763,7 +768,9 @@ cub_rule_staged(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPa
     double* sh = sc + rpb * CUB_DIM;                                // [rpb][DIM]
     double* sdiff = sh + rpb * CUB_DIM;                             // [rpb][DIM]
     double* serr = sdiff + rpb * CUB_DIM;                           // [rpb][FDIM]
-    long long* sslot = (long long*)(serr + (long long)rpb * CUB_FDIM);  // [rpb]
+    long long* sslot = (long long*)(serr + (long long)rpb * CUB_FDIM);  // [rpb] the item's slot
+    long long* ssrc = sslot + rpb;                                      // [rpb] where its geometry is read (BISECT: the parent)
+    int* ssplit = (int*)(ssrc + rpb);                                   // [rpb] the parent's split dimension (BISECT)
 
     const long long n = work.n_items;
     const CubExactIntegrand fn(prm.v, CUB_FDIM);
@@ -771,14 +778,43 @@ cub_rule_staged(CubPoolView pool, CubWork work_in, const __grid_constant__ CubPa
 
     for (long long first = (long long)blockIdx.x * rpb; first < n; first += (long long)gridDim.x * rpb) {
         const int nr = (int)(n - first < rpb ? n - first : rpb);
-        for (int r = tid; r < nr; r += nt) sslot[r] = cub_item_slot(work, first + r);
+        for (int r = tid; r < nr; r += nt) {
+            const long long slot = cub_item_slot(work, first + r);
+            sslot[r] = slot;
+            if (work.mode == CUB_MODE_BISECT) {
+                const long long pi = (first + r) >> 1;
+                const long long parent = work.list ? (long long)work.list[pi] : pi;
+                ssrc[r] = parent;
+                ssplit[r] = pool.splitdim[parent];
+            } else {
+                ssrc[r] = slot;
+            }
+        }
         __syncthreads();
         for (int idx = tid; idx < nr * CUB_DIM; idx += nt) {
             const int r = idx / CUB_DIM, d = idx - r * CUB_DIM;
-            sc[idx] = pool.center[(long long)d * pool.cap + sslot[r]];
-            sh[idx] = pool.halfw[(long long)d * pool.cap + sslot[r]];
+            sc[idx] = pool.center[(long long)d * pool.cap + ssrc[r]];
+            sh[idx] = pool.halfw[(long long)d * pool.cap + ssrc[r]];
         }
         __syncthreads();
+        if (work.mode == CUB_MODE_BISECT) {
+            // Region.java:31-38 in shared memory; both children of a parent are items 2k, 2k + 1 of the SAME pass (rpb is
+            // even, the host's contract), and every read of the parent precedes the barrier above: the left child may
+            // now overwrite the parent's slot
+            for (int idx = tid; idx < nr * CUB_DIM; idx += nt) {
+                const int r = idx / CUB_DIM, d = idx - r * CUB_DIM;
+                double c = sc[idx], hw = sh[idx];
+                if (d == ssplit[r]) {
+                    hw = hw * 0.5;
+                    c = ((first + r) & 1) ? c + hw : c - hw;
+                    sc[idx] = c;
+                    sh[idx] = hw;
+                }
+                pool.center[(long long)d * pool.cap + sslot[r]] = c;
+                pool.halfw[(long long)d * pool.cap + sslot[r]] = hw;
+            }
+            __syncthreads();
+        }
         // phase 1
         for (int idx = tid; idx < nr * CUB_RULE_POINTS; idx += nt) {
             const int r = idx / CUB_RULE_POINTS, k = idx - r * CUB_RULE_POINTS;
