@@ -498,13 +498,14 @@ struct Session {
             const long long tiles = (work.n_items + threads - 1) / threads;
             static const int waves = [] { const char* e = getenv("CUBATURE_RULE_WAVES"); return e ? atoi(e) : 16; }();
             const unsigned grid = (unsigned)(waves > 0 ? std::min<long long>(tiles, (long long)n_sms * kern->gm_blocks_per_sm * waves) : tiles);
-            // Device-sized bisecting launches (the device-resident loops): a batch below `small` items goes to the
-            // point-parallel staged kernel instead (one thread per (region, point), then the serial sums: a few microseconds,
-            // where one thread per region costs the serial latency of a whole region, 10-25 us, however small the batch).
-            // Both kernels are enqueued; each reads the batch size from the control block and the other one retires at once.
-            // Same values, same sums in the same order: results are bit-identical.  CUBATURE_SMALL_BATCH=0 disables.
+            // Experiment, off by default (CUBATURE_SMALL_BATCH=n enables it for batches below n items): a small device-sized
+            // bisecting batch goes to the point-parallel staged kernel (one thread per (region, point), then the serial sums)
+            // instead of paying the serial latency of a whole region per thread.  Both kernels are enqueued; each reads the
+            // batch size from the control block and the other one retires at once.  Results are bit-identical (GPU suite green
+            // with n = 2048), but the second launch per iteration costs more (4-5 us) than the small batches gain: C3 time to
+            // tolerance +0.2-0.3 ms for five of six families (profiles/r02/late/small_batch_time_to_tol.log).
             const char* small_env = getenv("CUBATURE_SMALL_BATCH");  // (read per launch: tools toggle it within one process)
-            const long long small = small_env ? atoll(small_env) : 2048LL;
+            const long long small = small_env ? atoll(small_env) : 0LL;
             const bool split_by_size = small >= 2 && work.dyn && work.mode == MODE_BISECT && !work.stage_val && kern->staged;
             if (split_by_size) {
                 work.dyn_lo = small;
